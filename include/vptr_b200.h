@@ -1,0 +1,131 @@
+/* libvptr_b200.so -- C-ABI of the B200-native VPTR stage-2 hot path.
+ *
+ * The reference (XiYe20/VPTR) is pure PyTorch and has no FFI of its own: every kernel it runs is an ATen /
+ * cuBLAS / cuDNN call made from model/*.py.  Each entry point below therefore cites the reference call site
+ * (file:line under the reference root) whose library kernels it replaces.  The host side that mirrors the
+ * reference's nn.Module API (vptr_b200/model) binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - all tensors fp32, device pointers borrowed for the duration of the call (never retained, allocated or
+ *     freed here); activations are token-major / channel-last: rows ordered (n, t, h, w), C contiguous.
+ *   - every function is asynchronous on `stream` and returns int: 0 ok, <0 invalid shape / alignment /
+ *     unsupported configuration, >0 a cudaError_t.  vptr_last_error() gives the thread-local message.
+ *   - nothing synchronises the device and nothing allocates, so every call is CUDA-graph capturable.
+ */
+#ifndef VPTR_B200_H
+#define VPTR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vptr_stream_t; /* == cudaStream_t */
+
+int vptr_version(void);
+const char* vptr_last_error(void);
+
+/* ---- dense contractions (tcgen05 kind::tf32, TMEM accumulators, TMA operands) -------------------------
+ * D[M,N] (+)= act(alpha * sum_k Aop[m,k]*Bop[n,k] + bias[n]) + residual[m,n]
+ *   a_mn=0: A is [M][K] (pitch lda)   a_mn=1: A is [K][M]      b_mn=0: B is [N][K] (pitch ldb)   b_mn=1: B is [K][N]
+ *   act: 0 none, 1 exact GELU, 2 ReLU.  flags: bit0 atomic accumulate into D (split-K allowed: k_splits 0 = auto),
+ *   bit1 round stored values to tf32 (round-to-nearest) so a following tf32 contraction reads exact operands.
+ * Replaces: q/k/v/out nn.Linear (model/MultiHeadAttentionRPE.py:543-545,688), nn.MultiheadAttention in/out
+ * projections (model/VidHRFormer_modules.py:79-84,185-187,204-205), MlpDWBN 1x1 convs (:424-442), linear1/linear2
+ * (:87-89,190-192), NCE_projector (model/VPTR_modules.py:133-135), and -- on im2col operands -- the ResNet 3x3
+ * Conv2d / ConvTranspose2d (model/ResNetAutoEncoder.py:26-47,74-90), with their autograd dgrad / wgrad. */
+int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D, long long ldd,
+                   int M, int N, int K, const float* bias, const float* residual, long long ldr, float alpha, int act,
+                   int flags, int k_splits, vptr_stream_t stream);
+/* same contract on fp32 FFMA; for pitches TMA cannot address and as the on-device cross-check in tests */
+int vptr_gemm_simt(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D, long long ldd,
+                   int M, int N, int K, const float* bias, const float* residual, long long ldr, float alpha, int act,
+                   int flags, int k_splits, vptr_stream_t stream);
+
+/* ---- LayerNorm over C (model/VidHRFormer_modules.py:44-56,137-161,25-26,114-115) ---------------------
+ * y = LN(x)*gamma+beta [relu]; y2 = y + add[(row/add_div) % add_mod] (positional add of :75-84,176-178,200). */
+int vptr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* add,
+                       int add_div, int add_mod, float* mean, float* rstd, long long rows, int C, float eps, int relu,
+                       vptr_stream_t stream);
+/* dx = dres + dLN(dy1 + dy2); dgamma/dbeta accumulated (+=); any of dy2, dres, dx, dgamma may be NULL */
+int vptr_layernorm_bwd(const float* dy1, const float* dy2, const float* x, const float* gamma, const float* beta,
+                       const float* mean, const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                       long long rows, int C, int relu, vptr_stream_t stream);
+
+/* ---- MlpDWBN norms (model/VidHRFormer_modules.py:397-400,424-442) ------------------------------------- */
+int vptr_bn_stats(const float* x, long long rows, int ch, float* mean, float* rstd, float* running_mean, float* running_var,
+                  float eps, float momentum, double* ws /* 2*ch doubles */, vptr_stream_t stream);
+int vptr_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* rstd, int ch, float eps,
+                       vptr_stream_t stream);
+int vptr_group_stats(const float* x, int groups, long long gsize, float* mean, float* rstd, float eps, vptr_stream_t stream);
+/* y = GELU(norm(x)) (+res). mode 0 BatchNorm (per channel), 1 LayerNorm((ch,H,W)) per frame, affine laid [hw][ch] */
+int vptr_norm_act_fwd(const float* x, float* y, const float* res, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, vptr_stream_t stream);
+/* mode 0 train BatchNorm, 1 frame LayerNorm, 2 eval BatchNorm. ws: 2*ch (modes 0,2) or 2*frames (mode 1) floats */
+int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
+                      float* ws, vptr_stream_t stream);
+
+/* ---- attention cores ---------------------------------------------------------------------------------
+ * mode 0: local-window attention + relative-position bias (model/VidHRFormer_modules.py:321-357,503-525;
+ *         model/MultiHeadAttentionRPE.py:586-590,623,635-650,677-686); F_or_N = frames.
+ * mode 1: temporal / encoder-decoder attention per pixel (model/VidHRFormer_modules.py:79-84,185-187,204-205),
+ *         causal = FAR mask of :78; F_or_N = clips.
+ * Q,K,V,O are token-major with row pitches ld*; head h uses columns [h*d, (h+1)*d). */
+int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
+                  long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead,
+                  int d, int causal, float scale, vptr_stream_t stream);
+int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO,
+                  long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV, long long lddv,
+                  const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
+                  int nhead, int d, int causal, float scale, vptr_stream_t stream);
+/* integer artefacts from the kernels' own index functions (bit-exact contract): relative_position_index
+ * (model/MultiHeadAttentionRPE.py:373-387) as int64 [L][L]; window token map (model/VidHRFormer_modules.py:503-513)
+ * as int64 [L][B]; causal mask (model/VidHRFormer_modules.py:78) as uint8 [T][T] */
+int vptr_window_index_maps(int F, int H, int W, int ws, long long* rpi, long long* wmap, vptr_stream_t stream);
+int vptr_causal_mask(int T, unsigned char* mask, vptr_stream_t stream);
+
+/* ---- depthwise 3x3 of MlpDWBN (model/VidHRFormer_modules.py:405-410) ----------------------------------- */
+int vptr_dwconv3x3(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, int flip,
+                   vptr_stream_t stream);
+int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9, float* dbias, int F, int H, int W, int ch,
+                         vptr_stream_t stream);
+
+/* ---- elementwise / layout helpers ----------------------------------------------------------------------- */
+int vptr_axpby(const float* a, const float* b, float* out, long long n, float alpha, float beta, vptr_stream_t stream);
+int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, vptr_stream_t stream);
+int vptr_rowgroup_sum(const float* dy, float* out, long long group_elems, int reps, vptr_stream_t stream);
+int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, vptr_stream_t stream);
+int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, vptr_stream_t stream);
+int vptr_relu_fwd(const float* x, float* y, long long n, vptr_stream_t stream);
+int vptr_relu_bwd(const float* dy, const float* y, float* dx, long long n, vptr_stream_t stream);
+int vptr_colsum(const float* x, float* out, long long rows, int C, long long ld, vptr_stream_t stream);
+int vptr_transpose(const float* in, float* out, int batch, int R, int C, int accumulate, vptr_stream_t stream);
+/* PadBlock (model/VidHRFormer_modules.py:527-561): dir 0 centre zero-pad, dir 1 crop */
+int vptr_pad_crop(const float* in, float* out, int F, int H, int W, int Hp, int Wp, int ph0, int pw0, int C, int dir,
+                  vptr_stream_t stream);
+/* gradient clipping pieces (train_NAR.py:85): sqnorm += sum x^2 ; x *= min(1, max_norm/(sqrt(sqnorm)+1e-6)) */
+int vptr_sqnorm_accumulate(const float* x, long long n, double* sqnorm_out, vptr_stream_t stream);
+int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm, vptr_stream_t stream);
+
+/* ---- ResNet encoder / decoder (model/ResNetAutoEncoder.py:26-48,70-98) ---------------------------------- */
+int vptr_im2col(const float* x, const float* mask, float* col, int F, int H, int W, int Cin, int k, int stride, int pad,
+                int pad_mode /* 0 zero, 1 reflect, 2 replicate */, vptr_stream_t stream);
+int vptr_convT_gather(const float* col, const float* shift, float* out, int F, int H, int W, int Cout, int relu,
+                      vptr_stream_t stream);
+int vptr_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                 float* scale, float* shift, int C, vptr_stream_t stream);
+int vptr_pack_conv_weight(const float* w, const float* scale, float* out, int Co, int Ci, int k, int mode, vptr_stream_t stream);
+int vptr_stem_conv7x7(const float* x, const float* wpk, const float* shift, float* out, int F, int Ci, int H, int W, int Co,
+                      vptr_stream_t stream);
+int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const float* bias, float* out, int F, int Ci, int Co, int H, int W,
+                          int act /* 0 none, 1 tanh, 2 sigmoid */, vptr_stream_t stream);
+int vptr_head_conv7x7_bwd(const float* dout, const float* out, const float* w, float* dx, int F, int Ci, int Co, int H, int W,
+                          int act, vptr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPTR_B200_H */

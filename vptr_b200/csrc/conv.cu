@@ -1,0 +1,331 @@
+// ResNet encoder / decoder support kernels (model/ResNetAutoEncoder.py:26-48 encoder, :70-98 decoder), channel-last.
+// The k x k convolutions run as GEMMs on the tcgen05 kernel (gemm_tcgen05.cu); this file holds what surrounds them:
+//   * im2col gather (zero / reflect / replicate padding, stride 1|2, optional ReLU-mask for the decoder's backward),
+//   * the ConvTranspose2d(3, s2, p1, op1) output gather ("col2im") with folded eval-BatchNorm shift + ReLU,
+//   * weight re-layout with the eval-BatchNorm scale folded in,
+//   * the 7x7 stem (Cimg -> 64, reads the NCHW frames directly) and the 7x7 head (64 -> Cimg, + bias, Tanh|Sigmoid,
+//     writes NCHW frames) as direct HBM-bound kernels, and the head's input gradient.
+#include "common.cuh"
+
+namespace {
+
+int ew_grid(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    long long cap = 148LL * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+__device__ __forceinline__ int pad_index(int i, int n, int mode) {  // returns -1 for a zero tap
+    if (i >= 0 && i < n) return i;
+    if (mode == 1) return i < 0 ? -i : 2 * (n - 1) - i;  // reflect (no edge repeat), as nn.ReflectionPad2d
+    if (mode == 2) return i < 0 ? 0 : n - 1;             // replicate
+    return -1;
+}
+
+// col[(f,oh,ow)][(kh,kw,ci)] = x[f][oh*s+kh-p][ow*s+kw-p][ci] (* (mask > 0))
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ col,
+                                                     long long total4, int H, int W, int C4, int Ho, int Wo, int k, int stride, int pad,
+                                                     int pad_mode) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        long long t = i / C4;
+        const int kw = (int)(t % k); t /= k;
+        const int kh = (int)(t % k); t /= k;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho);
+        const long long f = t / Ho;
+        const int ih = pad_index(oh * stride + kh - pad, H, pad_mode);
+        const int iw = pad_index(ow * stride + kw - pad, W, pad_mode);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && iw >= 0) {
+            const long long src = ((f * H + ih) * W + iw) * C4 + c;
+            v = reinterpret_cast<const float4*>(x)[src];
+            if (mask) {
+                float4 m = reinterpret_cast<const float4*>(mask)[src];
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+            }
+        }
+        reinterpret_cast<float4*>(col)[i] = v;
+    }
+}
+
+// ConvTranspose2d(k3,s2,p1,op1) output gather: out[f][oh][ow][co] = relu( sum_{kh,kw} col[(f,ih,iw)][(kh,kw,co)] + shift[co] )
+// with oh = 2*ih - 1 + kh.
+__global__ void __launch_bounds__(256) convT_gather_kernel(const float* __restrict__ col, const float* __restrict__ shift,
+                                                           float* __restrict__ out, long long total4, int H, int W, int C4, int relu) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        long long t = i / C4;
+        const int ow = (int)(t % Wo); t /= Wo;
+        const int oh = (int)(t % Ho);
+        const long long f = t / Ho;
+        float4 acc = shift ? __ldg(reinterpret_cast<const float4*>(shift) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int th = oh + 1 - kh;
+            if (th < 0 || (th & 1)) continue;
+            const int ih = th >> 1;
+            if (ih >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int tw = ow + 1 - kw;
+                if (tw < 0 || (tw & 1)) continue;
+                const int iw = tw >> 1;
+                if (iw >= W) continue;
+                float4 v = reinterpret_cast<const float4*>(col)[(((f * H + ih) * W + iw) * 9 + kh * 3 + kw) * C4 + c];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        reinterpret_cast<float4*>(out)[i] = acc;
+    }
+}
+
+// eval BatchNorm fold: scale = gamma / sqrt(var + eps); shift = beta - mean * scale
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps, float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - rm[c] * s;
+}
+
+// mode 0: Conv2d weight [Co][Ci][k][k]           -> out[co][(kh,kw,ci)] * scale[co]        (GEMM B operand, K-major)
+// mode 1: ConvTranspose2d weight [Ci][Co][k][k]  -> out[(kh,kw,co)][ci] * scale[co]        (GEMM B operand, K-major, N = k*k*Co)
+// mode 2: Conv2d weight [Co][Ci][k][k]           -> out[(kh,kw,ci)][co] * scale[co]        (stem: tap-major, Co contiguous)
+// mode 3: Conv2d weight [Co][Ci][k][k]           -> out[(kh,kw)][co][ci]                   (head)
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ out, int Co, int Ci,
+                                   int k, int mode) {
+    const long long total = (long long)Co * Ci * k * k;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kw = (int)(i % k);
+        long long t = i / k;
+        const int kh = (int)(t % k); t /= k;
+        int co, ci;
+        if (mode == 1) { co = (int)(t % Co); ci = (int)(t / Co); } else { ci = (int)(t % Ci); co = (int)(t / Ci); }
+        const float v = w[i] * (scale ? scale[co] : 1.f);
+        long long dst;
+        if (mode == 0) dst = ((long long)co * k * k + kh * k + kw) * Ci + ci;
+        else if (mode == 1) dst = ((long long)(kh * k + kw) * Co + co) * Ci + ci;
+        else if (mode == 2) dst = ((long long)(kh * k + kw) * Ci + ci) * Co + co;
+        else dst = ((long long)(kh * k + kw) * Co + co) * Ci + ci;
+        out[dst] = v;
+    }
+}
+
+// 7x7 stem: x NCHW [F][Ci][H][W] (reflect pad 3) -> out NHWC [F][H][W][64] = relu(conv + shift); wpk [(kh,kw,ci)][64] (scale folded)
+constexpr int STEM_CO = 64;
+__global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
+                                                           const float* __restrict__ shift, float* __restrict__ out, int Ci, int H, int W) {
+    extern __shared__ float sm[];
+    float* sw = sm;                          // [49*Ci][64]
+    float* sp = sm + 49 * Ci * STEM_CO;      // [Ci][22][22]
+    const int f = blockIdx.z;
+    const int oh0 = blockIdx.y * 16, ow0 = blockIdx.x * 16;
+    for (int e = threadIdx.x; e < 49 * Ci * STEM_CO; e += 256) sw[e] = wpk[e];
+    for (int e = threadIdx.x; e < Ci * 22 * 22; e += 256) {
+        const int ci = e / 484, r = e % 484;
+        const int ph = r / 22, pw = r % 22;
+        int ih = pad_index(oh0 + ph - 3, H, 1), iw = pad_index(ow0 + pw - 3, W, 1);
+        ih = min(max(ih, 0), H - 1); iw = min(max(iw, 0), W - 1);  // tile overhang past the image (never used by valid outputs)
+        sp[e] = x[(((long long)f * Ci + ci) * H + ih) * W + iw];
+    }
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    float acc[STEM_CO];
+#pragma unroll
+    for (int c = 0; c < STEM_CO; ++c) acc[c] = shift[c];
+    for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw)
+            for (int ci = 0; ci < Ci; ++ci) {
+                const float v = sp[ci * 484 + (ty + kh) * 22 + tx + kw];
+                const float4* wrow = reinterpret_cast<const float4*>(sw + ((kh * 7 + kw) * Ci + ci) * STEM_CO);
+#pragma unroll
+                for (int c4 = 0; c4 < STEM_CO / 4; ++c4) {
+                    const float4 k = wrow[c4];
+                    acc[c4 * 4 + 0] = fmaf(v, k.x, acc[c4 * 4 + 0]);
+                    acc[c4 * 4 + 1] = fmaf(v, k.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(v, k.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(v, k.w, acc[c4 * 4 + 3]);
+                }
+            }
+    if (oh < H && ow < W) {
+        float4* o = reinterpret_cast<float4*>(out + (((long long)f * H + oh) * W + ow) * STEM_CO);
+#pragma unroll
+        for (int c4 = 0; c4 < STEM_CO / 4; ++c4)
+            o[c4] = make_float4(fmaxf(acc[c4 * 4], 0.f), fmaxf(acc[c4 * 4 + 1], 0.f), fmaxf(acc[c4 * 4 + 2], 0.f), fmaxf(acc[c4 * 4 + 3], 0.f));
+    }
+}
+
+// 7x7 head: x NHWC [F][H][W][Ci] (reflect pad 3) -> out NCHW [F][Co][H][W] = act(conv + bias); wpk [(kh,kw)][co][ci]
+constexpr int HEAD_MAXCO = 4;
+__device__ __forceinline__ float head_act(float v, int act) {
+    if (act == 1) return tanhf(v);
+    if (act == 2) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+__global__ void __launch_bounds__(256) head_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int Ci, int Co, int H,
+                                                           int W, int act) {
+    extern __shared__ float sm[];
+    constexpr int CC = 16;                 // channel chunk
+    float* sp = sm;                        // [22][22][CC]
+    float* sw = sm + 22 * 22 * CC;         // [49][Co][CC]
+    const int f = blockIdx.z;
+    const int oh0 = blockIdx.y * 16, ow0 = blockIdx.x * 16;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[HEAD_MAXCO] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < Ci; c0 += CC) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 484 * (CC / 4); e += 256) {
+            const int c4 = e % (CC / 4), r = e / (CC / 4);
+            const int ph = r / 22, pw = r % 22;
+            int ih = pad_index(oh0 + ph - 3, H, 1), iw = pad_index(ow0 + pw - 3, W, 1);
+            ih = min(max(ih, 0), H - 1); iw = min(max(iw, 0), W - 1);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + c4 * 4 < Ci) v = *reinterpret_cast<const float4*>(x + (((long long)f * H + ih) * W + iw) * Ci + c0 + c4 * 4);
+            reinterpret_cast<float4*>(sp)[e] = v;
+        }
+        for (int e = threadIdx.x; e < 49 * Co * CC; e += 256) {
+            const int c = e % CC, r = e / CC;  // r = tap*Co + co
+            sw[e] = (c0 + c < Ci) ? wpk[(long long)r * Ci + c0 + c] : 0.f;
+        }
+        __syncthreads();
+        for (int kh = 0; kh < 7; ++kh)
+            for (int kw = 0; kw < 7; ++kw) {
+                const float4* p = reinterpret_cast<const float4*>(sp + ((ty + kh) * 22 + tx + kw) * CC);
+                float4 v[CC / 4];
+#pragma unroll
+                for (int q = 0; q < CC / 4; ++q) v[q] = p[q];
+                for (int co = 0; co < Co; ++co) {
+                    const float4* wv = reinterpret_cast<const float4*>(sw + ((kh * 7 + kw) * Co + co) * CC);
+                    float s = 0.f;
+#pragma unroll
+                    for (int q = 0; q < CC / 4; ++q) {
+                        const float4 k = wv[q];
+                        s = fmaf(v[q].x, k.x, s); s = fmaf(v[q].y, k.y, s); s = fmaf(v[q].z, k.z, s); s = fmaf(v[q].w, k.w, s);
+                    }
+                    acc[co] += s;
+                }
+            }
+    }
+    const int oh = oh0 + ty, ow = ow0 + tx;
+    if (oh < H && ow < W)
+        for (int co = 0; co < Co; ++co)
+            out[(((long long)f * Co + co) * H + oh) * W + ow] = head_act(acc[co] + bias[co], act);
+}
+
+// Head input gradient: dx NHWC [F][H][W][Ci] from dout/out NCHW [F][Co][H][W]; w original layout [Co][Ci][7][7].
+// The reflect padding folds up to 2x2 padded positions onto one source pixel.
+__global__ void __launch_bounds__(256) head_conv7x7_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ outv,
+                                                               const float* __restrict__ w, float* __restrict__ dx, int Ci, int Co, int H,
+                                                               int W, int act) {
+    extern __shared__ float sm[];  // [49][Co][Ci]
+    for (int e = threadIdx.x; e < 49 * Co * Ci; e += blockDim.x) {
+        const int ci = e % Ci;
+        int r = e / Ci;
+        const int co = r % Co, tap = r / Co;
+        sm[e] = w[((long long)co * Ci + ci) * 49 + tap];
+    }
+    __syncthreads();
+    const int f = blockIdx.z;
+    const int ppb = blockDim.x / Ci;  // pixels per block
+    const int ci = threadIdx.x % Ci;
+    const int pix = blockIdx.x * ppb + threadIdx.x / Ci;
+    if (pix >= H * W || threadIdx.x / Ci >= ppb) return;
+    const int i = pix / W, j = pix % W;
+    int ps[3], qs[3], np = 1, nq = 1;
+    ps[0] = i + 3; qs[0] = j + 3;
+    if (i >= 1 && i <= 3) ps[np++] = 3 - i;
+    if (i >= H - 4 && i <= H - 2) ps[np++] = 2 * H + 1 - i;
+    if (j >= 1 && j <= 3) qs[nq++] = 3 - j;
+    if (j >= W - 4 && j <= W - 2) qs[nq++] = 2 * W + 1 - j;
+    float acc = 0.f;
+    for (int a = 0; a < np; ++a)
+        for (int b = 0; b < nq; ++b)
+            for (int kh = 0; kh < 7; ++kh) {
+                const int oh = ps[a] - kh;
+                if (oh < 0 || oh >= H) continue;
+                for (int kw = 0; kw < 7; ++kw) {
+                    const int ow = qs[b] - kw;
+                    if (ow < 0 || ow >= W) continue;
+                    for (int co = 0; co < Co; ++co) {
+                        const long long o = (((long long)f * Co + co) * H + oh) * W + ow;
+                        float g = dout[o];
+                        if (act == 1) { const float y = outv[o]; g *= (1.f - y * y); }
+                        else if (act == 2) { const float y = outv[o]; g *= y * (1.f - y); }
+                        acc = fmaf(g, sm[((kh * 7 + kw) * Co + co) * Ci + ci], acc);
+                    }
+                }
+            }
+    dx[(((long long)f * H + i) * W + j) * Ci + ci] = acc;
+}
+
+}  // namespace
+
+extern "C" int vptr_im2col(const float* x, const float* mask, float* col, int F, int H, int W, int Cin, int k, int stride, int pad,
+                           int pad_mode, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 4 == 0 && k > 0 && stride > 0, VPTR_ERR_SHAPE,
+                 "vptr_im2col: F=%d H=%d W=%d Cin=%d k=%d stride=%d", F, H, W, Cin, k, stride);
+    VPTR_REQUIRE(pad_mode == 0 || (pad < H && pad < W), VPTR_ERR_SHAPE, "vptr_im2col: reflect/replicate pad %d too large for %dx%d", pad, H, W);
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    const long long total4 = (long long)F * Ho * Wo * k * k * (Cin / 4);
+    im2col_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, mask, col, total4, H, W, Cin / 4, Ho, Wo, k, stride, pad, pad_mode);
+    return vptr_check_launch("im2col_kernel");
+}
+
+extern "C" int vptr_convT_gather(const float* col, const float* shift, float* out, int F, int H, int W, int Cout, int relu,
+                                 cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0, VPTR_ERR_SHAPE, "vptr_convT_gather: F=%d H=%d W=%d Cout=%d", F, H, W, Cout);
+    const long long total4 = (long long)F * 4 * H * W * (Cout / 4);
+    convT_gather_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(col, shift, out, total4, H, W, Cout / 4, relu);
+    return vptr_check_launch("convT_gather_kernel");
+}
+
+extern "C" int vptr_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                            float* scale, float* shift, int C, cudaStream_t stream) {
+    bn_fold_kernel<<<vptr_cdiv(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
+    return vptr_check_launch("bn_fold_kernel");
+}
+
+extern "C" int vptr_pack_conv_weight(const float* w, const float* scale, float* out, int Co, int Ci, int k, int mode, cudaStream_t stream) {
+    VPTR_REQUIRE(Co > 0 && Ci > 0 && k > 0 && mode >= 0 && mode <= 3, VPTR_ERR_SHAPE, "vptr_pack_conv_weight: Co=%d Ci=%d k=%d mode=%d", Co, Ci, k, mode);
+    pack_weight_kernel<<<ew_grid((long long)Co * Ci * k * k, 256), 256, 0, stream>>>(w, scale, out, Co, Ci, k, mode);
+    return vptr_check_launch("pack_weight_kernel");
+}
+
+extern "C" int vptr_stem_conv7x7(const float* x, const float* wpk, const float* shift, float* out, int F, int Ci, int H, int W, int Co,
+                                 cudaStream_t stream) {
+    VPTR_REQUIRE(Co == STEM_CO, VPTR_ERR_UNSUPPORTED, "vptr_stem_conv7x7: Co=%d (only %d, the reference's fixed ngf)", Co, STEM_CO);
+    VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci <= 4 && H > 3 && W > 3, VPTR_ERR_SHAPE, "vptr_stem_conv7x7: F=%d Ci=%d H=%d W=%d", F, Ci, H, W);
+    size_t smem = sizeof(float) * ((size_t)49 * Ci * STEM_CO + (size_t)Ci * 484);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(vptr_cdiv(W, 16), vptr_cdiv(H, 16), F);
+    stem_conv7x7_kernel<<<grid, 256, smem, stream>>>(x, wpk, shift, out, Ci, H, W);
+    return vptr_check_launch("stem_conv7x7_kernel");
+}
+
+extern "C" int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const float* bias, float* out, int F, int Ci, int Co, int H, int W,
+                                     int act, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci % 4 == 0 && Co > 0 && Co <= HEAD_MAXCO && H > 3 && W > 3, VPTR_ERR_SHAPE,
+                 "vptr_head_conv7x7_fwd: F=%d Ci=%d Co=%d H=%d W=%d", F, Ci, Co, H, W);
+    size_t smem = sizeof(float) * ((size_t)484 * 16 + (size_t)49 * Co * 16);
+    dim3 grid(vptr_cdiv(W, 16), vptr_cdiv(H, 16), F);
+    head_conv7x7_kernel<<<grid, 256, smem, stream>>>(x, wpk, bias, out, Ci, Co, H, W, act);
+    return vptr_check_launch("head_conv7x7_kernel");
+}
+
+extern "C" int vptr_head_conv7x7_bwd(const float* dout, const float* out, const float* w, float* dx, int F, int Ci, int Co, int H, int W,
+                                     int act, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci <= 256 && Co > 0 && Co <= HEAD_MAXCO && H > 6 && W > 6, VPTR_ERR_SHAPE,
+                 "vptr_head_conv7x7_bwd: F=%d Ci=%d Co=%d H=%d W=%d", F, Ci, Co, H, W);
+    const int ppb = 256 / Ci > 0 ? 256 / Ci : 1;
+    const int threads = ppb * Ci;
+    size_t smem = sizeof(float) * (size_t)49 * Co * Ci;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(head_conv7x7_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(vptr_cdiv(H * W, ppb), 1, F);
+    head_conv7x7_bwd_kernel<<<grid, threads, smem, stream>>>(dout, out, w, dx, Ci, Co, H, W, act);
+    return vptr_check_launch("head_conv7x7_bwd_kernel");
+}

@@ -1,0 +1,431 @@
+// TF32 tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, operands
+// staged by TMA (128B swizzle) through a multi-stage mbarrier ring, persistent CTAs (one per SM),
+// double-buffered accumulators so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+//   D[M,N] (+)= act(alpha * sum_k Aop[m,k] * Bop[n,k] + bias[n]) + residual[m,n]
+//
+// Operand storage ("major"):
+//   a_mn = 0 : A stored [M][K] row-major (K contiguous)  -> forward / dgrad left operand
+//   a_mn = 1 : A stored [K][M] row-major (M contiguous)  -> wgrad  (dY^T, contraction over tokens)
+//   b_mn = 0 : B stored [N][K] row-major (K contiguous)  -> forward (nn.Linear weight [out][in])
+//   b_mn = 1 : B stored [K][N] row-major (N contiguous)  -> dgrad (weight read as is) / wgrad (X)
+//
+// This one kernel stands in for every cuBLAS sgemm/addmm the reference issues on the hot path
+// (q/k/v/out projections MultiHeadAttentionRPE.py:543-545,688; nn.MultiheadAttention in/out
+// projections; 1x1 convs VidHRFormer_modules.py:424-442; linear1/linear2 :87-89) and, fed with
+// an im2col / padded-NHWC view, for the ResNet 3x3 convolutions (ResNetAutoEncoder.py:26-47).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;   // fp32 elements per k-chunk == one 128-byte swizzle row
+constexpr int UMMA_K = 8;     // kind::tf32: 32 bytes of K per instruction
+constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct GemmParams {
+    int M, N, K;
+    int m_tiles, n_tiles, k_splits, chunks_per_split, total_chunks;
+    float* D;
+    long long ldd;
+    const float* bias;
+    const float* residual;
+    long long ldr;
+    float alpha;
+    int act;    // 0 none, 1 gelu, 2 relu
+    int flags;  // bit0: atomic accumulate into D, bit1: round stored values to tf32 (rna)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) {  // ~seconds: turn a protocol bug into a trap instead of a hung GPU
+            printf("vptr gemm: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (canonical value 1).
+//   MN-major: 32-float MN groups `lbo_bytes` apart, 8-k-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, int m, int n_base) {
+    if (m >= p.M) return;
+    float* drow = p.D + (long long)m * p.ldd;
+    const float* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
+#pragma unroll
+    for (int j = 0; j < NCOLS; j += 4) {
+        int n = n_base + j;
+        if (n < p.N) {  // N % 4 == 0 is a launch precondition
+            float4 o = make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
+            if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (p.act == 1) {
+                o.x = vptr_gelu(o.x); o.y = vptr_gelu(o.y); o.z = vptr_gelu(o.z); o.w = vptr_gelu(o.w);
+            } else if (p.act == 2) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (rrow) {
+                float4 r = *reinterpret_cast<const float4*>(rrow + n);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (p.flags & 2) {
+                o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
+            }
+            if (p.flags & 1) {
+                atomicAdd(drow + n, o.x); atomicAdd(drow + n + 1, o.y);
+                atomicAdd(drow + n + 2, o.z); atomicAdd(drow + n + 3, o.w);
+            } else {
+                *reinterpret_cast<float4*>(drow + n) = o;
+            }
+        }
+    }
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * 128;
+    static constexpr int B_GROUPS = (BLOCK_N + 31) / 32;
+    static constexpr int B_BYTES = B_MN ? B_GROUPS * 4096 : BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // barriers + manual 1024 B alignment slack
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
+    static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+};
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: 512 columns = two BLOCK_N-wide fp32 accumulators (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ks = tile % p.k_splits;
+                const int mn = tile / p.k_splits;
+                const int n_tile = mn % p.n_tiles;
+                const int m_tile = mn / p.n_tiles;
+                const int k0 = ks * p.chunks_per_split;
+                const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB = sA + Cfg::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m_tile * BLOCK_M);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BLOCK_M / 32; ++g)
+                            tma_load_2d(&tma_a, &full_bar[stage], sA + g * 4096, m_tile * BLOCK_M + g * 32, kc * BLOCK_K);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(&tma_b, &full_bar[stage], sB, kc * BLOCK_K, n_tile * BLOCK_N);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < Cfg::B_GROUPS; ++g)
+                            tma_load_2d(&tma_b, &full_bar[stage], sB + g * 4096, n_tile * BLOCK_N + g * 32, kc * BLOCK_K);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer (single thread) =====
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
+                                       (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int ks = tile % p.k_splits;
+                const int k0 = ks * p.chunks_per_split;
+                const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 1024)
+                                                 : make_smem_desc(a_base + k * 32, 16, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 1024, 4096, 1024)
+                                                 : make_smem_desc(b_base + k * 32, 16, 1024);
+                        umma_tf32(d_tmem, da, db, idesc, (kc > k0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {  // ===== epilogue warps 2..5: TMEM -> registers -> global =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int mn = tile / p.k_splits;
+            const int n_tile = mn % p.n_tiles;
+            const int m_tile = mn / p.n_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int m = m_tile * BLOCK_M + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c0 = 0; c0 + 32 <= BLOCK_N; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+                epilogue_chunk<32>(p, v, m, n_tile * BLOCK_N + c0);
+            }
+            if (BLOCK_N % 32) {
+                float v[16];
+                tmem_ld16(taddr + (BLOCK_N / 32) * 32, v);
+                tmem_ld_wait();
+                epilogue_chunk<16>(p, v, m, n_tile * BLOCK_N + (BLOCK_N / 32) * 32);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `pitch` elements apart.
+int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long pitch, int box_inner, int box_outer) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d ptr=%p",
+                 (int)r, inner, outer, pitch, box_inner, box_outer, (const void*)ptr);
+    return VPTR_OK;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N, A_MN, B_MN, STAGES>;
+    auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int total = p.m_tiles * p.n_tiles * p.k_splits;
+    int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+    return vptr_check_launch("gemm_tf32_kernel");
+}
+
+}  // namespace
+
+extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D,
+                              long long ldd, int M, int N, int K, const float* bias, const float* residual, long long ldr,
+                              float alpha, int act, int flags, int k_splits, cudaStream_t stream) {
+    VPTR_REQUIRE(M > 0 && N > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_gemm_tf32: empty problem M=%d N=%d K=%d", M, N, K);
+    VPTR_REQUIRE(N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0), VPTR_ERR_ALIGN,
+                 "vptr_gemm_tf32: N, ldd, ldr must be multiples of 4 (N=%d ldd=%lld ldr=%lld)", N, ldd, ldr);
+    VPTR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, VPTR_ERR_ALIGN, "vptr_gemm_tf32: operand pitches must be multiples of 4 floats (TMA 16 B rule): lda=%lld ldb=%lld", lda, ldb);
+    VPTR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0) &&
+                     ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
+                 VPTR_ERR_ALIGN, "vptr_gemm_tf32: pointers must be 16-byte aligned");
+    VPTR_REQUIRE(!(flags & 1) || (bias == nullptr && residual == nullptr && act == 0), VPTR_ERR_UNSUPPORTED,
+                 "vptr_gemm_tf32: atomic accumulate excludes bias/residual/activation");
+    constexpr int BN = 176;
+    constexpr int ST = 5;
+    GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.m_tiles = vptr_cdiv(M, BLOCK_M);
+    p.n_tiles = vptr_cdiv(N, BN);
+    p.total_chunks = vptr_cdiv(K, BLOCK_K);
+    if (!(flags & 1)) k_splits = 1;
+    if (k_splits <= 0) {  // auto split-K for accumulate mode: aim for >= 2 tiles per SM
+        int tiles = p.m_tiles * p.n_tiles;
+        k_splits = (2 * num_sms() + tiles - 1) / tiles;
+        int max_splits = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;  // keep >= 8 chunks per split
+        if (k_splits > max_splits) k_splits = max_splits;
+        if (k_splits < 1) k_splits = 1;
+    }
+    if (k_splits > p.total_chunks) k_splits = p.total_chunks;
+    p.chunks_per_split = vptr_cdiv(p.total_chunks, k_splits);
+    p.k_splits = vptr_cdiv(p.total_chunks, p.chunks_per_split);  // no empty splits
+    p.D = D; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr;
+    p.alpha = alpha; p.act = act; p.flags = flags;
+
+    CUtensorMap ma, mb;
+    int rc;
+    if (!a_mn) rc = make_map_2d(&ma, A, K, M, lda, BLOCK_K, BLOCK_M);
+    else rc = make_map_2d(&ma, A, M, K, lda, 32, BLOCK_K);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map_2d(&mb, B, K, N, ldb, BLOCK_K, BN);
+    else rc = make_map_2d(&mb, B, N, K, ldb, 32, BLOCK_K);
+    if (rc) return rc;
+
+    if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0, ST>(ma, mb, p, stream);
+    if (!a_mn && b_mn) return launch_gemm<BN, 0, 1, ST>(ma, mb, p, stream);
+    if (a_mn && b_mn) return launch_gemm<BN, 1, 1, ST>(ma, mb, p, stream);
+    return launch_gemm<BN, 1, 0, ST>(ma, mb, p, stream);
+}

@@ -1,0 +1,431 @@
+// Normalisation kernels of the VidHRFormer blocks (token-major fp32 activations [rows][C]):
+//   * LayerNorm over C (pre-LN of every sub-block, VidHRFormer_modules.py:44-56,137-161) with the
+//     positional add fused as a second output (q/k source = LN(x)+pos, v source = LN(x)).
+//   * the MlpDWBN norms (VidHRFormer_modules.py:397-400,424-442): BatchNorm2d(ch) (NAR encoder) or
+//     LayerNorm((ch,H,W)) per frame (FAR, NAR decoder), each followed by exact GELU; norm3 also
+//     carries the residual add.  Statistics are reduced in fp64.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm(C) forward
+// one warp per row; y = LN(x)*g+b ; y2 = y + add[((row / add_div) % add_mod)]  (both optional)
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ y,
+                                                            float* __restrict__ y2, const float* __restrict__ add,
+                                                            int add_div, int add_mod, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, long long rows, int C, float eps,
+                                                            int relu) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * C;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        s += v.x + v.y + v.z + v.w;
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        float a = v.x - mean, b = v.y - mean, d = v.z - mean, e = v.w - mean;
+        q += a * a + b * b + d * d + e * e;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    const float* ar = add ? add + (long long)((row / add_div) % add_mod) * C : nullptr;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(xr + c);
+        float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x + b.x;
+        o.y = (v.y - mean) * rstd * g.y + b.y;
+        o.z = (v.z - mean) * rstd * g.z + b.z;
+        o.w = (v.w - mean) * rstd * g.w + b.w;
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (y) *reinterpret_cast<float4*>(y + row * C + c) = o;
+        if (y2) {
+            float4 p = __ldg(reinterpret_cast<const float4*>(ar + c));
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            *reinterpret_cast<float4*>(y2 + row * C + c) = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm(C) backward (dx)
+// g = (dy1 + dy2) [* (y>0) when relu] ; dx = dres + rstd*(g*gamma - mean(g*gamma) - xhat*mean(g*gamma*xhat))
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                                               const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in, const float* __restrict__ dres,
+                                                               float* __restrict__ dx, long long rows, int C, int relu) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float* xr = x + row * C;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float g = dy1[row * C + c];
+        if (dy2) g += dy2[row * C + c];
+        float xh = (xr[c] - mean) * rstd;
+        if (relu && xh * gamma[c] + beta[c] <= 0.f) g = 0.f;
+        g *= gamma[c];
+        s1 += g;
+        s2 += g * xh;
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    for (int c = lane; c < C; c += 32) {
+        float g = dy1[row * C + c];
+        if (dy2) g += dy2[row * C + c];
+        float xh = (xr[c] - mean) * rstd;
+        if (relu && xh * gamma[c] + beta[c] <= 0.f) g = 0.f;
+        g *= gamma[c];
+        float o = rstd * (g - s1 - xh * s2);
+        if (dres) o += dres[row * C + c];
+        dx[row * C + c] = o;
+    }
+}
+
+// dgamma[c] += sum_r g*xhat ; dbeta[c] += sum_r g   (thread per column, row chunk per blockIdx.y)
+__global__ void __launch_bounds__(128) layernorm_bwd_affine_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                                                   const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const float* __restrict__ mean_in,
+                                                                   const float* __restrict__ rstd_in, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta, long long rows, int C, int rows_per_block,
+                                                                   int relu) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    const float gm = gamma[c], bt = beta[c];
+    float ag = 0.f, ab = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+        float g = dy1[r * C + c];
+        if (dy2) g += dy2[r * C + c];
+        float xh = (x[r * C + c] - mean_in[r]) * rstd_in[r];
+        if (relu && xh * gm + bt <= 0.f) g = 0.f;
+        ag += g * xh;
+        ab += g;
+    }
+    atomicAdd(dgamma + c, ag);
+    atomicAdd(dbeta + c, ab);
+}
+
+// ------------------------------------------------------------------ statistics
+// per-column sum / sum of squares over rows (BatchNorm batch statistics), fp64 accumulators
+__global__ void __launch_bounds__(128) colstats_kernel(const float* __restrict__ x, double* __restrict__ sum, double* __restrict__ sumsq,
+                                                       long long rows, int ch, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ch) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    float s = 0.f, q = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+        float v = x[r * ch + c];
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    atomicAdd(sum + c, (double)s);
+    atomicAdd(sumsq + c, (double)q);
+}
+
+// mean/rstd from the fp64 sums; updates running stats like torch BatchNorm2d (momentum, unbiased var)
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* running_mean, float* running_var, long long n, int ch,
+                                   float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ch) return;
+    double m = sum[c] / (double)n;
+    double var = sumsq[c] / (double)n - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// eval-mode BatchNorm: mean = running_mean, rstd = 1/sqrt(running_var + eps)
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                     float* __restrict__ mean, float* __restrict__ rstd, int ch, float eps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ch) return;
+    mean[c] = running_mean[c];
+    rstd[c] = rsqrtf(running_var[c] + eps);
+}
+
+// per-group (frame) mean / rstd over `gsize` contiguous elements: one block per group
+__global__ void __launch_bounds__(512) groupstats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ rstd,
+                                                         long long gsize, float eps) {
+    __shared__ double red[2][16];
+    const float* xg = x + (long long)blockIdx.x * gsize;
+    float s = 0.f, q = 0.f;
+    for (long long i = threadIdx.x * 4; i < gsize; i += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(xg + i);
+        s += v.x + v.y + v.z + v.w;
+        q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    double ds = warp_sum(s), dq = warp_sum(q);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { red[0][w] = ds; red[1][w] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0, tq = 0;
+        for (int i = 0; i < (blockDim.x >> 5); ++i) { ts += red[0][i]; tq += red[1][i]; }
+        double m = ts / (double)gsize;
+        double var = tq / (double)gsize - m * m;
+        if (var < 0) var = 0;
+        mean[blockIdx.x] = (float)m;
+        rstd[blockIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+// ------------------------------------------------------------------ norm + GELU (+ residual) forward
+// mode 0 (BatchNorm): stats and affine indexed by channel c.
+// mode 1 (frame LayerNorm): stats indexed by frame = row / hw, affine indexed by (row % hw)*ch + c.
+template <int MODE>
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ res, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, long long total4, int ch, int hw,
+                                                           int round_tf32) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        const long long row = e / ch;
+        const int c = (int)(e - row * ch);
+        float4 v = *reinterpret_cast<const float4*>(x + e);
+        float4 m, r, g, b;
+        if (MODE == 0) {
+            m = __ldg(reinterpret_cast<const float4*>(mean + c));
+            r = __ldg(reinterpret_cast<const float4*>(rstd + c));
+            g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        } else {
+            const long long f = row / hw;
+            const long long a = (row - f * hw) * ch + c;
+            const float mm = __ldg(mean + f), rr = __ldg(rstd + f);
+            m = make_float4(mm, mm, mm, mm);
+            r = make_float4(rr, rr, rr, rr);
+            g = __ldg(reinterpret_cast<const float4*>(gamma + a));
+            b = __ldg(reinterpret_cast<const float4*>(beta + a));
+        }
+        float4 o;
+        o.x = vptr_gelu((v.x - m.x) * r.x * g.x + b.x);
+        o.y = vptr_gelu((v.y - m.y) * r.y * g.y + b.y);
+        o.z = vptr_gelu((v.z - m.z) * r.z * g.z + b.z);
+        o.w = vptr_gelu((v.w - m.w) * r.w * g.w + b.w);
+        if (res) {
+            float4 q = *reinterpret_cast<const float4*>(res + e);
+            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+        }
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        *reinterpret_cast<float4*>(y + e) = o;
+    }
+}
+
+// ------------------------------------------------------------------ norm + GELU backward
+// Reduction pass, BatchNorm: per channel S1 = sum g, S2 = sum g*xhat with g = dy*GELU'(z)  (dbeta = S1, dgamma = S2)
+__global__ void __launch_bounds__(128) bn_act_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                float* __restrict__ s1, float* __restrict__ s2,
+                                                                long long rows, int ch, int rows_per_block) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ch) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    const float m = mean[c], r = rstd[c], g = gamma[c], b = beta[c];
+    float a1 = 0.f, a2 = 0.f;
+    for (long long row = r0; row < r1; ++row) {
+        float xh = (x[row * ch + c] - m) * r;
+        float gg = dy[row * ch + c] * vptr_gelu_grad(xh * g + b);
+        a1 += gg;
+        a2 = fmaf(gg, xh, a2);
+    }
+    atomicAdd(s1 + c, a1);
+    atomicAdd(s2 + c, a2);
+    atomicAdd(dbeta + c, a1);
+    atomicAdd(dgamma + c, a2);
+}
+
+// Reduction pass A, frame LayerNorm: per frame P1 = sum g*gamma, P2 = sum g*gamma*xhat (one block per frame)
+__global__ void __launch_bounds__(512) ln3_act_bwd_frame_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                float* __restrict__ p1, float* __restrict__ p2, long long gsize) {
+    __shared__ float red[32];
+    const long long base = (long long)blockIdx.x * gsize;
+    const float m = mean[blockIdx.x], r = rstd[blockIdx.x];
+    float a1 = 0.f, a2 = 0.f;
+    for (long long i = threadIdx.x; i < gsize; i += blockDim.x) {
+        float xh = (x[base + i] - m) * r;
+        float g = gamma[i];
+        float gg = dy[base + i] * vptr_gelu_grad(xh * g + beta[i]) * g;
+        a1 += gg;
+        a2 = fmaf(gg, xh, a2);
+    }
+    a1 = block_sum(a1, red);
+    a2 = block_sum(a2, red);
+    if (threadIdx.x == 0) { p1[blockIdx.x] = a1; p2[blockIdx.x] = a2; }
+}
+
+// Reduction pass B, frame LayerNorm: dgamma[a] += sum_f g*xhat ; dbeta[a] += sum_f g   (thread per affine index)
+__global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 long long gsize, int frames, int frames_per_block) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= gsize) return;
+    const int f0 = blockIdx.y * frames_per_block;
+    const int f1 = min(f0 + frames_per_block, frames);
+    const float g = gamma[a], b = beta[a];
+    float ag = 0.f, ab = 0.f;
+    for (int f = f0; f < f1; ++f) {
+        float xh = (x[f * gsize + a] - mean[f]) * rstd[f];
+        float gg = dy[f * gsize + a] * vptr_gelu_grad(xh * g + b);
+        ag = fmaf(gg, xh, ag);
+        ab += gg;
+    }
+    atomicAdd(dgamma + a, ag);
+    atomicAdd(dbeta + a, ab);
+}
+
+// Elementwise pass: dx from the reduced sums.
+//  MODE 0: dx = gamma*rstd*(g - S1/n - xhat*S2/n)        (S indexed by channel, n = rows)
+//  MODE 1: dx = rstd_f*(g*gamma - P1_f/n - xhat*P2_f/n)   (P indexed by frame,  n = hw*ch)
+//  MODE 2: eval BatchNorm (statistics are constants): dx = gamma*rstd*g
+template <int MODE>
+__global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ s1, const float* __restrict__ s2,
+                                                              float* __restrict__ dx, long long total, int ch, int hw, float inv_n) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / ch;
+        const int c = (int)(e - row * ch);
+        float m, r, g, b, t1, t2;
+        if (MODE == 1) {
+            const long long f = row / hw;
+            const long long a = (row - f * hw) * ch + c;
+            m = mean[f]; r = rstd[f]; g = gamma[a]; b = beta[a]; t1 = s1[f]; t2 = s2[f];
+        } else {
+            m = mean[c]; r = rstd[c]; g = gamma[c]; b = beta[c];
+            t1 = MODE == 0 ? s1[c] : 0.f; t2 = MODE == 0 ? s2[c] : 0.f;
+        }
+        const float xh = (x[e] - m) * r;
+        const float gg = dy[e] * vptr_gelu_grad(xh * g + b);
+        float o;
+        if (MODE == 0) o = g * r * (gg - t1 * inv_n - xh * t2 * inv_n);
+        else if (MODE == 1) o = r * (gg * g - t1 * inv_n - xh * t2 * inv_n);
+        else o = g * r * gg;
+        dx[e] = o;
+    }
+}
+
+int ew_grid(long long n, int block) {
+    long long g = (n + block - 1) / block;
+    long long cap = 148LL * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int vptr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* add,
+                                  int add_div, int add_mod, float* mean, float* rstd, long long rows, int C, float eps, int relu,
+                                  cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, VPTR_ERR_SHAPE, "vptr_layernorm_fwd: rows=%lld C=%d (C %% 4 == 0 required)", rows, C);
+    VPTR_REQUIRE(y2 == nullptr || (add != nullptr && add_div > 0 && add_mod > 0), VPTR_ERR_SHAPE, "vptr_layernorm_fwd: y2 needs add/add_div/add_mod");
+    layernorm_fwd_kernel<<<vptr_cdiv(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, y2, add, add_div, add_mod, mean, rstd, rows, C, eps, relu);
+    return vptr_check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int vptr_layernorm_bwd(const float* dy1, const float* dy2, const float* x, const float* gamma, const float* beta,
+                                  const float* mean, const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                                  long long rows, int C, int relu, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && C > 0, VPTR_ERR_SHAPE, "vptr_layernorm_bwd: rows=%lld C=%d", rows, C);
+    if (dx) {
+        layernorm_bwd_dx_kernel<<<vptr_cdiv(rows, 8), 256, 0, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, rows, C, relu);
+        int rc = vptr_check_launch("layernorm_bwd_dx_kernel");
+        if (rc) return rc;
+    }
+    if (dgamma) {
+        int rpb = 256;
+        dim3 grid(vptr_cdiv(C, 128), vptr_cdiv(rows, rpb));
+        layernorm_bwd_affine_kernel<<<grid, 128, 0, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dgamma, dbeta, rows, C, rpb, relu);
+        return vptr_check_launch("layernorm_bwd_affine_kernel");
+    }
+    return VPTR_OK;
+}
+
+// BatchNorm statistics over rows (training) -> mean/rstd [ch]; ws = 2*ch doubles of scratch.
+extern "C" int vptr_bn_stats(const float* x, long long rows, int ch, float* mean, float* rstd, float* running_mean, float* running_var,
+                             float eps, float momentum, double* ws, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_bn_stats: rows=%lld ch=%d", rows, ch);
+    cudaMemsetAsync(ws, 0, sizeof(double) * 2 * ch, stream);
+    int rpb = 256;
+    dim3 grid(vptr_cdiv(ch, 128), vptr_cdiv(rows, rpb));
+    colstats_kernel<<<grid, 128, 0, stream>>>(x, ws, ws + ch, rows, ch, rpb);
+    bn_finalize_kernel<<<vptr_cdiv(ch, 128), 128, 0, stream>>>(ws, ws + ch, mean, rstd, running_mean, running_var, rows, ch, eps, momentum);
+    return vptr_check_launch("vptr_bn_stats");
+}
+
+extern "C" int vptr_bn_eval_stats(const float* running_mean, const float* running_var, float* mean, float* rstd, int ch, float eps,
+                                  cudaStream_t stream) {
+    bn_eval_stats_kernel<<<vptr_cdiv(ch, 128), 128, 0, stream>>>(running_mean, running_var, mean, rstd, ch, eps);
+    return vptr_check_launch("bn_eval_stats_kernel");
+}
+
+extern "C" int vptr_group_stats(const float* x, int groups, long long gsize, float* mean, float* rstd, float eps, cudaStream_t stream) {
+    VPTR_REQUIRE(groups > 0 && gsize > 0 && gsize % 4 == 0, VPTR_ERR_SHAPE, "vptr_group_stats: groups=%d gsize=%lld", groups, gsize);
+    groupstats_kernel<<<groups, 512, 0, stream>>>(x, mean, rstd, gsize, eps);
+    return vptr_check_launch("groupstats_kernel");
+}
+
+// y = GELU(norm(x)) (+ res).  mode 0: BatchNorm (per-channel stats/affine); mode 1: LayerNorm((ch,H,W)) per frame with
+// affine stored token-major [hw][ch].
+extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_fwd: rows=%lld ch=%d", rows, ch);
+    long long total4 = rows * ch / 4;
+    int grid = ew_grid(total4, 256);
+    if (mode == 0) norm_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32);
+    else norm_act_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32);
+    return vptr_check_launch("norm_act_fwd_kernel");
+}
+
+// Backward of y = GELU(norm(x)).  mode 0: train BatchNorm, 1: frame LayerNorm, 2: eval BatchNorm.
+// ws: mode 0 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).
+extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
+                                 float* ws, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d", rows, ch);
+    const long long total = rows * ch;
+    const int grid = ew_grid(total, 256);
+    if (mode == 0 || mode == 2) {
+        cudaMemsetAsync(ws, 0, sizeof(float) * 2 * ch, stream);
+        int rpb = 256;
+        dim3 g2(vptr_cdiv(ch, 128), vptr_cdiv(rows, rpb));
+        bn_act_bwd_reduce_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, ws, ws + ch, rows, ch, rpb);
+        if (mode == 0)
+            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows);
+        else
+            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f);
+    } else {
+        const long long gsize = (long long)hw * ch;
+        const int frames = (int)(rows / hw);
+        ln3_act_bwd_frame_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, gsize);
+        int fpb = 32;
+        dim3 g2(vptr_cdiv(gsize, 128), vptr_cdiv(frames, fpb));
+        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, gsize, frames, fpb);
+        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize);
+    }
+    return vptr_check_launch("vptr_norm_act_bwd");
+}

@@ -1,0 +1,425 @@
+"""Forward / backward schedule of the VidHRFormer blocks on token-major fp32 activations, expressed as calls into
+libvptr_b200.so (vptr_b200.ops).  No autograd graph is built: every sub-block saves what its hand-written backward
+needs, and the whole Transformer is exposed to torch.autograd as ONE Function (vptr_b200.model).
+
+Restates (reference paths under /root/reference):
+  VidHRFormerBlockEnc.forward     model/VidHRFormer_modules.py:60-93
+  VidHRFormerBlockDecNAR.forward  model/VidHRFormer_modules.py:164-211
+  SpatialLocalMultiheadAttention  model/VidHRFormer_modules.py:321-357  (+ MultiheadAttentionRPE, MultiHeadAttentionRPE.py:527-697)
+  MlpDWBN.forward                 model/VidHRFormer_modules.py:424-442
+  VidHRFormerNAR/FAR.forward      model/VidHRFormer.py:28-53,71-88
+Dropout / DropPath are the identity here (eval mode or p = 0); the module layer refuses p > 0 in train mode until the
+fused Philox epilogues land.
+"""
+import math
+
+import torch
+
+from . import ops
+
+ROUND_TF32 = True  # producers of GEMM operands round-to-nearest to tf32 so the tensor core's truncation is exact
+
+
+class Params:
+    """name -> parameter tensor / gradient buffer (views into one flat fp32 buffer when grads are wanted)."""
+
+    def __init__(self, named, want_grads):
+        self.t = {k: v for k, v in named}
+        self.gflat = None
+        self.gv = {}
+        if want_grads:
+            names = [k for k, v in self.t.items() if v.requires_grad]
+            total = sum(self.t[k].numel() for k in names)
+            dev = next(iter(self.t.values())).device
+            self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+            off = 0
+            for k in names:
+                n = self.t[k].numel()
+                self.gv[k] = self.gflat[off:off + n].view(self.t[k].shape)
+                off += n
+
+    def w(self, name):
+        return self.t[name]
+
+    def g(self, name):
+        return self.gv.get(name)
+
+
+class Geom:
+    def __init__(self, N, T, H, W, C, nhead, ws):
+        self.N, self.T, self.H, self.W, self.C, self.nhead, self.ws = N, T, H, W, C, nhead, ws
+        self.d = C // nhead
+        self.HW = H * W
+        self.F = N * T
+        self.R = N * T * H * W
+        self.scale = float(self.d) ** -0.5
+        pad_h = math.ceil(H / ws) * ws - H
+        pad_w = math.ceil(W / ws) * ws - W
+        self.ph0, self.pw0 = pad_h // 2, pad_w // 2      # PadBlock: pad//2 before, the rest after (VidHRFormer_modules.py:538-550)
+        self.Hp, self.Wp = H + pad_h, W + pad_w
+        self.padded = pad_h + pad_w > 0
+
+
+def _wgrad(P, name, dY, X):
+    """dW[name] += dY^T X (contraction over tokens; both operands read as stored)."""
+    g = P.g(name)
+    if g is not None:
+        ops.gemm(dY, X, out=g.view(g.shape[0], -1), a_mn=True, b_mn=True, accumulate=True)
+
+
+def _bgrad(P, name, dY):
+    g = P.g(name)
+    if g is not None:
+        ops.colsum(dY, g)
+
+
+# =================================================================================================== window attention
+def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save):
+    """x (R,C) -> x + SLMHSA(LN(x)).  qpos (T*H*W, C) or None: q/k source = LN(x)+qpos (decoder)."""
+    C = g.C
+    lnw, lnb = P.w(ln + ".weight"), P.w(ln + ".bias")
+    if qpos is not None:
+        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb, add=qpos, add_div=1, add_mod=qpos.shape[0])
+    else:
+        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb)
+        aq = a
+    Fr = g.F
+    if g.padded:
+        a_in = ops.pad_hw(a, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
+        aq_in = a_in if aq is a else ops.pad_hw(aq, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
+    else:
+        a_in, aq_in = a, aq
+    if not rpe:   # VidHRFormer_modules.py:341: q = k = x + lw_pos (per in-window position), v = x
+        aq_in = ops.add_rows(aq_in, lw_tab, 1, lw_tab.shape[0])
+    Rp = a_in.shape[0]
+    qkv = ops.empty(Rp, 3 * C, like=x)
+    at = pre + ".attn."
+    if rpe:
+        ops.gemm(aq_in, P.w(at + "q_proj.weight"), out=qkv[:, :C], bias=P.w(at + "q_proj.bias"))
+        ops.gemm(aq_in, P.w(at + "k_proj.weight"), out=qkv[:, C:2 * C], bias=P.w(at + "k_proj.bias"))
+        ops.gemm(a_in, P.w(at + "v_proj.weight"), out=qkv[:, 2 * C:], bias=P.w(at + "v_proj.bias"))
+        table = P.w(at + "relative_position_bias_table")
+        wo, bo = P.w(at + "out_proj.weight"), P.w(at + "out_proj.bias")
+    else:
+        Wi, bi = P.w(at + "in_proj_weight"), P.w(at + "in_proj_bias")
+        ops.gemm(aq_in, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
+        ops.gemm(a_in, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
+        table = None
+        wo, bo = P.w(at + "out_proj.weight"), P.w(at + "out_proj.bias")
+    o = ops.empty(Rp, C, like=x)
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale)
+    if g.padded:
+        yp = ops.gemm(o, wo, bias=bo)
+        y = ops.crop_hw(yp, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
+        out = ops.axpby(x, y)
+    else:
+        out = ops.gemm(o, wo, bias=bo, residual=x)
+    if save is not None:
+        save.append(("win", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, a_in=a_in, aq_in=aq_in, qkv=qkv, o=o, rpe=rpe,
+                                 has_qpos=qpos is not None, g=g)))
+    return out
+
+
+def window_attn_bwd(P, s, dout, dqpos):
+    g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
+    at = pre + ".attn."
+    Fr = g.F
+    dy = ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout
+    qkv, o = s["qkv"], s["o"]
+    _wgrad(P, at + "out_proj.weight", dy, o)
+    _bgrad(P, at + "out_proj.bias", dy)
+    do = ops.gemm(dy, P.w(at + "out_proj.weight"), b_mn=True)
+    dqkv = torch.empty_like(qkv)
+    if s["rpe"]:
+        table = P.w(at + "relative_position_bias_table")
+        dtable = P.g(at + "relative_position_bias_table")
+    else:
+        table = dtable = None
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtable, 0, Fr,
+                 g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale)
+    a_in, aq_in = s["a_in"], s["aq_in"]
+    if s["rpe"]:
+        for i, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+            src = a_in if nm == "v_proj" else aq_in
+            _wgrad(P, at + nm + ".weight", dqkv[:, i * C:(i + 1) * C], src)
+            _bgrad(P, at + nm + ".bias", dqkv[:, i * C:(i + 1) * C])
+        d_aq = ops.gemm(dqkv[:, :C], P.w(at + "q_proj.weight"), b_mn=True)
+        ops.gemm(dqkv[:, C:2 * C], P.w(at + "k_proj.weight"), b_mn=True, out=d_aq, residual=d_aq)
+        d_a = ops.gemm(dqkv[:, 2 * C:], P.w(at + "v_proj.weight"), b_mn=True)
+    else:
+        Wi = P.w(at + "in_proj_weight")
+        gW, gb = P.g(at + "in_proj_weight"), P.g(at + "in_proj_bias")
+        if gW is not None:
+            ops.gemm(dqkv[:, :2 * C], aq_in, out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
+            ops.gemm(dqkv[:, 2 * C:], a_in, out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+            ops.colsum(dqkv, gb)
+        d_aq = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
+        d_a = ops.gemm(dqkv[:, 2 * C:], Wi[2 * C:], b_mn=True)
+    if g.padded:
+        d_aq = ops.crop_hw(d_aq, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
+        d_a = ops.crop_hw(d_a, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
+    if s["has_qpos"] and dqpos is not None:
+        ops.rowgroup_sum(d_aq, dqpos, g.N)
+    return ops.layernorm_bwd(d_a, d_aq, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"))
+
+
+# =================================================================================================== conv FFN (MlpDWBN)
+def _ffn_norm_params(P, pre, name, hw, layer_norm):
+    """(gamma, beta) in engine layout: BatchNorm (ch,) as is; LayerNorm((ch,H,W)) re-laid [hw][ch]."""
+    w, b = P.w(pre + "." + name + ".weight"), P.w(pre + "." + name + ".bias")
+    if not layer_norm:
+        return w, b
+    ch = w.shape[0]
+    return ops.transpose(w, 1, ch, hw), ops.transpose(b, 1, ch, hw)
+
+
+def _ffn_norm_stats(P, pre, name, h, g, layer_norm, training, bufs):
+    if layer_norm:
+        return ops.group_stats(h, g.F)
+    rm, rv = bufs[pre + "." + name + ".running_mean"], bufs[pre + "." + name + ".running_var"]
+    if training:
+        bufs[pre + "." + name + ".num_batches_tracked"].add_(1)
+        return ops.bn_stats(h, rm, rv)
+    return ops.bn_eval_stats(rm, rv)
+
+
+def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
+    """x (R,C) -> x + MlpDWBN(LN(x)).  layer_norm: LayerNorm((ch,H,W)) flavour (FAR, NAR decoder) else BatchNorm2d."""
+    mode = 1 if layer_norm else 0
+    b_, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"))
+    w1 = P.w(pre + ".fc1.weight")
+    Ch = w1.shape[0]
+    h1 = ops.gemm(b_, w1.view(Ch, g.C), bias=P.w(pre + ".fc1.bias"))
+    st1 = _ffn_norm_stats(P, pre, "norm1", h1, g, layer_norm, training, bufs)
+    g1, b1 = _ffn_norm_params(P, pre, "norm1", g.HW, layer_norm)
+    u1 = ops.norm_act_fwd(h1, st1[0], st1[1], g1, b1, g.HW, mode)
+    w9 = ops.transpose(P.w(pre + ".dw3x3.weight"), 1, Ch, 9)
+    h2 = ops.dwconv3x3(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
+    st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
+    g2, b2 = _ffn_norm_params(P, pre, "norm2", g.HW, layer_norm)
+    u2 = ops.norm_act_fwd(h2, st2[0], st2[1], g2, b2, g.HW, mode, round_tf32=ROUND_TF32)
+    w2 = P.w(pre + ".fc2.weight")
+    h3 = ops.gemm(u2, w2.view(g.C, Ch), bias=P.w(pre + ".fc2.bias"))
+    st3 = _ffn_norm_stats(P, pre, "norm3", h3, g, layer_norm, training, bufs)
+    g3, b3 = _ffn_norm_params(P, pre, "norm3", g.HW, layer_norm)
+    out = ops.norm_act_fwd(h3, st3[0], st3[1], g3, b3, g.HW, mode, res=x)
+    if save is not None:
+        bwd_mode = mode if (layer_norm or training) else 2
+        save.append(("ffn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, b=b_, h1=h1, st1=st1, u1=u1, h2=h2, st2=st2, u2=u2, h3=h3,
+                                 st3=st3, g=g, layer_norm=layer_norm, mode=bwd_mode, w9=w9, aff=((g1, b1), (g2, b2), (g3, b3)))))
+    return out
+
+
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode):
+    gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
+    ch = h.shape[1]
+    if layer_norm:
+        dg = ops.zeros(g.HW * ch, like=h)
+        db = ops.zeros(g.HW * ch, like=h)
+        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode)
+        if gw is not None:
+            ops.transpose(dg, 1, g.HW, ch, out=gw, accumulate=True)
+            ops.transpose(db, 1, g.HW, ch, out=gb, accumulate=True)
+        return dx
+    if gw is None:
+        gw, gb = ops.zeros(ch, like=h), ops.zeros(ch, like=h)
+    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode)
+
+
+def conv_ffn_bwd(P, s, dout):
+    g, pre, ln, lnm, mode = s["g"], s["pre"], s["ln"], s["layer_norm"], s["mode"]
+    Ch = s["h1"].shape[1]
+    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode)
+    _wgrad(P, pre + ".fc2.weight", dh3, s["u2"])
+    _bgrad(P, pre + ".fc2.bias", dh3)
+    du2 = ops.gemm(dh3, P.w(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
+    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode)
+    gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
+    if gdw is not None:
+        dw9 = ops.zeros(9 * Ch, like=dh2)
+        ops.dwconv3x3_wgrad(s["u1"], dh2, dw9, gdb, g.F, g.H, g.W)
+        ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
+    du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
+    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode)
+    _wgrad(P, pre + ".fc1.weight", dh1, s["b"])
+    _bgrad(P, pre + ".fc1.bias", dh1)
+    db = ops.gemm(dh1, P.w(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)
+    return ops.layernorm_bwd(db, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"))
+
+
+# =================================================================================================== temporal self-attention
+def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save):
+    """x + MHA_t(q=k=LN(x)+pos_t, v=LN(x)) per pixel (VidHRFormer_modules.py:74-84,183-187)."""
+    C = g.C
+    z, zp, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), add=pos, add_div=g.HW, add_mod=g.T)
+    Wi, bi = P.w(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
+    qkv = ops.empty(g.R, 3 * C, like=x)
+    ops.gemm(zp, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
+    ops.gemm(z, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
+    o = ops.empty(g.R, C, like=x)
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale)
+    out = ops.gemm(o, P.w(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    if save is not None:
+        save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g)))
+    return out
+
+
+def temporal_attn_bwd(P, s, dout):
+    g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
+    qkv, o = s["qkv"], s["o"]
+    _wgrad(P, pre + ".out_proj.weight", dout, o)
+    _bgrad(P, pre + ".out_proj.bias", dout)
+    do = ops.gemm(dout, P.w(pre + ".out_proj.weight"), b_mn=True)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], None, None, 1, g.N,
+                 g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale)
+    Wi = P.w(pre + ".in_proj_weight")
+    gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
+    if gW is not None:
+        ops.gemm(dqkv[:, :2 * C], s["zp"], out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dqkv[:, 2 * C:], s["z"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dqkv, gb)
+    dzp = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
+    dz = ops.gemm(dqkv[:, 2 * C:], Wi[2 * C:], b_mn=True)
+    return ops.layernorm_bwd(dz, dzp, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"))
+
+
+# =================================================================================================== MLP FFN
+def mlp_fwd(P, pre, ln, x, g, save):
+    """x + linear2(GELU(linear1(LN(x)))) (VidHRFormer_modules.py:87-89,190-192); pre = block prefix."""
+    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"))
+    h = ops.gemm(y, P.w(pre + ".linear1.weight"), bias=P.w(pre + ".linear1.bias"))
+    u = ops.gelu_fwd(h, round_tf32=ROUND_TF32)
+    out = ops.gemm(u, P.w(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x)
+    if save is not None:
+        save.append(("mlp", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, y=y, h=h, u=u, g=g)))
+    return out
+
+
+def mlp_bwd(P, s, dout):
+    pre, ln = s["pre"], s["ln"]
+    _wgrad(P, pre + ".linear2.weight", dout, s["u"])
+    _bgrad(P, pre + ".linear2.bias", dout)
+    du = ops.gemm(dout, P.w(pre + ".linear2.weight"), b_mn=True)
+    dh = ops.gelu_bwd(du, s["h"], out=du)
+    _wgrad(P, pre + ".linear1.weight", dh, s["y"])
+    _bgrad(P, pre + ".linear1.bias", dh)
+    dy = ops.gemm(dh, P.w(pre + ".linear1.weight"), b_mn=True)
+    return ops.layernorm_bwd(dy, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"))
+
+
+# =================================================================================================== encoder-decoder attention
+def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save):
+    """x + MHA(q = LN(x)+query_pos+pos_future, k = memory+pos_past, v = memory) per pixel (VidHRFormer_modules.py:200-206).
+    g: geometry of the target stream, gm: of the memory stream; qadd (T2*H*W, C) = query_pos + pos_future."""
+    C = g.C
+    _, zq, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=qadd, add_div=1, add_mod=qadd.shape[0])
+    Wi, bi = P.w(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
+    q = ops.gemm(zq, Wi[:C], bias=bi[:C])
+    kv = ops.empty(gm.R, 2 * C, like=x)
+    ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C])
+    ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:])
+    o = ops.empty(g.R, C, like=x)
+    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale)
+    out = ops.gemm(o, P.w(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    if save is not None:
+        save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k)))
+    return out
+
+
+def cross_attn_bwd(P, s, dout, dqpos, dmem):
+    g, gm, C, pre, ln = s["g"], s["gm"], s["g"].C, s["pre"], s["ln"]
+    q, kv, o = s["q"], s["kv"], s["o"]
+    _wgrad(P, pre + ".out_proj.weight", dout, o)
+    _bgrad(P, pre + ".out_proj.bias", dout)
+    do = ops.gemm(dout, P.w(pre + ".out_proj.weight"), b_mn=True)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d,
+                 False, g.scale)
+    Wi = P.w(pre + ".in_proj_weight")
+    gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
+    if gW is not None:
+        ops.gemm(dq, s["zq"], out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dkv[:, :C], s["mem_k"], out=gW[C:2 * C], a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dkv[:, C:], s["mem"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        ops.colsum(dq, gb[:C])
+        ops.colsum(dkv, gb[C:])
+    dzq = ops.gemm(dq, Wi[:C], b_mn=True)
+    ops.gemm(dkv[:, :C], Wi[C:2 * C], b_mn=True, out=dmem, residual=dmem)
+    ops.gemm(dkv[:, C:], Wi[2 * C:], b_mn=True, out=dmem, residual=dmem)
+    if dqpos is not None:
+        ops.rowgroup_sum(dzq, dqpos, g.N)
+    return ops.layernorm_bwd(dzq, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"))
+
+
+# =================================================================================================== final norm
+def final_norm_fwd(P, ln, x, relu, save):
+    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), relu=relu)
+    if save is not None:
+        save.append(("fnorm", dict(ln=ln, x=x, mean=mean, rstd=rstd, relu=relu)))
+    return y
+
+
+def final_norm_bwd(P, s, dout):
+    ln = s["ln"]
+    return ops.layernorm_bwd(dout, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], None,
+                             P.g(ln + ".weight"), P.g(ln + ".bias"), relu=s["relu"])
+
+
+# =================================================================================================== stacks
+def lw_table(lw_pos, g):
+    """(Hp*Wp, C) table of lw_pos[(h % ws), (w % ws)] over the padded grid (rpe=False path)."""
+    ws = g.ws
+    hh = torch.arange(g.Hp, device=lw_pos.device) % ws
+    ww = torch.arange(g.Wp, device=lw_pos.device) % ws
+    return lw_pos[hh][:, ww].reshape(g.Hp * g.Wp, -1).contiguous()
+
+
+def encoder_fwd(P, bufs, x, g, n_layers, far, rpe, tpos, lw_tab, training, save):
+    for i in range(n_layers):
+        pre = "transformer.encoder.layers.%d" % i
+        x = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", x, g, rpe, None, lw_tab, save)
+        x = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", x, g, far, training, save)
+        x = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", x, g, tpos, far, save)
+        x = mlp_fwd(P, pre, pre + ".norm4", x, g, save)
+    return x
+
+
+def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save):
+    for i in range(n_layers):
+        pre = "transformer.decoder.layers.%d" % i
+        tgt = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", tgt, g, rpe, qpos, lw_tab, save)
+        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", tgt, g, True, False, save)
+        tgt = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", tgt, g, tpos_f, False, save)
+        tgt = mlp_fwd(P, pre, pre + ".norm4", tgt, g, save)
+        tgt = cross_attn_fwd(P, pre + ".EncDecAttn", pre + ".norm5", tgt, g, gm, qadd, mem, mem_k, save)
+        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN1", pre + ".norm6", tgt, g, True, False, save)
+    return tgt
+
+
+def backward_tape(P, save, dout, dqpos=None, dmem=None, stop=0):
+    """Walks the saved sub-blocks in reverse down to index `stop`; returns the gradient at that point."""
+    d = dout
+    while len(save) > stop:
+        kind, s = save.pop()
+        if kind == "win":
+            d = window_attn_bwd(P, s, d, dqpos)
+        elif kind == "ffn":
+            d = conv_ffn_bwd(P, s, d)
+        elif kind == "tattn":
+            d = temporal_attn_bwd(P, s, d)
+        elif kind == "mlp":
+            d = mlp_bwd(P, s, d)
+        elif kind == "xattn":
+            d = cross_attn_bwd(P, s, d, dqpos, dmem)
+        elif kind == "fnorm":
+            d = final_norm_bwd(P, s, d)
+        else:
+            raise RuntimeError("unknown tape entry " + kind)
+    return d

@@ -1,0 +1,193 @@
+"""ResNet conv encoder / transposed-conv decoder (reference model/ResNetAutoEncoder.py:8-158) on channel-last
+activations.  The nn.Sequential layout (and therefore every state_dict key, including the padding_type-dependent
+indices of the ResnetBlocks) is the reference's; compute is libvptr_b200.so:
+  7x7 stem / head      -> direct kernels (csrc/conv.cu)
+  3x3 (stride 1 | 2)   -> im2col gather + tcgen05 TF32 GEMM with the eval-BatchNorm folded into weights (scale) and
+                          epilogue (shift, ReLU, residual)
+  ConvTranspose2d      -> GEMM to per-tap columns + output gather (shift + ReLU); its input gradient is the stride-2
+                          im2col of the ReLU-masked output gradient times the same packed weight.
+BatchNorm runs with running statistics (stage 2 keeps both modules in .eval(), train_NAR.py:190-191)."""
+import functools
+
+import torch
+import torch.nn as nn
+from torch.nn import init
+
+from .. import ops
+
+
+class ResnetBlock(nn.Module):
+    """conv_block = [pad?, Conv3x3, BN, ReLU, pad?, Conv3x3, BN]; out = x + conv_block(x) (reference :104-158)."""
+
+    def __init__(self, dim, padding_type, norm_layer, use_dropout, use_bias):
+        super().__init__()
+        self.padding_type = padding_type
+        block = []
+        p = 0
+        for half in range(2):
+            if padding_type == 'reflect':
+                block += [nn.ReflectionPad2d(1)]
+            elif padding_type == 'replicate':
+                block += [nn.ReplicationPad2d(1)]
+            elif padding_type == 'zero':
+                p = 1
+            else:
+                raise NotImplementedError('padding [%s] is not implemented' % padding_type)
+            block += [nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim)]
+            if half == 0:
+                block += [nn.ReLU(True)]
+                if use_dropout:
+                    block += [nn.Dropout(0.5)]
+        self.conv_block = nn.Sequential(*block)
+
+    def convs(self):
+        mods = [m for m in self.conv_block if isinstance(m, (nn.Conv2d, nn.BatchNorm2d))]
+        return mods[0], mods[1], mods[2], mods[3]
+
+
+def _use_bias(norm_layer):
+    inst = norm_layer.func if isinstance(norm_layer, functools.partial) else norm_layer
+    return inst == nn.InstanceNorm2d
+
+
+class ResnetEncoder(nn.Module):
+    def __init__(self, input_nc, ngf=64, out_dim=528, n_downsampling=2, norm_layer=nn.BatchNorm2d, use_dropout=False,
+                 padding_type='reflect'):
+        super().__init__()
+        use_bias = _use_bias(norm_layer)
+        self.padding_type, self.n_downsampling = padding_type, n_downsampling
+        model = [nn.ReflectionPad2d(3), nn.Conv2d(input_nc, ngf, kernel_size=7, padding=0, bias=use_bias), norm_layer(ngf), nn.ReLU(True)]
+        ch = ngf
+        for i in range(n_downsampling):
+            nxt = out_dim if i == n_downsampling - 1 else ch * 2
+            model += [nn.Conv2d(ch, nxt, kernel_size=3, stride=2, padding=1, bias=use_bias), norm_layer(nxt), nn.ReLU(True)]
+            ch = nxt
+        for _ in range(9):
+            model += [ResnetBlock(out_dim, padding_type=padding_type, norm_layer=norm_layer, use_dropout=use_dropout, use_bias=use_bias)]
+        model += [nn.ReLU()]
+        self.model = nn.Sequential(*model)
+
+
+class ResnetDecoder(nn.Module):
+    def __init__(self, output_nc, ngf=64, feat_dim=528, n_downsampling=2, norm_layer=nn.BatchNorm2d, use_dropout=False,
+                 padding_type='reflect', out_layer='Tanh'):
+        super().__init__()
+        use_bias = _use_bias(norm_layer)
+        self.n_downsampling, self.out_layer = n_downsampling, out_layer
+        model = []
+        ch = feat_dim
+        for i in range(n_downsampling):
+            nxt = ngf * 2 ** (n_downsampling - 1 - i)
+            model += [nn.ConvTranspose2d(ch, nxt, kernel_size=3, stride=2, padding=1, output_padding=1, bias=use_bias), norm_layer(nxt),
+                      nn.ReLU(True)]
+            ch = nxt
+        model += [nn.ReflectionPad2d(3), nn.Conv2d(ngf, output_nc, kernel_size=7, padding=0)]
+        if out_layer == 'Tanh':
+            model += [nn.Tanh()]
+        elif out_layer == 'Sigmoid':
+            model += [nn.Sigmoid()]
+        else:
+            raise ValueError("Unsupported output layer")
+        self.model = nn.Sequential(*model)
+
+
+def init_weights(net, init_type='normal', init_gain=0.02):
+    """Same policy as the reference's init_weights (:160-189): Conv/Linear weights ~ init_type, biases 0,
+    BatchNorm2d weight ~ N(1, gain), bias 0; matched on class names."""
+    def init_func(m):
+        cls = m.__class__.__name__
+        if hasattr(m, 'weight') and ('Conv' in cls or 'Linear' in cls):
+            if init_type == 'normal':
+                init.normal_(m.weight.data, 0.0, init_gain)
+            elif init_type == 'xavier':
+                init.xavier_normal_(m.weight.data, gain=init_gain)
+            elif init_type == 'kaiming':
+                init.kaiming_normal_(m.weight.data, a=0, mode='fan_in')
+            elif init_type == 'orthogonal':
+                init.orthogonal_(m.weight.data, gain=init_gain)
+            else:
+                raise NotImplementedError('initialization method [%s] is not implemented' % init_type)
+            if getattr(m, 'bias', None) is not None:
+                init.constant_(m.bias.data, 0.0)
+        elif 'BatchNorm2d' in cls:
+            init.normal_(m.weight.data, 1.0, init_gain)
+            init.constant_(m.bias.data, 0.0)
+
+    print('initialize network with %s' % init_type)
+    net.apply(init_func)
+
+
+# ----------------------------------------------------------------------------------------------- functional compute
+def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_after_residual=False):
+    """x (F*H*W, Cin) channel-last -> (F*Ho*Wo, Cout).  y = act(conv(x)*scale + shift) (+ residual)."""
+    Cout, Cin = conv.weight.shape[:2]
+    scale, shift = ops.bn_fold(bn)
+    wpk = ops.pack_conv_weight(conv.weight.data, scale, 0).view(Cout, 9 * Cin)
+    col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode)
+    if residual is not None and act_after_residual:
+        y = ops.gemm(col, wpk, bias=shift, residual=residual)
+        y = ops.relu_fwd(y, out=y)
+    else:
+        y = ops.gemm(col, wpk, bias=shift, act=ops.ACT_RELU if relu else ops.ACT_NONE, residual=residual)
+    return y, Ho, Wo
+
+
+def encoder_forward(enc, x):
+    """x (F, Cimg, H, W) NCHW frames -> ((F*h*w, C) channel-last features, h, w).  Reference :26-51."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("vptr_b200.VPTREnc: input must be a CUDA float32 tensor (got %s, %s); there is no CPU fallback" % (x.device, x.dtype))
+    x = x.contiguous()
+    F_, Ci, H, W = x.shape
+    m = enc.model
+    scale, shift = ops.bn_fold(m[2])
+    wpk = ops.pack_conv_weight(m[1].weight.data, scale, 2)
+    h = ops.stem_conv7x7(x, wpk, shift, F_, Ci, H, W, m[1].weight.shape[0])
+    idx = 4
+    for _ in range(enc.n_downsampling):
+        h, H, W = _conv3x3(h, F_, H, W, m[idx], m[idx + 1], 2, 0, True)
+        idx += 3
+    pad_mode = ops.PAD_MODES[enc.padding_type]
+    for b in range(9):
+        c1, n1, c2, n2 = m[idx + b].convs()
+        r, _, _ = _conv3x3(h, F_, H, W, c1, n1, 1, pad_mode, True)
+        h, _, _ = _conv3x3(r, F_, H, W, c2, n2, 1, pad_mode, False, residual=h, act_after_residual=(b == 8))   # final nn.ReLU of :48
+    return h, H, W
+
+
+_ACT = {"Tanh": 1, "Sigmoid": 2}
+
+
+def decoder_forward(dec, feat, F_, H, W, save):
+    """feat (F*H*W, C) channel-last -> frames (F, Cimg, 2^n H, 2^n W) NCHW.  Reference :70-101."""
+    m = dec.model
+    h = feat
+    saved = []
+    idx = 0
+    for _ in range(dec.n_downsampling):
+        convT, bn = m[idx], m[idx + 1]
+        Cin, Cout = convT.weight.shape[:2]
+        scale, shift = ops.bn_fold(bn)
+        wpk = ops.pack_conv_weight(convT.weight.data, scale, 1).view(9 * Cout, Cin)
+        col = ops.gemm(h, wpk)
+        y = ops.convT_gather(col, shift, F_, H, W, Cout, relu=True)
+        if save:
+            saved.append((wpk, y, H, W, Cin, Cout))
+        h, H, W = y, 2 * H, 2 * W
+        idx += 3
+    head = m[idx + 1]
+    Co, Ci = head.weight.shape[:2]
+    wpk = ops.pack_conv_weight(head.weight.data, None, 3)
+    act = _ACT[dec.out_layer]
+    out = ops.head_conv7x7_fwd(h, wpk, head.bias.data, F_, Ci, Co, H, W, act)
+    return out, ((saved, out, head, act, F_, H, W) if save else None)
+
+
+def decoder_backward(dec, saved_all, dout):
+    saved, out, head, act, F_, H, W = saved_all
+    Co, Ci = head.weight.shape[:2]
+    d = ops.head_conv7x7_bwd(dout, out, head.weight.data, F_, Ci, Co, H, W, act)     # (F*H*W, 64) gradient at the last ReLU output
+    for wpk, y, h_in, w_in, Cin, Cout in reversed(saved):
+        # y = relu(convT(x)*scale + shift): dx = conv_s2(d * (y > 0)) with the same packed weight
+        col, _, _ = ops.im2col(d, F_, 2 * h_in, 2 * w_in, Cout, 3, 2, 1, 0, mask=y)
+        d = ops.gemm(col, wpk, b_mn=True)                                             # (F*h*w, Cin)
+    return d

@@ -1,0 +1,309 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/vptr_b200.h).  torch is used here only for device memory and
+the current CUDA stream; every computation is a kernel of libvptr_b200.so."""
+import torch
+
+from . import _lib
+
+_call = _lib.call
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name="tensor"):
+    if t is not None:
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError("vptr_b200: %s must be a CUDA float32 tensor (got %s %s); there is no CPU path" % (name, t.device, t.dtype))
+    return t
+
+
+def empty(*shape, like=None, device=None):
+    return torch.empty(*shape, dtype=torch.float32, device=like.device if like is not None else device)
+
+
+def zeros(*shape, like=None, device=None):
+    return torch.zeros(*shape, dtype=torch.float32, device=like.device if like is not None else device)
+
+
+# --------------------------------------------------------------------------------------------------- GEMM
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+FORCE_SIMT = False  # tests flip this to cross-check the tensor-core kernel against the fp32 FFMA kernel
+
+
+def _mat(t):
+    """(ptr, pitch) of a 2-D row-major view whose inner stride is 1."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise RuntimeError("vptr_b200.gemm: operand must be 2-D with unit inner stride, got shape %s strides %s" % (tuple(t.shape), t.stride()))
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha=1.0, act=ACT_NONE, accumulate=False,
+         round_tf32=False, k_splits=0):
+    """out[M,N] (+)= act(alpha * Aop @ Bop^T + bias) + residual.  a_mn: A stored [K,M]; b_mn: B stored [K,N]."""
+    _chk(A, "A"); _chk(B, "B"); _chk(bias, "bias"); _chk(residual, "residual")
+    if a_mn:
+        K, M = A.shape
+    else:
+        M, K = A.shape
+    if b_mn:
+        Kb, N = B.shape
+    else:
+        N, Kb = B.shape
+    if K != Kb:
+        raise RuntimeError("vptr_b200.gemm: contraction mismatch %d vs %d" % (K, Kb))
+    if out is None:
+        if accumulate:
+            raise RuntimeError("vptr_b200.gemm: accumulate needs an output buffer")
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    if out.shape[0] != M or out.shape[1] != N:
+        raise RuntimeError("vptr_b200.gemm: out shape %s != (%d,%d)" % (tuple(out.shape), M, N))
+    pa, lda = _mat(A)
+    pb, ldb = _mat(B)
+    pd, ldd = _mat(out)
+    pr, ldr = (0, 0) if residual is None else _mat(residual)
+    flags = (1 if accumulate else 0) | (2 if round_tf32 else 0)
+    aligned = (lda % 4 == 0 and ldb % 4 == 0 and ldd % 4 == 0 and ldr % 4 == 0 and N % 4 == 0 and pa % 16 == 0 and pb % 16 == 0
+               and pd % 16 == 0 and pr % 16 == 0 and _p(bias) % 16 == 0)
+    name = "vptr_gemm_tf32" if (aligned and not FORCE_SIMT) else "vptr_gemm_simt"
+    _call(name, pa, lda, int(a_mn), pb, ldb, int(b_mn), pd, ldd, M, N, K, _p(bias), pr, ldr, float(alpha), int(act), flags,
+          int(k_splits), _s())
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- norms
+def layernorm_fwd(x, gamma, beta, want_y=True, add=None, add_div=1, add_mod=1, save_stats=True, relu=False, eps=1e-5):
+    rows, C = x.shape
+    y = torch.empty_like(x) if want_y else None
+    y2 = torch.empty_like(x) if add is not None else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
+    _call("vptr_layernorm_fwd", _p(_chk(x)), _p(gamma), _p(beta), _p(y), _p(y2), _p(add), int(add_div), int(add_mod), _p(mean),
+          _p(rstd), rows, C, float(eps), int(relu), _s())
+    return y, y2, mean, rstd
+
+
+def layernorm_bwd(dy1, dy2, x, gamma, beta, mean, rstd, dres, dgamma, dbeta, relu=False, want_dx=True):
+    rows, C = x.shape
+    dx = torch.empty_like(x) if want_dx else None
+    _call("vptr_layernorm_bwd", _p(_chk(dy1)), _p(dy2), _p(x), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dgamma),
+          _p(dbeta), rows, C, int(relu), _s())
+    return dx
+
+
+def bn_stats(x, running_mean, running_var, momentum=0.1, eps=1e-5):
+    rows, ch = x.shape
+    mean = torch.empty(ch, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    ws = torch.empty(2 * ch, dtype=torch.float64, device=x.device)
+    _call("vptr_bn_stats", _p(x), rows, ch, _p(mean), _p(rstd), _p(running_mean), _p(running_var), float(eps), float(momentum), _p(ws), _s())
+    return mean, rstd
+
+
+def bn_eval_stats(running_mean, running_var, eps=1e-5):
+    ch = running_mean.numel()
+    mean = torch.empty(ch, dtype=torch.float32, device=running_mean.device)
+    rstd = torch.empty_like(mean)
+    _call("vptr_bn_eval_stats", _p(running_mean), _p(running_var), _p(mean), _p(rstd), ch, float(eps), _s())
+    return mean, rstd
+
+
+def group_stats(x, groups, eps=1e-5):
+    gsize = x.numel() // groups
+    mean = torch.empty(groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    _call("vptr_group_stats", _p(x), groups, gsize, _p(mean), _p(rstd), float(eps), _s())
+    return mean, rstd
+
+
+def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round_tf32=False):
+    rows, ch = x.shape
+    y = torch.empty_like(x) if out is None else out
+    _call("vptr_norm_act_fwd", _p(x), _p(y), _p(res), _p(mean), _p(rstd), _p(gamma), _p(beta), rows, ch, hw, mode, int(round_tf32), _s())
+    return y
+
+
+def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode):
+    rows, ch = x.shape
+    dx = torch.empty_like(x)
+    n_ws = 2 * ch if mode != 1 else 2 * (rows // hw)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
+    _call("vptr_norm_act_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
+          _p(ws), _s())
+    return dx
+
+
+# --------------------------------------------------------------------------------------------------- attention
+def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale):
+    _call("vptr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode,
+          F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), _s())
+    return out
+
+
+def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale):
+    _call("vptr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
+          _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(rpe_table), _p(d_rpe_table), mode, F_or_N, H, W, ws, Tq, Tk, nhead, d,
+          int(causal), float(scale), _s())
+
+
+def window_index_maps(F, H, W, ws, device):
+    L = ws * ws
+    B = F * (H // ws) * (W // ws)
+    rpi = torch.empty(L, L, dtype=torch.int64, device=device)
+    wmap = torch.empty(L, B, dtype=torch.int64, device=device)
+    _call("vptr_window_index_maps", F, H, W, ws, rpi.data_ptr(), wmap.data_ptr(), _s())
+    return rpi, wmap
+
+
+def causal_mask(T, device):
+    m = torch.empty(T, T, dtype=torch.uint8, device=device)
+    _call("vptr_causal_mask", T, m.data_ptr(), _s())
+    return m.bool()
+
+
+# --------------------------------------------------------------------------------------------------- dw conv / elementwise
+def dwconv3x3(x, w9, bias, F, H, W, flip=False):
+    y = torch.empty_like(x)
+    _call("vptr_dwconv3x3", _p(x), _p(w9), _p(bias), _p(y), F, H, W, x.shape[-1], int(flip), _s())
+    return y
+
+
+def dwconv3x3_wgrad(x, dy, dw9, dbias, F, H, W):
+    _call("vptr_dwconv3x3_wgrad", _p(x), _p(dy), _p(dw9), _p(dbias), F, H, W, x.shape[-1], _s())
+
+
+def axpby(a, b, alpha=1.0, beta=1.0, out=None):
+    out = torch.empty_like(a) if out is None else out
+    _call("vptr_axpby", _p(a), _p(b), _p(out), a.numel(), float(alpha), float(beta), _s())
+    return out
+
+
+def add_rows(x, add, div, mod):
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    _call("vptr_add_rows", _p(x), _p(add), _p(out), rows, C, div, mod, _s())
+    return out
+
+
+def rowgroup_sum(dy, out, reps):
+    _call("vptr_rowgroup_sum", _p(dy), _p(out), out.numel(), reps, _s())
+
+
+def gelu_fwd(x, round_tf32=False):
+    y = torch.empty_like(x)
+    _call("vptr_gelu_fwd", _p(x), _p(y), x.numel(), int(round_tf32), _s())
+    return y
+
+
+def gelu_bwd(dy, x, out=None):
+    dx = torch.empty_like(x) if out is None else out
+    _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), _s())
+    return dx
+
+
+def relu_fwd(x, out=None):
+    y = torch.empty_like(x) if out is None else out
+    _call("vptr_relu_fwd", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+def relu_bwd(dy, y, out=None):
+    dx = torch.empty_like(y) if out is None else out
+    _call("vptr_relu_bwd", _p(dy), _p(y), _p(dx), y.numel(), _s())
+    return dx
+
+
+def colsum(x, out):
+    """out[c] += sum_r x[r, c]; x may be a column slice of a wider buffer."""
+    rows, C = x.shape
+    _call("vptr_colsum", _p(x), _p(out), rows, C, x.stride(0), _s())
+
+
+def transpose(x, batch, R, C, out=None, accumulate=False):
+    """[batch][R][C] -> [batch][C][R] (out += when accumulate)."""
+    if out is None:
+        out = torch.empty(batch * R * C, dtype=torch.float32, device=x.device)
+    _call("vptr_transpose", _p(x), _p(out), batch, R, C, int(accumulate), _s())
+    return out
+
+
+def pad_hw(x, F, H, W, Hp, Wp, ph0, pw0):
+    C = x.shape[-1]
+    out = torch.empty(F * Hp * Wp, C, dtype=torch.float32, device=x.device)
+    _call("vptr_pad_crop", _p(x), _p(out), F, H, W, Hp, Wp, ph0, pw0, C, 0, _s())
+    return out
+
+
+def crop_hw(x, F, H, W, Hp, Wp, ph0, pw0):
+    C = x.shape[-1]
+    out = torch.empty(F * H * W, C, dtype=torch.float32, device=x.device)
+    _call("vptr_pad_crop", _p(x), _p(out), F, H, W, Hp, Wp, ph0, pw0, C, 1, _s())
+    return out
+
+
+def sqnorm_accumulate(x, acc):
+    _call("vptr_sqnorm_accumulate", _p(x), x.numel(), acc.data_ptr(), _s())
+
+
+def clip_scale(x, sqnorm, max_norm):
+    _call("vptr_clip_scale", _p(x), x.numel(), sqnorm.data_ptr(), float(max_norm), _s())
+
+
+# --------------------------------------------------------------------------------------------------- ResNet pieces
+PAD_MODES = {"zero": 0, "reflect": 1, "replicate": 2}
+
+
+def im2col(x, F, H, W, Cin, k, stride, pad, pad_mode, mask=None):
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    col = torch.empty(F * Ho * Wo, k * k * Cin, dtype=torch.float32, device=x.device)
+    _call("vptr_im2col", _p(x), _p(mask), _p(col), F, H, W, Cin, k, stride, pad, pad_mode, _s())
+    return col, Ho, Wo
+
+
+def convT_gather(col, shift, F, H, W, Cout, relu=True):
+    out = torch.empty(F * 4 * H * W, Cout, dtype=torch.float32, device=col.device)
+    _call("vptr_convT_gather", _p(col), _p(shift), _p(out), F, H, W, Cout, int(relu), _s())
+    return out
+
+
+def bn_fold(bn, eps=None):
+    C = bn.weight.numel()
+    scale = torch.empty(C, dtype=torch.float32, device=bn.weight.device)
+    shift = torch.empty_like(scale)
+    _call("vptr_bn_fold", _p(bn.weight.data), _p(bn.bias.data), _p(bn.running_mean), _p(bn.running_var), float(bn.eps if eps is None else eps),
+          _p(scale), _p(shift), C, _s())
+    return scale, shift
+
+
+def pack_conv_weight(w, scale, mode):
+    """mode 0: Conv2d -> [Co][(kh,kw,ci)]; 1: ConvT -> [(kh,kw,co)][ci]; 2: Conv2d -> [(kh,kw,ci)][co]; 3: Conv2d -> [(kh,kw)][co][ci]."""
+    if mode == 1:
+        Ci, Co, k, _ = w.shape
+    else:
+        Co, Ci, k, _ = w.shape
+    out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    _call("vptr_pack_conv_weight", _p(w), _p(scale), _p(out), Co, Ci, k, mode, _s())
+    return out
+
+
+def stem_conv7x7(x, wpk, shift, F, Ci, H, W, Co):
+    out = torch.empty(F * H * W, Co, dtype=torch.float32, device=x.device)
+    _call("vptr_stem_conv7x7", _p(x), _p(wpk), _p(shift), _p(out), F, Ci, H, W, Co, _s())
+    return out
+
+
+def head_conv7x7_fwd(x, wpk, bias, F, Ci, Co, H, W, act):
+    out = torch.empty(F, Co, H, W, dtype=torch.float32, device=x.device)
+    _call("vptr_head_conv7x7_fwd", _p(x), _p(wpk), _p(bias), _p(out), F, Ci, Co, H, W, act, _s())
+    return out
+
+
+def head_conv7x7_bwd(dout, out, w, F, Ci, Co, H, W, act):
+    dx = torch.empty(F * H * W, Ci, dtype=torch.float32, device=dout.device)
+    _call("vptr_head_conv7x7_bwd", _p(dout), _p(out), _p(w), _p(dx), F, Ci, Co, H, W, act, _s())
+    return dx
