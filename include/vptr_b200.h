@@ -48,7 +48,7 @@ int vptr_gemm_simt(const float* A, long long lda, int a_mn, const float* B, long
  * y = LN(x)*gamma+beta [relu]; y2 = y + add[(row/add_div) % add_mod] (positional add of :75-84,176-178,200). */
 int vptr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* add,
                        int add_div, int add_mod, float* mean, float* rstd, long long rows, int C, float eps, int relu,
-                       vptr_stream_t stream);
+                       int round_tf32, vptr_stream_t stream);
 /* dx = dres + dLN(dy1 + dy2); dgamma/dbeta accumulated (+=); any of dy2, dres, dx, dgamma may be NULL */
 int vptr_layernorm_bwd(const float* dy1, const float* dy2, const float* x, const float* gamma, const float* beta,
                        const float* mean, const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
@@ -66,7 +66,7 @@ int vptr_norm_act_fwd(const float* x, float* y, const float* res, const float* m
 /* mode 0 train BatchNorm, 1 frame LayerNorm, 2 eval BatchNorm. ws: 2*ch (modes 0,2) or 2*frames (mode 1) floats */
 int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
-                      float* ws, vptr_stream_t stream);
+                      float* ws, int round_tf32, vptr_stream_t stream);
 
 /* ---- attention cores ---------------------------------------------------------------------------------
  * mode 0: local-window attention + relative-position bias (model/VidHRFormer_modules.py:321-357,503-525;
@@ -76,11 +76,11 @@ int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const 
  * Q,K,V,O are token-major with row pitches ld*; head h uses columns [h*d, (h+1)*d). */
 int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                   long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead,
-                  int d, int causal, float scale, vptr_stream_t stream);
+                  int d, int causal, float scale, int round_tf32, vptr_stream_t stream);
 int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO,
                   long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV, long long lddv,
                   const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
-                  int nhead, int d, int causal, float scale, vptr_stream_t stream);
+                  int nhead, int d, int causal, float scale, int round_tf32, vptr_stream_t stream);
 /* integer artefacts from the kernels' own index functions (bit-exact contract): relative_position_index
  * (model/MultiHeadAttentionRPE.py:373-387) as int64 [L][L]; window token map (model/VidHRFormer_modules.py:503-513)
  * as int64 [L][B]; causal mask (model/VidHRFormer_modules.py:78) as uint8 [T][T] */
@@ -95,10 +95,14 @@ int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9, float* dbi
 
 /* ---- elementwise / layout helpers ----------------------------------------------------------------------- */
 int vptr_axpby(const float* a, const float* b, float* out, long long n, float alpha, float beta, vptr_stream_t stream);
-int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, vptr_stream_t stream);
+int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, int round_tf32,
+                  vptr_stream_t stream);
 int vptr_rowgroup_sum(const float* dy, float* out, long long group_elems, int reps, vptr_stream_t stream);
 int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, vptr_stream_t stream);
-int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, vptr_stream_t stream);
+int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, vptr_stream_t stream);
+/* y = x rounded to nearest tf32: operands of vptr_gemm_tf32 are pre-rounded by their producers (or by this copy) so the
+ * tensor core's mantissa truncation is exact and unbiased */
+int vptr_round_copy(const float* x, float* y, long long n, vptr_stream_t stream);
 int vptr_relu_fwd(const float* x, float* y, long long n, vptr_stream_t stream);
 int vptr_relu_bwd(const float* dy, const float* y, float* dx, long long n, vptr_stream_t stream);
 int vptr_colsum(const float* x, float* out, long long rows, int C, long long ld, vptr_stream_t stream);
@@ -112,7 +116,7 @@ int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm,
 
 /* ---- ResNet encoder / decoder (model/ResNetAutoEncoder.py:26-48,70-98) ---------------------------------- */
 int vptr_im2col(const float* x, const float* mask, float* col, int F, int H, int W, int Cin, int k, int stride, int pad,
-                int pad_mode /* 0 zero, 1 reflect, 2 replicate */, vptr_stream_t stream);
+                int pad_mode /* 0 zero, 1 reflect, 2 replicate */, int round_tf32, vptr_stream_t stream);
 int vptr_convT_gather(const float* col, const float* shift, float* out, int F, int H, int W, int Cout, int relu,
                       vptr_stream_t stream);
 int vptr_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,

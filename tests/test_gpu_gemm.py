@@ -1,0 +1,85 @@
+"""GPU: the tcgen05 TF32 GEMM (through the C-ABI) against fp64 torch.matmul on tf32-exact inputs, and against the
+fp32 FFMA kernel on arbitrary inputs.  Covers all operand majors, ragged M/N/K tails, epilogues and split-K."""
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32_exact(shape, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(*shape, generator=g)
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32).cuda()   # low 13 mantissa bits cleared: exact in tf32
+
+
+def ref_gemm(A, B, a_mn, b_mn):
+    A64 = A.double().t() if a_mn else A.double()
+    B64 = B.double() if b_mn else B.double().t()
+    return A64 @ B64
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 176, 32), (256, 528, 528), (300, 48, 100), (1000, 2112, 528), (77, 12, 8), (4096, 528, 2112)])
+def test_gemm_majors_and_tails(a_mn, b_mn, M, N, K):
+    from vptr_b200 import ops
+    A = tf32_exact((K, M) if a_mn else (M, K), 1)
+    B = tf32_exact((K, N) if b_mn else (N, K), 2)
+    D = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    ref = ref_gemm(A, B, a_mn, b_mn)
+    assert rel_l2(D, ref) < 1e-5, (M, N, K)   # fp32 accumulation over K
+
+
+def test_gemm_epilogues():
+    from vptr_b200 import ops
+    M, N, K = 520, 528, 264
+    A, B = tf32_exact((M, K), 3), tf32_exact((N, K), 4)
+    bias, res = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+    base = ref_gemm(A, B, False, False)
+    D = ops.gemm(A, B, bias=bias, act=ops.ACT_GELU, residual=res, alpha=0.5)
+    ref = torch.nn.functional.gelu(0.5 * base + bias.double()) + res.double()
+    assert rel_l2(D, ref) < 2e-6
+    D = ops.gemm(A, B, bias=bias, act=ops.ACT_RELU)
+    assert rel_l2(D, torch.relu(base + bias.double())) < 2e-6
+    # strided output / operands (column slices of wider buffers, as the fused qkv buffer uses)
+    wide = torch.zeros(M, 3 * N, device="cuda")
+    ops.gemm(A, B, out=wide[:, N:2 * N], bias=bias)
+    assert rel_l2(wide[:, N:2 * N], base + bias.double()) < 2e-6
+    assert float(wide[:, :N].abs().max()) == 0.0 and float(wide[:, 2 * N:].abs().max()) == 0.0
+    # in-place accumulate through the residual pointer
+    acc = res.clone()
+    ops.gemm(A, B, out=acc, residual=acc)
+    assert rel_l2(acc, base + res.double()) < 2e-6
+
+
+def test_gemm_splitk_accumulate():
+    from vptr_b200 import ops
+    tokens, Nout, Kin = 5000, 528, 2112
+    dY, X = tf32_exact((tokens, Nout), 5), tf32_exact((tokens, Kin), 6)
+    dW = torch.ones(Nout, Kin, device="cuda")
+    ops.gemm(dY, X, out=dW, a_mn=True, b_mn=True, accumulate=True)
+    ref = dY.double().t() @ X.double() + 1.0
+    assert rel_l2(dW, ref) < 5e-6
+
+
+def test_gemm_tf32_vs_fp32_kernel():
+    """arbitrary fp32 inputs: tensor-core result within tf32 truncation error of the FFMA kernel"""
+    from vptr_b200 import ops
+    M, N, K = 2048, 528, 528
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    D = ops.gemm(A, B)
+    ops.FORCE_SIMT = True
+    try:
+        Ds = ops.gemm(A, B)
+    finally:
+        ops.FORCE_SIMT = False
+    assert rel_l2(Ds, A.double() @ B.double().t()) < 1e-6
+    assert rel_l2(D, Ds) < 2e-3
+
+
+def test_gemm_rejects_cpu_tensor():
+    from vptr_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.randn(8, 8), torch.randn(8, 8))

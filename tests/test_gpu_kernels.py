@@ -1,0 +1,269 @@
+"""GPU: every non-GEMM kernel of libvptr_b200.so against the oracle / torch autograd on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load_golden, rel_l2
+
+import vptr_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda()
+
+
+def test_integer_artefacts_bit_exact():
+    from vptr_b200 import ops
+    z = load_golden("integer_artefacts")
+    for key in [k for k in z.files if k.startswith("wmap_")]:
+        Fr, H, W, ws = map(int, key.split("_")[1:])
+        rpi, wmap = ops.window_index_maps(Fr, H, W, ws, "cuda")
+        assert np.array_equal(wmap.cpu().numpy(), z[key]), key
+        assert np.array_equal(rpi.cpu().numpy(), z["rpi_%d" % ws]), key
+    for ws in (2, 7):
+        rpi, _ = ops.window_index_maps(1, ws, ws, ws, "cuda")
+        assert np.array_equal(rpi.cpu().numpy(), z["rpi_%d" % ws])
+    for T in (1, 5, 29):
+        assert np.array_equal(ops.causal_mask(T, "cuda").cpu().numpy(), z["causal_%d" % T])
+    for hw in (6, 7, 8, 9):   # PadBlock offsets through the pad kernel
+        from vptr_b200.engine import Geom
+        g = Geom(1, 1, hw, hw, 4, 1, 4)
+        m = ops.pad_hw(torch.ones(hw * hw, 4, device="cuda"), 1, hw, hw, g.Hp, g.Wp, g.ph0, g.pw0).view(g.Hp, g.Wp, 4)[:, :, 0]
+        assert np.array_equal(m.cpu().numpy(), z["padmask_%d" % hw]), hw
+
+
+@pytest.mark.parametrize("rows,C", [(640, 528), (37, 48), (1, 8)])
+def test_layernorm_fwd_bwd(rows, C):
+    from vptr_b200 import ops
+    x, gm, bt = rnd(rows, C, seed=1), rnd(C, seed=2) * 0.2 + 1, rnd(C, seed=3) * 0.1
+    add = rnd(5, C, seed=4)
+    y, y2, mean, rstd = ops.layernorm_fwd(x, gm, bt, add=add, add_div=2, add_mod=5)
+    xr = x.clone().requires_grad_(True); gr = gm.clone().requires_grad_(True); br = bt.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), gr, br)
+    idx = (torch.arange(rows, device="cuda") // 2) % 5
+    assert rel_l2(y, yr) < TOL and rel_l2(y2, yr + add[idx]) < TOL
+    dy1, dy2, dres = rnd(rows, C, seed=5), rnd(rows, C, seed=6), rnd(rows, C, seed=7)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx = ops.layernorm_bwd(dy1, dy2, x, gm, bt, mean, rstd, dres, dg, db)
+    (yr * (dy1 + dy2)).sum().backward()
+    assert rel_l2(dx, xr.grad + dres) < 5 * TOL and rel_l2(dg, gr.grad) < 5 * TOL and rel_l2(db, br.grad) < 5 * TOL
+    # relu flavour (final norm + F.relu_)
+    yq, _, mean, rstd = ops.layernorm_fwd(x, gm, bt, relu=True)
+    xr.grad = None
+    yr = F.relu(F.layer_norm(xr, (C,), gm, bt))
+    (yr * dy1).sum().backward()
+    dx = ops.layernorm_bwd(dy1, None, x, gm, bt, mean, rstd, None, None, None, relu=True)
+    assert rel_l2(yq, yr) < TOL and rel_l2(dx, xr.grad) < 5 * TOL
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_norm_act(mode):
+    """MlpDWBN norm + GELU (+ residual): BatchNorm train (0), LayerNorm((ch,H,W)) (1), BatchNorm eval (2)."""
+    from vptr_b200 import ops
+    Fr, H, W, ch = 6, 4, 4, 48
+    hw, rows = H * W, Fr * H * W
+    x = rnd(rows, ch, seed=1) * 2 + 0.3
+    res, dy = rnd(rows, ch, seed=2), rnd(rows, ch, seed=3)
+    xr = x.clone().requires_grad_(True)
+    if mode == 1:
+        gm, bt = rnd(hw, ch, seed=4) * 0.2 + 1, rnd(hw, ch, seed=5) * 0.1
+        gr, br = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        mean, rstd = ops.group_stats(x, Fr)
+        z = F.layer_norm(xr.view(Fr, hw, ch), (hw, ch), gr, br).view(rows, ch)
+    else:
+        gm, bt = rnd(ch, seed=4) * 0.2 + 1, rnd(ch, seed=5) * 0.1
+        gr, br = gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+        rm, rv = rnd(ch, seed=6) * 0.1, rnd(ch, seed=7).abs() + 0.5
+        if mode == 0:
+            rm2, rv2 = rm.clone(), rv.clone()
+            mean, rstd = ops.bn_stats(x, rm2, rv2)
+            rm3, rv3 = rm.clone(), rv.clone()
+            z = F.batch_norm(xr, rm3, rv3, gr, br, training=True, momentum=0.1, eps=1e-5)
+            assert rel_l2(rm2, rm3) < TOL and rel_l2(rv2, rv3) < TOL
+        else:
+            mean, rstd = ops.bn_eval_stats(rm, rv)
+            z = F.batch_norm(xr, rm, rv, gr, br, training=False, eps=1e-5)
+    yr = F.gelu(z) + res
+    y = ops.norm_act_fwd(x, mean, rstd, gm, bt, hw, 1 if mode == 1 else 0, res=res)
+    assert rel_l2(y, yr) < TOL
+    (yr * dy).sum().backward()
+    dg, db = torch.zeros_like(gm), torch.zeros_like(bt)
+    dx = ops.norm_act_bwd(dy, x, mean, rstd, gm, bt, dg, db, hw, mode)
+    assert rel_l2(dx, xr.grad) < 1e-4 and rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+
+
+def _attn_ref(q, k, v, nhead, scale, bias=None, mask=None):
+    """(B,L,C) oracle core with q scaled first, as the reference does"""
+    return O._mha_core(q * scale, k, v, nhead, bias=bias, mask=mask)
+
+
+@pytest.mark.parametrize("ws,H,W,nhead,d", [(4, 8, 8, 8, 66), (2, 4, 6, 4, 12), (8, 8, 8, 2, 20)])
+def test_window_attention_core(ws, H, W, nhead, d):
+    from vptr_b200 import ops
+    Fr, C, L = 3, nhead * d, ws * ws
+    rows = Fr * H * W
+    qkv = rnd(rows, 3 * C, seed=1)
+    table = rnd((2 * ws - 1) ** 2, nhead, seed=2) * 0.5
+    scale = d ** -0.5
+    o = torch.empty(rows, C, device="cuda")
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, H, W, ws, 0, 0, nhead, d, False, scale)
+    tmap = O.window_token_map(Fr, H, W, ws).cuda()                  # (L,B)
+    qr = qkv.clone().requires_grad_(True); tr = table.clone().requires_grad_(True)
+    g = lambda t: t[tmap.t()]                                        # (B,L,C)
+    bias = tr[O.relative_position_index(ws).cuda().reshape(-1)].reshape(L, L, nhead).permute(2, 0, 1)
+    ob = _attn_ref(g(qr[:, :C]), g(qr[:, C:2 * C]), g(qr[:, 2 * C:]), nhead, scale, bias=bias)
+    oref = torch.zeros(rows, C, device="cuda").index_put((tmap.t().reshape(-1),), ob.reshape(-1, C))
+    assert rel_l2(o, oref) < TOL
+    do = rnd(rows, C, seed=3)
+    (oref * do).sum().backward()
+    dqkv, dtab = torch.empty_like(qkv), torch.zeros_like(table)
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtab, 0, Fr, H,
+                 W, ws, 0, 0, nhead, d, False, scale)
+    assert rel_l2(dqkv, qr.grad) < 1e-4 and rel_l2(dtab, tr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("Tq,Tk,causal", [(10, 10, False), (29, 29, True), (5, 2, False), (1, 1, True)])
+def test_temporal_attention_core(Tq, Tk, causal):
+    from vptr_b200 import ops
+    N, H, W, nhead, d = 2, 4, 4, 8, 66
+    C, HW = nhead * d, H * W
+    q, kv = rnd(N * Tq * HW, C, seed=1), rnd(N * Tk * HW, 2 * C, seed=2)
+    scale = d ** -0.5
+    o = torch.empty_like(q)
+    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, N, H, W, 0, Tq, Tk, nhead, d, causal, scale)
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    seq = lambda t, T: t.view(N, T, HW, -1).permute(0, 2, 1, 3).reshape(N * HW, T, -1)
+    mask = O.causal_mask(Tq).cuda() if causal else None
+    ob = _attn_ref(seq(qr, Tq), seq(kvr[:, :C], Tk), seq(kvr[:, C:], Tk), nhead, scale, mask=mask)
+    oref = ob.view(N, HW, Tq, C).permute(0, 2, 1, 3).reshape(N * Tq * HW, C)
+    assert rel_l2(o, oref) < TOL
+    do = rnd(N * Tq * HW, C, seed=3)
+    (oref * do).sum().backward()
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, 1, N, H, W, 0, Tq, Tk, nhead, d, causal, scale)
+    assert rel_l2(dq, qr.grad) < 1e-4 and rel_l2(dkv, kvr.grad) < 1e-4
+
+
+def test_dwconv3x3():
+    from vptr_b200 import ops
+    Fr, H, W, ch = 5, 8, 6, 48
+    x = rnd(Fr * H * W, ch, seed=1)
+    w, b = rnd(ch, 1, 3, 3, seed=2), rnd(ch, seed=3)
+    w9 = ops.transpose(w, 1, ch, 9)
+    y = ops.dwconv3x3(x, w9, b, Fr, H, W)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr.view(Fr, H, W, ch).permute(0, 3, 1, 2), wr, br, padding=1, groups=ch).permute(0, 2, 3, 1).reshape(-1, ch)
+    assert rel_l2(y, yr) < TOL
+    dy = rnd(Fr * H * W, ch, seed=4)
+    (yr * dy).sum().backward()
+    dx = ops.dwconv3x3(dy, w9, None, Fr, H, W, flip=True)
+    dw9, db = torch.zeros(9 * ch, device="cuda"), torch.zeros(ch, device="cuda")
+    ops.dwconv3x3_wgrad(x, dy, dw9, db, Fr, H, W)
+    dw = torch.zeros_like(w)
+    ops.transpose(dw9, 1, 9, ch, out=dw, accumulate=True)
+    assert rel_l2(dx, xr.grad) < TOL and rel_l2(dw, wr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+
+
+def test_elementwise_helpers():
+    from vptr_b200 import ops
+    x, y = rnd(300, 48, seed=1), rnd(300, 48, seed=2)
+    assert rel_l2(ops.axpby(x, y, 2.0, -0.5), 2 * x - 0.5 * y) < 1e-6
+    assert rel_l2(ops.gelu_fwd(x), F.gelu(x)) < 1e-6
+    xr = x.clone().requires_grad_(True)
+    (F.gelu(xr) * y).sum().backward()
+    assert rel_l2(ops.gelu_bwd(y, x), xr.grad) < 1e-5
+    assert rel_l2(ops.relu_bwd(y, ops.relu_fwd(x)), y * (x > 0)) < 1e-6
+    out = torch.ones(48, device="cuda")
+    ops.colsum(x, out)
+    assert rel_l2(out, x.sum(0) + 1) < 1e-5
+    t = ops.transpose(x.view(3, 100, 48), 3, 100, 48).view(3, 48, 100)
+    assert torch.equal(t, x.view(3, 100, 48).transpose(1, 2).contiguous())
+    add = rnd(5, 48, seed=3)
+    idx = (torch.arange(300, device="cuda") // 4) % 5
+    assert rel_l2(ops.add_rows(x, add, 4, 5), x + add[idx]) < 1e-6
+    acc = torch.zeros(100 * 48, device="cuda")
+    ops.rowgroup_sum(x, acc, 3)
+    assert rel_l2(acc.view(100, 48), x.view(3, 100, 48).sum(0)) < 1e-5
+    p = ops.pad_hw(x[:6 * 7 * 2].contiguous().view(-1, 48)[:84], 2, 6, 7, 8, 8, 1, 0)
+    ref = F.pad(x[:84].view(2, 6, 7, 48), (0, 0, 0, 1, 1, 1))
+    assert torch.equal(p.view(2, 8, 8, 48), ref)
+    assert torch.equal(ops.crop_hw(p, 2, 6, 7, 8, 8, 1, 0), x[:84])
+    sq = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ops.sqnorm_accumulate(x, sq)
+    assert abs(float(sq) - float(x.double().square().sum())) < 1e-6 * float(sq)
+    xc = x.clone()
+    ops.clip_scale(xc, sq, 1.0)
+    assert rel_l2(xc, x * (1.0 / (float(sq) ** 0.5 + 1e-6))) < 1e-5
+
+
+@pytest.mark.parametrize("k,stride,pad,mode", [(3, 1, 1, "reflect"), (3, 1, 1, "zero"), (3, 2, 1, "zero"), (3, 1, 1, "replicate")])
+def test_im2col_gemm_is_conv(k, stride, pad, mode):
+    from vptr_b200 import ops
+    Fr, H, W, Ci, Co = 2, 8, 8, 16, 24
+    x = rnd(Fr * H * W, Ci, seed=1)
+    w = rnd(Co, Ci, k, k, seed=2) * 0.1
+    scale = rnd(Co, seed=3) * 0.1 + 1
+    col, Ho, Wo = ops.im2col(x, Fr, H, W, Ci, k, stride, pad, ops.PAD_MODES[mode], round_tf32=False)
+    wpk = ops.pack_conv_weight(w, scale, 0).view(Co, k * k * Ci)
+    ops.FORCE_SIMT = True
+    try:
+        y = ops.gemm(col, wpk)
+    finally:
+        ops.FORCE_SIMT = False
+    xn = x.view(Fr, H, W, Ci).permute(0, 3, 1, 2)
+    xp = F.pad(xn, (pad,) * 4, mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
+    yr = (F.conv2d(xp, w, stride=stride) * scale[None, :, None, None]).permute(0, 2, 3, 1).reshape(-1, Co)
+    assert rel_l2(y, yr) < TOL
+
+
+def test_convT_gather_and_backward():
+    from vptr_b200 import ops
+    Fr, H, W, Ci, Co = 2, 4, 4, 24, 16
+    x = rnd(Fr * H * W, Ci, seed=1)
+    w = rnd(Ci, Co, 3, 3, seed=2) * 0.2
+    scale, shift = rnd(Co, seed=3) * 0.1 + 1, rnd(Co, seed=4) * 0.1
+    wpk = ops.pack_conv_weight(w, scale, 1).view(9 * Co, Ci)
+    ops.FORCE_SIMT = True
+    try:
+        col = ops.gemm(x, wpk)
+        y = ops.convT_gather(col, shift, Fr, H, W, Co, relu=True)
+        xr = x.clone().requires_grad_(True)
+        z = F.conv_transpose2d(xr.view(Fr, H, W, Ci).permute(0, 3, 1, 2), w, stride=2, padding=1, output_padding=1)
+        yr = F.relu(z * scale[None, :, None, None] + shift[None, :, None, None]).permute(0, 2, 3, 1).reshape(-1, Co)
+        assert rel_l2(y, yr) < TOL
+        dy = rnd(Fr * 4 * H * W, Co, seed=5)
+        (yr * dy).sum().backward()
+        colb, _, _ = ops.im2col(dy, Fr, 2 * H, 2 * W, Co, 3, 2, 1, 0, mask=y, round_tf32=False)
+        dx = ops.gemm(colb, wpk, b_mn=True)
+    finally:
+        ops.FORCE_SIMT = False
+    assert rel_l2(dx, xr.grad) < TOL
+
+
+@pytest.mark.parametrize("Ci", [1, 3])
+def test_stem_and_head(Ci):
+    from vptr_b200 import ops
+    Fr, H, W = 2, 32, 24
+    x = rnd(Fr, Ci, H, W, seed=1)
+    w = rnd(64, Ci, 7, 7, seed=2) * 0.1
+    scale, shift = rnd(64, seed=3) * 0.1 + 1, rnd(64, seed=4) * 0.1
+    y = ops.stem_conv7x7(x, ops.pack_conv_weight(w, scale, 2), shift, Fr, Ci, H, W, 64)
+    yr = F.relu(F.conv2d(F.pad(x, (3,) * 4, mode="reflect"), w) * scale[None, :, None, None] + shift[None, :, None, None])
+    assert rel_l2(y.view(Fr, H, W, 64).permute(0, 3, 1, 2), yr) < TOL
+    # head: 64 -> Ci, bias, tanh / sigmoid, and its input gradient
+    for act, fn in ((1, torch.tanh), (2, torch.sigmoid)):
+        h = rnd(Fr * H * W, 64, seed=5)
+        wh, bh = rnd(Ci, 64, 7, 7, seed=6) * 0.05, rnd(Ci, seed=7) * 0.1
+        out = ops.head_conv7x7_fwd(h, ops.pack_conv_weight(wh, None, 3), bh, Fr, 64, Ci, H, W, act)
+        hr = h.clone().requires_grad_(True)
+        outr = fn(F.conv2d(F.pad(hr.view(Fr, H, W, 64).permute(0, 3, 1, 2), (3,) * 4, mode="reflect"), wh, bh))
+        assert rel_l2(out, outr) < TOL
+        dout = rnd(Fr, Ci, H, W, seed=8)
+        (outr * dout).sum().backward()
+        dx = ops.head_conv7x7_bwd(dout, out, wh, Fr, 64, Ci, H, W, act)
+        assert rel_l2(dx, hr.grad) < 5 * TOL

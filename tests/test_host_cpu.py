@@ -1,0 +1,97 @@
+"""CPU: host-side logic -- C-ABI symbol table, API surface, loud failure off-GPU, data-parallel gradient mean (gloo, 2 ranks)."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT, build_former
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from vptr_b200 import _lib
+    l = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "vptr_b200.h")).read()
+    declared = set(re.findall(r"\b(vptr_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(l, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert l.vptr_version() >= 100
+
+
+def test_public_api_surface_matches_reference_names():
+    import vptr_b200.model as m
+    for name in ("VPTREnc", "VPTRDec", "VPTRDisc", "init_weights", "VPTRFormerNAR", "VPTRFormerFAR", "GDL", "MSELoss", "L1Loss",
+                 "GANLoss", "BiPatchNCE", "temporal_weight_func"):
+        assert hasattr(m, name), name
+    with pytest.raises(ValueError):
+        m.VPTRDec(1, out_layer="Softmax")
+    with pytest.raises(NotImplementedError):
+        m.VPTREnc(1, padding_type="circular")
+    with pytest.raises(NotImplementedError):
+        m.VPTRFormerNAR(2, 2, d_model=48, nhead=4, TSLMA_flag=True)
+
+
+def test_no_cpu_fallback():
+    net, x, c = build_former("far_rpe")
+    with pytest.raises(RuntimeError):
+        net.eval()(x)                       # CPU tensor -> loud failure, never a silent PyTorch path
+    from vptr_b200.model import VPTREnc
+    enc = VPTREnc(1, feat_dim=16).eval()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 1, 1, 32, 32))
+    with pytest.raises(NotImplementedError):
+        enc.train()(torch.zeros(1, 1, 1, 32, 32))
+
+
+def test_losses_match_closed_forms():
+    from vptr_b200.model import GDL, BiPatchNCE, L1Loss, MSELoss, temporal_weight_func
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(2, 3, 1, 8, 8, generator=g), torch.rand(2, 3, 1, 8, 8, generator=g)
+    assert torch.allclose(MSELoss()(a, b), ((a - b) ** 2).mean())
+    assert torch.allclose(L1Loss()(a, b), (a - b).abs().mean())
+    w = temporal_weight_func(3)
+    assert torch.allclose(w[0], torch.tensor(1.0)) and torch.allclose(w[-1], torch.tensor(3.0))
+    import vptr_oracle as O
+    assert torch.allclose(GDL()(a, b), O.gdl_loss(a, b))
+    f1, f2 = torch.rand(2, 3, 16, 4, 4, generator=g), torch.rand(2, 3, 16, 4, 4, generator=g)
+    import train_step as TS
+    assert torch.allclose(BiPatchNCE(2, 3, 4, 4, 0.5)(f1, f2), TS.bi_patch_nce(f1, f2, 0.5), atol=1e-6)
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from vptr_b200.parallel import allreduce_mean_grads, broadcast_parameters
+    torch.manual_seed(100 + rank)
+    lin = torch.nn.Linear(6, 4)
+    extra = torch.nn.Parameter(torch.zeros(3))          # never gets a grad (like NCE_projector in train_NAR_mp.py)
+    broadcast_parameters(lin)
+    x = torch.full((5, 6), float(rank + 1))
+    lin(x).sum().backward()
+    n = allreduce_mean_grads(list(lin.parameters()) + [extra], world)
+    q.put((rank, lin.weight.detach().clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), n))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_mean_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w0, gw0, gb0, n0), (_, w1, gw1, gb1, n1) = res
+    assert torch.equal(w0, w1)                                   # rank-0 weights broadcast
+    assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)       # identical after the mean
+    assert torch.allclose(gw0, torch.full((4, 6), 5 * 1.5)) and torch.allclose(gb0, torch.full((4,), 5.0))
+    assert n0 == n1 == 4 * 6 + 4

@@ -17,24 +17,25 @@ _SIGS = {
     "vptr_version": ([], I),
     "vptr_gemm_tf32": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P], I),
     "vptr_gemm_simt": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P], I),
-    "vptr_layernorm_fwd": ([P, P, P, P, P, P, I, I, P, P, L, I, F, I, P], I),
+    "vptr_layernorm_fwd": ([P, P, P, P, P, P, I, I, P, P, L, I, F, I, I, P], I),
     "vptr_layernorm_bwd": ([P, P, P, P, P, P, P, P, P, P, P, L, I, I, P], I),
     "vptr_bn_stats": ([P, L, I, P, P, P, P, F, F, P, P], I),
     "vptr_bn_eval_stats": ([P, P, P, P, I, F, P], I),
     "vptr_group_stats": ([P, I, L, P, P, F, P], I),
     "vptr_norm_act_fwd": ([P, P, P, P, P, P, P, L, I, I, I, I, P], I),
-    "vptr_norm_act_bwd": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, P], I),
-    "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, P], I),
-    "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, P], I),
+    "vptr_norm_act_bwd": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P], I),
+    "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, P], I),
+    "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, P], I),
     "vptr_window_index_maps": ([I, I, I, I, P, P, P], I),
     "vptr_causal_mask": ([I, P, P], I),
     "vptr_dwconv3x3": ([P, P, P, P, I, I, I, I, I, P], I),
     "vptr_dwconv3x3_wgrad": ([P, P, P, P, I, I, I, I, P], I),
     "vptr_axpby": ([P, P, P, L, F, F, P], I),
-    "vptr_add_rows": ([P, P, P, L, I, I, I, P], I),
+    "vptr_add_rows": ([P, P, P, L, I, I, I, I, P], I),
     "vptr_rowgroup_sum": ([P, P, L, I, P], I),
     "vptr_gelu_fwd": ([P, P, L, I, P], I),
-    "vptr_gelu_bwd": ([P, P, P, L, P], I),
+    "vptr_gelu_bwd": ([P, P, P, L, I, P], I),
+    "vptr_round_copy": ([P, P, L, P], I),
     "vptr_relu_fwd": ([P, P, L, P], I),
     "vptr_relu_bwd": ([P, P, P, L, P], I),
     "vptr_colsum": ([P, P, L, I, L, P], I),
@@ -42,7 +43,7 @@ _SIGS = {
     "vptr_pad_crop": ([P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_sqnorm_accumulate": ([P, L, P, P], I),
     "vptr_clip_scale": ([P, L, P, F, P], I),
-    "vptr_im2col": ([P, P, P, I, I, I, I, I, I, I, I, P], I),
+    "vptr_im2col": ([P, P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_convT_gather": ([P, P, P, I, I, I, I, I, P], I),
     "vptr_bn_fold": ([P, P, P, P, F, P, P, I, P], I),
     "vptr_pack_conv_weight": ([P, P, P, I, I, I, I, P], I),

@@ -20,6 +20,7 @@ struct AttnGeom {
     int nhead, d;
     int causal;
     float scale;
+    int round_tf32;  // round stored outputs (they only feed tf32 contractions)
 };
 
 __device__ __forceinline__ long long window_row(const AttnGeom& g, int b, int l) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
             const int i = e / g.d, c = e - i * g.d;
             float o = 0.f;
             for (int j = 0; j < g.Lk; ++j) o = fmaf(sS[i * lp + j], sV[j * dp + c], o);
-            O[q_row(g, b, i) * ldo + col0 + c] = o;
+            O[q_row(g, b, i) * ldo + col0 + c] = g.round_tf32 ? vptr_round_tf32(o) : o;
         }
         __syncthreads();
     }
@@ -183,15 +184,17 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
                 dk = fmaf(sdS[i * lp + j], sQ[i * dp + c], dk);
             }
             const long long r = k_row(g, b, j);
-            dV[r * lddv + col0 + c] = dv;
-            dK[r * lddk + col0 + c] = dk * g.scale;
+            dk *= g.scale;
+            dV[r * lddv + col0 + c] = g.round_tf32 ? vptr_round_tf32(dv) : dv;
+            dK[r * lddk + col0 + c] = g.round_tf32 ? vptr_round_tf32(dk) : dk;
         }
         // dQ = scale * dS K
         for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
             const int i = e / g.d, c = e - i * g.d;
             float dq = 0.f;
             for (int j = 0; j < g.Lk; ++j) dq = fmaf(sdS[i * lp + j], sK[j * dp + c], dq);
-            dQ[q_row(g, b, i) * lddq + col0 + c] = dq * g.scale;
+            dq *= g.scale;
+            dQ[q_row(g, b, i) * lddq + col0 + c] = g.round_tf32 ? vptr_round_tf32(dq) : dq;
         }
         __syncthreads();
     }
@@ -239,11 +242,12 @@ int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, i
 // mode 0: F_or_N = number of frames (N*T); mode 1: F_or_N = number of clips N.
 extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                              long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
-                             int nhead, int d, int causal, float scale, cudaStream_t stream) {
+                             int nhead, int d, int causal, float scale, int round_tf32, cudaStream_t stream) {
     AttnGeom g;
     int batches = 0;
     int rc = fill_geom(g, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, &batches);
     if (rc) return rc;
+    g.round_tf32 = round_tf32;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_fwd: empty problem");
     size_t smem = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (d + 1) + (size_t)g.Lq * (g.Lk + 1));
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_fwd: tile too large (%zu B of shared memory)", smem);
@@ -256,11 +260,12 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
 extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
                              const float* dO, long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV,
                              long long lddv, const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws,
-                             int Tq, int Tk, int nhead, int d, int causal, float scale, cudaStream_t stream) {
+                             int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, cudaStream_t stream) {
     AttnGeom g;
     int batches = 0;
     int rc = fill_geom(g, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, &batches);
     if (rc) return rc;
+    g.round_tf32 = round_tf32;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_bwd: empty problem");
     size_t smem = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (d + 1) + (size_t)2 * g.Lq * (g.Lk + 1) + (size_t)g.Lq * g.Lk);
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_bwd: tile too large (%zu B of shared memory)", smem);

@@ -25,7 +25,7 @@ __device__ __forceinline__ int pad_index(int i, int n, int mode) {  // returns -
 // col[(f,oh,ow)][(kh,kw,ci)] = x[f][oh*s+kh-p][ow*s+kw-p][ci] (* (mask > 0))
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ col,
                                                      long long total4, int H, int W, int C4, int Ho, int Wo, int k, int stride, int pad,
-                                                     int pad_mode) {
+                                                     int pad_mode, int round_tf32) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         long long t = i / C4;
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
                 v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
             }
         }
+        if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
         reinterpret_cast<float4*>(col)[i] = v;
     }
 }
@@ -266,13 +267,13 @@ __global__ void __launch_bounds__(256) head_conv7x7_bwd_kernel(const float* __re
 }  // namespace
 
 extern "C" int vptr_im2col(const float* x, const float* mask, float* col, int F, int H, int W, int Cin, int k, int stride, int pad,
-                           int pad_mode, cudaStream_t stream) {
+                           int pad_mode, int round_tf32, cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 4 == 0 && k > 0 && stride > 0, VPTR_ERR_SHAPE,
                  "vptr_im2col: F=%d H=%d W=%d Cin=%d k=%d stride=%d", F, H, W, Cin, k, stride);
     VPTR_REQUIRE(pad_mode == 0 || (pad < H && pad < W), VPTR_ERR_SHAPE, "vptr_im2col: reflect/replicate pad %d too large for %dx%d", pad, H, W);
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     const long long total4 = (long long)F * Ho * Wo * k * k * (Cin / 4);
-    im2col_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, mask, col, total4, H, W, Cin / 4, Ho, Wo, k, stride, pad, pad_mode);
+    im2col_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, mask, col, total4, H, W, Cin / 4, Ho, Wo, k, stride, pad, pad_mode, round_tf32);
     return vptr_check_launch("im2col_kernel");
 }
 

@@ -23,13 +23,22 @@ __global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, c
 
 // out[row] = x[row] + add[(row / div) % mod]
 __global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ x, const float* __restrict__ add, float* __restrict__ out,
-                                                       long long total4, int C4, int div, int mod) {
+                                                       long long total4, int C4, int div, int mod, int round_tf32) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / C4;
         const int c = (int)(i - row * C4);
         float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 p = __ldg(reinterpret_cast<const float4*>(add) + (long long)((row / div) % mod) * C4 + c);
-        reinterpret_cast<float4*>(out)[i] = make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+        float4 o = make_float4(v.x + p.x, v.y + p.y, v.z + p.z, v.w + p.w);
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        reinterpret_cast<float4*>(out)[i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        reinterpret_cast<float4*>(y)[i] = make_float4(vptr_round_tf32(v.x), vptr_round_tf32(v.y), vptr_round_tf32(v.z), vptr_round_tf32(v.w));
     }
 }
 
@@ -52,12 +61,13 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__
     }
 }
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
-                                                       long long n4) {
+                                                       long long n4, int round_tf32) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 g = reinterpret_cast<const float4*>(dy)[i];
         float4 v = reinterpret_cast<const float4*>(x)[i];
-        reinterpret_cast<float4*>(dx)[i] = make_float4(g.x * vptr_gelu_grad(v.x), g.y * vptr_gelu_grad(v.y), g.z * vptr_gelu_grad(v.z),
-                                                      g.w * vptr_gelu_grad(v.w));
+        float4 o = make_float4(g.x * vptr_gelu_grad(v.x), g.y * vptr_gelu_grad(v.y), g.z * vptr_gelu_grad(v.z), g.w * vptr_gelu_grad(v.w));
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        reinterpret_cast<float4*>(dx)[i] = o;
     }
 }
 // dx = dy * (y > 0)
@@ -154,9 +164,10 @@ extern "C" int vptr_axpby(const float* a, const float* b, float* out, long long 
     add_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(a, b, out, n / 4, alpha, beta);
     return vptr_check_launch("add_kernel");
 }
-extern "C" int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, cudaStream_t stream) {
+extern "C" int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, int round_tf32,
+                             cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && div > 0 && mod > 0, VPTR_ERR_SHAPE, "vptr_add_rows: rows=%lld C=%d div=%d mod=%d", rows, C, div, mod);
-    add_rows_kernel<<<ew_grid(rows * C / 4, 256), 256, 0, stream>>>(x, add, out, rows * C / 4, C / 4, div, mod);
+    add_rows_kernel<<<ew_grid(rows * C / 4, 256), 256, 0, stream>>>(x, add, out, rows * C / 4, C / 4, div, mod, round_tf32);
     return vptr_check_launch("add_rows_kernel");
 }
 extern "C" int vptr_rowgroup_sum(const float* dy, float* out, long long group_elems, int reps, cudaStream_t stream) {
@@ -169,10 +180,17 @@ extern "C" int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf
     gelu_fwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, round_tf32);
     return vptr_check_launch("gelu_fwd_kernel");
 }
-extern "C" int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, cudaStream_t stream) {
+extern "C" int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, cudaStream_t stream) {
     REQ4(n, "vptr_gelu_bwd");
-    gelu_bwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(dy, x, dx, n / 4);
+    gelu_bwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(dy, x, dx, n / 4, round_tf32);
     return vptr_check_launch("gelu_bwd_kernel");
+}
+// y = round-to-nearest tf32 of x (element count need not be a multiple of 4: the tail is handled by padding rules of the caller)
+extern "C" int vptr_round_copy(const float* x, float* y, long long n, cudaStream_t stream) {
+    REQ4(n, "vptr_round_copy");
+    if (n == 0) return VPTR_OK;
+    round_copy_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4);
+    return vptr_check_launch("round_copy_kernel");
 }
 extern "C" int vptr_relu_fwd(const float* x, float* y, long long n, cudaStream_t stream) {
     REQ4(n, "vptr_relu_fwd");

@@ -86,16 +86,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
-//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (canonical value 1).
-//   MN-major: 32-float MN groups `lbo_bytes` apart, 8-k-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (sm_100 "version 1").
+//   K-major : SWIZZLE_128B (layout 2): rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused (canonical value 1).
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (layout 1; 32-byte chunks permuted inside each
+//             128-byte row, period 4 rows; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-float MN groups
+//             `lbo_bytes` apart, 4-k-row groups `sbo_bytes` (512 B) apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -263,10 +265,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     const uint32_t b_base = a_base + Cfg::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 1024)
-                                                 : make_smem_desc(a_base + k * 32, 16, 1024);
-                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 1024, 4096, 1024)
-                                                 : make_smem_desc(b_base + k * 32, 16, 1024);
+                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(a_base + k * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(b_base + k * 32, 16, 1024, 2);
                         umma_tf32(d_tmem, da, db, idesc, (kc > k0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -338,7 +340,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map: `inner` contiguous elements, `outer` rows `pitch` elements apart.
-int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long pitch, int box_inner, int box_outer) {
+int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long outer, long long pitch, int box_inner, int box_outer,
+                CUtensorMapSwizzle swizzle) {
     EncodeTiledFn enc = get_encode_fn();
     VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -346,7 +349,7 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long o
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d ptr=%p",
                  (int)r, inner, outer, pitch, box_inner, box_outer, (const void*)ptr);
@@ -417,11 +420,11 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
 
     CUtensorMap ma, mb;
     int rc;
-    if (!a_mn) rc = make_map_2d(&ma, A, K, M, lda, BLOCK_K, BLOCK_M);
-    else rc = make_map_2d(&ma, A, M, K, lda, 32, BLOCK_K);
+    if (!a_mn) rc = make_map_2d(&ma, A, K, M, lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map_2d(&ma, A, M, K, lda, 32, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map_2d(&mb, B, K, N, ldb, BLOCK_K, BN);
-    else rc = make_map_2d(&mb, B, N, K, ldb, 32, BLOCK_K);
+    if (!b_mn) rc = make_map_2d(&mb, B, K, N, ldb, BLOCK_K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    else rc = make_map_2d(&mb, B, N, K, ldb, 32, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
 
     if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0, ST>(ma, mb, p, stream);

@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             float* __restrict__ y2, const float* __restrict__ add,
                                                             int add_div, int add_mod, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, long long rows, int C, float eps,
-                                                            int relu) {
+                                                            int relu, int round_tf32) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -45,10 +45,15 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
         o.z = (v.z - mean) * rstd * g.z + b.z;
         o.w = (v.w - mean) * rstd * g.w + b.w;
         if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (y) *reinterpret_cast<float4*>(y + row * C + c) = o;
+        if (y) {
+            float4 w = o;
+            if (round_tf32) { w.x = vptr_round_tf32(w.x); w.y = vptr_round_tf32(w.y); w.z = vptr_round_tf32(w.z); w.w = vptr_round_tf32(w.w); }
+            *reinterpret_cast<float4*>(y + row * C + c) = w;
+        }
         if (y2) {
             float4 p = __ldg(reinterpret_cast<const float4*>(ar + c));
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
             *reinterpret_cast<float4*>(y2 + row * C + c) = o;
         }
     }
@@ -307,7 +312,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __res
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ s1, const float* __restrict__ s2,
-                                                              float* __restrict__ dx, long long total, int ch, int hw, float inv_n) {
+                                                              float* __restrict__ dx, long long total, int ch, int hw, float inv_n,
+                                                              int round_tf32) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long row = e / ch;
         const int c = (int)(e - row * ch);
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __res
         if (MODE == 0) o = g * r * (gg - t1 * inv_n - xh * t2 * inv_n);
         else if (MODE == 1) o = r * (gg * g - t1 * inv_n - xh * t2 * inv_n);
         else o = g * r * gg;
-        dx[e] = o;
+        dx[e] = round_tf32 ? vptr_round_tf32(o) : o;
     }
 }
 
@@ -340,10 +346,10 @@ int ew_grid(long long n, int block) {
 
 extern "C" int vptr_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* add,
                                   int add_div, int add_mod, float* mean, float* rstd, long long rows, int C, float eps, int relu,
-                                  cudaStream_t stream) {
+                                  int round_tf32, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && C > 0 && C % 4 == 0, VPTR_ERR_SHAPE, "vptr_layernorm_fwd: rows=%lld C=%d (C %% 4 == 0 required)", rows, C);
     VPTR_REQUIRE(y2 == nullptr || (add != nullptr && add_div > 0 && add_mod > 0), VPTR_ERR_SHAPE, "vptr_layernorm_fwd: y2 needs add/add_div/add_mod");
-    layernorm_fwd_kernel<<<vptr_cdiv(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, y2, add, add_div, add_mod, mean, rstd, rows, C, eps, relu);
+    layernorm_fwd_kernel<<<vptr_cdiv(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, y2, add, add_div, add_mod, mean, rstd, rows, C, eps, relu, round_tf32);
     return vptr_check_launch("layernorm_fwd_kernel");
 }
 
@@ -405,7 +411,7 @@ extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, con
 // ws: mode 0 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).
 extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
-                                 float* ws, cudaStream_t stream) {
+                                 float* ws, int round_tf32, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d", rows, ch);
     const long long total = rows * ch;
     const int grid = ew_grid(total, 256);
@@ -415,9 +421,9 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
         dim3 g2(vptr_cdiv(ch, 128), vptr_cdiv(rows, rpb));
         bn_act_bwd_reduce_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, ws, ws + ch, rows, ch, rpb);
         if (mode == 0)
-            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows);
+            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows, round_tf32);
         else
-            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f);
+            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f, round_tf32);
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
@@ -425,7 +431,7 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
         int fpb = 32;
         dim3 g2(vptr_cdiv(gsize, 128), vptr_cdiv(frames, fpb));
         ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, gsize, frames, fpb);
-        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize);
+        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize, round_tf32);
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }

@@ -17,7 +17,11 @@ import torch
 
 from . import ops
 
-ROUND_TF32 = True  # producers of GEMM operands round-to-nearest to tf32 so the tensor core's truncation is exact
+# Every operand of the tensor-core GEMM is rounded to nearest tf32 where it is produced (or by ops.round_copy):
+# tcgen05 kind::tf32 truncates the low 13 mantissa bits, which on raw fp32 data is a biased (towards zero) error that
+# compounds through the backward chain; on pre-rounded data it is exact.
+ROUND_TF32 = True
+RT = ROUND_TF32
 
 
 class Params:
@@ -27,6 +31,7 @@ class Params:
         self.t = {k: v for k, v in named}
         self.gflat = None
         self.gv = {}
+        self.rounded = {}
         if want_grads:
             names = [k for k, v in self.t.items() if v.requires_grad]
             total = sum(self.t[k].numel() for k in names)
@@ -43,6 +48,38 @@ class Params:
 
     def g(self, name):
         return self.gv.get(name)
+
+    def wr(self, name):
+        """tf32-rounded copy of a weight matrix (made once per forward / backward, shared by all its GEMMs)"""
+        if not ROUND_TF32:
+            return self.t[name]
+        r = self.rounded.get(name)
+        if r is None:
+            r = self.rounded[name] = ops.round_copy(self.t[name])
+        return r
+
+
+def _rc(x):
+    return ops.round_copy(x) if ROUND_TF32 else x
+
+
+class exact_fp32:
+    """Verification mode (tests only): every contraction runs on the fp32 FFMA kernel (vptr_gemm_simt) and nothing is
+    rounded to tf32, so the forward/backward schedule can be checked against the reference at fp32 accuracy -- the tf32
+    tensor-core path cannot be, because a ~5e-4 forward perturbation flips ReLU masks and moves gradients by percents."""
+
+    def __enter__(self):
+        global ROUND_TF32, RT
+        self.prev = (ROUND_TF32, ops.FORCE_SIMT)
+        ROUND_TF32 = RT = False
+        ops.FORCE_SIMT = True
+        return self
+
+    def __exit__(self, *a):
+        global ROUND_TF32, RT
+        ROUND_TF32 = RT = self.prev[0]
+        ops.FORCE_SIMT = self.prev[1]
+        return False
 
 
 class Geom:
@@ -79,9 +116,9 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save):
     C = g.C
     lnw, lnb = P.w(ln + ".weight"), P.w(ln + ".bias")
     if qpos is not None:
-        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb, add=qpos, add_div=1, add_mod=qpos.shape[0])
+        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb, add=qpos, add_div=1, add_mod=qpos.shape[0], round_tf32=RT)
     else:
-        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb)
+        a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb, round_tf32=RT)
         aq = a
     Fr = g.F
     if g.padded:
@@ -90,24 +127,24 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save):
     else:
         a_in, aq_in = a, aq
     if not rpe:   # VidHRFormer_modules.py:341: q = k = x + lw_pos (per in-window position), v = x
-        aq_in = ops.add_rows(aq_in, lw_tab, 1, lw_tab.shape[0])
+        aq_in = ops.add_rows(aq_in, lw_tab, 1, lw_tab.shape[0], round_tf32=RT)
     Rp = a_in.shape[0]
     qkv = ops.empty(Rp, 3 * C, like=x)
     at = pre + ".attn."
     if rpe:
-        ops.gemm(aq_in, P.w(at + "q_proj.weight"), out=qkv[:, :C], bias=P.w(at + "q_proj.bias"))
-        ops.gemm(aq_in, P.w(at + "k_proj.weight"), out=qkv[:, C:2 * C], bias=P.w(at + "k_proj.bias"))
-        ops.gemm(a_in, P.w(at + "v_proj.weight"), out=qkv[:, 2 * C:], bias=P.w(at + "v_proj.bias"))
+        ops.gemm(aq_in, P.wr(at + "q_proj.weight"), out=qkv[:, :C], bias=P.w(at + "q_proj.bias"))
+        ops.gemm(aq_in, P.wr(at + "k_proj.weight"), out=qkv[:, C:2 * C], bias=P.w(at + "k_proj.bias"))
+        ops.gemm(a_in, P.wr(at + "v_proj.weight"), out=qkv[:, 2 * C:], bias=P.w(at + "v_proj.bias"))
         table = P.w(at + "relative_position_bias_table")
-        wo, bo = P.w(at + "out_proj.weight"), P.w(at + "out_proj.bias")
+        wo, bo = P.wr(at + "out_proj.weight"), P.w(at + "out_proj.bias")
     else:
-        Wi, bi = P.w(at + "in_proj_weight"), P.w(at + "in_proj_bias")
+        Wi, bi = P.wr(at + "in_proj_weight"), P.w(at + "in_proj_bias")
         ops.gemm(aq_in, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
         ops.gemm(a_in, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
         table = None
-        wo, bo = P.w(at + "out_proj.weight"), P.w(at + "out_proj.bias")
+        wo, bo = P.wr(at + "out_proj.weight"), P.w(at + "out_proj.bias")
     o = ops.empty(Rp, C, like=x)
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale)
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT)
     if g.padded:
         yp = ops.gemm(o, wo, bias=bo)
         y = ops.crop_hw(yp, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
@@ -124,11 +161,11 @@ def window_attn_bwd(P, s, dout, dqpos):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     at = pre + ".attn."
     Fr = g.F
-    dy = ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout
+    dy = _rc(ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout)
     qkv, o = s["qkv"], s["o"]
     _wgrad(P, at + "out_proj.weight", dy, o)
     _bgrad(P, at + "out_proj.bias", dy)
-    do = ops.gemm(dy, P.w(at + "out_proj.weight"), b_mn=True)
+    do = ops.gemm(dy, P.wr(at + "out_proj.weight"), b_mn=True)
     dqkv = torch.empty_like(qkv)
     if s["rpe"]:
         table = P.w(at + "relative_position_bias_table")
@@ -136,18 +173,18 @@ def window_attn_bwd(P, s, dout, dqpos):
     else:
         table = dtable = None
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtable, 0, Fr,
-                 g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale)
+                 g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT)
     a_in, aq_in = s["a_in"], s["aq_in"]
     if s["rpe"]:
         for i, nm in enumerate(("q_proj", "k_proj", "v_proj")):
             src = a_in if nm == "v_proj" else aq_in
             _wgrad(P, at + nm + ".weight", dqkv[:, i * C:(i + 1) * C], src)
             _bgrad(P, at + nm + ".bias", dqkv[:, i * C:(i + 1) * C])
-        d_aq = ops.gemm(dqkv[:, :C], P.w(at + "q_proj.weight"), b_mn=True)
-        ops.gemm(dqkv[:, C:2 * C], P.w(at + "k_proj.weight"), b_mn=True, out=d_aq, residual=d_aq)
-        d_a = ops.gemm(dqkv[:, 2 * C:], P.w(at + "v_proj.weight"), b_mn=True)
+        d_aq = ops.gemm(dqkv[:, :C], P.wr(at + "q_proj.weight"), b_mn=True)
+        ops.gemm(dqkv[:, C:2 * C], P.wr(at + "k_proj.weight"), b_mn=True, out=d_aq, residual=d_aq)
+        d_a = ops.gemm(dqkv[:, 2 * C:], P.wr(at + "v_proj.weight"), b_mn=True)
     else:
-        Wi = P.w(at + "in_proj_weight")
+        Wi = P.wr(at + "in_proj_weight")
         gW, gb = P.g(at + "in_proj_weight"), P.g(at + "in_proj_bias")
         if gW is not None:
             ops.gemm(dqkv[:, :2 * C], aq_in, out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
@@ -187,8 +224,8 @@ def _ffn_norm_stats(P, pre, name, h, g, layer_norm, training, bufs):
 def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
     """x (R,C) -> x + MlpDWBN(LN(x)).  layer_norm: LayerNorm((ch,H,W)) flavour (FAR, NAR decoder) else BatchNorm2d."""
     mode = 1 if layer_norm else 0
-    b_, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"))
-    w1 = P.w(pre + ".fc1.weight")
+    b_, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT)
+    w1 = P.wr(pre + ".fc1.weight")
     Ch = w1.shape[0]
     h1 = ops.gemm(b_, w1.view(Ch, g.C), bias=P.w(pre + ".fc1.bias"))
     st1 = _ffn_norm_stats(P, pre, "norm1", h1, g, layer_norm, training, bufs)
@@ -199,7 +236,7 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
     st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
     g2, b2 = _ffn_norm_params(P, pre, "norm2", g.HW, layer_norm)
     u2 = ops.norm_act_fwd(h2, st2[0], st2[1], g2, b2, g.HW, mode, round_tf32=ROUND_TF32)
-    w2 = P.w(pre + ".fc2.weight")
+    w2 = P.wr(pre + ".fc2.weight")
     h3 = ops.gemm(u2, w2.view(g.C, Ch), bias=P.w(pre + ".fc2.bias"))
     st3 = _ffn_norm_stats(P, pre, "norm3", h3, g, layer_norm, training, bufs)
     g3, b3 = _ffn_norm_params(P, pre, "norm3", g.HW, layer_norm)
@@ -211,29 +248,29 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
     return out
 
 
-def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode):
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False):
     gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
     ch = h.shape[1]
     if layer_norm:
         dg = ops.zeros(g.HW * ch, like=h)
         db = ops.zeros(g.HW * ch, like=h)
-        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode)
+        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd)
         if gw is not None:
             ops.transpose(dg, 1, g.HW, ch, out=gw, accumulate=True)
             ops.transpose(db, 1, g.HW, ch, out=gb, accumulate=True)
         return dx
     if gw is None:
         gw, gb = ops.zeros(ch, like=h), ops.zeros(ch, like=h)
-    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode)
+    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd)
 
 
 def conv_ffn_bwd(P, s, dout):
     g, pre, ln, lnm, mode = s["g"], s["pre"], s["ln"], s["layer_norm"], s["mode"]
     Ch = s["h1"].shape[1]
-    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode)
+    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT)
     _wgrad(P, pre + ".fc2.weight", dh3, s["u2"])
     _bgrad(P, pre + ".fc2.bias", dh3)
-    du2 = ops.gemm(dh3, P.w(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
+    du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
     dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode)
     gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
     if gdw is not None:
@@ -241,10 +278,10 @@ def conv_ffn_bwd(P, s, dout):
         ops.dwconv3x3_wgrad(s["u1"], dh2, dw9, gdb, g.F, g.H, g.W)
         ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
     du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
-    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode)
+    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT)
     _wgrad(P, pre + ".fc1.weight", dh1, s["b"])
     _bgrad(P, pre + ".fc1.bias", dh1)
-    db = ops.gemm(dh1, P.w(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)
+    db = ops.gemm(dh1, P.wr(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)
     return ops.layernorm_bwd(db, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
 
@@ -253,14 +290,14 @@ def conv_ffn_bwd(P, s, dout):
 def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save):
     """x + MHA_t(q=k=LN(x)+pos_t, v=LN(x)) per pixel (VidHRFormer_modules.py:74-84,183-187)."""
     C = g.C
-    z, zp, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), add=pos, add_div=g.HW, add_mod=g.T)
-    Wi, bi = P.w(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
+    z, zp, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), add=pos, add_div=g.HW, add_mod=g.T, round_tf32=RT)
+    Wi, bi = P.wr(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
     qkv = ops.empty(g.R, 3 * C, like=x)
     ops.gemm(zp, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
     ops.gemm(z, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale)
-    out = ops.gemm(o, P.w(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale, round_tf32=RT)
+    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
     if save is not None:
         save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g)))
     return out
@@ -269,13 +306,14 @@ def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save):
 def temporal_attn_bwd(P, s, dout):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     qkv, o = s["qkv"], s["o"]
+    dres, dout = dout, _rc(dout)
     _wgrad(P, pre + ".out_proj.weight", dout, o)
     _bgrad(P, pre + ".out_proj.bias", dout)
-    do = ops.gemm(dout, P.w(pre + ".out_proj.weight"), b_mn=True)
+    do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], None, None, 1, g.N,
-                 g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale)
-    Wi = P.w(pre + ".in_proj_weight")
+                 g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale, round_tf32=RT)
+    Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
         ops.gemm(dqkv[:, :2 * C], s["zp"], out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
@@ -283,17 +321,17 @@ def temporal_attn_bwd(P, s, dout):
         ops.colsum(dqkv, gb)
     dzp = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
     dz = ops.gemm(dqkv[:, 2 * C:], Wi[2 * C:], b_mn=True)
-    return ops.layernorm_bwd(dz, dzp, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+    return ops.layernorm_bwd(dz, dzp, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
 
 
 # =================================================================================================== MLP FFN
 def mlp_fwd(P, pre, ln, x, g, save):
     """x + linear2(GELU(linear1(LN(x)))) (VidHRFormer_modules.py:87-89,190-192); pre = block prefix."""
-    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"))
-    h = ops.gemm(y, P.w(pre + ".linear1.weight"), bias=P.w(pre + ".linear1.bias"))
+    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT)
+    h = ops.gemm(y, P.wr(pre + ".linear1.weight"), bias=P.w(pre + ".linear1.bias"))
     u = ops.gelu_fwd(h, round_tf32=ROUND_TF32)
-    out = ops.gemm(u, P.w(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x)
+    out = ops.gemm(u, P.wr(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x)
     if save is not None:
         save.append(("mlp", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, y=y, h=h, u=u, g=g)))
     return out
@@ -301,14 +339,15 @@ def mlp_fwd(P, pre, ln, x, g, save):
 
 def mlp_bwd(P, s, dout):
     pre, ln = s["pre"], s["ln"]
+    dres, dout = dout, _rc(dout)
     _wgrad(P, pre + ".linear2.weight", dout, s["u"])
     _bgrad(P, pre + ".linear2.bias", dout)
-    du = ops.gemm(dout, P.w(pre + ".linear2.weight"), b_mn=True)
-    dh = ops.gelu_bwd(du, s["h"], out=du)
+    du = ops.gemm(dout, P.wr(pre + ".linear2.weight"), b_mn=True)
+    dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT)
     _wgrad(P, pre + ".linear1.weight", dh, s["y"])
     _bgrad(P, pre + ".linear1.bias", dh)
-    dy = ops.gemm(dh, P.w(pre + ".linear1.weight"), b_mn=True)
-    return ops.layernorm_bwd(dy, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+    dy = ops.gemm(dh, P.wr(pre + ".linear1.weight"), b_mn=True)
+    return ops.layernorm_bwd(dy, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
 
 
@@ -317,15 +356,15 @@ def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save):
     """x + MHA(q = LN(x)+query_pos+pos_future, k = memory+pos_past, v = memory) per pixel (VidHRFormer_modules.py:200-206).
     g: geometry of the target stream, gm: of the memory stream; qadd (T2*H*W, C) = query_pos + pos_future."""
     C = g.C
-    _, zq, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=qadd, add_div=1, add_mod=qadd.shape[0])
-    Wi, bi = P.w(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
+    _, zq, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=qadd, add_div=1, add_mod=qadd.shape[0], round_tf32=RT)
+    Wi, bi = P.wr(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
     q = ops.gemm(zq, Wi[:C], bias=bi[:C])
     kv = ops.empty(gm.R, 2 * C, like=x)
     ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C])
     ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
-    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale)
-    out = ops.gemm(o, P.w(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale, round_tf32=RT)
+    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
     if save is not None:
         save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k)))
     return out
@@ -334,14 +373,15 @@ def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save):
 def cross_attn_bwd(P, s, dout, dqpos, dmem):
     g, gm, C, pre, ln = s["g"], s["gm"], s["g"].C, s["pre"], s["ln"]
     q, kv, o = s["q"], s["kv"], s["o"]
+    dres, dout = dout, _rc(dout)
     _wgrad(P, pre + ".out_proj.weight", dout, o)
     _bgrad(P, pre + ".out_proj.bias", dout)
-    do = ops.gemm(dout, P.w(pre + ".out_proj.weight"), b_mn=True)
+    do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
     ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d,
-                 False, g.scale)
-    Wi = P.w(pre + ".in_proj_weight")
+                 False, g.scale, round_tf32=RT)
+    Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
         ops.gemm(dq, s["zq"], out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
@@ -354,13 +394,13 @@ def cross_attn_bwd(P, s, dout, dqpos, dmem):
     ops.gemm(dkv[:, C:], Wi[2 * C:], b_mn=True, out=dmem, residual=dmem)
     if dqpos is not None:
         ops.rowgroup_sum(dzq, dqpos, g.N)
-    return ops.layernorm_bwd(dzq, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
+    return ops.layernorm_bwd(dzq, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
 
 
 # =================================================================================================== final norm
-def final_norm_fwd(P, ln, x, relu, save):
-    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), relu=relu)
+def final_norm_fwd(P, ln, x, relu, save, round_out=False):
+    y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), relu=relu, round_tf32=round_out and RT)
     if save is not None:
         save.append(("fnorm", dict(ln=ln, x=x, mean=mean, rstd=rstd, relu=relu)))
     return y

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 from torch.nn import init
 
+from .. import engine as E
 from .. import ops
 
 
@@ -122,8 +123,8 @@ def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_a
     """x (F*H*W, Cin) channel-last -> (F*Ho*Wo, Cout).  y = act(conv(x)*scale + shift) (+ residual)."""
     Cout, Cin = conv.weight.shape[:2]
     scale, shift = ops.bn_fold(bn)
-    wpk = ops.pack_conv_weight(conv.weight.data, scale, 0).view(Cout, 9 * Cin)
-    col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode)
+    wpk = E._rc(ops.pack_conv_weight(conv.weight.data, scale, 0)).view(Cout, 9 * Cin)
+    col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode, round_tf32=E.ROUND_TF32)
     if residual is not None and act_after_residual:
         y = ops.gemm(col, wpk, bias=shift, residual=residual)
         y = ops.relu_fwd(y, out=y)
@@ -167,8 +168,8 @@ def decoder_forward(dec, feat, F_, H, W, save):
         convT, bn = m[idx], m[idx + 1]
         Cin, Cout = convT.weight.shape[:2]
         scale, shift = ops.bn_fold(bn)
-        wpk = ops.pack_conv_weight(convT.weight.data, scale, 1).view(9 * Cout, Cin)
-        col = ops.gemm(h, wpk)
+        wpk = E._rc(ops.pack_conv_weight(convT.weight.data, scale, 1)).view(9 * Cout, Cin)
+        col = ops.gemm(E._rc(h), wpk)      # operands of the tf32 GEMM are pre-rounded (engine.ROUND_TF32)
         y = ops.convT_gather(col, shift, F_, H, W, Cout, relu=True)
         if save:
             saved.append((wpk, y, H, W, Cin, Cout))
@@ -188,6 +189,6 @@ def decoder_backward(dec, saved_all, dout):
     d = ops.head_conv7x7_bwd(dout, out, head.weight.data, F_, Ci, Co, H, W, act)     # (F*H*W, 64) gradient at the last ReLU output
     for wpk, y, h_in, w_in, Cin, Cout in reversed(saved):
         # y = relu(convT(x)*scale + shift): dx = conv_s2(d * (y > 0)) with the same packed weight
-        col, _, _ = ops.im2col(d, F_, 2 * h_in, 2 * w_in, Cout, 3, 2, 1, 0, mask=y)
+        col, _, _ = ops.im2col(d, F_, 2 * h_in, 2 * w_in, Cout, 3, 2, 1, 0, mask=y, round_tf32=E.ROUND_TF32)
         d = ops.gemm(col, wpk, b_mn=True)                                             # (F*h*w, Cin)
     return d

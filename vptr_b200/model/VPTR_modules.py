@@ -201,6 +201,7 @@ class _LinearFunction(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
+        x2, w = E._rc(x2), E._rc(w)
         y = ops.gemm(x2, w, bias=b)
         ctx.save_for_backward(x2, w)
         ctx.xshape = x.shape
@@ -212,6 +213,7 @@ class _LinearFunction(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
+        dy2 = E._rc(dy2)
         dx = ops.gemm(dy2, w, b_mn=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1]:
@@ -263,7 +265,7 @@ class _FARFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, names, *params):
         N, T, C, H, W = x.shape
-        want = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        want = any(ctx.needs_input_grad)
         P = E.Params(zip(names, params), want_grads=False)
         bufs = dict(mod.named_buffers())
         g = E.Geom(N, T, H, W, C, mod.nhead, mod.window_size)
@@ -291,7 +293,7 @@ class _NARFunction(torch.autograd.Function):
     def forward(ctx, mod, x, names, *params):
         N, Tp, C, H, W = x.shape
         Tf = mod.num_future_frames
-        want = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        want = any(ctx.needs_input_grad)
         P = E.Params(zip(names, params), want_grads=False)
         bufs = dict(mod.named_buffers())
         ge = E.Geom(N, Tp, H, W, C, mod.nhead, mod.window_size)
@@ -301,11 +303,11 @@ class _NARFunction(torch.autograd.Function):
         tpos_p = mod.temporal_pos[:Tp].contiguous()
         tpos_f = mod.temporal_pos[Tp:Tp + Tf].contiguous()
         h = E.encoder_fwd(P, bufs, _tokens(x), ge, mod.num_encoder_layers, False, mod.rpe, tpos_p, lw_tab, mod.training, save)
-        mem = E.final_norm_fwd(P, "transformer.encoder.norm", h, False, save)
+        mem = E.final_norm_fwd(P, "transformer.encoder.norm", h, False, save, round_out=True)
         n_enc = len(save) if want else 0
         qpos = P.w("frame_queries").reshape(Tf * H * W, C)                       # query_pos (VidHRFormer.py:46)
         qadd = ops.add_rows(qpos, tpos_f, H * W, Tf)                             # query_pos + pos_future (VidHRFormer_modules.py:200)
-        mem_k = ops.add_rows(mem, tpos_p, H * W, Tp)                             # memory + pos_past
+        mem_k = ops.add_rows(mem, tpos_p, H * W, Tp, round_tf32=E.ROUND_TF32)                             # memory + pos_past
         tgt = ops.zeros(gd.R, C, like=x)                                         # init_tgt = zeros (VidHRFormer.py:48)
         tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save)
         y = E.final_norm_fwd(P, "transformer.decoder.norm", tgt, True, save)

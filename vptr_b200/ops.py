@@ -76,14 +76,14 @@ def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha
 
 
 # --------------------------------------------------------------------------------------------------- norms
-def layernorm_fwd(x, gamma, beta, want_y=True, add=None, add_div=1, add_mod=1, save_stats=True, relu=False, eps=1e-5):
+def layernorm_fwd(x, gamma, beta, want_y=True, add=None, add_div=1, add_mod=1, save_stats=True, relu=False, eps=1e-5, round_tf32=False):
     rows, C = x.shape
     y = torch.empty_like(x) if want_y else None
     y2 = torch.empty_like(x) if add is not None else None
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_stats else None
     _call("vptr_layernorm_fwd", _p(_chk(x)), _p(gamma), _p(beta), _p(y), _p(y2), _p(add), int(add_div), int(add_mod), _p(mean),
-          _p(rstd), rows, C, float(eps), int(relu), _s())
+          _p(rstd), rows, C, float(eps), int(relu), int(round_tf32), _s())
     return y, y2, mean, rstd
 
 
@@ -127,27 +127,27 @@ def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round
     return y
 
 
-def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode):
+def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode, round_tf32=False):
     rows, ch = x.shape
     dx = torch.empty_like(x)
     n_ws = 2 * ch if mode != 1 else 2 * (rows // hw)
     ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
     _call("vptr_norm_act_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
-          _p(ws), _s())
+          _p(ws), int(round_tf32), _s())
     return dx
 
 
 # --------------------------------------------------------------------------------------------------- attention
-def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale):
+def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False):
     _call("vptr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode,
-          F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), _s())
+          F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), int(round_tf32), _s())
     return out
 
 
-def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale):
+def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False):
     _call("vptr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
           _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(rpe_table), _p(d_rpe_table), mode, F_or_N, H, W, ws, Tq, Tk, nhead, d,
-          int(causal), float(scale), _s())
+          int(causal), float(scale), int(round_tf32), _s())
 
 
 def window_index_maps(F, H, W, ws, device):
@@ -182,10 +182,10 @@ def axpby(a, b, alpha=1.0, beta=1.0, out=None):
     return out
 
 
-def add_rows(x, add, div, mod):
+def add_rows(x, add, div, mod, round_tf32=False):
     rows, C = x.shape
     out = torch.empty_like(x)
-    _call("vptr_add_rows", _p(x), _p(add), _p(out), rows, C, div, mod, _s())
+    _call("vptr_add_rows", _p(x), _p(add), _p(out), rows, C, div, mod, int(round_tf32), _s())
     return out
 
 
@@ -199,10 +199,17 @@ def gelu_fwd(x, round_tf32=False):
     return y
 
 
-def gelu_bwd(dy, x, out=None):
+def gelu_bwd(dy, x, out=None, round_tf32=False):
     dx = torch.empty_like(x) if out is None else out
-    _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), _s())
+    _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), int(round_tf32), _s())
     return dx
+
+
+def round_copy(x):
+    """round-to-nearest tf32 copy (operands of the tensor-core GEMM are pre-rounded so its truncation is exact)"""
+    y = torch.empty_like(x)
+    _call("vptr_round_copy", _p(x), _p(y), x.numel(), _s())
+    return y
 
 
 def relu_fwd(x, out=None):
@@ -257,11 +264,11 @@ def clip_scale(x, sqnorm, max_norm):
 PAD_MODES = {"zero": 0, "reflect": 1, "replicate": 2}
 
 
-def im2col(x, F, H, W, Cin, k, stride, pad, pad_mode, mask=None):
+def im2col(x, F, H, W, Cin, k, stride, pad, pad_mode, mask=None, round_tf32=True):
     Ho = (H + 2 * pad - k) // stride + 1
     Wo = (W + 2 * pad - k) // stride + 1
     col = torch.empty(F * Ho * Wo, k * k * Cin, dtype=torch.float32, device=x.device)
-    _call("vptr_im2col", _p(x), _p(mask), _p(col), F, H, W, Cin, k, stride, pad, pad_mode, _s())
+    _call("vptr_im2col", _p(x), _p(mask), _p(col), F, H, W, Cin, k, stride, pad, pad_mode, int(round_tf32), _s())
     return col, Ho, Wo
 
 
