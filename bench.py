@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the 64 of cfg1)")
-    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--dropout", type=float, default=0.1, help="Transformer dropout / DropPath rate (reference default 0.1, train_NAR.py:199)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (use under ncu --profile-from-start off)")
     args = ap.parse_args()

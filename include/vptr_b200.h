@@ -38,11 +38,16 @@ const char* vptr_last_error(void);
  * Conv2d / ConvTranspose2d (model/ResNetAutoEncoder.py:26-47,74-90), with their autograd dgrad / wgrad. */
 int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D, long long ldd,
                    int M, int N, int K, const float* bias, const float* residual, long long ldr, float alpha, int act,
-                   int flags, int k_splits, vptr_stream_t stream);
-/* same contract on fp32 FFMA; for pitches TMA cannot address and as the on-device cross-check in tests */
+                   int flags, int k_splits, const float* rowscale, int rows_per_group, unsigned long long drop_seed, float drop_p,
+                   vptr_stream_t stream);
+/* Branch regularisation shared by the entry points below: out = rowscale[row / rows_per_group] * dropout_p(...) (+ residual).
+ * rowscale = DropPath keep-scales per clip (reference model/VidHRFormer_modules.py:563-575; vptr_droppath_scales) or NULL;
+ * dropout masks come from a counter-based RNG keyed by (drop_seed, element index), so the backward regenerates them.
+ * same contract on fp32 FFMA; for pitches TMA cannot address and as the on-device cross-check in tests */
 int vptr_gemm_simt(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D, long long ldd,
                    int M, int N, int K, const float* bias, const float* residual, long long ldr, float alpha, int act,
-                   int flags, int k_splits, vptr_stream_t stream);
+                   int flags, int k_splits, const float* rowscale, int rows_per_group, unsigned long long drop_seed, float drop_p,
+                   vptr_stream_t stream);
 
 /* ---- LayerNorm over C (model/VidHRFormer_modules.py:44-56,137-161,25-26,114-115) ---------------------
  * y = LN(x)*gamma+beta [relu]; y2 = y + add[(row/add_div) % add_mod] (positional add of :75-84,176-178,200). */
@@ -62,11 +67,13 @@ int vptr_bn_eval_stats(const float* running_mean, const float* running_var, floa
 int vptr_group_stats(const float* x, int groups, long long gsize, float* mean, float* rstd, float eps, vptr_stream_t stream);
 /* y = GELU(norm(x)) (+res). mode 0 BatchNorm (per channel), 1 LayerNorm((ch,H,W)) per frame, affine laid [hw][ch] */
 int vptr_norm_act_fwd(const float* x, float* y, const float* res, const float* mean, const float* rstd, const float* gamma,
-                      const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, vptr_stream_t stream);
+                      const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, const float* rowscale,
+                      int rows_per_group, unsigned long long drop_seed, float drop_p, vptr_stream_t stream);
 /* mode 0 train BatchNorm, 1 frame LayerNorm, 2 eval BatchNorm. ws: 2*ch (modes 0,2) or 2*frames (mode 1) floats */
 int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                       const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
-                      float* ws, int round_tf32, vptr_stream_t stream);
+                      float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed, float drop_p,
+                      vptr_stream_t stream);
 
 /* ---- attention cores ---------------------------------------------------------------------------------
  * mode 0: local-window attention + relative-position bias (model/VidHRFormer_modules.py:321-357,503-525;
@@ -76,11 +83,12 @@ int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const 
  * Q,K,V,O are token-major with row pitches ld*; head h uses columns [h*d, (h+1)*d). */
 int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                   long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead,
-                  int d, int causal, float scale, int round_tf32, vptr_stream_t stream);
+                  int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p, vptr_stream_t stream);
 int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO,
                   long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV, long long lddv,
                   const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
-                  int nhead, int d, int causal, float scale, int round_tf32, vptr_stream_t stream);
+                  int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p,
+                  vptr_stream_t stream);
 /* integer artefacts from the kernels' own index functions (bit-exact contract): relative_position_index
  * (model/MultiHeadAttentionRPE.py:373-387) as int64 [L][L]; window token map (model/VidHRFormer_modules.py:503-513)
  * as int64 [L][B]; causal mask (model/VidHRFormer_modules.py:78) as uint8 [T][T] */
@@ -98,11 +106,15 @@ int vptr_axpby(const float* a, const float* b, float* out, long long n, float al
 int vptr_add_rows(const float* x, const float* add, float* out, long long rows, int C, int div, int mod, int round_tf32,
                   vptr_stream_t stream);
 int vptr_rowgroup_sum(const float* dy, float* out, long long group_elems, int reps, vptr_stream_t stream);
-int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, vptr_stream_t stream);
-int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, vptr_stream_t stream);
+int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, unsigned long long drop_seed, float drop_p,
+                  vptr_stream_t stream);
+int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, unsigned long long drop_seed, float drop_p,
+                  vptr_stream_t stream);
 /* y = x rounded to nearest tf32: operands of vptr_gemm_tf32 are pre-rounded by their producers (or by this copy) so the
  * tensor core's mantissa truncation is exact and unbiased */
-int vptr_round_copy(const float* x, float* y, long long n, vptr_stream_t stream);
+int vptr_round_copy(const float* x, float* y, long long n, int do_round, const float* rowscale, long long group_elems,
+                    unsigned long long drop_seed, float drop_p, vptr_stream_t stream);
+int vptr_droppath_scales(float* out, int n, unsigned long long seed, float p, vptr_stream_t stream);
 int vptr_relu_fwd(const float* x, float* y, long long n, vptr_stream_t stream);
 int vptr_relu_bwd(const float* dy, const float* y, float* dx, long long n, vptr_stream_t stream);
 int vptr_colsum(const float* x, float* out, long long rows, int C, long long ld, vptr_stream_t stream);

@@ -12,20 +12,21 @@ P = ctypes.c_void_p
 I = ctypes.c_int
 L = ctypes.c_longlong
 F = ctypes.c_float
+U = ctypes.c_ulonglong
 
 _SIGS = {
     "vptr_version": ([], I),
-    "vptr_gemm_tf32": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P], I),
-    "vptr_gemm_simt": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P], I),
+    "vptr_gemm_tf32": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P, I, U, F, P], I),
+    "vptr_gemm_simt": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P, I, U, F, P], I),
     "vptr_layernorm_fwd": ([P, P, P, P, P, P, I, I, P, P, L, I, F, I, I, P], I),
     "vptr_layernorm_bwd": ([P, P, P, P, P, P, P, P, P, P, P, L, I, I, P], I),
     "vptr_bn_stats": ([P, L, I, P, P, P, P, F, F, P, P], I),
     "vptr_bn_eval_stats": ([P, P, P, P, I, F, P], I),
     "vptr_group_stats": ([P, I, L, P, P, F, P], I),
-    "vptr_norm_act_fwd": ([P, P, P, P, P, P, P, L, I, I, I, I, P], I),
-    "vptr_norm_act_bwd": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P], I),
-    "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, P], I),
-    "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, P], I),
+    "vptr_norm_act_fwd": ([P, P, P, P, P, P, P, L, I, I, I, I, P, I, U, F, P], I),
+    "vptr_norm_act_bwd": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P, I, U, F, P], I),
+    "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
+    "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
     "vptr_window_index_maps": ([I, I, I, I, P, P, P], I),
     "vptr_causal_mask": ([I, P, P], I),
     "vptr_dwconv3x3": ([P, P, P, P, I, I, I, I, I, P], I),
@@ -33,9 +34,10 @@ _SIGS = {
     "vptr_axpby": ([P, P, P, L, F, F, P], I),
     "vptr_add_rows": ([P, P, P, L, I, I, I, I, P], I),
     "vptr_rowgroup_sum": ([P, P, L, I, P], I),
-    "vptr_gelu_fwd": ([P, P, L, I, P], I),
-    "vptr_gelu_bwd": ([P, P, P, L, I, P], I),
-    "vptr_round_copy": ([P, P, L, P], I),
+    "vptr_gelu_fwd": ([P, P, L, I, U, F, P], I),
+    "vptr_gelu_bwd": ([P, P, P, L, I, U, F, P], I),
+    "vptr_round_copy": ([P, P, L, I, P, L, U, F, P], I),
+    "vptr_droppath_scales": ([P, I, U, F, P], I),
     "vptr_relu_fwd": ([P, P, L, P], I),
     "vptr_relu_bwd": ([P, P, P, L, P], I),
     "vptr_colsum": ([P, P, L, I, L, P], I),

@@ -21,7 +21,14 @@ struct AttnGeom {
     int causal;
     float scale;
     int round_tf32;  // round stored outputs (they only feed tf32 contractions)
+    unsigned long long drop_seed;  // attention-probability dropout (MultiHeadAttentionRPE.py:678 / nn.MultiheadAttention)
+    float drop_p;
 };
+
+// dropout keep-scale of probability (b, h, i, j)
+__device__ __forceinline__ float prob_drop(const AttnGeom& g, int b, int h, int i, int j) {
+    return vptr_drop_scale(g.drop_seed, (((unsigned long long)b * g.nhead + h) * g.Lq + i) * g.Lk + j, g.drop_p);
+}
 
 __device__ __forceinline__ long long window_row(const AttnGeom& g, int b, int l) {
     const int per = g.nwh * g.nww;
@@ -105,6 +112,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
         }
         __syncthreads();
         scores_softmax(g, h, sQ, sK, sS, rpe_table);
+        if (g.drop_p > 0.f) {
+            for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) {
+                const int i = e / g.Lk, j = e - i * g.Lk;
+                sS[i * lp + j] *= prob_drop(g, b, h, i, j);
+            }
+            __syncthreads();
+        }
         for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
             const int i = e / g.d, c = e - i * g.d;
             float o = 0.f;
@@ -132,7 +146,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
     float* sdO = sV + g.Lk * dp;
     float* sP = sdO + g.Lq * dp;
     float* sdS = sP + g.Lq * lp;
-    float* sdB = sdS + g.Lq * lp;  // only when d_rpe_table
+    float* sdB = sdS + g.Lq * lp;  // [Lq][Lk] bias-gradient accumulator (only when d_rpe_table)
+    float* sM = sdB + g.Lq * g.Lk;  // [Lq][Lk] dropout keep-scales of this (b, h) (only when drop_p > 0)
     const int h = blockIdx.y;
     const int col0 = h * g.d;
     if (d_rpe_table)
@@ -152,11 +167,17 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
         }
         __syncthreads();
         scores_softmax(g, h, sQ, sK, sP, rpe_table);
-        // dP = dO V^T
+        // dP = (dO V^T) * keep-scale   (gradient w.r.t. the undropped probabilities)
+        const bool drop = g.drop_p > 0.f;
         for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) {
             const int i = e / g.Lk, j = e - i * g.Lk;
             float s = 0.f;
             for (int c = 0; c < g.d; ++c) s = fmaf(sdO[i * dp + c], sV[j * dp + c], s);
+            if (drop) {
+                const float m = prob_drop(g, b, h, i, j);
+                sM[e] = m;
+                s *= m;
+            }
             sdS[i * lp + j] = s;
         }
         __syncthreads();
@@ -180,7 +201,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
             const int j = e / g.d, c = e - j * g.d;
             float dv = 0.f, dk = 0.f;
             for (int i = 0; i < g.Lq; ++i) {
-                dv = fmaf(sP[i * lp + j], sdO[i * dp + c], dv);
+                dv = fmaf(drop ? sP[i * lp + j] * sM[i * g.Lk + j] : sP[i * lp + j], sdO[i * dp + c], dv);
                 dk = fmaf(sdS[i * lp + j], sQ[i * dp + c], dk);
             }
             const long long r = k_row(g, b, j);
@@ -242,12 +263,15 @@ int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, i
 // mode 0: F_or_N = number of frames (N*T); mode 1: F_or_N = number of clips N.
 extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                              long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
-                             int nhead, int d, int causal, float scale, int round_tf32, cudaStream_t stream) {
+                             int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p,
+                             cudaStream_t stream) {
     AttnGeom g;
     int batches = 0;
     int rc = fill_geom(g, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, &batches);
     if (rc) return rc;
     g.round_tf32 = round_tf32;
+    g.drop_seed = drop_seed;
+    g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_fwd: empty problem");
     size_t smem = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (d + 1) + (size_t)g.Lq * (g.Lk + 1));
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_fwd: tile too large (%zu B of shared memory)", smem);
@@ -260,14 +284,17 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
 extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
                              const float* dO, long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV,
                              long long lddv, const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws,
-                             int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, cudaStream_t stream) {
+                             int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed,
+                             float drop_p, cudaStream_t stream) {
     AttnGeom g;
     int batches = 0;
     int rc = fill_geom(g, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, &batches);
     if (rc) return rc;
     g.round_tf32 = round_tf32;
+    g.drop_seed = drop_seed;
+    g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_bwd: empty problem");
-    size_t smem = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (d + 1) + (size_t)2 * g.Lq * (g.Lk + 1) + (size_t)g.Lq * g.Lk);
+    size_t smem = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (d + 1) + (size_t)2 * g.Lq * (g.Lk + 1) + (size_t)2 * g.Lq * g.Lk);
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_bwd: tile too large (%zu B of shared memory)", smem);
     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int gx = batches;

@@ -39,6 +39,20 @@ __device__ __forceinline__ float vptr_round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Counter-based RNG for dropout / DropPath: splitmix64 of (seed, element index) -> uniform [0,1).  Stateless, so the
+// backward pass regenerates the very mask the forward used instead of storing it.
+__device__ __forceinline__ float vptr_uniform(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = idx * 0x9E3779B97F4A7C15ULL + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+// dropout keep-scale of element idx: 0 with probability p, else 1/(1-p)  (p == 0 -> 1)
+__device__ __forceinline__ float vptr_drop_scale(unsigned long long seed, unsigned long long idx, float p) {
+    if (p <= 0.f) return 1.f;
+    return vptr_uniform(seed, idx) >= p ? 1.f / (1.f - p) : 0.f;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

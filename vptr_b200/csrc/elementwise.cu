@@ -35,11 +35,30 @@ __global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__
     }
 }
 
-__global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4) {
+// y = [round_tf32]( x * rowscale[i / group_elems] * dropmask(seed, i) )
+__global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int do_round,
+                                                         const float* __restrict__ rowscale, long long group_elems,
+                                                         unsigned long long seed, float p) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
-        reinterpret_cast<float4*>(y)[i] = make_float4(vptr_round_tf32(v.x), vptr_round_tf32(v.y), vptr_round_tf32(v.z), vptr_round_tf32(v.w));
+        if (p > 0.f) {
+            const unsigned long long e = (unsigned long long)i * 4;
+            v.x *= vptr_drop_scale(seed, e, p); v.y *= vptr_drop_scale(seed, e + 1, p);
+            v.z *= vptr_drop_scale(seed, e + 2, p); v.w *= vptr_drop_scale(seed, e + 3, p);
+        }
+        if (rowscale) {
+            const float rs = __ldg(rowscale + (i * 4) / group_elems);
+            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        }
+        if (do_round) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+        reinterpret_cast<float4*>(y)[i] = v;
     }
+}
+
+// DropPath keep-scales per sample: 0 with probability p else 1/(1-p) (drop_path, VidHRFormer_modules.py:563-575)
+__global__ void droppath_scales_kernel(float* __restrict__ out, int n, unsigned long long seed, float p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = vptr_drop_scale(seed, (unsigned long long)i, p);
 }
 
 // out[g][c] += sum_n dy[(n*mod + g)][c]   (gradient of a per-(t,h,w) learned query broadcast over clips)
@@ -52,20 +71,31 @@ __global__ void __launch_bounds__(256) rowgroup_sum_kernel(const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int round_tf32) {
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n4, int round_tf32,
+                                                       unsigned long long seed, float p) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 o = make_float4(vptr_gelu(v.x), vptr_gelu(v.y), vptr_gelu(v.z), vptr_gelu(v.w));
+        if (p > 0.f) {
+            const unsigned long long e = (unsigned long long)i * 4;
+            o.x *= vptr_drop_scale(seed, e, p); o.y *= vptr_drop_scale(seed, e + 1, p);
+            o.z *= vptr_drop_scale(seed, e + 2, p); o.w *= vptr_drop_scale(seed, e + 3, p);
+        }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
         reinterpret_cast<float4*>(y)[i] = o;
     }
 }
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
-                                                       long long n4, int round_tf32) {
+                                                       long long n4, int round_tf32, unsigned long long seed, float p) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 g = reinterpret_cast<const float4*>(dy)[i];
         float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 o = make_float4(g.x * vptr_gelu_grad(v.x), g.y * vptr_gelu_grad(v.y), g.z * vptr_gelu_grad(v.z), g.w * vptr_gelu_grad(v.w));
+        if (p > 0.f) {
+            const unsigned long long e = (unsigned long long)i * 4;
+            o.x *= vptr_drop_scale(seed, e, p); o.y *= vptr_drop_scale(seed, e + 1, p);
+            o.z *= vptr_drop_scale(seed, e + 2, p); o.w *= vptr_drop_scale(seed, e + 3, p);
+        }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
         reinterpret_cast<float4*>(dx)[i] = o;
     }
@@ -175,22 +205,31 @@ extern "C" int vptr_rowgroup_sum(const float* dy, float* out, long long group_el
     rowgroup_sum_kernel<<<ew_grid(group_elems, 256), 256, 0, stream>>>(dy, out, group_elems, reps);
     return vptr_check_launch("rowgroup_sum_kernel");
 }
-extern "C" int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, cudaStream_t stream) {
+extern "C" int vptr_gelu_fwd(const float* x, float* y, long long n, int round_tf32, unsigned long long drop_seed, float drop_p,
+                             cudaStream_t stream) {
     REQ4(n, "vptr_gelu_fwd");
-    gelu_fwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, round_tf32);
+    gelu_fwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, round_tf32, drop_seed, drop_p);
     return vptr_check_launch("gelu_fwd_kernel");
 }
-extern "C" int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, cudaStream_t stream) {
+extern "C" int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int round_tf32, unsigned long long drop_seed,
+                             float drop_p, cudaStream_t stream) {
     REQ4(n, "vptr_gelu_bwd");
-    gelu_bwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(dy, x, dx, n / 4, round_tf32);
+    gelu_bwd_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(dy, x, dx, n / 4, round_tf32, drop_seed, drop_p);
     return vptr_check_launch("gelu_bwd_kernel");
 }
 // y = round-to-nearest tf32 of x (element count need not be a multiple of 4: the tail is handled by padding rules of the caller)
-extern "C" int vptr_round_copy(const float* x, float* y, long long n, cudaStream_t stream) {
+extern "C" int vptr_round_copy(const float* x, float* y, long long n, int do_round, const float* rowscale, long long group_elems,
+                               unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     REQ4(n, "vptr_round_copy");
     if (n == 0) return VPTR_OK;
-    round_copy_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4);
+    VPTR_REQUIRE(rowscale == nullptr || (group_elems > 0 && group_elems % 4 == 0), VPTR_ERR_SHAPE, "vptr_round_copy: group_elems=%lld", group_elems);
+    round_copy_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, do_round, rowscale, group_elems, drop_seed, drop_p);
     return vptr_check_launch("round_copy_kernel");
+}
+extern "C" int vptr_droppath_scales(float* out, int n, unsigned long long seed, float p, cudaStream_t stream) {
+    VPTR_REQUIRE(n > 0 && p >= 0.f && p < 1.f, VPTR_ERR_SHAPE, "vptr_droppath_scales: n=%d p=%g", n, p);
+    droppath_scales_kernel<<<vptr_cdiv(n, 128), 128, 0, stream>>>(out, n, seed, p);
+    return vptr_check_launch("droppath_scales_kernel");
 }
 extern "C" int vptr_relu_fwd(const float* x, float* y, long long n, cudaStream_t stream) {
     REQ4(n, "vptr_relu_fwd");

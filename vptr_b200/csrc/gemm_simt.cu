@@ -14,6 +14,7 @@ struct SimtParams {
     int M, N, K;
     const float* bias; const float* residual; long long ldr;
     float alpha; int act; int flags;
+    const float* rowscale; int rows_per_group; unsigned long long drop_seed; float drop_p;
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
@@ -63,6 +64,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
             if (p.bias) o += p.bias[n];
             if (p.act == 1) o = vptr_gelu(o);
             else if (p.act == 2) o = fmaxf(o, 0.f);
+            if (p.drop_p > 0.f) o *= vptr_drop_scale(p.drop_seed, (unsigned long long)m * p.N + n, p.drop_p);
+            if (p.rowscale) o *= p.rowscale[m / p.rows_per_group];
             if (p.residual) o += p.residual[m * p.ldr + n];
             if (p.flags & 2) o = vptr_round_tf32(o);
             float* d = p.D + m * p.ldd + n;
@@ -74,7 +77,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
 
 extern "C" int vptr_gemm_simt(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D,
                               long long ldd, int M, int N, int K, const float* bias, const float* residual, long long ldr,
-                              float alpha, int act, int flags, int k_splits, cudaStream_t stream) {
+                              float alpha, int act, int flags, int k_splits, const float* rowscale, int rows_per_group,
+                              unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     (void)k_splits;
     VPTR_REQUIRE(M > 0 && N > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_gemm_simt: empty problem M=%d N=%d K=%d", M, N, K);
     SimtParams p;
@@ -82,6 +86,7 @@ extern "C" int vptr_gemm_simt(const float* A, long long lda, int a_mn, const flo
     p.B = B; p.sb_n = b_mn ? 1 : ldb; p.sb_k = b_mn ? ldb : 1;
     p.D = D; p.ldd = ldd; p.M = M; p.N = N; p.K = K;
     p.bias = bias; p.residual = residual; p.ldr = ldr; p.alpha = alpha; p.act = act; p.flags = flags;
+    p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     dim3 grid(vptr_cdiv(N, TN), vptr_cdiv(M, TM));
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
     return vptr_check_launch("gemm_simt_kernel");

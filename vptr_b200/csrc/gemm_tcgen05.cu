@@ -34,6 +34,11 @@ struct GemmParams {
     float alpha;
     int act;    // 0 none, 1 gelu, 2 relu
     int flags;  // bit0: atomic accumulate into D, bit1: round stored values to tf32 (rna)
+    // branch regularisation fused into the epilogue: out = rowscale[m / rows_per_group] * dropout(act(...)) + residual
+    const float* rowscale;  // DropPath keep-scales per clip (VidHRFormer_modules.py:563-575) or NULL
+    int rows_per_group;
+    unsigned long long drop_seed;  // elementwise nn.Dropout on the branch (drop1/drop3, VidHRFormer_modules.py:53-55)
+    float drop_p;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,6 +134,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     if (m >= p.M) return;
     float* drow = p.D + (long long)m * p.ldd;
     const float* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
+    const float rs = p.rowscale ? __ldg(p.rowscale + m / p.rows_per_group) : 1.f;
 #pragma unroll
     for (int j = 0; j < NCOLS; j += 4) {
         int n = n_base + j;
@@ -143,6 +149,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
             } else if (p.act == 2) {
                 o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
+            if (p.drop_p > 0.f) {
+                const unsigned long long e = (unsigned long long)m * p.N + n;
+                o.x *= vptr_drop_scale(p.drop_seed, e, p.drop_p); o.y *= vptr_drop_scale(p.drop_seed, e + 1, p.drop_p);
+                o.z *= vptr_drop_scale(p.drop_seed, e + 2, p.drop_p); o.w *= vptr_drop_scale(p.drop_seed, e + 3, p.drop_p);
+            }
+            if (p.rowscale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
             if (rrow) {
                 float4 r = *reinterpret_cast<const float4*>(rrow + n);
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -387,7 +399,8 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
 
 extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D,
                               long long ldd, int M, int N, int K, const float* bias, const float* residual, long long ldr,
-                              float alpha, int act, int flags, int k_splits, cudaStream_t stream) {
+                              float alpha, int act, int flags, int k_splits, const float* rowscale, int rows_per_group,
+                              unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(M > 0 && N > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_gemm_tf32: empty problem M=%d N=%d K=%d", M, N, K);
     VPTR_REQUIRE(N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0), VPTR_ERR_ALIGN,
                  "vptr_gemm_tf32: N, ldd, ldr must be multiples of 4 (N=%d ldd=%lld ldr=%lld)", N, ldd, ldr);
@@ -395,8 +408,9 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     VPTR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0) &&
                      ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
                  VPTR_ERR_ALIGN, "vptr_gemm_tf32: pointers must be 16-byte aligned");
-    VPTR_REQUIRE(!(flags & 1) || (bias == nullptr && residual == nullptr && act == 0), VPTR_ERR_UNSUPPORTED,
-                 "vptr_gemm_tf32: atomic accumulate excludes bias/residual/activation");
+    VPTR_REQUIRE(!(flags & 1) || (bias == nullptr && residual == nullptr && act == 0 && rowscale == nullptr && drop_p <= 0.f),
+                 VPTR_ERR_UNSUPPORTED, "vptr_gemm_tf32: atomic accumulate excludes bias/residual/activation/dropout");
+    VPTR_REQUIRE(rowscale == nullptr || rows_per_group > 0, VPTR_ERR_SHAPE, "vptr_gemm_tf32: rowscale needs rows_per_group > 0");
     constexpr int BN = 176;
     constexpr int ST = 5;
     GemmParams p;
@@ -417,6 +431,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.k_splits = vptr_cdiv(p.total_chunks, p.chunks_per_split);  // no empty splits
     p.D = D; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.alpha = alpha; p.act = act; p.flags = flags;
+    p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
 
     CUtensorMap ma, mb;
     int rc;

@@ -8,6 +8,20 @@
 
 namespace {
 
+// branch regularisation around the MlpDWBN activations: y = rowscale[row / rows_per_group] * dropout(GELU(norm(x)))
+// (nn.Dropout after act2 / act3, VidHRFormer_modules.py:436-441; DropPath on the branch, :68-71,563-575)
+struct DropArgs {
+    const float* rowscale;
+    int rows_per_group;
+    unsigned long long seed;
+    float p;
+};
+__device__ __forceinline__ float drop_factor(const DropArgs& d, long long row, long long e) {
+    float f = vptr_drop_scale(d.seed, (unsigned long long)e, d.p);
+    if (d.rowscale) f *= __ldg(d.rowscale + row / d.rows_per_group);
+    return f;
+}
+
 // ------------------------------------------------------------------ LayerNorm(C) forward
 // one warp per row; y = LN(x)*g+b ; y2 = y + add[((row / add_div) % add_mod)]  (both optional)
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restri
                                                            const float* __restrict__ res, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, long long total4, int ch, int hw,
-                                                           int round_tf32) {
+                                                           int round_tf32, const DropArgs da) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 4;
         const long long row = e / ch;
@@ -225,6 +239,10 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restri
         o.y = vptr_gelu((v.y - m.y) * r.y * g.y + b.y);
         o.z = vptr_gelu((v.z - m.z) * r.z * g.z + b.z);
         o.w = vptr_gelu((v.w - m.w) * r.w * g.w + b.w);
+        if (da.p > 0.f || da.rowscale) {
+            o.x *= drop_factor(da, row, e); o.y *= drop_factor(da, row, e + 1);
+            o.z *= drop_factor(da, row, e + 2); o.w *= drop_factor(da, row, e + 3);
+        }
         if (res) {
             float4 q = *reinterpret_cast<const float4*>(res + e);
             o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(128) bn_act_bwd_reduce_kernel(const float* __r
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                 float* __restrict__ s1, float* __restrict__ s2,
-                                                                long long rows, int ch, int rows_per_block) {
+                                                                long long rows, int ch, int rows_per_block, const DropArgs da) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ch) return;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -250,7 +268,7 @@ __global__ void __launch_bounds__(128) bn_act_bwd_reduce_kernel(const float* __r
     float a1 = 0.f, a2 = 0.f;
     for (long long row = r0; row < r1; ++row) {
         float xh = (x[row * ch + c] - m) * r;
-        float gg = dy[row * ch + c] * vptr_gelu_grad(xh * g + b);
+        float gg = dy[row * ch + c] * drop_factor(da, row, row * ch + c) * vptr_gelu_grad(xh * g + b);
         a1 += gg;
         a2 = fmaf(gg, xh, a2);
     }
@@ -264,7 +282,8 @@ __global__ void __launch_bounds__(128) bn_act_bwd_reduce_kernel(const float* __r
 __global__ void __launch_bounds__(512) ln3_act_bwd_frame_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float* __restrict__ p1, float* __restrict__ p2, long long gsize) {
+                                                                float* __restrict__ p1, float* __restrict__ p2, long long gsize, int ch,
+                                                                const DropArgs da) {
     __shared__ float red[32];
     const long long base = (long long)blockIdx.x * gsize;
     const float m = mean[blockIdx.x], r = rstd[blockIdx.x];
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(512) ln3_act_bwd_frame_kernel(const float* __r
     for (long long i = threadIdx.x; i < gsize; i += blockDim.x) {
         float xh = (x[base + i] - m) * r;
         float g = gamma[i];
-        float gg = dy[base + i] * vptr_gelu_grad(xh * g + beta[i]) * g;
+        float gg = dy[base + i] * drop_factor(da, (base + i) / ch, base + i) * vptr_gelu_grad(xh * g + beta[i]) * g;
         a1 += gg;
         a2 = fmaf(gg, xh, a2);
     }
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                 long long gsize, int frames, int frames_per_block) {
+                                                                 long long gsize, int frames, int frames_per_block, int ch, const DropArgs da) {
     const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= gsize) return;
     const int f0 = blockIdx.y * frames_per_block;
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __
     float ag = 0.f, ab = 0.f;
     for (int f = f0; f < f1; ++f) {
         float xh = (x[f * gsize + a] - mean[f]) * rstd[f];
-        float gg = dy[f * gsize + a] * vptr_gelu_grad(xh * g + b);
+        float gg = dy[f * gsize + a] * drop_factor(da, (f * gsize + a) / ch, f * gsize + a) * vptr_gelu_grad(xh * g + b);
         ag = fmaf(gg, xh, ag);
         ab += gg;
     }
@@ -313,7 +332,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ s1, const float* __restrict__ s2,
                                                               float* __restrict__ dx, long long total, int ch, int hw, float inv_n,
-                                                              int round_tf32) {
+                                                              int round_tf32, const DropArgs da) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long row = e / ch;
         const int c = (int)(e - row * ch);
@@ -327,7 +346,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __res
             t1 = MODE == 0 ? s1[c] : 0.f; t2 = MODE == 0 ? s2[c] : 0.f;
         }
         const float xh = (x[e] - m) * r;
-        const float gg = dy[e] * vptr_gelu_grad(xh * g + b);
+        const float gg = dy[e] * drop_factor(da, row, e) * vptr_gelu_grad(xh * g + b);
         float o;
         if (MODE == 0) o = g * r * (gg - t1 * inv_n - xh * t2 * inv_n);
         else if (MODE == 1) o = r * (gg * g - t1 * inv_n - xh * t2 * inv_n);
@@ -398,12 +417,14 @@ extern "C" int vptr_group_stats(const float* x, int groups, long long gsize, flo
 // y = GELU(norm(x)) (+ res).  mode 0: BatchNorm (per-channel stats/affine); mode 1: LayerNorm((ch,H,W)) per frame with
 // affine stored token-major [hw][ch].
 extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, const float* mean, const float* rstd, const float* gamma,
-                                 const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, cudaStream_t stream) {
+                                 const float* beta, long long rows, int ch, int hw, int mode, int round_tf32, const float* rowscale,
+                                 int rows_per_group, unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_fwd: rows=%lld ch=%d", rows, ch);
+    const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
     long long total4 = rows * ch / 4;
     int grid = ew_grid(total4, 256);
-    if (mode == 0) norm_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32);
-    else norm_act_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32);
+    if (mode == 0) norm_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32, da);
+    else norm_act_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32, da);
     return vptr_check_launch("norm_act_fwd_kernel");
 }
 
@@ -411,27 +432,29 @@ extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, con
 // ws: mode 0 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).
 extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
-                                 float* ws, int round_tf32, cudaStream_t stream) {
+                                 float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed,
+                                 float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d", rows, ch);
+    const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
     const long long total = rows * ch;
     const int grid = ew_grid(total, 256);
     if (mode == 0 || mode == 2) {
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * ch, stream);
         int rpb = 256;
         dim3 g2(vptr_cdiv(ch, 128), vptr_cdiv(rows, rpb));
-        bn_act_bwd_reduce_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, ws, ws + ch, rows, ch, rpb);
+        bn_act_bwd_reduce_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, ws, ws + ch, rows, ch, rpb, da);
         if (mode == 0)
-            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows, round_tf32);
+            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows, round_tf32, da);
         else
-            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f, round_tf32);
+            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f, round_tf32, da);
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
-        ln3_act_bwd_frame_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, gsize);
+        ln3_act_bwd_frame_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, gsize, ch, da);
         int fpb = 32;
         dim3 g2(vptr_cdiv(gsize, 128), vptr_cdiv(frames, fpb));
-        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, gsize, frames, fpb);
-        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize, round_tf32);
+        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, gsize, frames, fpb, ch, da);
+        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize, round_tf32, da);
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }

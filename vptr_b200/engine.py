@@ -8,8 +8,8 @@ Restates (reference paths under /root/reference):
   SpatialLocalMultiheadAttention  model/VidHRFormer_modules.py:321-357  (+ MultiheadAttentionRPE, MultiHeadAttentionRPE.py:527-697)
   MlpDWBN.forward                 model/VidHRFormer_modules.py:424-442
   VidHRFormerNAR/FAR.forward      model/VidHRFormer.py:28-53,71-88
-Dropout / DropPath are the identity here (eval mode or p = 0); the module layer refuses p > 0 in train mode until the
-fused Philox epilogues land.
+Dropout / DropPath (train mode, p > 0) are fused into the producing kernels' epilogues with a counter-based RNG (class Drop);
+exact parity with the reference's Philox stream is impossible, so p > 0 is checked statistically and parity is gated at p = 0.
 """
 import math
 
@@ -59,8 +59,46 @@ class Params:
         return r
 
 
-def _rc(x):
-    return ops.round_copy(x) if ROUND_TF32 else x
+def _rc(x, rowscale=None, group_elems=0, seed=0, p=0.0):
+    """GEMM-operand copy of x: tf32-rounded and, for the backward of a regularised branch, masked / DropPath-scaled"""
+    if not ROUND_TF32 and rowscale is None and p <= 0.0:
+        return x
+    return ops.round_copy(x, ROUND_TF32, rowscale, group_elems, seed, p)
+
+
+class Drop:
+    """Dropout / DropPath state of one forward call (train mode, p > 0).  Every site draws its own 64-bit seed; masks are
+    regenerated from (seed, element index) in the backward.  drop_path rate == dropout rate (VPTR_modules.py:114,170)."""
+
+    def __init__(self, p, n_clips, device):
+        self.p, self.n_clips, self.device = float(p), n_clips, device
+        self.p_path = float(p)
+        self.base = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.count = 0
+
+    def seed(self):
+        self.count += 1
+        return (self.base + self.count * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+    def path(self):
+        """(n_clips,) DropPath keep-scales: one Bernoulli per clip, shape (N,1,1,1,1) in the reference"""
+        if self.p_path <= 0.0:
+            self.seed()
+            return None
+        return ops.droppath_scales(self.n_clips, self.seed(), self.p_path, self.device)
+
+
+class _NoDrop:
+    p = 0.0
+
+    def seed(self):
+        return 0
+
+    def path(self):
+        return None
+
+
+NO_DROP = _NoDrop()
 
 
 class exact_fp32:
@@ -111,7 +149,7 @@ def _bgrad(P, name, dY):
 
 
 # =================================================================================================== window attention
-def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save):
+def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
     """x (R,C) -> x + SLMHSA(LN(x)).  qpos (T*H*W, C) or None: q/k source = LN(x)+qpos (decoder)."""
     C = g.C
     lnw, lnb = P.w(ln + ".weight"), P.w(ln + ".bias")
@@ -144,16 +182,19 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save):
         table = None
         wo, bo = P.wr(at + "out_proj.weight"), P.w(at + "out_proj.bias")
     o = ops.empty(Rp, C, like=x)
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT)
+    s_attn, dp = D.seed(), D.path()
+    rpg = g.T * g.Hp * g.Wp                      # rows per clip (DropPath is per clip)
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale,
+                 round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     if g.padded:
-        yp = ops.gemm(o, wo, bias=bo)
+        yp = ops.gemm(o, wo, bias=bo, rowscale=dp, rows_per_group=rpg)
         y = ops.crop_hw(yp, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)
         out = ops.axpby(x, y)
     else:
-        out = ops.gemm(o, wo, bias=bo, residual=x)
+        out = ops.gemm(o, wo, bias=bo, residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
         save.append(("win", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, a_in=a_in, aq_in=aq_in, qkv=qkv, o=o, rpe=rpe,
-                                 has_qpos=qpos is not None, g=g)))
+                                 has_qpos=qpos is not None, g=g, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
     return out
 
 
@@ -161,7 +202,7 @@ def window_attn_bwd(P, s, dout, dqpos):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     at = pre + ".attn."
     Fr = g.F
-    dy = _rc(ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout)
+    dy = _rc(ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout, s["dp"], s["rpg"] * C)
     qkv, o = s["qkv"], s["o"]
     _wgrad(P, at + "out_proj.weight", dy, o)
     _bgrad(P, at + "out_proj.bias", dy)
@@ -173,7 +214,7 @@ def window_attn_bwd(P, s, dout, dqpos):
     else:
         table = dtable = None
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtable, 0, Fr,
-                 g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT)
+                 g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
     a_in, aq_in = s["a_in"], s["aq_in"]
     if s["rpe"]:
         for i, nm in enumerate(("q_proj", "k_proj", "v_proj")):
@@ -221,7 +262,7 @@ def _ffn_norm_stats(P, pre, name, h, g, layer_norm, training, bufs):
     return ops.bn_eval_stats(rm, rv)
 
 
-def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
+def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     """x (R,C) -> x + MlpDWBN(LN(x)).  layer_norm: LayerNorm((ch,H,W)) flavour (FAR, NAR decoder) else BatchNorm2d."""
     mode = 1 if layer_norm else 0
     b_, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT)
@@ -235,43 +276,48 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save):
     h2 = ops.dwconv3x3(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
     st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
     g2, b2 = _ffn_norm_params(P, pre, "norm2", g.HW, layer_norm)
-    u2 = ops.norm_act_fwd(h2, st2[0], st2[1], g2, b2, g.HW, mode, round_tf32=ROUND_TF32)
+    s2, s3, dp = D.seed(), D.seed(), D.path()
+    rpg = g.T * g.HW
+    u2 = ops.norm_act_fwd(h2, st2[0], st2[1], g2, b2, g.HW, mode, round_tf32=ROUND_TF32, drop_seed=s2, drop_p=D.p)
     w2 = P.wr(pre + ".fc2.weight")
     h3 = ops.gemm(u2, w2.view(g.C, Ch), bias=P.w(pre + ".fc2.bias"))
     st3 = _ffn_norm_stats(P, pre, "norm3", h3, g, layer_norm, training, bufs)
     g3, b3 = _ffn_norm_params(P, pre, "norm3", g.HW, layer_norm)
-    out = ops.norm_act_fwd(h3, st3[0], st3[1], g3, b3, g.HW, mode, res=x)
+    out = ops.norm_act_fwd(h3, st3[0], st3[1], g3, b3, g.HW, mode, res=x, rowscale=dp, rows_per_group=rpg, drop_seed=s3, drop_p=D.p)
     if save is not None:
         bwd_mode = mode if (layer_norm or training) else 2
         save.append(("ffn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, b=b_, h1=h1, st1=st1, u1=u1, h2=h2, st2=st2, u2=u2, h3=h3,
-                                 st3=st3, g=g, layer_norm=layer_norm, mode=bwd_mode, w9=w9, aff=((g1, b1), (g2, b2), (g3, b3)))))
+                                 st3=st3, g=g, layer_norm=layer_norm, mode=bwd_mode, w9=w9, aff=((g1, b1), (g2, b2), (g3, b3)),
+                                 s2=s2, s3=s3, dp=dp, rpg=rpg, p=D.p)))
     return out
 
 
-def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False):
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None):
     gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
     ch = h.shape[1]
+    drop = drop or {}
     if layer_norm:
         dg = ops.zeros(g.HW * ch, like=h)
         db = ops.zeros(g.HW * ch, like=h)
-        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd)
+        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd, **drop)
         if gw is not None:
             ops.transpose(dg, 1, g.HW, ch, out=gw, accumulate=True)
             ops.transpose(db, 1, g.HW, ch, out=gb, accumulate=True)
         return dx
     if gw is None:
         gw, gb = ops.zeros(ch, like=h), ops.zeros(ch, like=h)
-    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd)
+    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd, **drop)
 
 
 def conv_ffn_bwd(P, s, dout):
     g, pre, ln, lnm, mode = s["g"], s["pre"], s["ln"], s["layer_norm"], s["mode"]
     Ch = s["h1"].shape[1]
-    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT)
+    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT,
+                        drop=dict(rowscale=s["dp"], rows_per_group=s["rpg"], drop_seed=s["s3"], drop_p=s["p"]))
     _wgrad(P, pre + ".fc2.weight", dh3, s["u2"])
     _bgrad(P, pre + ".fc2.bias", dh3)
     du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
-    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode)
+    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]))
     gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
     if gdw is not None:
         dw9 = ops.zeros(9 * Ch, like=dh2)
@@ -287,7 +333,7 @@ def conv_ffn_bwd(P, s, dout):
 
 
 # =================================================================================================== temporal self-attention
-def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save):
+def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save, D=NO_DROP):
     """x + MHA_t(q=k=LN(x)+pos_t, v=LN(x)) per pixel (VidHRFormer_modules.py:74-84,183-187)."""
     C = g.C
     z, zp, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), add=pos, add_div=g.HW, add_mod=g.T, round_tf32=RT)
@@ -296,23 +342,25 @@ def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save):
     ops.gemm(zp, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
     ops.gemm(z, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale, round_tf32=RT)
-    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    s_attn, s1 = D.seed(), D.seed()
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale,
+                 round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
+    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, drop_seed=s1, drop_p=D.p)
     if save is not None:
-        save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g)))
+        save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g, s_attn=s_attn, s1=s1, p=D.p)))
     return out
 
 
 def temporal_attn_bwd(P, s, dout):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     qkv, o = s["qkv"], s["o"]
-    dres, dout = dout, _rc(dout)
+    dres, dout = dout, _rc(dout, seed=s["s1"], p=s["p"])
     _wgrad(P, pre + ".out_proj.weight", dout, o)
     _bgrad(P, pre + ".out_proj.bias", dout)
     do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], None, None, 1, g.N,
-                 g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale, round_tf32=RT)
+                 g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
     Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
@@ -326,24 +374,25 @@ def temporal_attn_bwd(P, s, dout):
 
 
 # =================================================================================================== MLP FFN
-def mlp_fwd(P, pre, ln, x, g, save):
+def mlp_fwd(P, pre, ln, x, g, save, D=NO_DROP):
     """x + linear2(GELU(linear1(LN(x)))) (VidHRFormer_modules.py:87-89,190-192); pre = block prefix."""
     y, _, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT)
     h = ops.gemm(y, P.wr(pre + ".linear1.weight"), bias=P.w(pre + ".linear1.bias"))
-    u = ops.gelu_fwd(h, round_tf32=ROUND_TF32)
-    out = ops.gemm(u, P.wr(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x)
+    s2, s3 = D.seed(), D.seed()
+    u = ops.gelu_fwd(h, round_tf32=ROUND_TF32, drop_seed=s2, drop_p=D.p)
+    out = ops.gemm(u, P.wr(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x, drop_seed=s3, drop_p=D.p)
     if save is not None:
-        save.append(("mlp", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, y=y, h=h, u=u, g=g)))
+        save.append(("mlp", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, y=y, h=h, u=u, g=g, s2=s2, s3=s3, p=D.p)))
     return out
 
 
 def mlp_bwd(P, s, dout):
     pre, ln = s["pre"], s["ln"]
-    dres, dout = dout, _rc(dout)
+    dres, dout = dout, _rc(dout, seed=s["s3"], p=s["p"])
     _wgrad(P, pre + ".linear2.weight", dout, s["u"])
     _bgrad(P, pre + ".linear2.bias", dout)
     du = ops.gemm(dout, P.wr(pre + ".linear2.weight"), b_mn=True)
-    dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT)
+    dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT, drop_seed=s["s2"], drop_p=s["p"])
     _wgrad(P, pre + ".linear1.weight", dh, s["y"])
     _bgrad(P, pre + ".linear1.bias", dh)
     dy = ops.gemm(dh, P.wr(pre + ".linear1.weight"), b_mn=True)
@@ -352,7 +401,7 @@ def mlp_bwd(P, s, dout):
 
 
 # =================================================================================================== encoder-decoder attention
-def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save):
+def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save, D=NO_DROP):
     """x + MHA(q = LN(x)+query_pos+pos_future, k = memory+pos_past, v = memory) per pixel (VidHRFormer_modules.py:200-206).
     g: geometry of the target stream, gm: of the memory stream; qadd (T2*H*W, C) = query_pos + pos_future."""
     C = g.C
@@ -363,24 +412,27 @@ def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save):
     ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C])
     ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
-    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale, round_tf32=RT)
-    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x)
+    s_attn, dp = D.seed(), D.path()
+    rpg = g.T * g.HW
+    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale, round_tf32=RT,
+                 drop_seed=s_attn, drop_p=D.p)
+    out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
-        save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k)))
+        save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
     return out
 
 
 def cross_attn_bwd(P, s, dout, dqpos, dmem):
     g, gm, C, pre, ln = s["g"], s["gm"], s["g"].C, s["pre"], s["ln"]
     q, kv, o = s["q"], s["kv"], s["o"]
-    dres, dout = dout, _rc(dout)
+    dres, dout = dout, _rc(dout, s["dp"], s["rpg"] * C)
     _wgrad(P, pre + ".out_proj.weight", dout, o)
     _bgrad(P, pre + ".out_proj.bias", dout)
     do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
     ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d,
-                 False, g.scale, round_tf32=RT)
+                 False, g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
     Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
@@ -421,25 +473,25 @@ def lw_table(lw_pos, g):
     return lw_pos[hh][:, ww].reshape(g.Hp * g.Wp, -1).contiguous()
 
 
-def encoder_fwd(P, bufs, x, g, n_layers, far, rpe, tpos, lw_tab, training, save):
+def encoder_fwd(P, bufs, x, g, n_layers, far, rpe, tpos, lw_tab, training, save, D=NO_DROP):
     for i in range(n_layers):
         pre = "transformer.encoder.layers.%d" % i
-        x = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", x, g, rpe, None, lw_tab, save)
-        x = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", x, g, far, training, save)
-        x = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", x, g, tpos, far, save)
-        x = mlp_fwd(P, pre, pre + ".norm4", x, g, save)
+        x = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", x, g, rpe, None, lw_tab, save, D)
+        x = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", x, g, far, training, save, D)
+        x = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", x, g, tpos, far, save, D)
+        x = mlp_fwd(P, pre, pre + ".norm4", x, g, save, D)
     return x
 
 
-def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save):
+def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D=NO_DROP):
     for i in range(n_layers):
         pre = "transformer.decoder.layers.%d" % i
-        tgt = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", tgt, g, rpe, qpos, lw_tab, save)
-        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", tgt, g, True, False, save)
-        tgt = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", tgt, g, tpos_f, False, save)
-        tgt = mlp_fwd(P, pre, pre + ".norm4", tgt, g, save)
-        tgt = cross_attn_fwd(P, pre + ".EncDecAttn", pre + ".norm5", tgt, g, gm, qadd, mem, mem_k, save)
-        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN1", pre + ".norm6", tgt, g, True, False, save)
+        tgt = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", tgt, g, rpe, qpos, lw_tab, save, D)
+        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", tgt, g, True, False, save, D)
+        tgt = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", tgt, g, tpos_f, False, save, D)
+        tgt = mlp_fwd(P, pre, pre + ".norm4", tgt, g, save, D)
+        tgt = cross_attn_fwd(P, pre + ".EncDecAttn", pre + ".norm5", tgt, g, gm, qadd, mem, mem_k, save, D)
+        tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN1", pre + ".norm6", tgt, g, True, False, save, D)
     return tgt
 
 

@@ -37,16 +37,19 @@ class VPTREnc(nn.Module):
 
 class _DecFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dec, feat_cl, F_, H, W):
-        out, saved = decoder_forward(dec, feat_cl, F_, H, W, save=True)
-        ctx.dec, ctx.saved = dec, saved
+    def forward(ctx, dec, feat):
+        N, T, C, H, W = feat.shape
+        feat_cl = _channel_last(feat.flatten(0, 1)).view(N * T * H * W, C)
+        out, saved = decoder_forward(dec, feat_cl, N * T, H, W, save=True)
+        ctx.dec, ctx.saved, ctx.shape = dec, saved, (N, T, C, H, W)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        dfeat = decoder_backward(ctx.dec, ctx.saved, dout.contiguous())
+        N, T, C, H, W = ctx.shape
+        dfeat = decoder_backward(ctx.dec, ctx.saved, dout.contiguous())          # (F*H*W, C) channel-last
         ctx.saved = None
-        return None, dfeat, None, None, None
+        return None, dfeat.view(N, T, H, W, C).permute(0, 1, 4, 2, 3)
 
 
 class VPTRDec(nn.Module):
@@ -62,11 +65,13 @@ class VPTRDec(nn.Module):
             raise NotImplementedError("vptr_b200.VPTRDec: train-mode BatchNorm (stage-1 autoencoder training) is not on the "
                                       "stage-2 hot path; call .eval() as train_NAR.py:191 does")
         N, T, C, H, W = feat.shape
-        feat_cl = _channel_last(feat.flatten(0, 1))                           # (F, H, W, C) contiguous
+        if not feat.is_cuda or feat.dtype != torch.float32:
+            raise RuntimeError("vptr_b200.VPTRDec: input must be a CUDA float32 tensor (got %s, %s); there is no CPU fallback" % (feat.device, feat.dtype))
         if torch.is_grad_enabled() and feat.requires_grad:
-            out = _DecFunction.apply(self.decoder, feat_cl.view(N * T * H * W, C), N * T, H, W)
+            out = _DecFunction.apply(self.decoder, feat)
         else:
-            out, _ = decoder_forward(self.decoder, feat_cl.view(N * T * H * W, C), N * T, H, W, save=False)
+            feat_cl = _channel_last(feat.flatten(0, 1)).view(N * T * H * W, C)   # (F*H*W, C) contiguous
+            out, _ = decoder_forward(self.decoder, feat_cl, N * T, H, W, save=False)
         return out.view(N, T, *out.shape[1:])
 
 
@@ -249,10 +254,11 @@ def _check_input(x, what):
         raise RuntimeError("vptr_b200.%s: input must be a CUDA float32 tensor (got %s, %s); there is no CPU fallback" % (what, x.device, x.dtype))
 
 
-def _check_dropout(mod):
+def _drop_ctx(mod, n_clips, device):
+    """train mode with p > 0: dropout + DropPath (rate = dropout, reference VPTR_modules.py:114) fused into the kernels"""
     if mod.training and mod.dropout > 0:
-        raise NotImplementedError("vptr_b200: train-mode dropout/DropPath (p=%g) is not implemented yet; construct with dropout=0.0 "
-                                  "or call .eval()" % mod.dropout)
+        return E.Drop(mod.dropout, n_clips, device)
+    return E.NO_DROP
 
 
 def _tokens(x):
@@ -272,7 +278,8 @@ class _FARFunction(torch.autograd.Function):
         save = [] if want else None
         lw_tab = None if mod.rpe else E.lw_table(mod.lw_pos, g)
         tpos = mod.temporal_pos[:T].contiguous()
-        h = E.encoder_fwd(P, bufs, _tokens(x), g, mod.num_encoder_layers, True, mod.rpe, tpos, lw_tab, mod.training, save)
+        D = _drop_ctx(mod, N, x.device)
+        h = E.encoder_fwd(P, bufs, _tokens(x), g, mod.num_encoder_layers, True, mod.rpe, tpos, lw_tab, mod.training, save, D)
         y = E.final_norm_fwd(P, "transformer.encoder.norm", h, True, save)
         ctx.save, ctx.names, ctx.params, ctx.shape = save, names, params, (N, T, C, H, W)
         return y.view(N, T, H, W, C).permute(0, 1, 4, 2, 3)
@@ -302,14 +309,15 @@ class _NARFunction(torch.autograd.Function):
         lw_tab = None if mod.rpe else E.lw_table(mod.lw_pos, ge)
         tpos_p = mod.temporal_pos[:Tp].contiguous()
         tpos_f = mod.temporal_pos[Tp:Tp + Tf].contiguous()
-        h = E.encoder_fwd(P, bufs, _tokens(x), ge, mod.num_encoder_layers, False, mod.rpe, tpos_p, lw_tab, mod.training, save)
+        D = _drop_ctx(mod, N, x.device)
+        h = E.encoder_fwd(P, bufs, _tokens(x), ge, mod.num_encoder_layers, False, mod.rpe, tpos_p, lw_tab, mod.training, save, D)
         mem = E.final_norm_fwd(P, "transformer.encoder.norm", h, False, save, round_out=True)
         n_enc = len(save) if want else 0
         qpos = P.w("frame_queries").reshape(Tf * H * W, C)                       # query_pos (VidHRFormer.py:46)
         qadd = ops.add_rows(qpos, tpos_f, H * W, Tf)                             # query_pos + pos_future (VidHRFormer_modules.py:200)
         mem_k = ops.add_rows(mem, tpos_p, H * W, Tp, round_tf32=E.ROUND_TF32)                             # memory + pos_past
         tgt = ops.zeros(gd.R, C, like=x)                                         # init_tgt = zeros (VidHRFormer.py:48)
-        tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save)
+        tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D)
         y = E.final_norm_fwd(P, "transformer.decoder.norm", tgt, True, save)
         ctx.save, ctx.names, ctx.params, ctx.n_enc = save, names, params, n_enc
         ctx.shape = (N, Tp, Tf, C, H, W)
@@ -369,7 +377,6 @@ class VPTRFormerNAR(nn.Module):
     def forward(self, past_gt_feat):
         """past_gt_feat (N, Tp, C, H, W) -> predicted future features (N, Tf, C, H, W)."""
         _check_input(past_gt_feat, "VPTRFormerNAR")
-        _check_dropout(self)
         names, params = _fwd_params(self)
         return _NARFunction.apply(self, past_gt_feat, names, *params)
 
@@ -399,7 +406,6 @@ class VPTRFormerFAR(nn.Module):
     def forward(self, input_feats):
         """input_feats (N, T, C, H, W), any T <= Tp+Tf -> same shape; output t predicts frame t+1 (causal in time)."""
         _check_input(input_feats, "VPTRFormerFAR")
-        _check_dropout(self)
         names, params = _fwd_params(self)
         return _FARFunction.apply(self, input_feats, names, *params)
 

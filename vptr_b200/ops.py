@@ -43,7 +43,7 @@ def _mat(t):
 
 
 def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha=1.0, act=ACT_NONE, accumulate=False,
-         round_tf32=False, k_splits=0):
+         round_tf32=False, k_splits=0, rowscale=None, rows_per_group=0, drop_seed=0, drop_p=0.0):
     """out[M,N] (+)= act(alpha * Aop @ Bop^T + bias) + residual.  a_mn: A stored [K,M]; b_mn: B stored [K,N]."""
     _chk(A, "A"); _chk(B, "B"); _chk(bias, "bias"); _chk(residual, "residual")
     if a_mn:
@@ -71,7 +71,7 @@ def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha
                and pd % 16 == 0 and pr % 16 == 0 and _p(bias) % 16 == 0)
     name = "vptr_gemm_tf32" if (aligned and not FORCE_SIMT) else "vptr_gemm_simt"
     _call(name, pa, lda, int(a_mn), pb, ldb, int(b_mn), pd, ldd, M, N, K, _p(bias), pr, ldr, float(alpha), int(act), flags,
-          int(k_splits), _s())
+          int(k_splits), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
     return out
 
 
@@ -120,34 +120,38 @@ def group_stats(x, groups, eps=1e-5):
     return mean, rstd
 
 
-def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round_tf32=False):
+def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round_tf32=False, rowscale=None, rows_per_group=0,
+                 drop_seed=0, drop_p=0.0):
     rows, ch = x.shape
     y = torch.empty_like(x) if out is None else out
-    _call("vptr_norm_act_fwd", _p(x), _p(y), _p(res), _p(mean), _p(rstd), _p(gamma), _p(beta), rows, ch, hw, mode, int(round_tf32), _s())
+    _call("vptr_norm_act_fwd", _p(x), _p(y), _p(res), _p(mean), _p(rstd), _p(gamma), _p(beta), rows, ch, hw, mode, int(round_tf32),
+          _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
     return y
 
 
-def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode, round_tf32=False):
+def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode, round_tf32=False, rowscale=None, rows_per_group=0,
+                 drop_seed=0, drop_p=0.0):
     rows, ch = x.shape
     dx = torch.empty_like(x)
     n_ws = 2 * ch if mode != 1 else 2 * (rows // hw)
     ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
     _call("vptr_norm_act_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
-          _p(ws), int(round_tf32), _s())
+          _p(ws), int(round_tf32), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
     return dx
 
 
 # --------------------------------------------------------------------------------------------------- attention
-def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False):
+def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False, drop_seed=0, drop_p=0.0):
     _call("vptr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode,
-          F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), int(round_tf32), _s())
+          F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _s())
     return out
 
 
-def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False):
+def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False,
+             drop_seed=0, drop_p=0.0):
     _call("vptr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
           _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(rpe_table), _p(d_rpe_table), mode, F_or_N, H, W, ws, Tq, Tk, nhead, d,
-          int(causal), float(scale), int(round_tf32), _s())
+          int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _s())
 
 
 def window_index_maps(F, H, W, ws, device):
@@ -193,23 +197,30 @@ def rowgroup_sum(dy, out, reps):
     _call("vptr_rowgroup_sum", _p(dy), _p(out), out.numel(), reps, _s())
 
 
-def gelu_fwd(x, round_tf32=False):
+def gelu_fwd(x, round_tf32=False, drop_seed=0, drop_p=0.0):
     y = torch.empty_like(x)
-    _call("vptr_gelu_fwd", _p(x), _p(y), x.numel(), int(round_tf32), _s())
+    _call("vptr_gelu_fwd", _p(x), _p(y), x.numel(), int(round_tf32), int(drop_seed), float(drop_p), _s())
     return y
 
 
-def gelu_bwd(dy, x, out=None, round_tf32=False):
+def gelu_bwd(dy, x, out=None, round_tf32=False, drop_seed=0, drop_p=0.0):
     dx = torch.empty_like(x) if out is None else out
-    _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), int(round_tf32), _s())
+    _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), int(round_tf32), int(drop_seed), float(drop_p), _s())
     return dx
 
 
-def round_copy(x):
-    """round-to-nearest tf32 copy (operands of the tensor-core GEMM are pre-rounded so its truncation is exact)"""
+def round_copy(x, do_round=True, rowscale=None, group_elems=0, drop_seed=0, drop_p=0.0):
+    """y = [round-to-nearest tf32](x * rowscale[i / group_elems] * dropmask): operands of the tensor-core GEMM are pre-rounded
+    so its truncation is exact; the backward of a dropped / DropPath-scaled branch applies the same mask here."""
     y = torch.empty_like(x)
-    _call("vptr_round_copy", _p(x), _p(y), x.numel(), _s())
+    _call("vptr_round_copy", _p(x), _p(y), x.numel(), int(do_round), _p(rowscale), int(group_elems), int(drop_seed), float(drop_p), _s())
     return y
+
+
+def droppath_scales(n, seed, p, device):
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    _call("vptr_droppath_scales", _p(out), n, int(seed), float(p), _s())
+    return out
 
 
 def relu_fwd(x, out=None):
