@@ -40,6 +40,8 @@ int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long
                    int M, int N, int K, const float* bias, const float* residual, long long ldr, float alpha, int act,
                    int flags, int k_splits, const float* rowscale, int rows_per_group, unsigned long long drop_seed, float drop_p,
                    vptr_stream_t stream);
+/* debug aid: device buffer that CTA 0 of the next vptr_gemm_tf32 launches fills with clock64() stamps per tile; NULL disables */
+int vptr_gemm_debug_buffer(long long* buf);
 /* Branch regularisation shared by the entry points below: out = rowscale[row / rows_per_group] * dropout_p(...) (+ residual).
  * rowscale = DropPath keep-scales per clip (reference model/VidHRFormer_modules.py:563-575; vptr_droppath_scales) or NULL;
  * dropout masks come from a counter-based RNG keyed by (drop_seed, element index), so the backward regenerates them.
@@ -138,8 +140,9 @@ int vptr_stem_conv7x7(const float* x, const float* wpk, const float* shift, floa
                       vptr_stream_t stream);
 int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const float* bias, float* out, int F, int Ci, int Co, int H, int W,
                           int act /* 0 none, 1 tanh, 2 sigmoid */, vptr_stream_t stream);
+/* ws: F*(H+6)*(W+6)*Ci + 49*Co*Ci floats of scratch */
 int vptr_head_conv7x7_bwd(const float* dout, const float* out, const float* w, float* dx, int F, int Ci, int Co, int H, int W,
-                          int act, vptr_stream_t stream);
+                          int act, float* ws, vptr_stream_t stream);
 
 #ifdef __cplusplus
 }

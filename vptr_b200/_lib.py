@@ -17,6 +17,7 @@ U = ctypes.c_ulonglong
 _SIGS = {
     "vptr_version": ([], I),
     "vptr_gemm_tf32": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P, I, U, F, P], I),
+    "vptr_gemm_debug_buffer": ([P], I),
     "vptr_gemm_simt": ([P, L, I, P, L, I, P, L, I, I, I, P, P, L, F, I, I, I, P, I, U, F, P], I),
     "vptr_layernorm_fwd": ([P, P, P, P, P, P, I, I, P, P, L, I, F, I, I, P], I),
     "vptr_layernorm_bwd": ([P, P, P, P, P, P, P, P, P, P, P, L, I, I, P], I),
@@ -51,7 +52,7 @@ _SIGS = {
     "vptr_pack_conv_weight": ([P, P, P, I, I, I, I, P], I),
     "vptr_stem_conv7x7": ([P, P, P, P, I, I, I, I, I, P], I),
     "vptr_head_conv7x7_fwd": ([P, P, P, P, I, I, I, I, I, I, P], I),
-    "vptr_head_conv7x7_bwd": ([P, P, P, P, I, I, I, I, I, I, P], I),
+    "vptr_head_conv7x7_bwd": ([P, P, P, P, I, I, I, I, I, I, P, P], I),
 }
 
 EXPORTS = tuple(_SIGS) + ("vptr_last_error",)

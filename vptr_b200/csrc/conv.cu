@@ -218,50 +218,93 @@ __global__ void __launch_bounds__(256) head_conv7x7_kernel(const float* __restri
             out[(((long long)f * Co + co) * H + oh) * W + ow] = head_act(acc[co] + bias[co], act);
 }
 
-// Head input gradient: dx NHWC [F][H][W][Ci] from dout/out NCHW [F][Co][H][W]; w original layout [Co][Ci][7][7].
-// The reflect padding folds up to 2x2 padded positions onto one source pixel.
-__global__ void __launch_bounds__(256) head_conv7x7_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ outv,
-                                                               const float* __restrict__ w, float* __restrict__ dx, int Ci, int Co, int H,
-                                                               int W, int act) {
-    extern __shared__ float sm[];  // [49][Co][Ci]
-    for (int e = threadIdx.x; e < 49 * Co * Ci; e += blockDim.x) {
-        const int ci = e % Ci;
-        int r = e / Ci;
-        const int co = r % Co, tap = r / Co;
-        sm[e] = w[((long long)co * Ci + ci) * 49 + tap];
+// Head input gradient, step 1: full correlation into the reflect-PADDED frame
+//   dxpad[f][p][q][ci] = sum_{kh,kw,co} dz[f][co][p-kh][q-kw] * W[co][ci][kh][kw],   p in [0,H+6), q in [0,W+6),
+// with dz = dout * act'(out) (zero outside the image).  Same structure as the stem: a 1..4-channel image correlated with
+// 64 filters, 16x16 output tile per block, 64 accumulators per thread.  wf = flipped weights [(kh',kw',co)][64] with
+// kh' = 6-kh, so that dxpad[p][q] = sum dzz[p+kh'][q+kw'] * wf, dzz = dz zero-padded by 6.
+__global__ void __launch_bounds__(256) head_bwd_corr_kernel(const float* __restrict__ dout, const float* __restrict__ outv,
+                                                            const float* __restrict__ wf, float* __restrict__ dxpad, int Co, int H, int W,
+                                                            int act) {
+    extern __shared__ float sm[];
+    float* sw = sm;                          // [49*Co][64]
+    float* sp = sm + 49 * Co * STEM_CO;      // [Co][22][22]
+    const int Hp = H + 6, Wp = W + 6;
+    const int f = blockIdx.z;
+    const int p0 = blockIdx.y * 16, q0 = blockIdx.x * 16;
+    for (int e = threadIdx.x; e < 49 * Co * STEM_CO; e += 256) sw[e] = wf[e];
+    for (int e = threadIdx.x; e < Co * 484; e += 256) {
+        const int co = e / 484, r = e % 484;
+        const int ih = p0 + r / 22 - 6, iw = q0 + r % 22 - 6;
+        float g = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+            const long long o = (((long long)f * Co + co) * H + ih) * W + iw;
+            g = dout[o];
+            if (act == 1) { const float y = outv[o]; g *= (1.f - y * y); }
+            else if (act == 2) { const float y = outv[o]; g *= y * (1.f - y); }
+        }
+        sp[e] = g;
     }
     __syncthreads();
-    const int f = blockIdx.z;
-    const int ppb = blockDim.x / Ci;  // pixels per block
-    const int ci = threadIdx.x % Ci;
-    const int pix = blockIdx.x * ppb + threadIdx.x / Ci;
-    if (pix >= H * W || threadIdx.x / Ci >= ppb) return;
-    const int i = pix / W, j = pix % W;
-    int ps[3], qs[3], np = 1, nq = 1;
-    ps[0] = i + 3; qs[0] = j + 3;
-    if (i >= 1 && i <= 3) ps[np++] = 3 - i;
-    if (i >= H - 4 && i <= H - 2) ps[np++] = 2 * H + 1 - i;
-    if (j >= 1 && j <= 3) qs[nq++] = 3 - j;
-    if (j >= W - 4 && j <= W - 2) qs[nq++] = 2 * W + 1 - j;
-    float acc = 0.f;
-    for (int a = 0; a < np; ++a)
-        for (int b = 0; b < nq; ++b)
-            for (int kh = 0; kh < 7; ++kh) {
-                const int oh = ps[a] - kh;
-                if (oh < 0 || oh >= H) continue;
-                for (int kw = 0; kw < 7; ++kw) {
-                    const int ow = qs[b] - kw;
-                    if (ow < 0 || ow >= W) continue;
-                    for (int co = 0; co < Co; ++co) {
-                        const long long o = (((long long)f * Co + co) * H + oh) * W + ow;
-                        float g = dout[o];
-                        if (act == 1) { const float y = outv[o]; g *= (1.f - y * y); }
-                        else if (act == 2) { const float y = outv[o]; g *= y * (1.f - y); }
-                        acc = fmaf(g, sm[((kh * 7 + kw) * Co + co) * Ci + ci], acc);
-                    }
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    float acc[STEM_CO];
+#pragma unroll
+    for (int c = 0; c < STEM_CO; ++c) acc[c] = 0.f;
+    for (int kh = 0; kh < 7; ++kh)
+        for (int kw = 0; kw < 7; ++kw)
+            for (int co = 0; co < Co; ++co) {
+                const float v = sp[co * 484 + (ty + kh) * 22 + tx + kw];
+                const float4* wrow = reinterpret_cast<const float4*>(sw + ((kh * 7 + kw) * Co + co) * STEM_CO);
+#pragma unroll
+                for (int c4 = 0; c4 < STEM_CO / 4; ++c4) {
+                    const float4 k = wrow[c4];
+                    acc[c4 * 4 + 0] = fmaf(v, k.x, acc[c4 * 4 + 0]);
+                    acc[c4 * 4 + 1] = fmaf(v, k.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(v, k.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(v, k.w, acc[c4 * 4 + 3]);
                 }
             }
-    dx[(((long long)f * H + i) * W + j) * Ci + ci] = acc;
+    const int p = p0 + ty, q = q0 + tx;
+    if (p < Hp && q < Wp) {
+        float4* o = reinterpret_cast<float4*>(dxpad + (((long long)f * Hp + p) * Wp + q) * STEM_CO);
+#pragma unroll
+        for (int c4 = 0; c4 < STEM_CO / 4; ++c4) o[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+    }
+}
+
+// step 2: fold the reflect padding (pad 3): source pixel i receives padded rows i+3, 3-i (1<=i<=3) and 2H+1-i (H-4<=i<=H-2)
+__global__ void __launch_bounds__(256) head_bwd_fold_kernel(const float* __restrict__ dxpad, float* __restrict__ dx, long long total4, int H,
+                                                            int W) {
+    const int Hp = H + 6, Wp = W + 6, C4 = STEM_CO / 4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C4);
+        long long r = t / C4;
+        const int j = (int)(r % W); r /= W;
+        const int i = (int)(r % H);
+        const long long f = r / H;
+        int ps[3], qs[3], np = 1, nq = 1;
+        ps[0] = i + 3; qs[0] = j + 3;
+        if (i >= 1 && i <= 3) ps[np++] = 3 - i;
+        if (i >= H - 4 && i <= H - 2) ps[np++] = 2 * H + 1 - i;
+        if (j >= 1 && j <= 3) qs[nq++] = 3 - j;
+        if (j >= W - 4 && j <= W - 2) qs[nq++] = 2 * W + 1 - j;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < np; ++a)
+            for (int b = 0; b < nq; ++b) {
+                const float4 v = reinterpret_cast<const float4*>(dxpad)[((f * Hp + ps[a]) * Wp + qs[b]) * C4 + c];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        reinterpret_cast<float4*>(dx)[t] = acc;
+    }
+}
+
+// head weight [Co][64][7][7] -> flipped, tap-major [(6-kh, 6-kw, co)][64]
+__global__ void head_bwd_pack_kernel(const float* __restrict__ w, float* __restrict__ wf, int Co) {
+    const int total = Co * STEM_CO * 49;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int kw = e % 7, kh = (e / 7) % 7, ci = (e / 49) % STEM_CO, co = e / (49 * STEM_CO);
+        wf[(((6 - kh) * 7 + (6 - kw)) * Co + co) * STEM_CO + ci] = w[e];
+    }
 }
 
 }  // namespace
@@ -318,15 +361,20 @@ extern "C" int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const flo
     return vptr_check_launch("head_conv7x7_kernel");
 }
 
+// workspace `ws`: F*(H+6)*(W+6)*Ci + 49*Co*Ci floats
 extern "C" int vptr_head_conv7x7_bwd(const float* dout, const float* out, const float* w, float* dx, int F, int Ci, int Co, int H, int W,
-                                     int act, cudaStream_t stream) {
-    VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci <= 256 && Co > 0 && Co <= HEAD_MAXCO && H > 6 && W > 6, VPTR_ERR_SHAPE,
-                 "vptr_head_conv7x7_bwd: F=%d Ci=%d Co=%d H=%d W=%d", F, Ci, Co, H, W);
-    const int ppb = 256 / Ci > 0 ? 256 / Ci : 1;
-    const int threads = ppb * Ci;
-    size_t smem = sizeof(float) * (size_t)49 * Co * Ci;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(head_conv7x7_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid(vptr_cdiv(H * W, ppb), 1, F);
-    head_conv7x7_bwd_kernel<<<grid, threads, smem, stream>>>(dout, out, w, dx, Ci, Co, H, W, act);
-    return vptr_check_launch("head_conv7x7_bwd_kernel");
+                                     int act, float* ws, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && F < 65536 && Ci == STEM_CO && Co > 0 && Co <= HEAD_MAXCO && H > 6 && W > 6, VPTR_ERR_SHAPE,
+                 "vptr_head_conv7x7_bwd: F=%d Ci=%d (must be %d) Co=%d H=%d W=%d", F, Ci, STEM_CO, Co, H, W);
+    VPTR_REQUIRE(ws != nullptr, VPTR_ERR_SHAPE, "vptr_head_conv7x7_bwd: workspace missing");
+    float* dxpad = ws;
+    float* wf = ws + (long long)F * (H + 6) * (W + 6) * Ci;
+    head_bwd_pack_kernel<<<vptr_cdiv(Co * Ci * 49, 256), 256, 0, stream>>>(w, wf, Co);
+    size_t smem = sizeof(float) * ((size_t)49 * Co * STEM_CO + (size_t)Co * 484);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(head_bwd_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(vptr_cdiv(W + 6, 16), vptr_cdiv(H + 6, 16), F);
+    head_bwd_corr_kernel<<<grid, 256, smem, stream>>>(dout, out, wf, dxpad, Co, H, W, act);
+    const long long total4 = (long long)F * H * W * (Ci / 4);
+    head_bwd_fold_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(dxpad, dx, total4, H, W);
+    return vptr_check_launch("vptr_head_conv7x7_bwd");
 }

@@ -12,68 +12,98 @@ int ew_grid(long long n, int block) {
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// One block row per (frame, image row h); thread = one float4 channel group, walking along w with a 3x3 register window so
+// every input element is loaded once per output row it touches (3 loads per output instead of 9).
 // flip = 0: y[h][w] = b + sum_t w[t] x[h+dh-1][w+dw-1]  (forward)
 // flip = 1: the adjoint w.r.t. x (input gradient): uses tap 8-t and no bias.
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w9,
-                                                        const float* __restrict__ bias, float* __restrict__ y, long long total4,
-                                                        int H, int W, int C4, int flip) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long t = i / C4;
-        const int w = (int)(t % W); t /= W;
-        const int h = (int)(t % H);
-        const long long f = t / H;
-        float4 acc = (bias && !flip) ? __ldg(reinterpret_cast<const float4*>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float4 ld_col(const float* __restrict__ x, long long frame_base, int hh, int j, int H, int W, int C4, int c) {
+    if (hh < 0 || hh >= H || j < 0 || j >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return reinterpret_cast<const float4*>(x)[(frame_base + (long long)hh * W + j) * C4 + c];
+}
+__device__ __forceinline__ void fma4(float4& a, const float4& k, const float4& v) {
+    a.x = fmaf(k.x, v.x, a.x); a.y = fmaf(k.y, v.y, a.y); a.z = fmaf(k.z, v.z, a.z); a.w = fmaf(k.w, v.w, a.w);
+}
+__global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int H, int W, int C4,
+                                                        int flip) {
+    const int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= C4) return;
+    const int f = blockIdx.x / H, h = blockIdx.x - f * H;
+    const long long fb = (long long)f * H * W;
+    float4 k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w9) + (flip ? 8 - t : t) * C4 + c);
+    const float4 b = (bias && !flip) ? __ldg(reinterpret_cast<const float4*>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 win[3][3];
+#pragma unroll
+    for (int dh = 0; dh < 3; ++dh) {
+        win[dh][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        win[dh][1] = ld_col(x, fb, h + dh - 1, 0, H, W, C4, c);
+        win[dh][2] = ld_col(x, fb, h + dh - 1, 1, H, W, C4, c);
+    }
+    for (int w = 0; w < W; ++w) {
+        float4 acc = b;
+#pragma unroll
+        for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw) fma4(acc, k[dh * 3 + dw], win[dh][dw]);
+        reinterpret_cast<float4*>(y)[(fb + (long long)h * W + w) * C4 + c] = acc;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh) {
-            const int hh = h + dh - 1;
-            if (hh < 0 || hh >= H) continue;
-#pragma unroll
-            for (int dw = 0; dw < 3; ++dw) {
-                const int ww = w + dw - 1;
-                if (ww < 0 || ww >= W) continue;
-                const int tap = flip ? 8 - (dh * 3 + dw) : dh * 3 + dw;
-                float4 k = __ldg(reinterpret_cast<const float4*>(w9) + tap * C4 + c);
-                float4 v = reinterpret_cast<const float4*>(x)[((f * H + hh) * W + ww) * C4 + c];
-                acc.x = fmaf(k.x, v.x, acc.x); acc.y = fmaf(k.y, v.y, acc.y);
-                acc.z = fmaf(k.z, v.z, acc.z); acc.w = fmaf(k.w, v.w, acc.w);
-            }
+            win[dh][0] = win[dh][1];
+            win[dh][1] = win[dh][2];
+            win[dh][2] = ld_col(x, fb, h + dh - 1, w + 2, H, W, C4, c);
         }
-        reinterpret_cast<float4*>(y)[i] = acc;
     }
 }
 
-// dW9[t][c] += sum_{f,h,w} dy[f,h,w,c] * x[f,h+dh-1,w+dw-1,c] ; dbias[c] += sum dy.  Thread per channel, a chunk of
-// frames per blockIdx.y.
+// dW9[t][c] += sum_{f,h,w} dy[f,h,w,c] * x[f,h+dh-1,w+dw-1,c] ; dbias[c] += sum dy.  Thread = float4 channel group, a chunk of
+// frames per blockIdx.y, same sliding window over x.
 __global__ void __launch_bounds__(128) dwconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                               float* __restrict__ dw9, float* __restrict__ dbias, int F, int H, int W,
-                                                              int ch, int frames_per_block) {
+                                                              int C4, int frames_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ch) return;
+    if (c >= C4) return;
     const int f0 = blockIdx.y * frames_per_block;
     const int f1 = min(f0 + frames_per_block, F);
-    float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float ab = 0.f;
-    for (int f = f0; f < f1; ++f)
-        for (int h = 0; h < H; ++h)
+    float4 acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int f = f0; f < f1; ++f) {
+        const long long fb = (long long)f * H * W;
+        for (int h = 0; h < H; ++h) {
+            float4 win[3][3];
+#pragma unroll
+            for (int dh = 0; dh < 3; ++dh) {
+                win[dh][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                win[dh][1] = ld_col(x, fb, h + dh - 1, 0, H, W, C4, c);
+                win[dh][2] = ld_col(x, fb, h + dh - 1, 1, H, W, C4, c);
+            }
             for (int w = 0; w < W; ++w) {
-                const float g = dy[(((long long)f * H + h) * W + w) * ch + c];
-                ab += g;
+                const float4 g = reinterpret_cast<const float4*>(dy)[(fb + (long long)h * W + w) * C4 + c];
+                ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+#pragma unroll
+                for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+                    for (int dw = 0; dw < 3; ++dw) fma4(acc[dh * 3 + dw], g, win[dh][dw]);
 #pragma unroll
                 for (int dh = 0; dh < 3; ++dh) {
-                    const int hh = h + dh - 1;
-                    if (hh < 0 || hh >= H) continue;
-#pragma unroll
-                    for (int dw = 0; dw < 3; ++dw) {
-                        const int ww = w + dw - 1;
-                        if (ww < 0 || ww >= W) continue;
-                        acc[dh * 3 + dw] = fmaf(g, x[(((long long)f * H + hh) * W + ww) * ch + c], acc[dh * 3 + dw]);
-                    }
+                    win[dh][0] = win[dh][1];
+                    win[dh][1] = win[dh][2];
+                    win[dh][2] = ld_col(x, fb, h + dh - 1, w + 2, H, W, C4, c);
                 }
             }
+        }
+    }
+    const int ch = C4 * 4;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) atomicAdd(dw9 + t * ch + c, acc[t]);
-    atomicAdd(dbias + c, ab);
+    for (int t = 0; t < 9; ++t) {
+        float* d = dw9 + t * ch + c * 4;
+        atomicAdd(d, acc[t].x); atomicAdd(d + 1, acc[t].y); atomicAdd(d + 2, acc[t].z); atomicAdd(d + 3, acc[t].w);
+    }
+    float* d = dbias + c * 4;
+    atomicAdd(d, ab.x); atomicAdd(d + 1, ab.y); atomicAdd(d + 2, ab.z); atomicAdd(d + 3, ab.w);
 }
 
 }  // namespace
@@ -81,17 +111,18 @@ __global__ void __launch_bounds__(128) dwconv3x3_wgrad_kernel(const float* __res
 extern "C" int vptr_dwconv3x3(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, int flip,
                               cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F=%d H=%d W=%d ch=%d", F, H, W, ch);
-    long long total4 = (long long)F * H * W * (ch / 4);
-    dwconv3x3_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, w9, bias, y, total4, H, W, ch / 4, flip);
+    VPTR_REQUIRE((long long)F * H < 2147483647LL, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F*H too large");
+    dim3 grid(F * H, vptr_cdiv(ch / 4, 128));
+    dwconv3x3_kernel<<<grid, 128, 0, stream>>>(x, w9, bias, y, H, W, ch / 4, flip);
     return vptr_check_launch("dwconv3x3_kernel");
 }
 
 extern "C" int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9, float* dbias, int F, int H, int W, int ch,
                                     cudaStream_t stream) {
-    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3_wgrad: F=%d H=%d W=%d ch=%d", F, H, W, ch);
+    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3_wgrad: F=%d H=%d W=%d ch=%d", F, H, W, ch);
     int fpb = (256 + H * W - 1) / (H * W);  // ~256 pixels per block
     if (fpb < 1) fpb = 1;
-    dim3 grid(vptr_cdiv(ch, 128), vptr_cdiv(F, fpb));
-    dwconv3x3_wgrad_kernel<<<grid, 128, 0, stream>>>(x, dy, dw9, dbias, F, H, W, ch, fpb);
+    dim3 grid(vptr_cdiv(ch / 4, 128), vptr_cdiv(F, fpb));
+    dwconv3x3_wgrad_kernel<<<grid, 128, 0, stream>>>(x, dy, dw9, dbias, F, H, W, ch / 4, fpb);
     return vptr_check_launch("dwconv3x3_wgrad_kernel");
 }

@@ -15,6 +15,7 @@
 // projections; 1x1 convs VidHRFormer_modules.py:424-442; linear1/linear2 :87-89) and, fed with
 // an im2col / padded-NHWC view, for the ResNet 3x3 convolutions (ResNetAutoEncoder.py:26-47).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -39,6 +40,7 @@ struct GemmParams {
     int rows_per_group;
     unsigned long long drop_seed;  // elementwise nn.Dropout on the branch (drop1/drop3, VidHRFormer_modules.py:53-55)
     float drop_p;
+    long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 26)) {  // ~seconds: turn a protocol bug into a trap instead of a hung GPU
+        if (++spins > (1u << 22)) {  // ~seconds: turn a protocol bug into a trap instead of a hung GPU
             printf("vptr gemm: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
             __trap();
         }
@@ -77,6 +79,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
             smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// One lane of a CONVERGED warp.  The role loops below are executed by all 32 lanes with warp-uniform values and only the
+// TMA / MMA / commit instructions are predicated on the elected lane: issued from a divergent `if (lane == 0)` region instead,
+// every tcgen05.mma costs ~110-140 cycles of uniform-register marshalling (R2UR + BRA.U.ANY loops in the SASS), which made the
+// single issuing thread -- not the tensor core -- the bottleneck (measured with tools/gemm_timeline.py).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,46 +140,126 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One NCOLS-wide chunk of a warp's 32 accumulator rows.  tcgen05.ld hands every lane one ROW (NCOLS consecutive columns);
+// storing that directly makes each warp instruction touch 32 different rows (32 half-used sectors).  The chunk is therefore
+// transposed through a warp-private shared-memory tile (row pitch 36 floats: 16-byte aligned, conflict-free for the
+// quarter-warp float4 accesses) so that global loads (residual) and stores (or split-K reductions) are whole 128-byte row
+// segments: NCOLS/4 lanes per row, float4 per lane, all iterations independent (loads in flight together).
+constexpr int EPI_PITCH = 36;
+// lane -> (row-in-iteration, 4-column group) mapping of the coalesced phase for an NCOLS-wide chunk
 template <int NCOLS>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, int m, int n_base) {
-    if (m >= p.M) return;
-    float* drow = p.D + (long long)m * p.ldd;
-    const float* rrow = p.residual ? p.residual + (long long)m * p.ldr : nullptr;
-    const float rs = p.rowscale ? __ldg(p.rowscale + m / p.rows_per_group) : 1.f;
+struct ChunkMap {
+    static constexpr int LPR = NCOLS / 4;   // lanes per row
+    static constexpr int RPI = 32 / LPR;    // rows per iteration
+    static constexpr int ITERS = 32 / RPI;
+};
+// Global loads of the epilogue (bias, residual) have 1-3k cycles of latency while TMA keeps the memory system busy, and the
+// chunk loop has nothing to overlap them with: issued inside the chunk they made every 32-column chunk cost ~3.3k cycles
+// (tools/gemm_timeline.py).  They are therefore issued early: bias for the whole tile and the residual of chunk 0 before the
+// accumulator-ready wait, the residual of chunk c+1 while chunk c is processed.
+// Rarely-used epilogue options (activation, dropout, DropPath scale) live out of line: inlined into the unrolled store loop they
+// made the epilogue several thousand instructions long and instruction fetch -- not memory -- bound it.
+__device__ __noinline__ float4 epilogue_options(const GemmParams& p, float4 o, int m, int n) {
+    if (p.act == 1) {
+        o.x = vptr_gelu(o.x); o.y = vptr_gelu(o.y); o.z = vptr_gelu(o.z); o.w = vptr_gelu(o.w);
+    } else if (p.act == 2) {
+        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    if (p.drop_p > 0.f) {
+        const unsigned long long e = (unsigned long long)m * p.N + n;
+        o.x *= vptr_drop_scale(p.drop_seed, e, p.drop_p); o.y *= vptr_drop_scale(p.drop_seed, e + 1, p.drop_p);
+        o.z *= vptr_drop_scale(p.drop_seed, e + 2, p.drop_p); o.w *= vptr_drop_scale(p.drop_seed, e + 3, p.drop_p);
+    }
+    if (p.rowscale) {
+        const float rs = __ldg(p.rowscale + m / p.rows_per_group);
+        o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
+    }
+    return o;
+}
+template <int NCOLS>
+__device__ __forceinline__ float4 load_bias(const GemmParams& p, int lane, int n_base) {
+    const int n = n_base + (lane % ChunkMap<NCOLS>::LPR) * 4;
+    if (p.bias && n < p.N) return __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int NCOLS>
+__device__ __forceinline__ void load_residual(const GemmParams& p, int lane, int m_base, int n_base, float4 (&res)[8]) {
+    using CM = ChunkMap<NCOLS>;
+    const int r_in = lane / CM::LPR, n = n_base + (lane % CM::LPR) * 4;
 #pragma unroll
-    for (int j = 0; j < NCOLS; j += 4) {
-        int n = n_base + j;
-        if (n < p.N) {  // N % 4 == 0 is a launch precondition
-            float4 o = make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
-            if (p.bias) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-            }
-            if (p.act == 1) {
-                o.x = vptr_gelu(o.x); o.y = vptr_gelu(o.y); o.z = vptr_gelu(o.z); o.w = vptr_gelu(o.w);
-            } else if (p.act == 2) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
-            if (p.drop_p > 0.f) {
-                const unsigned long long e = (unsigned long long)m * p.N + n;
-                o.x *= vptr_drop_scale(p.drop_seed, e, p.drop_p); o.y *= vptr_drop_scale(p.drop_seed, e + 1, p.drop_p);
-                o.z *= vptr_drop_scale(p.drop_seed, e + 2, p.drop_p); o.w *= vptr_drop_scale(p.drop_seed, e + 3, p.drop_p);
-            }
-            if (p.rowscale) { o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs; }
-            if (rrow) {
-                float4 r = *reinterpret_cast<const float4*>(rrow + n);
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-            }
-            if (p.flags & 2) {
-                o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
-            }
-            if (p.flags & 1) {
-                atomicAdd(drow + n, o.x); atomicAdd(drow + n + 1, o.y);
-                atomicAdd(drow + n + 2, o.z); atomicAdd(drow + n + 3, o.w);
-            } else {
-                *reinterpret_cast<float4*>(drow + n) = o;
-            }
+    for (int it = 0; it < CM::ITERS; ++it) {
+        const int m = m_base + it * CM::RPI + r_in;
+        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.residual && n < p.N && m < p.M) res[it] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
+    }
+}
+template <int NCOLS>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, float* sT, int lane, int m_base, int n_base,
+                                               const float4 bias, const float4 (&res)[8]) {
+    using CM = ChunkMap<NCOLS>;
+#pragma unroll
+    for (int j = 0; j < NCOLS; j += 4)
+        *reinterpret_cast<float4*>(sT + lane * EPI_PITCH + j) = make_float4(v[j] * p.alpha, v[j + 1] * p.alpha, v[j + 2] * p.alpha, v[j + 3] * p.alpha);
+    __syncwarp();
+    const int r_in = lane / CM::LPR, c = (lane % CM::LPR) * 4;
+    const int n = n_base + c;
+    const bool col_ok = n < p.N;          // N % 4 == 0 is a launch precondition
+    const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+#pragma unroll
+    for (int it = 0; it < CM::ITERS; ++it) {
+        const int rr = it * CM::RPI + r_in;
+        const int m = m_base + rr;
+        if (!col_ok || m >= p.M) continue;
+        float4 o = *reinterpret_cast<const float4*>(sT + rr * EPI_PITCH + c);
+        o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
+        if (fancy) o = epilogue_options(p, o, m, n);
+        o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
+        if (p.flags & 2) {
+            o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
         }
+        float* d = p.D + (long long)m * p.ldd + n;
+        if (p.flags & 1)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        else
+            *reinterpret_cast<float4*>(d) = o;
+    }
+    __syncwarp();
+}
+
+// Whole-tile epilogue of one warp (its 32 accumulator rows, BLOCK_N columns), software-pipelined as described above.
+// `wait_full` blocks until the accumulator is complete; it is called after the early loads are in flight.
+template <int BLOCK_N, class WaitFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0, WaitFn wait_full) {
+    constexpr int NFULL = BLOCK_N / 32;
+    constexpr bool TAIL = (BLOCK_N % 32) != 0;
+    float4 res[8];
+    float4 bias = load_bias<32>(p, lane, n0);
+    load_residual<32>(p, lane, m_base, n0, res);
+    wait_full();
+#pragma unroll 1
+    for (int c = 0; c < NFULL; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        tmem_ld_wait();
+        // stage this chunk in shared memory first, then start the next chunk's global loads so they fly during the stores
+        const float4 bias_c = bias;
+        float4 res_c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res_c[i] = res[i];
+        if (c + 1 < NFULL) {
+            bias = load_bias<32>(p, lane, n0 + (c + 1) * 32);
+            load_residual<32>(p, lane, m_base, n0 + (c + 1) * 32, res);
+        } else if (TAIL) {
+            bias = load_bias<16>(p, lane, n0 + (c + 1) * 32);
+            load_residual<16>(p, lane, m_base, n0 + (c + 1) * 32, res);
+        }
+        epilogue_chunk<32>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c);
+    }
+    if (TAIL) {
+        float v[16];
+        tmem_ld16(taddr + NFULL * 32, v);
+        tmem_ld_wait();
+        epilogue_chunk<16>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res);
     }
 }
 
@@ -178,7 +269,8 @@ struct GemmCfg {
     static constexpr int B_GROUPS = (BLOCK_N + 31) / 32;
     static constexpr int B_BYTES = B_MN ? B_GROUPS * 4096 : BLOCK_N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // barriers + manual 1024 B alignment slack
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                      // per-epilogue-warp transpose tiles
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_BYTES + 1024;  // + barriers + manual 1024 B alignment slack
     static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N constraint for M=128");
     static_assert(B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
 };
@@ -194,6 +286,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -222,7 +315,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
+        {  // ===== TMA producer (whole warp converged; one elected lane issues) =====
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -236,6 +329,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sB = sA + Cfg::A_BYTES;
+                    if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     if (!A_MN) {
                         tma_load_2d(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m_tile * BLOCK_M);
@@ -251,12 +345,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         for (int g = 0; g < Cfg::B_GROUPS; ++g)
                             tma_load_2d(&tma_b, &full_bar[stage], sB + g * 4096, n_tile * BLOCK_N + g * 32, kc * BLOCK_K);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer (single thread) =====
+        {  // ===== MMA issuer (whole warp converged; one elected lane issues) =====
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
                                        (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
             int stage = 0;
@@ -267,7 +363,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 const int ks = tile % p.k_splits;
                 const int k0 = ks * p.chunks_per_split;
                 const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 1] = clock64();
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
                 for (int kc = k0; kc < k1; ++kc) {
@@ -275,6 +373,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     tcgen05_fence_after();
                     const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t b_base = a_base + Cfg::A_BYTES;
+                    if (elect_one()) {
+                    if (BLOCK_N == 256 && STAGES == 3 && !A_MN && !B_MN) {
+                        // experiment: two independent 128-column accumulators interleaved (dependency-latency test)
+                        constexpr uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024, 2);
+                            umma_tf32(d_tmem, da, make_smem_desc(b_base + k * 32, 16, 1024, 2), idesc_h, (kc > k0 || k > 0) ? 1u : 0u);
+                            umma_tf32(d_tmem + 128, da, make_smem_desc(b_base + 16384 + k * 32, 16, 1024, 2), idesc_h, (kc > k0 || k > 0) ? 1u : 0u);
+                        }
+                    } else {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 512, 1)
@@ -283,10 +392,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                                                  : make_smem_desc(b_base + k * 32, 16, 1024, 2);
                         umma_tf32(d_tmem, da, db, idesc, (kc > k0 || k > 0) ? 1u : 0u);
                     }
+                    }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+                __syncwarp();
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 2] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -298,26 +412,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int mn = tile / p.k_splits;
             const int n_tile = mn % p.n_tiles;
             const int m_tile = mn / p.n_tiles;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tcgen05_fence_after();
-            const int m = m_tile * BLOCK_M + q * 32 + lane;
+            const int m_base = m_tile * BLOCK_M + q * 32;
+            float* sT = epi_tiles + (warp - 2) * 32 * EPI_PITCH;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
-#pragma unroll 1
-            for (int c0 = 0; c0 + 32 <= BLOCK_N; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld_wait();
-                epilogue_chunk<32>(p, v, m, n_tile * BLOCK_N + c0);
-            }
-            if (BLOCK_N % 32) {
-                float v[16];
-                tmem_ld16(taddr + (BLOCK_N / 32) * 32, v);
-                tmem_ld_wait();
-                epilogue_chunk<16>(p, v, m, n_tile * BLOCK_N + (BLOCK_N / 32) * 32);
-            }
+            const bool stamp = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
+            if (stamp) p.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
+            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                if (stamp) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
+                tcgen05_fence_after();
+            });
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 5] = clock64();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -327,6 +435,227 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (warp == 1) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BLOCK_N tile.  Each CTA stages its own 128 rows
+// of A and HALF of the B tile; the pair's tensor cores read B halves from both shared memories, so per SM the operand
+// traffic through shared memory drops from (128 + N) to (128 + N/2) rows per k-chunk.  That matters because the 1-CTA
+// kernel is shared-memory-bandwidth bound: TMA writes + MMA operand reads of a 128x176 fp32 tile are 77.8 KB per
+// k-chunk = 608 cycles at 128 B/clk against 352 cycles of MMA (measured 590, tools/gemm_timeline.py), and the saturated
+// port also starves the epilogue's own loads/stores.
+//   * leader CTA (cluster rank 0): single thread issues tcgen05.mma.cta_group::2; full barriers live in the leader
+//     (one arrival: its own expect_tx for both CTAs' bytes; both CTAs' TMA complete_tx land there).
+//   * tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers.
+//   * both epilogues arrive on the leader's tmem_empty barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on CTA 0's copy of this barrier
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+struct Gemm2Cfg {
+    static constexpr int HALF_N = BLOCK_N / 2;
+    static constexpr int A_BYTES = BLOCK_M * 128;
+    static constexpr int B_GROUPS = HALF_N / 32;                       // MN-major only
+    static constexpr int B_BYTES = B_MN ? B_GROUPS * 4096 : HALF_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_BYTES + 1024;
+    static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "UMMA N constraint for M=256");
+    static_assert(!B_MN || HALF_N % 32 == 0, "MN-major B halves must be whole 32-float groups");
+    static_assert(B_MN || HALF_N % 8 == 0, "K-major B halves must be whole 8-row swizzle groups");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    // m_tiles here counts 256-row pair tiles
+    const int total_tiles = p.m_tiles * p.n_tiles * p.k_splits;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);    // the leader's expect_tx arrive (used in the leader only; the peer's TMA bytes
+                                           // can only land in the same phase because it waits on the multicast empty barrier)
+            mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);   // multicast tcgen05.commit
+            mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        {  // ===== TMA producer (both CTAs; whole warp converged, one elected lane issues) =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int ks = tile % p.k_splits;
+                const int mn = tile / p.k_splits;
+                const int n_tile = mn % p.n_tiles;
+                const int m_pair = mn / p.n_tiles;
+                const int k0 = ks * p.chunks_per_split;
+                const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
+                const int m0 = (m_pair * 2 + (int)rank) * BLOCK_M;
+                const int n0 = n_tile * BLOCK_N + (int)rank * Cfg::HALF_N;
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sB = sA + Cfg::A_BYTES;
+                    if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    if (!A_MN) {
+                        tma_load_2d_2cta(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BLOCK_M / 32; ++g)
+                            tma_load_2d_2cta(&tma_a, &full_bar[stage], sA + g * 4096, m0 + g * 32, kc * BLOCK_K);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d_2cta(&tma_b, &full_bar[stage], sB, kc * BLOCK_K, n0);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < Cfg::B_GROUPS; ++g)
+                            tma_load_2d_2cta(&tma_b, &full_bar[stage], sB + g * 4096, n0 + g * 32, kc * BLOCK_K);
+                    }
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {  // ===== MMA issuer: the leader CTA's warp 1 (converged), one elected lane drives both tensor cores =====
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
+                                       (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((2 * BLOCK_M) >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int ks = tile % p.k_splits;
+                const int k0 = ks * p.chunks_per_split;
+                const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 0] = clock64();
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 1] = clock64();
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int kc = k0; kc < k1; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_base = a_base + Cfg::A_BYTES;
+                    if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(a_base + k * 32, 16, 1024, 2);
+                        const uint64_t db = B_MN ? make_smem_desc(b_base + k * 1024, 4096, 512, 1)
+                                                 : make_smem_desc(b_base + k * 32, 16, 1024, 2);
+                        umma_tf32_2cta(d_tmem, da, db, idesc, (kc > k0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2cta(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (elect_one()) umma_commit_2cta(&tmem_full[acc]);
+                __syncwarp();
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 2] = clock64();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {  // ===== epilogue warps 2..5 of both CTAs: own 128 rows =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int mn = tile / p.k_splits;
+            const int n_tile = mn % p.n_tiles;
+            const int m_pair = mn / p.n_tiles;
+            const int m_base = (m_pair * 2 + (int)rank) * BLOCK_M + q * 32;
+            float* sT = epi_tiles + (warp - 2) * 32 * EPI_PITCH;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+            const bool stamp = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
+            if (stamp) p.dbg[(tile / n_clusters) * 8 + 3] = clock64();
+            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                if (stamp) p.dbg[(tile / n_clusters) * 8 + 4] = clock64();
+                tcgen05_fence_after();
+            });
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 5] = clock64();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -395,33 +724,59 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     return vptr_check_launch("gemm_tf32_kernel");
 }
 
+
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+int launch_gemm_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES>;
+    auto kern = gemm_tf32_2cta_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int total = p.m_tiles * p.n_tiles * p.k_splits;
+    int clusters = num_sms() / 2;
+    if (total < clusters) clusters = total;
+    kern<<<2 * clusters, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+    return vptr_check_launch("gemm_tf32_2cta_kernel");
+}
+
 }  // namespace
+
+static long long* g_gemm_dbg = nullptr;
+// debug: device buffer (>= 8 * tiles-per-CTA int64) that block 0 fills with clock64() stamps; NULL disables
+extern "C" int vptr_gemm_debug_buffer(long long* buf) { g_gemm_dbg = buf; return VPTR_OK; }
 
 extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const float* B, long long ldb, int b_mn, float* D,
                               long long ldd, int M, int N, int K, const float* bias, const float* residual, long long ldr,
                               float alpha, int act, int flags, int k_splits, const float* rowscale, int rows_per_group,
                               unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(M > 0 && N > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_gemm_tf32: empty problem M=%d N=%d K=%d", M, N, K);
+    VPTR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, VPTR_ERR_ALIGN, "vptr_gemm_tf32: operand pitches must be multiples of 4 floats (TMA 16 B rule): lda=%lld ldb=%lld", lda, ldb);
     VPTR_REQUIRE(N % 4 == 0 && ldd % 4 == 0 && (residual == nullptr || ldr % 4 == 0), VPTR_ERR_ALIGN,
                  "vptr_gemm_tf32: N, ldd, ldr must be multiples of 4 (N=%d ldd=%lld ldr=%lld)", N, ldd, ldr);
-    VPTR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, VPTR_ERR_ALIGN, "vptr_gemm_tf32: operand pitches must be multiples of 4 floats (TMA 16 B rule): lda=%lld ldb=%lld", lda, ldb);
     VPTR_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)D % 16 == 0) &&
                      ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
                  VPTR_ERR_ALIGN, "vptr_gemm_tf32: pointers must be 16-byte aligned");
     VPTR_REQUIRE(!(flags & 1) || (bias == nullptr && residual == nullptr && act == 0 && rowscale == nullptr && drop_p <= 0.f),
                  VPTR_ERR_UNSUPPORTED, "vptr_gemm_tf32: atomic accumulate excludes bias/residual/activation/dropout");
     VPTR_REQUIRE(rowscale == nullptr || rows_per_group > 0, VPTR_ERR_SHAPE, "vptr_gemm_tf32: rowscale needs rows_per_group > 0");
-    constexpr int BN = 176;
-    constexpr int ST = 5;
+    static const int mode_env = [] { const char* e = getenv("VPTR_GEMM_1CTA"); return (e && e[0] == '1') ? 1 : 0; }();
+    const bool two_cta = !mode_env && M > BLOCK_M;          // CTA pairs (cta_group::2) unless the problem has a single M tile
+    constexpr int BN1 = 176;                                 // 1-CTA N tile
+    static const int exp_bn = [] { const char* e = getenv("VPTR_GEMM_BN"); return e ? atoi(e) : 0; }();
+    const int BN = two_cta ? (b_mn ? 192 : 176) : ((exp_bn && !a_mn && !b_mn) ? (exp_bn == 257 ? 256 : exp_bn) : BN1);   // MN-major B halves: whole 32-column groups -> 192
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
-    p.m_tiles = vptr_cdiv(M, BLOCK_M);
+    p.m_tiles = vptr_cdiv(M, two_cta ? 2 * BLOCK_M : BLOCK_M);
     p.n_tiles = vptr_cdiv(N, BN);
     p.total_chunks = vptr_cdiv(K, BLOCK_K);
     if (!(flags & 1)) k_splits = 1;
-    if (k_splits <= 0) {  // auto split-K for accumulate mode: aim for >= 2 tiles per SM
+    const int workers = two_cta ? num_sms() / 2 : num_sms();
+    if (k_splits <= 0) {  // auto split-K for accumulate mode: aim for >= 2 tiles per worker
         int tiles = p.m_tiles * p.n_tiles;
-        k_splits = (2 * num_sms() + tiles - 1) / tiles;
+        k_splits = (2 * workers + tiles - 1) / tiles;
         int max_splits = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;  // keep >= 8 chunks per split
         if (k_splits > max_splits) k_splits = max_splits;
         if (k_splits < 1) k_splits = 1;
@@ -432,18 +787,33 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.D = D; p.ldd = ldd; p.bias = bias; p.residual = residual; p.ldr = ldr;
     p.alpha = alpha; p.act = act; p.flags = flags;
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
+    p.dbg = g_gemm_dbg;
 
     CUtensorMap ma, mb;
     int rc;
     if (!a_mn) rc = make_map_2d(&ma, A, K, M, lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
     else rc = make_map_2d(&ma, A, M, K, lda, 32, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
-    if (!b_mn) rc = make_map_2d(&mb, B, K, N, ldb, BLOCK_K, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!b_mn) rc = make_map_2d(&mb, B, K, N, ldb, BLOCK_K, two_cta ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
     else rc = make_map_2d(&mb, B, N, K, ldb, 32, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
 
-    if (!a_mn && !b_mn) return launch_gemm<BN, 0, 0, ST>(ma, mb, p, stream);
-    if (!a_mn && b_mn) return launch_gemm<BN, 0, 1, ST>(ma, mb, p, stream);
-    if (a_mn && b_mn) return launch_gemm<BN, 1, 1, ST>(ma, mb, p, stream);
-    return launch_gemm<BN, 1, 0, ST>(ma, mb, p, stream);
+    if (two_cta) {
+        constexpr int ST2 = 7;
+        if (!a_mn && !b_mn) return launch_gemm_2cta<176, 0, 0, ST2>(ma, mb, p, stream);
+        if (!a_mn && b_mn) return launch_gemm_2cta<192, 0, 1, ST2>(ma, mb, p, stream);
+        if (a_mn && b_mn) return launch_gemm_2cta<192, 1, 1, ST2>(ma, mb, p, stream);
+        return launch_gemm_2cta<176, 1, 0, ST2>(ma, mb, p, stream);
+    }
+    constexpr int ST = 5;
+    if (exp_bn && !a_mn && !b_mn) {   // experiment: MMA cost vs N (tools/gemm_timeline.py)
+        if (exp_bn == 128) return launch_gemm<128, 0, 0, 5>(ma, mb, p, stream);
+        if (exp_bn == 192) return launch_gemm<192, 0, 0, 4>(ma, mb, p, stream);
+        if (exp_bn == 256) return launch_gemm<256, 0, 0, 4>(ma, mb, p, stream);
+        if (exp_bn == 257) return launch_gemm<256, 0, 0, 3>(ma, mb, p, stream);   // split into two interleaved N=128 accumulators
+    }
+    if (!a_mn && !b_mn) return launch_gemm<BN1, 0, 0, ST>(ma, mb, p, stream);
+    if (!a_mn && b_mn) return launch_gemm<BN1, 0, 1, ST>(ma, mb, p, stream);
+    if (a_mn && b_mn) return launch_gemm<BN1, 1, 1, ST>(ma, mb, p, stream);
+    return launch_gemm<BN1, 1, 0, ST>(ma, mb, p, stream);
 }

@@ -253,105 +253,135 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------ norm + GELU backward
-// Reduction pass, BatchNorm: per channel S1 = sum g, S2 = sum g*xhat with g = dy*GELU'(z)  (dbeta = S1, dgamma = S2)
-__global__ void __launch_bounds__(128) bn_act_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+// Two-stage backward.  Pass A evaluates g0 = dy * dropfactor * GELU'(z) ONCE (the erf/exp are the expensive part), stores it in
+// the dx buffer (which may alias dy) and reduces what the normalisation's backward needs; the later passes read g0.
+//
+// BatchNorm, pass A: per channel S1 = sum g0, S2 = sum g0*xhat (dbeta = S1, dgamma = S2).  4 channels per thread.
+__global__ void __launch_bounds__(128) bn_act_bwd_pass_a_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                float* __restrict__ s1, float* __restrict__ s2,
+                                                                float* __restrict__ g0, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta, float* __restrict__ s1, float* __restrict__ s2,
                                                                 long long rows, int ch, int rows_per_block, const DropArgs da) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (c >= ch) return;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(r0 + rows_per_block, rows);
-    const float m = mean[c], r = rstd[c], g = gamma[c], b = beta[c];
-    float a1 = 0.f, a2 = 0.f;
+    const float4 m = *reinterpret_cast<const float4*>(mean + c), r = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+    const bool drop = da.p > 0.f || da.rowscale;
     for (long long row = r0; row < r1; ++row) {
-        float xh = (x[row * ch + c] - m) * r;
-        float gg = dy[row * ch + c] * drop_factor(da, row, row * ch + c) * vptr_gelu_grad(xh * g + b);
-        a1 += gg;
-        a2 = fmaf(gg, xh, a2);
+        const long long e = row * ch + c;
+        const float4 xv = *reinterpret_cast<const float4*>(x + e);
+        float4 d = *reinterpret_cast<const float4*>(dy + e);
+        if (drop) { d.x *= drop_factor(da, row, e); d.y *= drop_factor(da, row, e + 1); d.z *= drop_factor(da, row, e + 2); d.w *= drop_factor(da, row, e + 3); }
+        float4 xh = make_float4((xv.x - m.x) * r.x, (xv.y - m.y) * r.y, (xv.z - m.z) * r.z, (xv.w - m.w) * r.w);
+        d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
+        d.z *= vptr_gelu_grad(xh.z * g.z + b.z); d.w *= vptr_gelu_grad(xh.w * g.w + b.w);
+        *reinterpret_cast<float4*>(g0 + e) = d;
+        a1.x += d.x; a1.y += d.y; a1.z += d.z; a1.w += d.w;
+        a2.x = fmaf(d.x, xh.x, a2.x); a2.y = fmaf(d.y, xh.y, a2.y); a2.z = fmaf(d.z, xh.z, a2.z); a2.w = fmaf(d.w, xh.w, a2.w);
     }
-    atomicAdd(s1 + c, a1);
-    atomicAdd(s2 + c, a2);
-    atomicAdd(dbeta + c, a1);
-    atomicAdd(dgamma + c, a2);
+    atomicAdd(s1 + c, a1.x); atomicAdd(s1 + c + 1, a1.y); atomicAdd(s1 + c + 2, a1.z); atomicAdd(s1 + c + 3, a1.w);
+    atomicAdd(s2 + c, a2.x); atomicAdd(s2 + c + 1, a2.y); atomicAdd(s2 + c + 2, a2.z); atomicAdd(s2 + c + 3, a2.w);
+    atomicAdd(dbeta + c, a1.x); atomicAdd(dbeta + c + 1, a1.y); atomicAdd(dbeta + c + 2, a1.z); atomicAdd(dbeta + c + 3, a1.w);
+    atomicAdd(dgamma + c, a2.x); atomicAdd(dgamma + c + 1, a2.y); atomicAdd(dgamma + c + 2, a2.z); atomicAdd(dgamma + c + 3, a2.w);
 }
 
-// Reduction pass A, frame LayerNorm: per frame P1 = sum g*gamma, P2 = sum g*gamma*xhat (one block per frame)
-__global__ void __launch_bounds__(512) ln3_act_bwd_frame_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                float* __restrict__ p1, float* __restrict__ p2, long long gsize, int ch,
-                                                                const DropArgs da) {
+// frame LayerNorm, pass A: one block per frame; g0 stored, P1 = sum g0*gamma, P2 = sum g0*gamma*xhat
+__global__ void __launch_bounds__(512) ln3_act_bwd_pass_a_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 float* __restrict__ g0, float* __restrict__ p1, float* __restrict__ p2,
+                                                                 long long gsize, int ch, const DropArgs da) {
     __shared__ float red[32];
     const long long base = (long long)blockIdx.x * gsize;
     const float m = mean[blockIdx.x], r = rstd[blockIdx.x];
+    const bool drop = da.p > 0.f || da.rowscale;
     float a1 = 0.f, a2 = 0.f;
-    for (long long i = threadIdx.x; i < gsize; i += blockDim.x) {
-        float xh = (x[base + i] - m) * r;
-        float g = gamma[i];
-        float gg = dy[base + i] * drop_factor(da, (base + i) / ch, base + i) * vptr_gelu_grad(xh * g + beta[i]) * g;
-        a1 += gg;
-        a2 = fmaf(gg, xh, a2);
+    for (long long i = (long long)threadIdx.x * 4; i < gsize; i += (long long)blockDim.x * 4) {
+        const long long e = base + i;
+        const float4 xv = *reinterpret_cast<const float4*>(x + e);
+        float4 d = *reinterpret_cast<const float4*>(dy + e);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i)), b = __ldg(reinterpret_cast<const float4*>(beta + i));
+        if (drop) {
+            const long long row = e / ch;   // 4 consecutive elements share a row (ch % 4 == 0)
+            d.x *= drop_factor(da, row, e); d.y *= drop_factor(da, row, e + 1); d.z *= drop_factor(da, row, e + 2); d.w *= drop_factor(da, row, e + 3);
+        }
+        const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
+        d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
+        d.z *= vptr_gelu_grad(xh.z * g.z + b.z); d.w *= vptr_gelu_grad(xh.w * g.w + b.w);
+        *reinterpret_cast<float4*>(g0 + e) = d;
+        const float4 t = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        a1 += t.x + t.y + t.z + t.w;
+        a2 += t.x * xh.x + t.y * xh.y + t.z * xh.z + t.w * xh.w;
     }
     a1 = block_sum(a1, red);
     a2 = block_sum(a2, red);
     if (threadIdx.x == 0) { p1[blockIdx.x] = a1; p2[blockIdx.x] = a2; }
 }
 
-// Reduction pass B, frame LayerNorm: dgamma[a] += sum_f g*xhat ; dbeta[a] += sum_f g   (thread per affine index)
-__global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+// frame LayerNorm, pass B: dgamma[a] += sum_f g0*xhat ; dbeta[a] += sum_f g0   (4 affine indices per thread)
+__global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __restrict__ g0, const float* __restrict__ x,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                 long long gsize, int frames, int frames_per_block, int ch, const DropArgs da) {
-    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, long long gsize,
+                                                                 int frames, int frames_per_block) {
+    const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (a >= gsize) return;
     const int f0 = blockIdx.y * frames_per_block;
     const int f1 = min(f0 + frames_per_block, frames);
-    const float g = gamma[a], b = beta[a];
-    float ag = 0.f, ab = 0.f;
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
     for (int f = f0; f < f1; ++f) {
-        float xh = (x[f * gsize + a] - mean[f]) * rstd[f];
-        float gg = dy[f * gsize + a] * drop_factor(da, (f * gsize + a) / ch, f * gsize + a) * vptr_gelu_grad(xh * g + b);
-        ag = fmaf(gg, xh, ag);
-        ab += gg;
+        const float m = __ldg(mean + f), r = __ldg(rstd + f);
+        const float4 xv = *reinterpret_cast<const float4*>(x + f * gsize + a);
+        const float4 d = *reinterpret_cast<const float4*>(g0 + f * gsize + a);
+        ag.x = fmaf(d.x, (xv.x - m) * r, ag.x); ag.y = fmaf(d.y, (xv.y - m) * r, ag.y);
+        ag.z = fmaf(d.z, (xv.z - m) * r, ag.z); ag.w = fmaf(d.w, (xv.w - m) * r, ag.w);
+        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
     }
-    atomicAdd(dgamma + a, ag);
-    atomicAdd(dbeta + a, ab);
+    atomicAdd(dgamma + a, ag.x); atomicAdd(dgamma + a + 1, ag.y); atomicAdd(dgamma + a + 2, ag.z); atomicAdd(dgamma + a + 3, ag.w);
+    atomicAdd(dbeta + a, ab.x); atomicAdd(dbeta + a + 1, ab.y); atomicAdd(dbeta + a + 2, ab.z); atomicAdd(dbeta + a + 3, ab.w);
 }
 
-// Elementwise pass: dx from the reduced sums.
-//  MODE 0: dx = gamma*rstd*(g - S1/n - xhat*S2/n)        (S indexed by channel, n = rows)
-//  MODE 1: dx = rstd_f*(g*gamma - P1_f/n - xhat*P2_f/n)   (P indexed by frame,  n = hw*ch)
-//  MODE 2: eval BatchNorm (statistics are constants): dx = gamma*rstd*g
+// Final pass (in place on the g0 buffer): dx from g0 and the reduced sums.
+//  MODE 0: dx = gamma*rstd*(g0 - S1/n - xhat*S2/n)        (S indexed by channel, n = rows)
+//  MODE 1: dx = rstd_f*(g0*gamma - P1_f/n - xhat*P2_f/n)   (P indexed by frame,  n = hw*ch)
+//  MODE 2: eval BatchNorm (statistics are constants): dx = gamma*rstd*g0
 template <int MODE>
-__global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(float* __restrict__ g0dx, const float* __restrict__ x,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              const float* __restrict__ s1, const float* __restrict__ s2,
-                                                              float* __restrict__ dx, long long total, int ch, int hw, float inv_n,
-                                                              int round_tf32, const DropArgs da) {
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        const long long row = e / ch;
-        const int c = (int)(e - row * ch);
-        float m, r, g, b, t1, t2;
+                                                              const float* __restrict__ gamma, const float* __restrict__ s1,
+                                                              const float* __restrict__ s2, long long total4, int ch, long long gsize,
+                                                              float inv_n, int round_tf32) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 4;
+        const float4 d = *reinterpret_cast<const float4*>(g0dx + e);
+        const float4 xv = *reinterpret_cast<const float4*>(x + e);
+        float4 o;
         if (MODE == 1) {
-            const long long f = row / hw;
-            const long long a = (row - f * hw) * ch + c;
-            m = mean[f]; r = rstd[f]; g = gamma[a]; b = beta[a]; t1 = s1[f]; t2 = s2[f];
+            const long long f = e / gsize;
+            const long long a = e - f * gsize;
+            const float m = __ldg(mean + f), r = __ldg(rstd + f), t1 = __ldg(s1 + f) * inv_n, t2 = __ldg(s2 + f) * inv_n;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + a));
+            o.x = r * (d.x * g.x - t1 - (xv.x - m) * r * t2); o.y = r * (d.y * g.y - t1 - (xv.y - m) * r * t2);
+            o.z = r * (d.z * g.z - t1 - (xv.z - m) * r * t2); o.w = r * (d.w * g.w - t1 - (xv.w - m) * r * t2);
         } else {
-            m = mean[c]; r = rstd[c]; g = gamma[c]; b = beta[c];
-            t1 = MODE == 0 ? s1[c] : 0.f; t2 = MODE == 0 ? s2[c] : 0.f;
+            const int c = (int)(e % ch);
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c)), r = __ldg(reinterpret_cast<const float4*>(rstd + c));
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            if (MODE == 0) {
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(s1 + c)), t2 = __ldg(reinterpret_cast<const float4*>(s2 + c));
+                o.x = g.x * r.x * (d.x - t1.x * inv_n - (xv.x - m.x) * r.x * t2.x * inv_n);
+                o.y = g.y * r.y * (d.y - t1.y * inv_n - (xv.y - m.y) * r.y * t2.y * inv_n);
+                o.z = g.z * r.z * (d.z - t1.z * inv_n - (xv.z - m.z) * r.z * t2.z * inv_n);
+                o.w = g.w * r.w * (d.w - t1.w * inv_n - (xv.w - m.w) * r.w * t2.w * inv_n);
+            } else {
+                o.x = g.x * r.x * d.x; o.y = g.y * r.y * d.y; o.z = g.z * r.z * d.z; o.w = g.w * r.w * d.w;
+            }
         }
-        const float xh = (x[e] - m) * r;
-        const float gg = dy[e] * drop_factor(da, row, e) * vptr_gelu_grad(xh * g + b);
-        float o;
-        if (MODE == 0) o = g * r * (gg - t1 * inv_n - xh * t2 * inv_n);
-        else if (MODE == 1) o = r * (gg * g - t1 * inv_n - xh * t2 * inv_n);
-        else o = g * r * gg;
-        dx[e] = round_tf32 ? vptr_round_tf32(o) : o;
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        *reinterpret_cast<float4*>(g0dx + e) = o;
     }
 }
 
@@ -428,33 +458,33 @@ extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, con
     return vptr_check_launch("norm_act_fwd_kernel");
 }
 
-// Backward of y = GELU(norm(x)).  mode 0: train BatchNorm, 1: frame LayerNorm, 2: eval BatchNorm.
-// ws: mode 0 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).
+// Backward of y = rowscale*dropout(GELU(norm(x))).  mode 0: train BatchNorm, 1: frame LayerNorm, 2: eval BatchNorm.
+// ws: mode 0/2 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).  dx may alias dy (in place).
 extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
                                  float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed,
                                  float drop_p, cudaStream_t stream) {
-    VPTR_REQUIRE(rows > 0 && ch > 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d", rows, ch);
+    VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d (ch %% 4 == 0 required)", rows, ch);
     const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
-    const long long total = rows * ch;
-    const int grid = ew_grid(total, 256);
+    const long long total4 = rows * ch / 4;
+    const int grid = ew_grid(total4, 256);
     if (mode == 0 || mode == 2) {
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * ch, stream);
-        int rpb = 256;
-        dim3 g2(vptr_cdiv(ch, 128), vptr_cdiv(rows, rpb));
-        bn_act_bwd_reduce_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, ws, ws + ch, rows, ch, rpb, da);
+        int rpb = 128;
+        dim3 g2(vptr_cdiv(ch / 4, 128), vptr_cdiv(rows, rpb));
+        bn_act_bwd_pass_a_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, ws, ws + ch, rows, ch, rpb, da);
         if (mode == 0)
-            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 1.0f / (float)rows, round_tf32, da);
+            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, total4, ch, 0, 1.0f / (float)rows, round_tf32);
         else
-            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + ch, dx, total, ch, hw, 0.f, round_tf32, da);
+            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, total4, ch, 0, 0.f, round_tf32);
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
-        ln3_act_bwd_frame_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, gsize, ch, da);
+        ln3_act_bwd_pass_a_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, gsize, ch, da);
         int fpb = 32;
-        dim3 g2(vptr_cdiv(gsize, 128), vptr_cdiv(frames, fpb));
-        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, gsize, frames, fpb, ch, da);
-        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, ws, ws + frames, dx, total, ch, hw, 1.0f / (float)gsize, round_tf32, da);
+        dim3 g2(vptr_cdiv(gsize / 4, 128), vptr_cdiv(frames, fpb));
+        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dx, x, mean, rstd, dgamma, dbeta, gsize, frames, fpb);
+        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, total4, ch, gsize, 1.0f / (float)gsize, round_tf32);
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }

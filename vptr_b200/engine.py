@@ -292,21 +292,21 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     return out
 
 
-def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None):
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None, inplace=False):
     gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
     ch = h.shape[1]
     drop = drop or {}
     if layer_norm:
         dg = ops.zeros(g.HW * ch, like=h)
         db = ops.zeros(g.HW * ch, like=h)
-        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd, **drop)
+        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd, inplace=inplace, **drop)
         if gw is not None:
             ops.transpose(dg, 1, g.HW, ch, out=gw, accumulate=True)
             ops.transpose(db, 1, g.HW, ch, out=gb, accumulate=True)
         return dx
     if gw is None:
         gw, gb = ops.zeros(ch, like=h), ops.zeros(ch, like=h)
-    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd, **drop)
+    return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd, inplace=inplace, **drop)
 
 
 def conv_ffn_bwd(P, s, dout):
@@ -317,14 +317,15 @@ def conv_ffn_bwd(P, s, dout):
     _wgrad(P, pre + ".fc2.weight", dh3, s["u2"])
     _bgrad(P, pre + ".fc2.bias", dh3)
     du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
-    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]))
+    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]),
+                        inplace=True)
     gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
     if gdw is not None:
         dw9 = ops.zeros(9 * Ch, like=dh2)
         ops.dwconv3x3_wgrad(s["u1"], dh2, dw9, gdb, g.F, g.H, g.W)
         ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
     du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
-    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT)
+    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT, inplace=True)
     _wgrad(P, pre + ".fc1.weight", dh1, s["b"])
     _bgrad(P, pre + ".fc1.bias", dh1)
     db = ops.gemm(dh1, P.wr(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)

@@ -32,6 +32,7 @@ def zeros(*shape, like=None, device=None):
 
 # --------------------------------------------------------------------------------------------------- GEMM
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+DEBUG_FLAGS = 0     # gemm epilogue debug bits (4: no global store, 8: skip epilogue body)
 FORCE_SIMT = False  # tests flip this to cross-check the tensor-core kernel against the fp32 FFMA kernel
 
 
@@ -66,9 +67,9 @@ def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha
     pb, ldb = _mat(B)
     pd, ldd = _mat(out)
     pr, ldr = (0, 0) if residual is None else _mat(residual)
-    flags = (1 if accumulate else 0) | (2 if round_tf32 else 0)
+    flags = (1 if accumulate else 0) | (2 if round_tf32 else 0) | DEBUG_FLAGS
     aligned = (lda % 4 == 0 and ldb % 4 == 0 and ldd % 4 == 0 and ldr % 4 == 0 and N % 4 == 0 and pa % 16 == 0 and pb % 16 == 0
-               and pd % 16 == 0 and pr % 16 == 0 and _p(bias) % 16 == 0)
+               and pd % 16 == 0 and pr % 16 == 0 and _p(bias) % 16 == 0)             # TMA / float4 epilogue: 16-byte rules
     name = "vptr_gemm_tf32" if (aligned and not FORCE_SIMT) else "vptr_gemm_simt"
     _call(name, pa, lda, int(a_mn), pb, ldb, int(b_mn), pd, ldd, M, N, K, _p(bias), pr, ldr, float(alpha), int(act), flags,
           int(k_splits), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
@@ -130,9 +131,10 @@ def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round
 
 
 def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode, round_tf32=False, rowscale=None, rows_per_group=0,
-                 drop_seed=0, drop_p=0.0):
+                 drop_seed=0, drop_p=0.0, inplace=False):
+    """inplace: dx overwrites dy (for temporaries); otherwise a fresh buffer (which also holds the intermediate g0)"""
     rows, ch = x.shape
-    dx = torch.empty_like(x)
+    dx = dy if inplace else torch.empty_like(x)
     n_ws = 2 * ch if mode != 1 else 2 * (rows // hw)
     ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
     _call("vptr_norm_act_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
@@ -323,5 +325,6 @@ def head_conv7x7_fwd(x, wpk, bias, F, Ci, Co, H, W, act):
 
 def head_conv7x7_bwd(dout, out, w, F, Ci, Co, H, W, act):
     dx = torch.empty(F * H * W, Ci, dtype=torch.float32, device=dout.device)
-    _call("vptr_head_conv7x7_bwd", _p(dout), _p(out), _p(w), _p(dx), F, Ci, Co, H, W, act, _s())
+    ws = torch.empty(F * (H + 6) * (W + 6) * Ci + 49 * Co * Ci, dtype=torch.float32, device=dout.device)
+    _call("vptr_head_conv7x7_bwd", _p(dout), _p(out), _p(w), _p(dx), F, Ci, Co, H, W, act, _p(ws), _s())
     return dx
