@@ -193,7 +193,10 @@ __device__ __forceinline__ void load_residual(const GemmParams& p, int lane, int
         if (p.residual && n < p.N && m < p.M) res[it] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
     }
 }
-template <int NCOLS>
+// MODE (compile time, so the unrolled store loop carries no per-element flag tests -- the epilogue warps run one per scheduler
+// and are latency-bound, every branch costs): 0 plain store, 1 store rounded to tf32, 2 split-K reduction (red.add), 3 all
+// options (activation / dropout / DropPath scale, out of line).
+template <int NCOLS, int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, float* sT, int lane, int m_base, int n_base,
                                                const float4 bias, const float4 (&res)[8]) {
     using CM = ChunkMap<NCOLS>;
@@ -203,33 +206,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     __syncwarp();
     const int r_in = lane / CM::LPR, c = (lane % CM::LPR) * 4;
     const int n = n_base + c;
-    const bool col_ok = n < p.N;          // N % 4 == 0 is a launch precondition
-    const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+    const int rows_ok = (n < p.N) ? p.M - m_base - r_in : 0;          // rows of this lane's column group that exist (N % 4 == 0)
+    float* dcol = p.D + (long long)(m_base + r_in) * p.ldd + n;
+    const long long dstep = (long long)CM::RPI * p.ldd;
 #pragma unroll
     for (int it = 0; it < CM::ITERS; ++it) {
-        const int rr = it * CM::RPI + r_in;
-        const int m = m_base + rr;
-        if (!col_ok || m >= p.M) continue;
-        float4 o = *reinterpret_cast<const float4*>(sT + rr * EPI_PITCH + c);
-        o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
-        if (fancy) o = epilogue_options(p, o, m, n);
-        o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
-        if (p.flags & 2) {
-            o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
+        if (it * CM::RPI < rows_ok) {
+            float4 o = *reinterpret_cast<const float4*>(sT + (it * CM::RPI + r_in) * EPI_PITCH + c);
+            o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
+            if (MODE == 3) o = epilogue_options(p, o, m_base + it * CM::RPI + r_in, n);
+            o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
+            if (MODE == 1 || (MODE == 3 && (p.flags & 2))) {
+                o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
+            }
+            float* d = dcol + it * dstep;
+            if (MODE == 2)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            else
+                *reinterpret_cast<float4*>(d) = o;
         }
-        float* d = p.D + (long long)m * p.ldd + n;
-        if (p.flags & 1)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-        else
-            *reinterpret_cast<float4*>(d) = o;
     }
     __syncwarp();
 }
 
-// Whole-tile epilogue of one warp (its 32 accumulator rows, BLOCK_N columns), software-pipelined as described above.
-// `wait_full` blocks until the accumulator is complete; it is called after the early loads are in flight.
-template <int BLOCK_N, class WaitFn>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0, WaitFn wait_full) {
+// Whole-tile epilogue of one warp (its 32 accumulator rows, BLOCK_N columns).  Global loads (bias, residual) have 1-3k cycles
+// of latency while TMA keeps the memory system busy, so they are issued early: for chunk 0 before the accumulator-ready wait,
+// for chunk c+1 while chunk c is stored.
+template <int BLOCK_N, int MODE, class WaitFn>
+__device__ __forceinline__ void epilogue_tile_mode(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0,
+                                                   WaitFn wait_full) {
     constexpr int NFULL = BLOCK_N / 32;
     constexpr bool TAIL = (BLOCK_N % 32) != 0;
     float4 res[8];
@@ -241,7 +246,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         float v[32];
         tmem_ld32(taddr + c * 32, v);
         tmem_ld_wait();
-        // stage this chunk in shared memory first, then start the next chunk's global loads so they fly during the stores
         const float4 bias_c = bias;
         float4 res_c[8];
 #pragma unroll
@@ -253,14 +257,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
             bias = load_bias<16>(p, lane, n0 + (c + 1) * 32);
             load_residual<16>(p, lane, m_base, n0 + (c + 1) * 32, res);
         }
-        epilogue_chunk<32>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c);
+        epilogue_chunk<32, MODE>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c);
     }
     if (TAIL) {
         float v[16];
         tmem_ld16(taddr + NFULL * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<16>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res);
+        epilogue_chunk<16, MODE>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res);
     }
+}
+template <int BLOCK_N, class WaitFn>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0, WaitFn wait_full) {
+    const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+    if (p.flags & 1) epilogue_tile_mode<BLOCK_N, 2>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy) epilogue_tile_mode<BLOCK_N, 3>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (p.flags & 2) epilogue_tile_mode<BLOCK_N, 1>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else epilogue_tile_mode<BLOCK_N, 0>(p, taddr, sT, lane, m_base, n0, wait_full);
 }
 
 template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
@@ -461,7 +473,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on CTA 0's copy of this barrier
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(smem_u32(bar)));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    // relaxed: the barrier only orders TMEM reads (already fenced by tcgen05.wait::ld + fence::before_thread_sync); a release
+    // arrive would make the warp wait for all its outstanding global stores (ERRBAR, 5 % of the kernel's stall samples)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;   // same offset in the even (leader) CTA of the pair
