@@ -128,6 +128,13 @@ int vptr_pad_crop(const float* in, float* out, int F, int H, int W, int Hp, int 
 int vptr_sqnorm_accumulate(const float* x, long long n, double* sqnorm_out, vptr_stream_t stream);
 int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm, vptr_stream_t stream);
 
+/* Implicit-GEMM 3x3 stride-1 convolution on the tcgen05 kernel: A tiles are 4-D TMA boxes of the padded NHWC activation
+ * (no im2col matrix).  Replaces the 18 ResnetBlock convs (model/ResNetAutoEncoder.py:138,151) + their BN/ReLU/residual.
+ * Returns -3 (unsupported) when H x W does not tile into 128-pixel boxes; callers then use vptr_im2col + vptr_gemm_tf32. */
+int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                      const float* residual, int act, int flags, vptr_stream_t stream);
+int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, int C, int pad, int pad_mode, int round_tf32, vptr_stream_t stream);
+
 /* ---- ResNet encoder / decoder (model/ResNetAutoEncoder.py:26-48,70-98) ---------------------------------- */
 int vptr_im2col(const float* x, const float* mask, float* col, int F, int H, int W, int Cin, int k, int stride, int pad,
                 int pad_mode /* 0 zero, 1 reflect, 2 replicate */, int round_tf32, vptr_stream_t stream);

@@ -83,3 +83,22 @@ def test_gemm_rejects_cpu_tensor():
     from vptr_b200 import ops
     with pytest.raises(RuntimeError):
         ops.gemm(torch.randn(8, 8), torch.randn(8, 8))
+
+
+@pytest.mark.parametrize("Fr,H,W,Ci,Co,mode", [(5, 8, 8, 48, 64, "reflect"), (3, 4, 4, 16, 24, "zero"), (2, 16, 16, 32, 176, "replicate"),
+                                                (4, 8, 8, 528, 528, "reflect")])
+def test_implicit_gemm_conv3x3(Fr, H, W, Ci, Co, mode):
+    """4-D TMA implicit-GEMM convolution vs F.conv2d on tf32-exact operands (+ bias, ReLU, residual)"""
+    import torch.nn.functional as F
+    from vptr_b200 import ops
+    x = tf32_exact((Fr * H * W, Ci), 11)
+    w = tf32_exact((Co, Ci, 3, 3), 12) * 0.25
+    bias, res = torch.randn(Co, device="cuda"), torch.randn(Fr * H * W, Co, device="cuda")
+    assert ops.conv3x3_implicit_ok(H, W)
+    xpad = ops.pad_nhwc(x, Fr, H, W, Ci, 1, ops.PAD_MODES[mode], round_tf32=False)
+    wpk = ops.pack_conv_weight(w, None, 0).view(Co, 9 * Ci)
+    y = ops.conv3x3_tf32(xpad, wpk, Fr, H, W, Ci, Co, bias=bias, residual=res, act=ops.ACT_RELU)
+    xn = x.view(Fr, H, W, Ci).permute(0, 3, 1, 2).double()
+    xp = F.pad(xn, (1,) * 4, mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
+    ref = torch.relu(F.conv2d(xp, w.double(), bias.double())).permute(0, 2, 3, 1).reshape(-1, Co) + res.double()
+    assert rel_l2(y, ref) < 3e-5     # fp32 accumulation over K = 9*Ci

@@ -54,17 +54,53 @@ __device__ __forceinline__ int rel_pos_index(int ws, int i, int j) {
     return (ih - jh + ws - 1) * (2 * ws - 1) + (iw - jw + ws - 1);
 }
 
+// Shared tiles use a row pitch dp = (d rounded up to 4) + 4 floats: rows stay 16-byte aligned for float4 access and the
+// quarter-warp bank pattern is conflict-free; pad columns are zero-filled so whole float4 dot products are exact.
+__device__ __forceinline__ int tile_pitch(int d) { return ((d + 3) & ~3) + 4; }
+
+// rows [0, L) x d of head h -> tile; one warp per row (row index computed once per row, float2 global loads: h*d*4 bytes is
+// only 8-byte aligned for odd heads)
+__device__ __forceinline__ void load_rows(float* tile, const float* __restrict__ src, long long ld, const AttnGeom& g, int b, int L,
+                                          bool is_q, int col0, int dp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int l = w; l < L; l += nw) {
+        const float* r = src + (is_q ? q_row(g, b, l) : k_row(g, b, l)) * ld + col0;
+        for (int c2 = lane; 2 * c2 < dp; c2 += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            if (2 * c2 < g.d) v = __ldg(reinterpret_cast<const float2*>(r + 2 * c2));
+            *reinterpret_cast<float2*>(tile + l * dp + 2 * c2) = v;
+        }
+    }
+}
+__device__ __forceinline__ void store_rows(const float* tile, float* __restrict__ dst, long long ld, const AttnGeom& g, int b, int L,
+                                           bool is_q, int col0, int dp, float mul) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int l = w; l < L; l += nw) {
+        float* r = dst + (is_q ? q_row(g, b, l) : k_row(g, b, l)) * ld + col0;
+        for (int c2 = lane; 2 * c2 < g.d; c2 += 32) {
+            float2 v = *reinterpret_cast<const float2*>(tile + l * dp + 2 * c2);
+            v.x *= mul; v.y *= mul;
+            if (g.round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); }
+            *reinterpret_cast<float2*>(r + 2 * c2) = v;
+        }
+    }
+}
+__device__ __forceinline__ float dot_rows(const float* a, const float* b, int dp4) {
+    float s = 0.f;
+    for (int c = 0; c < dp4; ++c) {
+        const float4 x = reinterpret_cast<const float4*>(a)[c], y = reinterpret_cast<const float4*>(b)[c];
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    return s;
+}
+
 // scores + softmax into sS[Lq][Lk+1]; all threads participate
-__device__ __forceinline__ void scores_softmax(const AttnGeom& g, int h, const float* sQ, const float* sK, float* sS,
+__device__ __forceinline__ void scores_softmax(const AttnGeom& g, int h, const float* sQ, const float* sK, float* sS, int dp,
                                                const float* __restrict__ rpe_table) {
-    const int dp = g.d + 1, lp = g.Lk + 1;
+    const int lp = g.Lk + 1, dp4 = ((g.d + 3) & ~3) >> 2;
     for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) {
         const int i = e / g.Lk, j = e - i * g.Lk;
-        float s = 0.f;
-        const float* q = sQ + i * dp;
-        const float* k = sK + j * dp;
-        for (int c = 0; c < g.d; ++c) s = fmaf(q[c], k[c], s);
-        s *= g.scale;
+        float s = dot_rows(sQ + i * dp, sK + j * dp, dp4) * g.scale;
         if (rpe_table) s += __ldg(rpe_table + rel_pos_index(g.ws, i, j) * g.nhead + h);
         if (g.causal && j > i) s = -INFINITY;
         sS[i * lp + j] = s;
@@ -88,31 +124,39 @@ __device__ __forceinline__ void scores_softmax(const AttnGeom& g, int h, const f
     __syncthreads();
 }
 
+// out[i][c4] = mul * sum_j W[i*lw + j] * T[j][c4]  (i < Li, j < Lj) -> staged into dstTile rows (float4 per thread)
+__device__ __forceinline__ void weighted_rows(const float* W, int lw, bool transposed, const float* T, float* dstTile, int Li, int Lj,
+                                              int dp, int d4) {
+    for (int e = threadIdx.x; e < Li * d4; e += blockDim.x) {
+        const int i = e / d4, c = e - i * d4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < Lj; ++j) {
+            const float w = transposed ? W[j * lw + i] : W[i * lw + j];
+            const float4 t = reinterpret_cast<const float4*>(T + j * dp)[c];
+            acc.x = fmaf(w, t.x, acc.x); acc.y = fmaf(w, t.y, acc.y); acc.z = fmaf(w, t.z, acc.z); acc.w = fmaf(w, t.w, acc.w);
+        }
+        reinterpret_cast<float4*>(dstTile + i * dp)[c] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
                                                        long long ldk, const float* __restrict__ V, long long ldv,
                                                        float* __restrict__ O, long long ldo, const float* __restrict__ rpe_table,
                                                        const AttnGeom g, int batches) {
-    extern __shared__ float sm[];
-    const int dp = g.d + 1, lp = g.Lk + 1;
-    float* sQ = sm;
+    extern __shared__ __align__(16) float sm[];
+    const int dp = tile_pitch(g.d), lp = g.Lk + 1, d4 = ((g.d + 3) & ~3) >> 2;
+    float* sQ = sm;                       // also the output staging tile
     float* sK = sQ + g.Lq * dp;
     float* sV = sK + g.Lk * dp;
     float* sS = sV + g.Lk * dp;
     const int h = blockIdx.y;
     const int col0 = h * g.d;
     for (int b = blockIdx.x; b < batches; b += gridDim.x) {
-        for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
-            const int i = e / g.d, c = e - i * g.d;
-            sQ[i * dp + c] = Q[q_row(g, b, i) * ldq + col0 + c];
-        }
-        for (int e = threadIdx.x; e < g.Lk * g.d; e += blockDim.x) {
-            const int j = e / g.d, c = e - j * g.d;
-            const long long r = k_row(g, b, j);
-            sK[j * dp + c] = K[r * ldk + col0 + c];
-            sV[j * dp + c] = V[r * ldv + col0 + c];
-        }
+        load_rows(sQ, Q, ldq, g, b, g.Lq, true, col0, dp);
+        load_rows(sK, K, ldk, g, b, g.Lk, false, col0, dp);
+        load_rows(sV, V, ldv, g, b, g.Lk, false, col0, dp);
         __syncthreads();
-        scores_softmax(g, h, sQ, sK, sS, rpe_table);
+        scores_softmax(g, h, sQ, sK, sS, dp, rpe_table);
         if (g.drop_p > 0.f) {
             for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) {
                 const int i = e / g.Lk, j = e - i * g.Lk;
@@ -120,12 +164,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const float* __restrict__
             }
             __syncthreads();
         }
-        for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
-            const int i = e / g.d, c = e - i * g.d;
-            float o = 0.f;
-            for (int j = 0; j < g.Lk; ++j) o = fmaf(sS[i * lp + j], sV[j * dp + c], o);
-            O[q_row(g, b, i) * ldo + col0 + c] = g.round_tf32 ? vptr_round_tf32(o) : o;
-        }
+        weighted_rows(sS, lp, false, sV, sQ, g.Lq, g.Lk, dp, d4);      // O = P V, staged over the Q tile
+        __syncthreads();
+        store_rows(sQ, O, ldo, g, b, g.Lq, true, col0, dp, 1.f);
         __syncthreads();
     }
 }
@@ -139,46 +180,33 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dV, long long lddv,
                                                        const float* __restrict__ rpe_table, float* __restrict__ d_rpe_table,
                                                        const AttnGeom g, int batches) {
-    extern __shared__ float sm[];
-    const int dp = g.d + 1, lp = g.Lk + 1;
+    extern __shared__ __align__(16) float sm[];
+    const int dp = tile_pitch(g.d), lp = g.Lk + 1, d4 = ((g.d + 3) & ~3) >> 2, dp4 = d4;
     float* sQ = sm;
     float* sK = sQ + g.Lq * dp;
     float* sV = sK + g.Lk * dp;
     float* sdO = sV + g.Lk * dp;
-    float* sP = sdO + g.Lq * dp;
+    float* sOut = sdO + g.Lq * dp;                 // staging tile for dV / dK / dQ: max(Lq, Lk) rows
+    float* sP = sOut + max(g.Lq, g.Lk) * dp;       // P (undropped), later PD = P * keep-scale
     float* sdS = sP + g.Lq * lp;
-    float* sdB = sdS + g.Lq * lp;  // [Lq][Lk] bias-gradient accumulator (only when d_rpe_table)
-    float* sM = sdB + g.Lq * g.Lk;  // [Lq][Lk] dropout keep-scales of this (b, h) (only when drop_p > 0)
+    float* sdB = sdS + g.Lq * lp;                  // [Lq][Lk] bias-gradient accumulator
     const int h = blockIdx.y;
     const int col0 = h * g.d;
     if (d_rpe_table)
         for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) sdB[e] = 0.f;
     for (int b = blockIdx.x; b < batches; b += gridDim.x) {
-        for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
-            const int i = e / g.d, c = e - i * g.d;
-            const long long r = q_row(g, b, i);
-            sQ[i * dp + c] = Q[r * ldq + col0 + c];
-            sdO[i * dp + c] = dO[r * ldo + col0 + c];
-        }
-        for (int e = threadIdx.x; e < g.Lk * g.d; e += blockDim.x) {
-            const int j = e / g.d, c = e - j * g.d;
-            const long long r = k_row(g, b, j);
-            sK[j * dp + c] = K[r * ldk + col0 + c];
-            sV[j * dp + c] = V[r * ldv + col0 + c];
-        }
+        load_rows(sQ, Q, ldq, g, b, g.Lq, true, col0, dp);
+        load_rows(sdO, dO, ldo, g, b, g.Lq, true, col0, dp);
+        load_rows(sK, K, ldk, g, b, g.Lk, false, col0, dp);
+        load_rows(sV, V, ldv, g, b, g.Lk, false, col0, dp);
         __syncthreads();
-        scores_softmax(g, h, sQ, sK, sP, rpe_table);
-        // dP = (dO V^T) * keep-scale   (gradient w.r.t. the undropped probabilities)
+        scores_softmax(g, h, sQ, sK, sP, dp, rpe_table);
+        // dP = (dO V^T) * keep-scale   (gradient w.r.t. the undropped probabilities); PD = P * keep-scale
         const bool drop = g.drop_p > 0.f;
         for (int e = threadIdx.x; e < g.Lq * g.Lk; e += blockDim.x) {
             const int i = e / g.Lk, j = e - i * g.Lk;
-            float s = 0.f;
-            for (int c = 0; c < g.d; ++c) s = fmaf(sdO[i * dp + c], sV[j * dp + c], s);
-            if (drop) {
-                const float m = prob_drop(g, b, h, i, j);
-                sM[e] = m;
-                s *= m;
-            }
+            float s = dot_rows(sdO + i * dp, sV + j * dp, dp4);
+            if (drop) s *= prob_drop(g, b, h, i, j);
             sdS[i * lp + j] = s;
         }
         __syncthreads();
@@ -190,34 +218,26 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
                 for (int j = lane; j < g.Lk; j += 32) t = fmaf(sP[i * lp + j], sdS[i * lp + j], t);
                 t = warp_sum(t);
                 for (int j = lane; j < g.Lk; j += 32) {
-                    float ds = sP[i * lp + j] * (sdS[i * lp + j] - t);
+                    const float pj = sP[i * lp + j];
+                    const float ds = pj * (sdS[i * lp + j] - t);
                     sdS[i * lp + j] = ds;
+                    if (drop) sP[i * lp + j] = pj * prob_drop(g, b, h, i, j);
                     if (d_rpe_table) sdB[i * g.Lk + j] += ds;
                 }
             }
         }
         __syncthreads();
-        // dV = P^T dO ; dK = scale * dS^T Q
-        for (int e = threadIdx.x; e < g.Lk * g.d; e += blockDim.x) {
-            const int j = e / g.d, c = e - j * g.d;
-            float dv = 0.f, dk = 0.f;
-            for (int i = 0; i < g.Lq; ++i) {
-                dv = fmaf(drop ? sP[i * lp + j] * sM[i * g.Lk + j] : sP[i * lp + j], sdO[i * dp + c], dv);
-                dk = fmaf(sdS[i * lp + j], sQ[i * dp + c], dk);
-            }
-            const long long r = k_row(g, b, j);
-            dk *= g.scale;
-            dV[r * lddv + col0 + c] = g.round_tf32 ? vptr_round_tf32(dv) : dv;
-            dK[r * lddk + col0 + c] = g.round_tf32 ? vptr_round_tf32(dk) : dk;
-        }
-        // dQ = scale * dS K
-        for (int e = threadIdx.x; e < g.Lq * g.d; e += blockDim.x) {
-            const int i = e / g.d, c = e - i * g.d;
-            float dq = 0.f;
-            for (int j = 0; j < g.Lk; ++j) dq = fmaf(sdS[i * lp + j], sK[j * dp + c], dq);
-            dq *= g.scale;
-            dQ[q_row(g, b, i) * lddq + col0 + c] = g.round_tf32 ? vptr_round_tf32(dq) : dq;
-        }
+        weighted_rows(sP, lp, true, sdO, sOut, g.Lk, g.Lq, dp, d4);     // dV = PD^T dO
+        __syncthreads();
+        store_rows(sOut, dV, lddv, g, b, g.Lk, false, col0, dp, 1.f);
+        __syncthreads();
+        weighted_rows(sdS, lp, true, sQ, sOut, g.Lk, g.Lq, dp, d4);     // dK = scale * dS^T Q
+        __syncthreads();
+        store_rows(sOut, dK, lddk, g, b, g.Lk, false, col0, dp, g.scale);
+        __syncthreads();
+        weighted_rows(sdS, lp, false, sK, sOut, g.Lq, g.Lk, dp, d4);    // dQ = scale * dS K
+        __syncthreads();
+        store_rows(sOut, dQ, lddq, g, b, g.Lq, true, col0, dp, g.scale);
         __syncthreads();
     }
     if (d_rpe_table) {
@@ -565,7 +585,11 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
             return vptr_check_launch("attn_fwd_fast_kernel");
         }
     }
-    size_t smem = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (d + 1) + (size_t)g.Lq * (g.Lk + 1));
+    VPTR_REQUIRE(d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && ((uintptr_t)Q % 8 == 0) &&
+                     ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) && ((uintptr_t)O % 8 == 0),
+                 VPTR_ERR_ALIGN, "vptr_attn_fwd: head_dim and pitches must be even, pointers 8-byte aligned");
+    const int dpitch = ((d + 3) & ~3) + 4;
+    size_t smem = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * dpitch + (size_t)g.Lq * (g.Lk + 1));
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_fwd: tile too large (%zu B of shared memory)", smem);
     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(batches < 65535 * 8 ? batches : 65535 * 8, nhead);
@@ -611,7 +635,13 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
             return vptr_check_launch("attn_bwd_fast_kernel");
         }
     }
-    size_t smem = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (d + 1) + (size_t)2 * g.Lq * (g.Lk + 1) + (size_t)2 * g.Lq * g.Lk);
+    VPTR_REQUIRE(d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 &&
+                     ((uintptr_t)Q % 8 == 0) && ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) && ((uintptr_t)dO % 8 == 0) &&
+                     ((uintptr_t)dQ % 8 == 0) && ((uintptr_t)dK % 8 == 0) && ((uintptr_t)dV % 8 == 0),
+                 VPTR_ERR_ALIGN, "vptr_attn_bwd: head_dim and pitches must be even, pointers 8-byte aligned");
+    const int dpitch = ((d + 3) & ~3) + 4;
+    const int lmax = g.Lq > g.Lk ? g.Lq : g.Lk;
+    size_t smem = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk + lmax) * dpitch + (size_t)2 * g.Lq * (g.Lk + 1) + (size_t)g.Lq * g.Lk);
     VPTR_REQUIRE(smem <= 200 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_bwd: tile too large (%zu B of shared memory)", smem);
     if (smem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int gx = batches;

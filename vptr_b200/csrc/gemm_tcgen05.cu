@@ -40,6 +40,8 @@ struct GemmParams {
     int rows_per_group;
     unsigned long long drop_seed;  // elementwise nn.Dropout on the branch (drop1/drop3, VidHRFormer_modules.py:53-55)
     float drop_p;
+    // implicit-GEMM 3x3 convolution (A = 4-D TMA view of the padded NHWC activation): 0 = plain GEMM
+    int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C;
     long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
 };
 
@@ -485,6 +487,14 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* map, uint64_
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"((uint16_t)3)
@@ -577,7 +587,16 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                     uint8_t* sB = sA + Cfg::A_BYTES;
                     if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                    if (!A_MN) {
+                    if (!A_MN && p.conv_taps) {
+                        // implicit GEMM: k-chunk kc = (tap, 32-channel slice); the A tile is the tap-shifted window of the padded
+                        // NHWC activation, fetched as one 4-D box {32 ch, W, bh rows, bf frames} = 128 output pixels
+                        const int tap = kc / p.conv_cpt, cs = kc - tap * p.conv_cpt;
+                        const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
+                        const int t = m_pair * 2 + (int)rank;                   // 128-pixel tile index
+                        const int f0 = p.conv_bf > 1 ? t * p.conv_bf : t / p.conv_tiles_per_frame;
+                        const int oh0 = p.conv_bf > 1 ? 0 : (t - f0 * p.conv_tiles_per_frame) * p.conv_bh;
+                        tma_load_4d_2cta(&tma_a, &full_bar[stage], sA, cs * BLOCK_K, kw, oh0 + kh, f0);
+                    } else if (!A_MN) {
                         tma_load_2d_2cta(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m0);
                     } else {
 #pragma unroll
@@ -585,7 +604,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                             tma_load_2d_2cta(&tma_a, &full_bar[stage], sA + g * 4096, m0 + g * 32, kc * BLOCK_K);
                     }
                     if (!B_MN) {
-                        tma_load_2d_2cta(&tma_b, &full_bar[stage], sB, kc * BLOCK_K, n0);
+                        const int kcol = p.conv_taps ? (kc / p.conv_cpt) * p.conv_C + (kc % p.conv_cpt) * BLOCK_K : kc * BLOCK_K;
+                        tma_load_2d_2cta(&tma_b, &full_bar[stage], sB, kcol, n0);
                     } else {
 #pragma unroll
                         for (int g = 0; g < Cfg::B_GROUPS; ++g)
@@ -711,6 +731,22 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long o
     return VPTR_OK;
 }
 
+// 4-D fp32 tensor map over a padded NHWC activation [F][Hp][Wp][C]: box {32 channels, bw, bh, bf}
+int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, int bf) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)F};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wp * C * 4, (cuuint64_t)Hp * Wp * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bf};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): F=%lld Hp=%lld Wp=%lld C=%lld box=%dx%dx%d", (int)r,
+                 F, Hp, Wp, C, bw, bh, bf);
+    return VPTR_OK;
+}
+
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -802,6 +838,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.alpha = alpha; p.act = act; p.flags = flags;
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     p.dbg = g_gemm_dbg;
+    p.conv_taps = 0; p.conv_cpt = 1; p.conv_kw = 1; p.conv_bh = 1; p.conv_tiles_per_frame = 1; p.conv_bf = 1; p.conv_C = 0;
 
     CUtensorMap ma, mb;
     int rc;
@@ -830,4 +867,49 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     if (!a_mn && b_mn) return launch_gemm<BN1, 0, 1, ST>(ma, mb, p, stream);
     if (a_mn && b_mn) return launch_gemm<BN1, 1, 1, ST>(ma, mb, p, stream);
     return launch_gemm<BN1, 1, 0, ST>(ma, mb, p, stream);
+}
+
+// Implicit-GEMM 3x3 stride-1 convolution on the tcgen05 kernel (ResnetBlock convs, reference model/ResNetAutoEncoder.py:138,151):
+//   out[(f,oh,ow)][co] = act( sum_{kh,kw,ci} xpad[f][oh+kh][ow+kw][ci] * w[co][(kh,kw,ci)] + bias[co] ) (+ residual)
+// xpad: NHWC activation already padded by 1 (zero / reflect / replicate: vptr_pad_nhwc) [F][H+2][W+2][C]; w: [Cout][9*C]
+// (vptr_pack_conv_weight mode 0).  No im2col matrix is materialised: each k-chunk's A tile is a 4-D TMA box of xpad.
+// Returns VPTR_ERR_UNSUPPORTED when the grid does not tile into 128-pixel boxes (caller falls back to im2col + vptr_gemm_tf32).
+extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                                 const float* residual, int act, int flags, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32: empty problem");
+    VPTR_REQUIRE(C % 4 == 0 && Cout % 4 == 0 && ((uintptr_t)xpad % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
+                 VPTR_ERR_ALIGN, "vptr_conv3x3_tf32: channels must be multiples of 4 and pointers 16-byte aligned");
+    VPTR_REQUIRE(!(flags & 1), VPTR_ERR_UNSUPPORTED, "vptr_conv3x3_tf32: accumulate mode not supported");
+    int bw = W, bh, bf, tiles_per_frame;
+    const int px = H * W;
+    if (px <= BLOCK_M) {
+        if (BLOCK_M % px != 0 || W > 256 || H > 256) { vptr_set_error("vptr_conv3x3_tf32: %dx%d does not tile 128 pixels", H, W); return VPTR_ERR_UNSUPPORTED; }
+        bh = H; bf = BLOCK_M / px; tiles_per_frame = 1;
+    } else {
+        if (BLOCK_M % W != 0 || H % (BLOCK_M / W) != 0) { vptr_set_error("vptr_conv3x3_tf32: %dx%d does not tile 128 pixels", H, W); return VPTR_ERR_UNSUPPORTED; }
+        bh = BLOCK_M / W; bf = 1; tiles_per_frame = H / bh;
+    }
+    const long long M = (long long)F * px;
+    const long long tiles = bf > 1 ? (F + bf - 1) / bf : (long long)F * tiles_per_frame;
+    GemmParams p;
+    p.M = (int)M; p.N = Cout; p.K = 9 * C;
+    p.m_tiles = (int)((tiles + 1) / 2);
+    p.n_tiles = vptr_cdiv(Cout, 176);
+    p.conv_cpt = vptr_cdiv(C, BLOCK_K);
+    p.total_chunks = 9 * p.conv_cpt;
+    p.k_splits = 1; p.chunks_per_split = p.total_chunks;
+    p.D = out; p.ldd = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout;
+    p.alpha = 1.f; p.act = act; p.flags = flags;
+    p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
+    p.dbg = nullptr;
+    p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = bh; p.conv_tiles_per_frame = tiles_per_frame; p.conv_bf = bf; p.conv_C = C;
+    // rows of a tile beyond F*H*W (frames past the end) are zero-filled by TMA and masked by the epilogue (m < M) only when tiles
+    // map to whole frames in order, which holds for both tilings above.
+    CUtensorMap ma, mb;
+    int rc = make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, w, 9LL * C, Cout, 9LL * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    return launch_gemm_2cta<176, 0, 0, 7>(ma, mb, p, stream);
 }

@@ -124,6 +124,13 @@ def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_a
     Cout, Cin = conv.weight.shape[:2]
     scale, shift = ops.bn_fold(bn)
     wpk = E._rc(ops.pack_conv_weight(conv.weight.data, scale, 0)).view(Cout, 9 * Cin)
+    if stride == 1 and not ops.FORCE_SIMT and ops.conv3x3_implicit_ok(H, W) and Cin % 4 == 0 and Cout % 4 == 0:
+        # implicit GEMM: 4-D TMA boxes of the padded activation feed the tcgen05 kernel directly (no im2col matrix)
+        xpad = ops.pad_nhwc(x, F_, H, W, Cin, 1, pad_mode, round_tf32=E.ROUND_TF32)
+        y = ops.conv3x3_tf32(xpad, wpk, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE)
+        if residual is not None and act_after_residual:
+            y = ops.relu_fwd(y, out=y)
+        return y, H, W
     col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode, round_tf32=E.ROUND_TF32)
     if residual is not None and act_after_residual:
         y = ops.gemm(col, wpk, bias=shift, residual=residual)

@@ -285,6 +285,26 @@ def im2col(x, F, H, W, Cin, k, stride, pad, pad_mode, mask=None, round_tf32=True
     return col, Ho, Wo
 
 
+def pad_nhwc(x, F, H, W, C, pad, pad_mode, round_tf32=True):
+    out = torch.empty(F * (H + 2 * pad) * (W + 2 * pad), C, dtype=torch.float32, device=x.device)
+    _call("vptr_pad_nhwc", _p(x), _p(out), F, H, W, C, pad, pad_mode, int(round_tf32), _s())
+    return out
+
+
+def conv3x3_implicit_ok(H, W):
+    """does an H x W grid tile into the 128-pixel TMA boxes of vptr_conv3x3_tf32?"""
+    px = H * W
+    if px <= 128:
+        return 128 % px == 0 and H <= 256 and W <= 256
+    return 128 % W == 0 and H % (128 // W) == 0
+
+
+def conv3x3_tf32(xpad, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NONE, round_tf32=False):
+    out = torch.empty(F * H * W, Cout, dtype=torch.float32, device=xpad.device)
+    _call("vptr_conv3x3_tf32", _p(xpad), _p(w), _p(out), F, H, W, C, Cout, _p(bias), _p(residual), int(act), 2 if round_tf32 else 0, _s())
+    return out
+
+
 def convT_gather(col, shift, F, H, W, Cout, relu=True):
     out = torch.empty(F * 4 * H * W, Cout, dtype=torch.float32, device=col.device)
     _call("vptr_convT_gather", _p(col), _p(shift), _p(out), F, H, W, Cout, int(relu), _s())
