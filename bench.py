@@ -270,8 +270,11 @@ def run_cuda(args):
                 "h2d_bytes_per_step": int(host_p.numel() + host_f.numel()) * 4, "d2h_bytes_per_step": 4, "loss": loss_val},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "gemm_tf32_kernel (tcgen05 kind::tf32)", "bound": "tensor", "achieved": round(gemm_stats["tflops"], 1),
+        "roofline": {"kernel": "gemm_tf32_2cta_kernel (tcgen05.mma cta_group::2 kind::tf32, TMA operands, TMEM accumulators; all Linear/1x1/3x3-conv contractions, fwd+dgrad+wgrad)", "bound": "tensor", "achieved": round(gemm_stats["tflops"], 1),
                      "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_stats["tflops"] / tf32_peak, 4), "traffic": None,
+                     "traffic_sample": {"launch": "M=40960 N=2112 K=528 (fc1 / linear1 shape)", "dram_bytes": 386988288,
+                                        "algorithmic_bytes": 437000000, "tensor_pipe_active_pct": 55.1,
+                                        "source": "profiles/r01_ncu_gemm_fc1_final.txt (ncu --set full; achieved above is the aggregate over all GEMM shapes of a step, so a single per-launch traffic figure does not exist)"},
                      "peak_note": "tf32 dense = half of the %s bf16 sustained %.1f TFLOP/s (MEASURED_PEAKS.json has no tf32 entry)" % (pk["src"], pk["bf16"]),
                      "launches_per_step": gemm_stats["launches"], "gemm_ms_per_step": round(gemm_stats["ms"], 3),
                      "gemm_share_of_step": round(gemm_stats["ms"] / ms_dev, 3), "gemm_tflop_per_step": round(gemm_stats["flop"] / 1e12, 3)},
@@ -305,12 +308,24 @@ def profile_gemms(torch, ops, step_fn):
         records.append((e0, e1, 2.0 * M * N * K))
         return r
 
+    orig_conv = ops.conv3x3_tf32
+
+    def wrapped_conv(xpad, w, F_, H, W, C, Cout, **kw):      # implicit-GEMM convolution: same kernel, A via 4-D TMA
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_conv(xpad, w, F_, H, W, C, Cout, **kw)
+        e1.record()
+        records.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * C))
+        return r
+
     ops.gemm = wrapped
+    ops.conv3x3_tf32 = wrapped_conv
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
+        ops.conv3x3_tf32 = orig_conv
     ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
     flop = sum(f for _, _, f in records)
     return {"ms": ms, "flop": flop, "launches": len(records), "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}

@@ -249,6 +249,244 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const float* __restrict__
 }
 
 // =============================================================================================
+// Main path: ONE CTA PER BATCH ENTRY, ALL HEADS.  The Lq (Lk) token rows of a window / pixel sequence are whole C-float rows
+// in memory, so the CTA stages them with fully coalesced float4 loads (Q, K, V [, dO] tiles of [L][C+2] floats), then each
+// warp owns one head: scores -> softmax -> P.V (and the backward products) entirely out of shared memory, with no block
+// barrier between the load and the store phases.  Outputs are written back over dead tiles and stored as whole rows.
+// Row pitch C+2 floats makes the 16 float2 accesses of a half-warp hit 32 distinct banks.
+struct AhSmem {
+    int Cp;        // row pitch (floats)
+    float* q; float* k; float* v; float* go;   // tiles
+    float* s;      // [nhead][Lq][Lk+1] probabilities
+    float* ds;     // [nhead][Lq][Lk+1] (backward)
+    float* db;     // [nhead][Lq][Lk]   (backward, bias-gradient accumulator)
+    long long* rq; long long* rk;              // row indices of this batch entry
+};
+
+__device__ __forceinline__ void ah_load_tile(float* tile, int Cp, const float* __restrict__ src, long long ld, const long long* rows, int L,
+                                             int C4) {
+    for (int e = threadIdx.x; e < L * C4; e += blockDim.x) {
+        const int l = e / C4, c = e - l * C4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + rows[l] * ld) + c);
+        float2* d = reinterpret_cast<float2*>(tile + l * Cp + 4 * c);
+        d[0] = make_float2(v.x, v.y);
+        d[1] = make_float2(v.z, v.w);
+    }
+}
+__device__ __forceinline__ void ah_store_tile(const float* tile, int Cp, float* __restrict__ dst, long long ld, const long long* rows, int L,
+                                              int C4, float mul, int round_tf32) {
+    for (int e = threadIdx.x; e < L * C4; e += blockDim.x) {
+        const int l = e / C4, c = e - l * C4;
+        const float2* sp = reinterpret_cast<const float2*>(tile + l * Cp + 4 * c);
+        const float2 a = sp[0], b = sp[1];
+        float4 v = make_float4(a.x * mul, a.y * mul, b.x * mul, b.y * mul);
+        if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+        reinterpret_cast<float4*>(dst + rows[l] * ld)[c] = v;
+    }
+}
+// warp-level: out[i*lp + j] = sum_c A[i][col+c] * B[j][col+c]  (i < Li, j < Lj).  Work item = (key row j, group of 4 query
+// rows): the key element is loaded once for four independent accumulator chains (the plain one-pair-per-lane loop is latency
+// bound: two dependent shared loads per FMA pair with only two warps per scheduler to hide them).
+__device__ __forceinline__ void ah_dots(const float* A, const float* B, int Cp, int col, int Li, int Lj, int d2, float* out, int lp, int lane) {
+    const int groups = (Li + 3) >> 2;
+    for (int e = lane; e < Lj * groups; e += 32) {
+        const int ig = e / Lj, j = e - ig * Lj;
+        const int i0 = ig * 4;
+        const float2* b = reinterpret_cast<const float2*>(B + j * Cp + col);
+        const float2* a0 = reinterpret_cast<const float2*>(A + min(i0, Li - 1) * Cp + col);
+        const float2* a1 = reinterpret_cast<const float2*>(A + min(i0 + 1, Li - 1) * Cp + col);
+        const float2* a2 = reinterpret_cast<const float2*>(A + min(i0 + 2, Li - 1) * Cp + col);
+        const float2* a3 = reinterpret_cast<const float2*>(A + min(i0 + 3, Li - 1) * Cp + col);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll 3
+        for (int c = 0; c < d2; ++c) {
+            const float2 y = b[c];
+            const float2 x0 = a0[c], x1 = a1[c], x2 = a2[c], x3 = a3[c];
+            s0 = fmaf(x0.x, y.x, s0); t0 = fmaf(x0.y, y.y, t0);
+            s1 = fmaf(x1.x, y.x, s1); t1 = fmaf(x1.y, y.y, t1);
+            s2 = fmaf(x2.x, y.x, s2); t2 = fmaf(x2.y, y.y, t2);
+            s3 = fmaf(x3.x, y.x, s3); t3 = fmaf(x3.y, y.y, t3);
+        }
+        out[i0 * lp + j] = s0 + t0;
+        if (i0 + 1 < Li) out[(i0 + 1) * lp + j] = s1 + t1;
+        if (i0 + 2 < Li) out[(i0 + 2) * lp + j] = s2 + t2;
+        if (i0 + 3 < Li) out[(i0 + 3) * lp + j] = s3 + t3;
+    }
+    __syncwarp();
+}
+// warp-level: S[i][j] = softmax_j(scale * q_i.k_j + bias) for head h (probabilities, undropped)
+__device__ __forceinline__ void ah_scores_softmax(const AttnGeom& g, int h, const float* sq, const float* sk, int Cp, float* S,
+                                                  const float* __restrict__ rpe_table, int lane) {
+    const int lp = g.Lk + 1, d2 = g.d >> 1, col = h * g.d;
+    ah_dots(sq, sk, Cp, col, g.Lq, g.Lk, d2, S, lp, lane);
+    for (int e = lane; e < g.Lq * g.Lk; e += 32) {
+        const int i = e / g.Lk, j = e - i * g.Lk;
+        float s = S[i * lp + j] * g.scale;
+        if (rpe_table) s += __ldg(rpe_table + rel_pos_index(g.ws, i, j) * g.nhead + h);
+        if (g.causal && j > i) s = -INFINITY;
+        S[i * lp + j] = s;
+    }
+    __syncwarp();
+    for (int i = lane; i < g.Lq; i += 32) {          // one lane per row: rows are short (<= 64)
+        float m = -INFINITY;
+        for (int j = 0; j < g.Lk; ++j) m = fmaxf(m, S[i * lp + j]);
+        float sum = 0.f;
+        for (int j = 0; j < g.Lk; ++j) { const float p = __expf(S[i * lp + j] - m); S[i * lp + j] = p; sum += p; }
+        const float inv = 1.f / sum;
+        for (int j = 0; j < g.Lk; ++j) S[i * lp + j] *= inv;
+    }
+    __syncwarp();
+}
+// warp-level: out[i][col + c] = mul-free sum_j W(i,j) * T[j][col + c], i < Li, j < Lj; lane = float2 column, rows in registers chunks
+template <bool TRANSPOSED>
+__device__ __forceinline__ void ah_weighted(const float* W, int lw, const float* T, float* out, int Cp, int col, int Li, int Lj, int d2,
+                                            int lane) {
+    // work item = (float2 column c, group of 4 output rows): d2 = 33 columns do not divide the warp, so items (not columns) are
+    // spread over the lanes -- with one column per lane, lane 0 alone ran a second pass and doubled the time
+    const int groups = (Li + 3) >> 2;
+    for (int e = lane; e < d2 * groups; e += 32) {
+        const int rg = e / d2, c = e - rg * d2;
+        const int i0 = rg * 4;
+        float2 acc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int j = 0; j < Lj; ++j) {
+            const float2 t = *reinterpret_cast<const float2*>(T + j * Cp + col + 2 * c);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = min(i0 + r, Li - 1);
+                const float w = TRANSPOSED ? W[j * lw + i] : W[i * lw + j];
+                acc[r].x = fmaf(w, t.x, acc[r].x);
+                acc[r].y = fmaf(w, t.y, acc[r].y);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (i0 + r < Li) *reinterpret_cast<float2*>(out + (i0 + r) * Cp + col + 2 * c) = acc[r];
+    }
+}
+__device__ __forceinline__ void ah_rows(const AttnGeom& g, int b, long long* rq, long long* rk) {
+    for (int l = threadIdx.x; l < g.Lq; l += blockDim.x) rq[l] = q_row(g, b, l);
+    for (int l = threadIdx.x; l < g.Lk; l += blockDim.x) rk[l] = k_row(g, b, l);
+}
+
+__global__ void __launch_bounds__(256) attn_fwd_allheads_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
+                                                                long long ldk, const float* __restrict__ V, long long ldv,
+                                                                float* __restrict__ O, long long ldo,
+                                                                const float* __restrict__ rpe_table, const AttnGeom g, int batches) {
+    extern __shared__ __align__(16) float sm[];
+    const int C = g.nhead * g.d, C4 = C >> 2, Cp = C + 2, lp = g.Lk + 1, d2 = g.d >> 1;
+    float* sq = sm;
+    float* sk = sq + g.Lq * Cp;
+    float* sv = sk + g.Lk * Cp;
+    float* sS = sv + g.Lk * Cp;                                   // [nhead][Lq][lp]
+    long long* rq = reinterpret_cast<long long*>(sS + ((g.nhead * g.Lq * lp + 1) & ~1));
+    long long* rk = rq + g.Lq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int b = blockIdx.x; b < batches; b += gridDim.x) {
+        ah_rows(g, b, rq, rk);
+        __syncthreads();
+        ah_load_tile(sq, Cp, Q, ldq, rq, g.Lq, C4);
+        ah_load_tile(sk, Cp, K, ldk, rk, g.Lk, C4);
+        ah_load_tile(sv, Cp, V, ldv, rk, g.Lk, C4);
+        __syncthreads();
+        for (int h = warp; h < g.nhead; h += nwarps) {
+            float* S = sS + h * g.Lq * lp;
+            ah_scores_softmax(g, h, sq, sk, Cp, S, rpe_table, lane);
+            if (g.drop_p > 0.f) {
+                for (int e = lane; e < g.Lq * g.Lk; e += 32) {
+                    const int i = e / g.Lk, j = e - i * g.Lk;
+                    S[i * lp + j] *= prob_drop(g, b, h, i, j);
+                }
+                __syncwarp();
+            }
+            ah_weighted<false>(S, lp, sv, sq, Cp, h * g.d, g.Lq, g.Lk, d2, lane);     // O = P V over this head's Q columns
+        }
+        __syncthreads();
+        ah_store_tile(sq, Cp, O, ldo, rq, g.Lq, C4, 1.f, g.round_tf32);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) attn_bwd_allheads_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
+                                                                long long ldk, const float* __restrict__ V, long long ldv,
+                                                                const float* __restrict__ dO, long long ldo, float* __restrict__ dQ,
+                                                                long long lddq, float* __restrict__ dK, long long lddk,
+                                                                float* __restrict__ dV, long long lddv,
+                                                                const float* __restrict__ rpe_table, float* __restrict__ d_rpe_table,
+                                                                const AttnGeom g, int batches) {
+    extern __shared__ __align__(16) float sm[];
+    const int C = g.nhead * g.d, C4 = C >> 2, Cp = C + 2, lp = g.Lk + 1, d2 = g.d >> 1;
+    float* sq = sm;
+    float* sgo = sq + g.Lq * Cp;
+    float* sk = sgo + g.Lq * Cp;
+    float* sv = sk + g.Lk * Cp;
+    float* sP = sv + g.Lk * Cp;                                   // [nhead][Lq][lp]
+    float* sdS = sP + g.nhead * g.Lq * lp;
+    float* sdB = sdS + g.nhead * g.Lq * lp;                       // [nhead][Lq][Lk]
+    long long* rq = reinterpret_cast<long long*>(sdB + ((g.nhead * g.Lq * g.Lk + 1) & ~1));
+    long long* rk = rq + g.Lq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (d_rpe_table)
+        for (int e = threadIdx.x; e < g.nhead * g.Lq * g.Lk; e += blockDim.x) sdB[e] = 0.f;
+    for (int b = blockIdx.x; b < batches; b += gridDim.x) {
+        ah_rows(g, b, rq, rk);
+        __syncthreads();
+        ah_load_tile(sq, Cp, Q, ldq, rq, g.Lq, C4);
+        ah_load_tile(sgo, Cp, dO, ldo, rq, g.Lq, C4);
+        ah_load_tile(sk, Cp, K, ldk, rk, g.Lk, C4);
+        ah_load_tile(sv, Cp, V, ldv, rk, g.Lk, C4);
+        __syncthreads();
+        for (int h = warp; h < g.nhead; h += nwarps) {
+            float* P = sP + h * g.Lq * lp;
+            float* dS = sdS + h * g.Lq * lp;
+            const int col = h * g.d;
+            ah_scores_softmax(g, h, sq, sk, Cp, P, rpe_table, lane);
+            const bool drop = g.drop_p > 0.f;
+            // dP = (dO V^T) * keep-scale
+            ah_dots(sgo, sv, Cp, col, g.Lq, g.Lk, d2, dS, lp, lane);
+            if (drop) {
+                for (int e = lane; e < g.Lq * g.Lk; e += 32) {
+                    const int i = e / g.Lk, j = e - i * g.Lk;
+                    dS[i * lp + j] *= prob_drop(g, b, h, i, j);
+                }
+                __syncwarp();
+            }
+            // dS = P * (dP - rowsum(P*dP)); PD = P * keep-scale; bias-gradient accumulation
+            for (int i = lane; i < g.Lq; i += 32) {
+                float t = 0.f;
+                for (int j = 0; j < g.Lk; ++j) t = fmaf(P[i * lp + j], dS[i * lp + j], t);
+                for (int j = 0; j < g.Lk; ++j) {
+                    const float pj = P[i * lp + j];
+                    const float ds = pj * (dS[i * lp + j] - t);
+                    dS[i * lp + j] = ds;
+                    if (drop) P[i * lp + j] = pj * prob_drop(g, b, h, i, j);
+                    if (d_rpe_table) sdB[(h * g.Lq + i) * g.Lk + j] += ds;
+                }
+            }
+            __syncwarp();
+            ah_weighted<true>(P, lp, sgo, sv, Cp, col, g.Lk, g.Lq, d2, lane);      // dV = PD^T dO   -> over V (dead for this head)
+            __syncwarp();
+            ah_weighted<false>(dS, lp, sk, sgo, Cp, col, g.Lq, g.Lk, d2, lane);    // dQ = dS K      -> over dO (dead)
+            __syncwarp();
+            ah_weighted<true>(dS, lp, sq, sk, Cp, col, g.Lk, g.Lq, d2, lane);      // dK = dS^T Q    -> over K (dead)
+        }
+        __syncthreads();
+        ah_store_tile(sv, Cp, dV, lddv, rk, g.Lk, C4, 1.f, g.round_tf32);
+        ah_store_tile(sgo, Cp, dQ, lddq, rq, g.Lq, C4, g.scale, g.round_tf32);
+        ah_store_tile(sk, Cp, dK, lddk, rk, g.Lk, C4, g.scale, g.round_tf32);
+        __syncthreads();
+    }
+    if (d_rpe_table) {
+        for (int e = threadIdx.x; e < g.nhead * g.Lq * g.Lk; e += blockDim.x) {
+            const int h = e / (g.Lq * g.Lk), r = e - h * g.Lq * g.Lk;
+            atomicAdd(d_rpe_table + rel_pos_index(g.ws, r / g.Lk, r % g.Lk) * g.nhead + h, sdB[e]);
+        }
+    }
+}
+
+// =============================================================================================
 // Fast path for small problems (Lq, Lk <= 32: 4x4 windows, T <= 32 temporal / enc-dec): one LANE per query row.
 // A warp handles P = 32 / Lq problems (batch entries) of one head at a time; K and V tiles sit in shared memory and are read
 // as warp-broadcast float4 (one wavefront feeds 32 lanes x 4 FMAs), each lane keeps its score row in registers (softmax
@@ -533,6 +771,11 @@ bool attn_generic_only() {
     return v;
 }
 
+bool attn_no_allheads() {
+    static const bool v = [] { const char* e = getenv("VPTR_ATTN_PERHEAD"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead, int d, int causal, float scale, int* batches) {
     g = AttnGeom{};
     g.mode = mode; g.nhead = nhead; g.d = d; g.causal = causal; g.scale = scale;
@@ -564,6 +807,18 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_fwd: empty problem");
+    {   // main path: one CTA per batch entry, all heads
+        const int C = nhead * d;
+        const size_t ah = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (C + 2) + (((size_t)nhead * g.Lq * (g.Lk + 1) + 1) & ~(size_t)1)) +
+                          sizeof(long long) * (size_t)(g.Lq + g.Lk);
+        if (!attn_no_allheads() && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ah <= 220 * 1024 &&
+            ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0)) {
+            if (ah > 48 * 1024) cudaFuncSetAttribute(attn_fwd_allheads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ah);
+            const int gx = batches < 148 * 8 ? batches : 148 * 8;
+            attn_fwd_allheads_kernel<<<gx, 256, ah, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, rpe_table, g, batches);
+            return vptr_check_launch("attn_fwd_allheads_kernel");
+        }
+    }
     if (!attn_generic_only() && g.Lq <= 32 && g.Lk <= 32 && d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 &&
         ((uintptr_t)Q % 8 == 0) && ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) && ((uintptr_t)O % 8 == 0)) {
         const int dpad = (d + 3) & ~3, P = 32 / g.Lq;
@@ -610,6 +865,21 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_bwd: empty problem");
+    {   // main path: one CTA per batch entry, all heads
+        const int C = nhead * d;
+        const size_t ah = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (C + 2) + (size_t)2 * nhead * g.Lq * (g.Lk + 1) +
+                                           (((size_t)nhead * g.Lq * g.Lk + 1) & ~(size_t)1)) + sizeof(long long) * (size_t)(g.Lq + g.Lk);
+        if (!attn_no_allheads() && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 &&
+            lddk % 4 == 0 && lddv % 4 == 0 && ah <= 220 * 1024 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) &&
+            ((uintptr_t)V % 16 == 0) && ((uintptr_t)dO % 16 == 0) && ((uintptr_t)dQ % 16 == 0) && ((uintptr_t)dK % 16 == 0) &&
+            ((uintptr_t)dV % 16 == 0)) {
+            if (ah > 48 * 1024) cudaFuncSetAttribute(attn_bwd_allheads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ah);
+            int gx = batches < 148 * 4 ? batches : 148 * 4;
+            attn_bwd_allheads_kernel<<<gx, 256, ah, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, rpe_table,
+                                                              d_rpe_table, g, batches);
+            return vptr_check_launch("attn_bwd_allheads_kernel");
+        }
+    }
     if (!attn_generic_only() && g.Lq <= 32 && g.Lk <= 32 && d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && lddq % 2 == 0 &&
         lddk % 2 == 0 && lddv % 2 == 0 && ((uintptr_t)Q % 8 == 0) && ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) &&
         ((uintptr_t)dO % 8 == 0) && ((uintptr_t)dQ % 8 == 0) && ((uintptr_t)dK % 8 == 0) && ((uintptr_t)dV % 8 == 0)) {
