@@ -132,7 +132,10 @@ int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm,
  * (no im2col matrix).  Replaces the 18 ResnetBlock convs (model/ResNetAutoEncoder.py:138,151) + their BN/ReLU/residual.
  * Returns -3 (unsupported) when H x W does not tile into 128-pixel boxes; callers then use vptr_im2col + vptr_gemm_tf32. */
 int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
-                      const float* residual, int act, int flags, vptr_stream_t stream);
+                      const float* residual, int act, int flags, int w_planes /* 1, or 2 = [hi|lo] tf32 weight split */,
+                      vptr_stream_t stream);
+/* out[r] = [ rna_tf32(w[r]) | rna_tf32(w[r] - hi) ]: the two tf32 planes of a weight matrix (rows of K -> rows of 2K) */
+int vptr_split_tf32(const float* w, float* out, long long rows, long long K, vptr_stream_t stream);
 int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, int C, int pad, int pad_mode, int round_tf32, vptr_stream_t stream);
 
 /* ---- ResNet encoder / decoder (model/ResNetAutoEncoder.py:26-48,70-98) ---------------------------------- */

@@ -98,6 +98,12 @@ def test_implicit_gemm_conv3x3(Fr, H, W, Ci, Co, mode):
     xpad = ops.pad_nhwc(x, Fr, H, W, Ci, 1, ops.PAD_MODES[mode], round_tf32=False)
     wpk = ops.pack_conv_weight(w, None, 0).view(Co, 9 * Ci)
     y = ops.conv3x3_tf32(xpad, wpk, Fr, H, W, Ci, Co, bias=bias, residual=res, act=ops.ACT_RELU)
+    # weight-split variant on NON-tf32-exact weights: the [hi|lo] planes make the weights exact to ~2^-22
+    w2 = torch.randn(Co, Ci, 3, 3, device="cuda") * 0.25
+    y2 = ops.conv3x3_tf32(xpad, ops.split_tf32(ops.pack_conv_weight(w2, None, 0).view(Co, 9 * Ci)), Fr, H, W, Ci, Co, w_planes=2)
+    xn2 = x.view(Fr, H, W, Ci).permute(0, 3, 1, 2).double()
+    xp2 = F.pad(xn2, (1,) * 4, mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
+    assert rel_l2(y2, F.conv2d(xp2, w2.double()).permute(0, 2, 3, 1).reshape(-1, Co)) < 3e-5
     xn = x.view(Fr, H, W, Ci).permute(0, 3, 1, 2).double()
     xp = F.pad(xn, (1,) * 4, mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
     ref = torch.relu(F.conv2d(xp, w.double(), bias.double())).permute(0, 2, 3, 1).reshape(-1, Co) + res.double()

@@ -46,7 +46,8 @@ _SIGS = {
     "vptr_pad_crop": ([P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_sqnorm_accumulate": ([P, L, P, P], I),
     "vptr_clip_scale": ([P, L, P, F, P], I),
-    "vptr_conv3x3_tf32": ([P, P, P, I, I, I, I, I, P, P, I, I, P], I),
+    "vptr_conv3x3_tf32": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
+    "vptr_split_tf32": ([P, P, L, L, P], I),
     "vptr_pad_nhwc": ([P, P, I, I, I, I, I, I, I, P], I),
     "vptr_im2col": ([P, P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_convT_gather": ([P, P, P, I, I, I, I, I, P], I),

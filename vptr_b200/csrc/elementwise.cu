@@ -55,6 +55,18 @@ __global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict
     }
 }
 
+// out[r][0:K] = rna_tf32(w[r][:]) ; out[r][K:2K] = rna_tf32(w[r][:] - hi)   ("2xTF32" split of a weight matrix, rows of K)
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, long long rows, long long K) {
+    const long long total = rows * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K, c = i - r * K;
+        const float v = w[i];
+        const float hi = vptr_round_tf32(v);
+        out[r * 2 * K + c] = hi;
+        out[r * 2 * K + K + c] = vptr_round_tf32(v - hi);
+    }
+}
+
 // DropPath keep-scales per sample: 0 with probability p else 1/(1-p) (drop_path, VidHRFormer_modules.py:563-575)
 __global__ void droppath_scales_kernel(float* __restrict__ out, int n, unsigned long long seed, float p) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +237,11 @@ extern "C" int vptr_round_copy(const float* x, float* y, long long n, int do_rou
     VPTR_REQUIRE(rowscale == nullptr || (group_elems > 0 && group_elems % 4 == 0), VPTR_ERR_SHAPE, "vptr_round_copy: group_elems=%lld", group_elems);
     round_copy_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, do_round, rowscale, group_elems, drop_seed, drop_p);
     return vptr_check_launch("round_copy_kernel");
+}
+extern "C" int vptr_split_tf32(const float* w, float* out, long long rows, long long K, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_split_tf32: rows=%lld K=%lld", rows, K);
+    split_tf32_kernel<<<ew_grid(rows * K, 256), 256, 0, stream>>>(w, out, rows, K);
+    return vptr_check_launch("split_tf32_kernel");
 }
 extern "C" int vptr_droppath_scales(float* out, int n, unsigned long long seed, float p, cudaStream_t stream) {
     VPTR_REQUIRE(n > 0 && p >= 0.f && p < 1.f, VPTR_ERR_SHAPE, "vptr_droppath_scales: n=%d p=%g", n, p);

@@ -590,7 +590,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                     if (!A_MN && p.conv_taps) {
                         // implicit GEMM: k-chunk kc = (tap, 32-channel slice); the A tile is the tap-shifted window of the padded
                         // NHWC activation, fetched as one 4-D box {32 ch, W, bh rows, bf frames} = 128 output pixels
-                        const int tap = kc / p.conv_cpt, cs = kc - tap * p.conv_cpt;
+                        const int kk = kc % (p.conv_taps * p.conv_cpt);            // weight-split planes reuse the same A tiles
+                        const int tap = kk / p.conv_cpt, cs = kk - tap * p.conv_cpt;
                         const int kh = tap / p.conv_kw, kw = tap - kh * p.conv_kw;
                         const int t = m_pair * 2 + (int)rank;                   // 128-pixel tile index
                         const int f0 = p.conv_bf > 1 ? t * p.conv_bf : t / p.conv_tiles_per_frame;
@@ -604,7 +605,12 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                             tma_load_2d_2cta(&tma_a, &full_bar[stage], sA + g * 4096, m0 + g * 32, kc * BLOCK_K);
                     }
                     if (!B_MN) {
-                        const int kcol = p.conv_taps ? (kc / p.conv_cpt) * p.conv_C + (kc % p.conv_cpt) * BLOCK_K : kc * BLOCK_K;
+                        int kcol = kc * BLOCK_K;
+                        if (p.conv_taps) {
+                            const int per_plane = p.conv_taps * p.conv_cpt;
+                            const int plane = kc / per_plane, kk = kc - plane * per_plane;
+                            kcol = plane * p.conv_taps * p.conv_C + (kk / p.conv_cpt) * p.conv_C + (kk % p.conv_cpt) * BLOCK_K;
+                        }
                         tma_load_2d_2cta(&tma_b, &full_bar[stage], sB, kcol, n0);
                     } else {
 #pragma unroll
@@ -874,8 +880,12 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
 // xpad: NHWC activation already padded by 1 (zero / reflect / replicate: vptr_pad_nhwc) [F][H+2][W+2][C]; w: [Cout][9*C]
 // (vptr_pack_conv_weight mode 0).  No im2col matrix is materialised: each k-chunk's A tile is a 4-D TMA box of xpad.
 // Returns VPTR_ERR_UNSUPPORTED when the grid does not tile into 128-pixel boxes (caller falls back to im2col + vptr_gemm_tf32).
+// w_planes = 2: w is [Cout][2][9*C] = tf32 hi part followed by the tf32 lo part of each weight (vptr_split_tf32): the contraction
+// runs over both planes (2x the MMA work), which removes the weight-rounding half of the tf32 error (used by the frozen encoder,
+// whose 21 chained convolutions otherwise land at 1.16e-3 relative, just outside the 1e-3 gate).
 extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
-                                 const float* residual, int act, int flags, cudaStream_t stream) {
+                                 const float* residual, int act, int flags, int w_planes, cudaStream_t stream) {
+    VPTR_REQUIRE(w_planes == 1 || w_planes == 2, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32: w_planes must be 1 or 2");
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32: empty problem");
     VPTR_REQUIRE(C % 4 == 0 && Cout % 4 == 0 && ((uintptr_t)xpad % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
@@ -897,7 +907,7 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     p.m_tiles = (int)((tiles + 1) / 2);
     p.n_tiles = vptr_cdiv(Cout, 176);
     p.conv_cpt = vptr_cdiv(C, BLOCK_K);
-    p.total_chunks = 9 * p.conv_cpt;
+    p.total_chunks = w_planes * 9 * p.conv_cpt;
     p.k_splits = 1; p.chunks_per_split = p.total_chunks;
     p.D = out; p.ldd = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout;
     p.alpha = 1.f; p.act = act; p.flags = flags;
@@ -909,7 +919,7 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     CUtensorMap ma, mb;
     int rc = make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf);
     if (rc) return rc;
-    rc = make_map_2d(&mb, w, 9LL * C, Cout, 9LL * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     return launch_gemm_2cta<176, 0, 0, 7>(ma, mb, p, stream);
 }

@@ -299,9 +299,19 @@ def conv3x3_implicit_ok(H, W):
     return 128 % W == 0 and H % (128 // W) == 0
 
 
-def conv3x3_tf32(xpad, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NONE, round_tf32=False):
+def conv3x3_tf32(xpad, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NONE, round_tf32=False, w_planes=1):
+    """w: [Cout][9C] (w_planes=1) or the [hi|lo] tf32 split [Cout][2*9C] from split_tf32 (w_planes=2)"""
     out = torch.empty(F * H * W, Cout, dtype=torch.float32, device=xpad.device)
-    _call("vptr_conv3x3_tf32", _p(xpad), _p(w), _p(out), F, H, W, C, Cout, _p(bias), _p(residual), int(act), 2 if round_tf32 else 0, _s())
+    _call("vptr_conv3x3_tf32", _p(xpad), _p(w), _p(out), F, H, W, C, Cout, _p(bias), _p(residual), int(act), 2 if round_tf32 else 0,
+          int(w_planes), _s())
+    return out
+
+
+def split_tf32(w):
+    """[rows][K] -> [rows][2K]: tf32 hi plane followed by the tf32 lo plane"""
+    rows, K = w.shape
+    out = torch.empty(rows, 2 * K, dtype=torch.float32, device=w.device)
+    _call("vptr_split_tf32", _p(w), _p(out), rows, K, _s())
     return out
 
 
