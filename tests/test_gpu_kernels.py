@@ -245,10 +245,11 @@ def test_convT_gather_and_backward():
     assert rel_l2(dx, xr.grad) < TOL
 
 
-@pytest.mark.parametrize("Ci", [1, 3])
-def test_stem_and_head(Ci):
+@pytest.mark.parametrize("Ci,H,W", [(1, 32, 24), (3, 32, 24), (1, 64, 64), (3, 16, 32), (1, 40, 16)])
+def test_stem_and_head(Ci, H, W):
+    """W in {16, 32, 64} takes the ring-buffered head kernel (head_conv7x7_p_kernel), other widths the direct one"""
     from vptr_b200 import ops
-    Fr, H, W = 2, 32, 24
+    Fr = 2
     x = rnd(Fr, Ci, H, W, seed=1)
     w = rnd(64, Ci, 7, 7, seed=2) * 0.1
     scale, shift = rnd(64, seed=3) * 0.1 + 1, rnd(64, seed=4) * 0.1

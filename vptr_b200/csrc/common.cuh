@@ -39,19 +39,30 @@ __device__ __forceinline__ float vptr_round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-// Counter-based RNG for dropout / DropPath: splitmix64 of (seed, element index) -> uniform [0,1).  Stateless, so the
-// backward pass regenerates the very mask the forward used instead of storing it.
-__device__ __forceinline__ float vptr_uniform(unsigned long long seed, unsigned long long idx) {
-    unsigned long long z = idx * 0x9E3779B97F4A7C15ULL + seed;
+// Counter-based RNG for dropout / DropPath: ONE splitmix64 hash per group of four consecutive elements, 16 random bits per
+// element (the fused sites are float4-vectorised, and a hash per element made the 4-warp GEMM epilogue compute-bound).
+// Stateless, so the backward pass regenerates the very mask the forward used instead of storing it.
+__device__ __forceinline__ unsigned long long vptr_hash4(unsigned long long seed, unsigned long long idx4) {
+    unsigned long long z = idx4 * 0x9E3779B97F4A7C15ULL + seed;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    return (float)(z >> 40) * (1.0f / 16777216.0f);
+    return z ^ (z >> 31);
 }
+__device__ __forceinline__ unsigned vptr_drop_threshold(float p) { return (unsigned)(p * 65536.f); }
 // dropout keep-scale of element idx: 0 with probability p, else 1/(1-p)  (p == 0 -> 1)
 __device__ __forceinline__ float vptr_drop_scale(unsigned long long seed, unsigned long long idx, float p) {
     if (p <= 0.f) return 1.f;
-    return vptr_uniform(seed, idx) >= p ? 1.f / (1.f - p) : 0.f;
+    const unsigned r = (unsigned)(vptr_hash4(seed, idx >> 2) >> (16 * (unsigned)(idx & 3))) & 0xFFFFu;
+    return r >= vptr_drop_threshold(p) ? 1.f / (1.f - p) : 0.f;
+}
+// keep-scales of elements 4*idx4 .. 4*idx4+3 (identical to four vptr_drop_scale calls, one hash)
+__device__ __forceinline__ float4 vptr_drop_scale4(unsigned long long seed, unsigned long long idx4, float p) {
+    if (p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
+    const unsigned long long z = vptr_hash4(seed, idx4);
+    const unsigned thr = vptr_drop_threshold(p), lo = (unsigned)z, hi = (unsigned)(z >> 32);
+    const float inv = 1.f / (1.f - p);
+    return make_float4((lo & 0xFFFFu) >= thr ? inv : 0.f, (lo >> 16) >= thr ? inv : 0.f, (hi & 0xFFFFu) >= thr ? inv : 0.f,
+                       (hi >> 16) >= thr ? inv : 0.f);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -42,9 +42,8 @@ __global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(x)[i];
         if (p > 0.f) {
-            const unsigned long long e = (unsigned long long)i * 4;
-            v.x *= vptr_drop_scale(seed, e, p); v.y *= vptr_drop_scale(seed, e + 1, p);
-            v.z *= vptr_drop_scale(seed, e + 2, p); v.w *= vptr_drop_scale(seed, e + 3, p);
+            const float4 k = vptr_drop_scale4(seed, (unsigned long long)i, p);
+            v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
         }
         if (rowscale) {
             const float rs = __ldg(rowscale + (i * 4) / group_elems);
@@ -89,9 +88,8 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__
         float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 o = make_float4(vptr_gelu(v.x), vptr_gelu(v.y), vptr_gelu(v.z), vptr_gelu(v.w));
         if (p > 0.f) {
-            const unsigned long long e = (unsigned long long)i * 4;
-            o.x *= vptr_drop_scale(seed, e, p); o.y *= vptr_drop_scale(seed, e + 1, p);
-            o.z *= vptr_drop_scale(seed, e + 2, p); o.w *= vptr_drop_scale(seed, e + 3, p);
+            const float4 k = vptr_drop_scale4(seed, (unsigned long long)i, p);
+            o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
         }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
         reinterpret_cast<float4*>(y)[i] = o;
@@ -104,9 +102,8 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
         float4 v = reinterpret_cast<const float4*>(x)[i];
         float4 o = make_float4(g.x * vptr_gelu_grad(v.x), g.y * vptr_gelu_grad(v.y), g.z * vptr_gelu_grad(v.z), g.w * vptr_gelu_grad(v.w));
         if (p > 0.f) {
-            const unsigned long long e = (unsigned long long)i * 4;
-            o.x *= vptr_drop_scale(seed, e, p); o.y *= vptr_drop_scale(seed, e + 1, p);
-            o.z *= vptr_drop_scale(seed, e + 2, p); o.w *= vptr_drop_scale(seed, e + 3, p);
+            const float4 k = vptr_drop_scale4(seed, (unsigned long long)i, p);
+            o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
         }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
         reinterpret_cast<float4*>(dx)[i] = o;

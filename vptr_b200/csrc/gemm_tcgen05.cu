@@ -41,7 +41,9 @@ struct GemmParams {
     unsigned long long drop_seed;  // elementwise nn.Dropout on the branch (drop1/drop3, VidHRFormer_modules.py:53-55)
     float drop_p;
     // implicit-GEMM 3x3 convolution (A = 4-D TMA view of the padded NHWC activation): 0 = plain GEMM
-    int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C;
+    int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C, conv_a3d, conv_hp;
+    int conv_w8;       // W == 8 implicit conv (conv3x3_w8_kernel): tile rows are ordered (oh, frame, ow) -- see epi_row()
+    int conv_planes;
     long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
 };
 
@@ -168,15 +170,22 @@ __device__ __noinline__ float4 epilogue_options(const GemmParams& p, float4 o, i
         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
     if (p.drop_p > 0.f) {
-        const unsigned long long e = (unsigned long long)m * p.N + n;
-        o.x *= vptr_drop_scale(p.drop_seed, e, p.drop_p); o.y *= vptr_drop_scale(p.drop_seed, e + 1, p.drop_p);
-        o.z *= vptr_drop_scale(p.drop_seed, e + 2, p.drop_p); o.w *= vptr_drop_scale(p.drop_seed, e + 3, p.drop_p);
+        const float4 k = vptr_drop_scale4(p.drop_seed, ((unsigned long long)m * p.N + n) >> 2, p.drop_p);   // N % 4 == 0, n % 4 == 0
+        o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
     }
     if (p.rowscale) {
         const float rs = __ldg(p.rowscale + m / p.rows_per_group);
         o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
     }
     return o;
+}
+// Output row of accumulator row `rr` of the warp whose 32-row block starts at m_base.  Plain GEMM: m_base + rr.  W == 8 implicit
+// conv: the 128 rows of a CTA tile are ordered (oh, frame-in-tile, ow) so that every 8-row UMMA group is one image row and the
+// groups are a constant 10 padded pixels apart in the raw shared-memory tile (conv3x3_w8_kernel).
+__device__ __forceinline__ int epi_row(const GemmParams& p, int m_base, int rr) {
+    if (!p.conv_w8) return m_base + rr;
+    const int L = (m_base & 127) + rr, g = L >> 3;
+    return (m_base & ~127) + (g & 1) * 64 + (g >> 1) * 8 + (L & 7);
 }
 template <int NCOLS>
 __device__ __forceinline__ float4 load_bias(const GemmParams& p, int lane, int n_base) {
@@ -190,17 +199,34 @@ __device__ __forceinline__ void load_residual(const GemmParams& p, int lane, int
     const int r_in = lane / CM::LPR, n = n_base + (lane % CM::LPR) * 4;
 #pragma unroll
     for (int it = 0; it < CM::ITERS; ++it) {
-        const int m = m_base + it * CM::RPI + r_in;
+        const int m = epi_row(p, m_base, it * CM::RPI + r_in);
         res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.residual && n < p.N && m < p.M) res[it] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
     }
 }
 // MODE (compile time, so the unrolled store loop carries no per-element flag tests -- the epilogue warps run one per scheduler
 // and are latency-bound, every branch costs): 0 plain store, 1 store rounded to tf32, 2 split-K reduction (red.add), 3 all
-// options (activation / dropout / DropPath scale, out of line).
+// options (activation / dropout / DropPath scale, out of line), 4 DropPath row scale (inline), 5 dropout (+ row scale) inline.
+// Modes 4/5 exist because the out-of-line path made the regularised out-proj / linear2 GEMMs 3x slower than the plain ones
+// (234-245 us vs 81 us at M=40960 N=K=528, tools/bench_conv.py); rounding to tf32 is a runtime flag in modes 3-5.
+struct RowScale {   // DropPath keep-scales of a warp's 32 rows: at most two clips when rows_per_group >= 32
+    float s0, s1;
+    int boundary;   // first row of the second clip
+};
+__device__ __forceinline__ RowScale load_rowscale(const GemmParams& p, int m_base) {
+    RowScale r{1.f, 1.f, 0x7fffffff};
+    if (p.rowscale) {
+        const int g0 = m_base / p.rows_per_group;
+        const int last = (p.M - 1) / p.rows_per_group;
+        r.s0 = __ldg(p.rowscale + min(g0, last));
+        r.s1 = __ldg(p.rowscale + min(g0 + 1, last));
+        r.boundary = (g0 + 1) * p.rows_per_group;
+    }
+    return r;
+}
 template <int NCOLS, int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, float* sT, int lane, int m_base, int n_base,
-                                               const float4 bias, const float4 (&res)[8]) {
+                                               const float4 bias, const float4 (&res)[8], const RowScale rsc) {
     using CM = ChunkMap<NCOLS>;
 #pragma unroll
     for (int j = 0; j < NCOLS; j += 4)
@@ -208,20 +234,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     __syncwarp();
     const int r_in = lane / CM::LPR, c = (lane % CM::LPR) * 4;
     const int n = n_base + c;
-    const int rows_ok = (n < p.N) ? p.M - m_base - r_in : 0;          // rows of this lane's column group that exist (N % 4 == 0)
-    float* dcol = p.D + (long long)(m_base + r_in) * p.ldd + n;
-    const long long dstep = (long long)CM::RPI * p.ldd;
 #pragma unroll
     for (int it = 0; it < CM::ITERS; ++it) {
-        if (it * CM::RPI < rows_ok) {
+        const int m = epi_row(p, m_base, it * CM::RPI + r_in);
+        if (n < p.N && m < p.M) {
             float4 o = *reinterpret_cast<const float4*>(sT + (it * CM::RPI + r_in) * EPI_PITCH + c);
             o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
-            if (MODE == 3) o = epilogue_options(p, o, m_base + it * CM::RPI + r_in, n);
+            if (MODE == 3) o = epilogue_options(p, o, m, n);
+            if (MODE == 5) {   // (no activation in this mode)
+                const float4 k = vptr_drop_scale4(p.drop_seed, ((unsigned long long)m * p.N + n) >> 2, p.drop_p);
+                o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+            }
+            if (MODE == 4 || MODE == 5) {
+                if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                const float rs = m < rsc.boundary ? rsc.s0 : rsc.s1;
+                o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
+            }
             o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w;
-            if (MODE == 1 || (MODE == 3 && (p.flags & 2))) {
+            if (MODE == 1 || (MODE >= 3 && (p.flags & 2))) {
                 o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
             }
-            float* d = dcol + it * dstep;
+            float* d = p.D + (long long)m * p.ldd + n;
             if (MODE == 2)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             else
@@ -242,6 +275,7 @@ __device__ __forceinline__ void epilogue_tile_mode(const GemmParams& p, uint32_t
     float4 res[8];
     float4 bias = load_bias<32>(p, lane, n0);
     load_residual<32>(p, lane, m_base, n0, res);
+    const RowScale rsc = (MODE == 4 || MODE == 5) ? load_rowscale(p, m_base) : RowScale{1.f, 1.f, 0x7fffffff};
     wait_full();
 #pragma unroll 1
     for (int c = 0; c < NFULL; ++c) {
@@ -259,19 +293,23 @@ __device__ __forceinline__ void epilogue_tile_mode(const GemmParams& p, uint32_t
             bias = load_bias<16>(p, lane, n0 + (c + 1) * 32);
             load_residual<16>(p, lane, m_base, n0 + (c + 1) * 32, res);
         }
-        epilogue_chunk<32, MODE>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c);
+        epilogue_chunk<32, MODE>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c, rsc);
     }
     if (TAIL) {
         float v[16];
         tmem_ld16(taddr + NFULL * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<16, MODE>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res);
+        epilogue_chunk<16, MODE>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res, rsc);
     }
 }
 template <int BLOCK_N, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0, WaitFn wait_full) {
     const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+    const bool inline_ok = (p.act == 0 || p.act == 2) && (p.rowscale == nullptr || (p.rows_per_group >= 32 && !p.conv_w8));
     if (p.flags & 1) epilogue_tile_mode<BLOCK_N, 2>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok && p.drop_p > 0.f && p.act == 0) epilogue_tile_mode<BLOCK_N, 5>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok && p.drop_p <= 0.f) epilogue_tile_mode<BLOCK_N, 4>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok) epilogue_tile_mode<BLOCK_N, 4>(p, taddr, sT, lane, m_base, n0, wait_full);
     else if (fancy) epilogue_tile_mode<BLOCK_N, 3>(p, taddr, sT, lane, m_base, n0, wait_full);
     else if (p.flags & 2) epilogue_tile_mode<BLOCK_N, 1>(p, taddr, sT, lane, m_base, n0, wait_full);
     else epilogue_tile_mode<BLOCK_N, 0>(p, taddr, sT, lane, m_base, n0, wait_full);
@@ -495,6 +533,14 @@ __device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* map, uint64_
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                  "h"((uint16_t)3)
@@ -596,6 +642,11 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                         const int t = m_pair * 2 + (int)rank;                   // 128-pixel tile index
                         const int f0 = p.conv_bf > 1 ? t * p.conv_bf : t / p.conv_tiles_per_frame;
                         const int oh0 = p.conv_bf > 1 ? 0 : (t - f0 * p.conv_tiles_per_frame) * p.conv_bh;
+                        if (p.conv_a3d) {   // experiment: bf 3-D boxes {32 ch, W, bh} over [C][Wp][F*Hp] instead of one 4-D box
+                            for (int i = 0; i < p.conv_bf; ++i)
+                                tma_load_3d_2cta(&tma_a, &full_bar[stage], sA + i * (Cfg::A_BYTES / p.conv_bf), cs * BLOCK_K, kw,
+                                                 (f0 + i) * p.conv_hp + oh0 + kh);
+                        } else
                         tma_load_4d_2cta(&tma_a, &full_bar[stage], sA, cs * BLOCK_K, kw, oh0 + kh, f0);
                     } else if (!A_MN) {
                         tma_load_2d_2cta(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m0);
@@ -699,6 +750,167 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     }
 }
 
+
+// =============================================================================================
+// Implicit-GEMM 3x3 stride-1 convolution for W == 8 feature grids (the 8x8 ResnetBlock grid of every 64x64 config).
+// Feeding each (tap, 32-channel slice) k-chunk with its own 4-D TMA box (the generic path above) makes TMA the limit: boxes of
+// 8-pixel runs cost ~6 cycles per 128-byte row, 943 cycles per k-chunk against 352 cycles of MMA (tools/bench_conv.py).  Here
+// the RAW padded tile of a channel slice -- {32 ch, 10 w, 2 frames, 10 h} = 200 padded pixels x 128 B, stored [h][frame][w] --
+// is loaded ONCE and all 9 taps (x weight planes) read it in place: the A descriptor of tap (kh,kw) starts kh*20+kw rows into
+// the tile, every 8-row UMMA group is one image row (8 consecutive padded pixels), and consecutive groups (oh, frame) are a
+// constant 10 rows = 1280 B apart (SBO).  Operand traffic through TMA drops from 9 x 16 KB to 25.6 KB per channel slice;
+// only the weight chunks stream through the mbarrier ring.  Tile rows are therefore ordered (oh, frame, ow): epi_row().
+constexpr int CW_BSTAGES = 10;
+constexpr int CW_A_BYTES = 200 * 128;          // raw tile of one CTA (2 frames)
+constexpr int CW_B_BYTES = 88 * 128;           // half of a 176-row weight chunk
+constexpr int CW_SMEM_BYTES = 2 * CW_A_BYTES + CW_BSTAGES * CW_B_BYTES + 256 + 4 * 32 * EPI_PITCH * 4 + 1024;
+static_assert(CW_A_BYTES % 1024 == 0 && CW_B_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+static_assert(CW_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv3x3_w8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    constexpr int BLOCK_N = 176;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sAraw = smem;
+    uint8_t* sBring = smem + 2 * CW_A_BYTES;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(sBring + CW_BSTAGES * CW_B_BYTES);
+    uint64_t* b_empty = b_full + CW_BSTAGES;
+    uint64_t* a_full = b_empty + CW_BSTAGES;
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* tmem_full = a_empty + 2;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_tiles = reinterpret_cast<float*>(sBring + CW_BSTAGES * CW_B_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int chunks_per_slice = p.conv_planes * 9;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < CW_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_full[a], 1);
+            mbar_init(&a_empty[a], 1);
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {   // ===== TMA producer (both CTAs) =====
+        int bs = 0, ab = 0;
+        uint32_t bphase = 0, aphase = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+            const int f0 = (m_pair * 2 + (int)rank) * 2;                       // first of this CTA's two frames
+            const int n0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
+            for (int cs = 0; cs < p.conv_cpt; ++cs) {
+                mbar_wait(&a_empty[ab], aphase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&a_full[ab], 2 * CW_A_BYTES);
+                    tma_load_4d_2cta(&tma_a, &a_full[ab], sAraw + ab * CW_A_BYTES, cs * BLOCK_K, 0, f0, 0);   // dims (c, w, frame, h)
+                }
+                __syncwarp();
+                if (++ab == 2) { ab = 0; aphase ^= 1; }
+                for (int j = 0; j < chunks_per_slice; ++j) {                   // j = plane * 9 + tap
+                    mbar_wait(&b_empty[bs], bphase ^ 1);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * CW_B_BYTES);
+                        tma_load_2d_2cta(&tma_b, &b_full[bs], sBring + bs * CW_B_BYTES, j * p.conv_C + cs * BLOCK_K, n0);
+                    }
+                    __syncwarp();
+                    if (++bs == CW_BSTAGES) { bs = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {   // ===== MMA issuer (leader CTA) =====
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((2 * BLOCK_M) >> 4) << 24);
+            int bs = 0, ab = 0, acc = 0;
+            uint32_t bphase = 0, aphase = 0, acc_phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 0] = clock64();
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 1] = clock64();
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int cs = 0; cs < p.conv_cpt; ++cs) {
+                    mbar_wait(&a_full[ab], aphase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(sAraw + ab * CW_A_BYTES);
+                    for (int j = 0; j < chunks_per_slice; ++j) {
+                        const int tap = j % 9, kh = tap / 3, kw = tap - kh * 3;
+                        const uint32_t a_tap = a_base + uint32_t(kh * 20 + kw) * 128u;        // [h][frame][w] rows of 128 B
+                        mbar_wait(&b_full[bs], bphase);
+                        tcgen05_fence_after();
+                        const uint32_t b_base = smem_u32(sBring + bs * CW_B_BYTES);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                // the start is NOT on the 1024-byte swizzle repeat; the hardware swizzle is a function of the absolute
+                                // shared-memory address (like TMA's), so the descriptor's base-offset field stays 0 (measured: setting it
+                                // to (addr >> 7) & 7 gives wrong results, tools/bench_conv.py)
+                                const uint64_t da = make_smem_desc(a_tap + k * 32, 16, 1280, 2);
+                                const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024, 2);
+                                umma_tf32_2cta(d_tmem, da, db, idesc, (cs > 0 || j > 0 || k > 0) ? 1u : 0u);
+                            }
+                            umma_commit_2cta(&b_empty[bs]);
+                            if (j == chunks_per_slice - 1) umma_commit_2cta(&a_empty[ab]);
+                        }
+                        __syncwarp();
+                        if (++bs == CW_BSTAGES) { bs = 0; bphase ^= 1; }
+                    }
+                    if (++ab == 2) { ab = 0; aphase ^= 1; }
+                }
+                if (elect_one()) umma_commit_2cta(&tmem_full[acc]);
+                __syncwarp();
+                if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 2] = clock64();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {   // ===== epilogue warps 2..5 of both CTAs =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+            const int m_base = (m_pair * 2 + (int)rank) * BLOCK_M + q * 32;
+            float* sT = epi_tiles + (warp - 2) * 32 * EPI_PITCH;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+            });
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -738,7 +950,8 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long o
 }
 
 // 4-D fp32 tensor map over a padded NHWC activation [F][Hp][Wp][C]: box {32 channels, bw, bh, bf}
-int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, int bf) {
+int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, int bf,
+                  bool no_promo = false) {
     EncodeTiledFn enc = get_encode_fn();
     VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)F};
@@ -746,10 +959,38 @@ int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp,
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bf};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     no_promo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): F=%lld Hp=%lld Wp=%lld C=%lld box=%dx%dx%d", (int)r,
                  F, Hp, Wp, C, bw, bh, bf);
+    return VPTR_OK;
+}
+// 3-D variant: [C][Wp][F*Hp], box {32 channels, bw, bh}
+int make_map_nhwc3(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, bool no_promo) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)(Hp * F)};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)Wp * C * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)bw, (cuuint32_t)bh};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     no_promo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+    return VPTR_OK;
+}
+
+// W == 8 raw-tile map: dims ordered (c, w, frame, h) so the box {32, 10, 2, 10} lands in shared memory as [h][frame][w][32 ch]
+int make_map_nhwc_w8(CUtensorMap* map, const float* ptr, long long F, long long C) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, 10, (cuuint64_t)F, 10};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)100 * C * 4, (cuuint64_t)10 * C * 4};
+    cuuint32_t box[4] = {32, 10, 2, 10};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(w8) failed (%d): F=%lld C=%lld", (int)r, F, C);
     return VPTR_OK;
 }
 
@@ -845,6 +1086,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 0; p.conv_cpt = 1; p.conv_kw = 1; p.conv_bh = 1; p.conv_tiles_per_frame = 1; p.conv_bf = 1; p.conv_C = 0;
+    p.conv_a3d = 0; p.conv_hp = 0; p.conv_w8 = 0; p.conv_planes = 1;
 
     CUtensorMap ma, mb;
     int rc;
@@ -912,12 +1154,35 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     p.D = out; p.ldd = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout;
     p.alpha = 1.f; p.act = act; p.flags = flags;
     p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
-    p.dbg = nullptr;
+    p.dbg = g_gemm_dbg;
     p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = bh; p.conv_tiles_per_frame = tiles_per_frame; p.conv_bf = bf; p.conv_C = C;
+    p.conv_a3d = 0; p.conv_hp = H + 2; p.conv_w8 = 0; p.conv_planes = w_planes;
     // rows of a tile beyond F*H*W (frames past the end) are zero-filled by TMA and masked by the epilogue (m < M) only when tiles
     // map to whole frames in order, which holds for both tilings above.
     CUtensorMap ma, mb;
-    int rc = make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf);
+    static const int a_mode = [] { const char* e = getenv("VPTR_CONV_A"); return e ? atoi(e) : 0; }();
+    if (H == 8 && W == 8 && !(a_mode & 8)) {   // raw-tile kernel: one TMA box per channel slice serves all 9 taps (and both planes)
+        p.conv_w8 = 1; p.conv_planes = w_planes;
+        p.m_tiles = vptr_cdiv(F, 4);           // pair tile = 4 frames = 256 output pixels
+        int rc = make_map_nhwc_w8(&ma, xpad, F, C);
+        if (rc) return rc;
+        rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(conv3x3_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM_BYTES);
+            VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(conv3x3_w8, smem=%d): %s", CW_SMEM_BYTES, cudaGetErrorString(e));
+            attr_set = true;
+        }
+        const int total = p.m_tiles * p.n_tiles;
+        int clusters = num_sms() / 2;
+        if (total < clusters) clusters = total;
+        conv3x3_w8_kernel<<<2 * clusters, NUM_THREADS, CW_SMEM_BYTES, stream>>>(ma, mb, p);
+        return vptr_check_launch("conv3x3_w8_kernel");
+    }
+    p.conv_a3d = (a_mode & 1); p.conv_hp = H + 2;
+    int rc = p.conv_a3d ? make_map_nhwc3(&ma, xpad, F, H + 2, W + 2, C, bw, bh, (a_mode & 2) != 0)
+                        : make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf, (a_mode & 2) != 0);
     if (rc) return rc;
     rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;

@@ -16,9 +16,13 @@ struct DropArgs {
     unsigned long long seed;
     float p;
 };
-__device__ __forceinline__ float drop_factor(const DropArgs& d, long long row, long long e) {
-    float f = vptr_drop_scale(d.seed, (unsigned long long)e, d.p);
-    if (d.rowscale) f *= __ldg(d.rowscale + row / d.rows_per_group);
+// the four consecutive elements e .. e+3 (e % 4 == 0, one row): one hash
+__device__ __forceinline__ float4 drop_factor4(const DropArgs& d, long long row, long long e) {
+    float4 f = vptr_drop_scale4(d.seed, (unsigned long long)e >> 2, d.p);
+    if (d.rowscale) {
+        const float rs = __ldg(d.rowscale + row / d.rows_per_group);
+        f.x *= rs; f.y *= rs; f.z *= rs; f.w *= rs;
+    }
     return f;
 }
 
@@ -240,8 +244,8 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restri
         o.z = vptr_gelu((v.z - m.z) * r.z * g.z + b.z);
         o.w = vptr_gelu((v.w - m.w) * r.w * g.w + b.w);
         if (da.p > 0.f || da.rowscale) {
-            o.x *= drop_factor(da, row, e); o.y *= drop_factor(da, row, e + 1);
-            o.z *= drop_factor(da, row, e + 2); o.w *= drop_factor(da, row, e + 3);
+            const float4 k = drop_factor4(da, row, e);
+            o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
         }
         if (res) {
             float4 q = *reinterpret_cast<const float4*>(res + e);
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(128) bn_act_bwd_pass_a_kernel(const float* __r
         const long long e = row * ch + c;
         const float4 xv = *reinterpret_cast<const float4*>(x + e);
         float4 d = *reinterpret_cast<const float4*>(dy + e);
-        if (drop) { d.x *= drop_factor(da, row, e); d.y *= drop_factor(da, row, e + 1); d.z *= drop_factor(da, row, e + 2); d.w *= drop_factor(da, row, e + 3); }
+        if (drop) { const float4 k = drop_factor4(da, row, e); d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w; }
         float4 xh = make_float4((xv.x - m.x) * r.x, (xv.y - m.y) * r.y, (xv.z - m.z) * r.z, (xv.w - m.w) * r.w);
         d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
         d.z *= vptr_gelu_grad(xh.z * g.z + b.z); d.w *= vptr_gelu_grad(xh.w * g.w + b.w);
@@ -307,7 +311,8 @@ __global__ void __launch_bounds__(512) ln3_act_bwd_pass_a_kernel(const float* __
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i)), b = __ldg(reinterpret_cast<const float4*>(beta + i));
         if (drop) {
             const long long row = e / ch;   // 4 consecutive elements share a row (ch % 4 == 0)
-            d.x *= drop_factor(da, row, e); d.y *= drop_factor(da, row, e + 1); d.z *= drop_factor(da, row, e + 2); d.w *= drop_factor(da, row, e + 3);
+            const float4 k = drop_factor4(da, row, e);
+            d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
         }
         const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
         d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
