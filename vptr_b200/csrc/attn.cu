@@ -763,6 +763,433 @@ __global__ void causal_mask_kernel(int T, unsigned char* mask) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < T * T; e += gridDim.x * blockDim.x) mask[e] = (e % T) > (e / T);
 }
 
+// =============================================================================================
+// Tensor-core path (Lq, Lk <= 32, head_dim in (64, 72]): warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, d += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), which keeps fp32-level accuracy -- the attention core is HBM-bound
+// (AI ~ 4 FLOP/B), so the extra MMAs are free, while the scalar kernels above are shared-memory-latency bound at 4-7x the HBM
+// floor.  One CTA = HPC heads of one batch entry (window / pixel sequence): the HPC*d-float row segments of Q, K, V (and dO) are
+// staged with coalesced float4 loads, then every warp owns one head and keeps S / P / dS and all accumulators in registers:
+//   S = Q K^T (A = Q rows, B = K rows, contraction over d),  P = softmax(scale*S + rpe),  O = P V,
+//   dP = dO V^T,  dS = P o (dP - rowsum(P o dP)),  dV = PD^T dO,  dQ = dS K,  dK = dS^T Q.
+// Contractions over the key index reuse the S accumulator registers directly as the A operand: a k-slot permutation
+// (slot t <-> key 2t, slot t+4 <-> key 2t+1, applied to the B rows as well) makes the m16n8 accumulator layout coincide with
+// the m16k8 operand layout, so P and dS never leave registers for O and dQ.  The transposed products (dV, dK) read P / dS back
+// from a small per-warp shared tile.  Tile row pitches are chosen so every fragment load is bank-conflict free.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(x - __uint_as_float(hi)));
+}
+struct Frag4 { uint32_t hi[4], lo[4]; };
+struct Frag2 { uint32_t hi[2], lo[2]; };
+__device__ __forceinline__ void mma3(float (&d)[4], const Frag4& a, const Frag2& b) {
+    mma_tf32_16x8x8(d, a.lo, b.hi);
+    mma_tf32_16x8x8(d, a.hi, b.lo);
+    mma_tf32_16x8x8(d, a.hi, b.hi);
+}
+
+template <int MT, int NT, int HPC>
+struct MmaCfg {
+    static constexpr int DT = 9;                       // head_dim padded to 72 = 9 k-steps / n-tiles of 8
+    static constexpr int LQP = 16 * MT, LKP = 8 * NT;  // padded tile rows
+    static constexpr int MTK = (LKP + 15) / 16;        // m-tiles over the key index (dV, dK)
+    static constexpr int LP = NT > 2 ? 36 : 20;        // pitch of the per-warp P / dS tiles ([LQP][LP])
+};
+__host__ __device__ inline int mma_pitch(int hpc, int d) {   // tile row pitch (floats): == 4 or 12 (mod 32), multiple of 4
+    int w = hpc * d;
+    w = (w + 3) & ~3;
+    while ((w & 31) != 4 && (w & 31) != 12) w += 4;
+    return w;
+}
+
+// C[i][j] += sum_c A[i][c0 + c] * B[j][c0 + c], c < d (contraction over the head dim; columns >= d are masked on the A side)
+template <int MT, int NT>
+__device__ __forceinline__ void mma_rows_dot(float (&acc)[MT][NT][4], const float* sA, const float* sB, int Cp, int c0, int d, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 9; ++ks) {
+        const int c = ks * 8 + t;
+        const bool ok0 = c < d, ok1 = c + 4 < d;
+        Frag4 a[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const float* r0 = sA + (mt * 16 + g) * Cp + c0 + c;
+            const float* r1 = r0 + 8 * Cp;
+            split_tf32(ok0 ? r0[0] : 0.f, a[mt].hi[0], a[mt].lo[0]);
+            split_tf32(ok0 ? r1[0] : 0.f, a[mt].hi[1], a[mt].lo[1]);
+            split_tf32(ok1 ? r0[4] : 0.f, a[mt].hi[2], a[mt].lo[2]);
+            split_tf32(ok1 ? r1[4] : 0.f, a[mt].hi[3], a[mt].lo[3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float* rb = sB + (nt * 8 + g) * Cp + c0 + c;
+            Frag2 b;
+            split_tf32(rb[0], b.hi[0], b.lo[0]);
+            split_tf32(rb[4], b.hi[1], b.lo[1]);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma3(acc[mt][nt], a[mt], b);
+        }
+    }
+}
+// out[i][c0 + c] = mul * sum_j W[i][j] * T[j][c0 + c] with W in accumulator registers (k-slot permutation), T rows in shared
+// memory; the result is written to dst rows (this head's columns, c < d) as float2.
+template <int MT, int NT>
+__device__ __forceinline__ void mma_regs_times_rows(const float (&W)[MT][NT][4], const float* sT, float* dst, int Cp, int c0, int d, float mul,
+                                                    int g, int t) {
+    Frag4 a[MT][NT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt) {
+            split_tf32(W[mt][kt][0], a[mt][kt].hi[0], a[mt][kt].lo[0]);   // (row g,   key 2t)   -> slot t
+            split_tf32(W[mt][kt][2], a[mt][kt].hi[1], a[mt][kt].lo[1]);   // (row g+8, key 2t)
+            split_tf32(W[mt][kt][1], a[mt][kt].hi[2], a[mt][kt].lo[2]);   // (row g,   key 2t+1) -> slot t+4
+            split_tf32(W[mt][kt][3], a[mt][kt].hi[3], a[mt][kt].lo[3]);   // (row g+8, key 2t+1)
+        }
+#pragma unroll 3
+    for (int n9 = 0; n9 < 9; ++n9) {
+        float o[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < NT; ++kt) {
+            const float* rb = sT + (kt * 8 + 2 * t) * Cp + c0 + n9 * 8 + g;
+            Frag2 b;
+            split_tf32(rb[0], b.hi[0], b.lo[0]);
+            split_tf32(rb[Cp], b.hi[1], b.lo[1]);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) mma3(o[mt], a[mt][kt], b);
+        }
+        const int c = n9 * 8 + 2 * t;
+        if (c < d) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                *reinterpret_cast<float2*>(dst + (mt * 16 + g) * Cp + c0 + c) = make_float2(o[mt][0] * mul, o[mt][1] * mul);
+                *reinterpret_cast<float2*>(dst + (mt * 16 + g + 8) * Cp + c0 + c) = make_float2(o[mt][2] * mul, o[mt][3] * mul);
+            }
+        }
+    }
+}
+// out[j][c0 + c] = mul * sum_i Wt[i][j] * T[i][c0 + c]: Wt = per-warp shared tile [LQP][LP] read transposed, T rows in shared
+// memory (k index = query i, same slot permutation so the T-row loads stay conflict free).  MTK m-tiles over j, KS k-steps over i.
+template <int MTK, int KS>
+__device__ __forceinline__ void mma_smemT_times_rows(const float* Wt, int lp, const float* sT, float* dst, int Cp, int c0, int d, float mul,
+                                                     int g, int t) {
+    Frag4 a[MTK][KS];
+#pragma unroll
+    for (int mk = 0; mk < MTK; ++mk)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const float* w0 = Wt + (ks * 8 + 2 * t) * lp + mk * 16 + g;
+            split_tf32(w0[0], a[mk][ks].hi[0], a[mk][ks].lo[0]);
+            split_tf32(w0[8], a[mk][ks].hi[1], a[mk][ks].lo[1]);
+            split_tf32(w0[lp], a[mk][ks].hi[2], a[mk][ks].lo[2]);
+            split_tf32(w0[lp + 8], a[mk][ks].hi[3], a[mk][ks].lo[3]);
+        }
+#pragma unroll 3
+    for (int n9 = 0; n9 < 9; ++n9) {
+        float o[MTK][4];
+#pragma unroll
+        for (int mk = 0; mk < MTK; ++mk) o[mk][0] = o[mk][1] = o[mk][2] = o[mk][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const float* rb = sT + (ks * 8 + 2 * t) * Cp + c0 + n9 * 8 + g;
+            Frag2 b;
+            split_tf32(rb[0], b.hi[0], b.lo[0]);
+            split_tf32(rb[Cp], b.hi[1], b.lo[1]);
+#pragma unroll
+            for (int mk = 0; mk < MTK; ++mk) mma3(o[mk], a[mk][ks], b);
+        }
+        const int c = n9 * 8 + 2 * t;
+        if (c < d) {
+#pragma unroll
+            for (int mk = 0; mk < MTK; ++mk) {
+                *reinterpret_cast<float2*>(dst + (mk * 16 + g) * Cp + c0 + c) = make_float2(o[mk][0] * mul, o[mk][1] * mul);
+                *reinterpret_cast<float2*>(dst + (mk * 16 + g + 8) * Cp + c0 + c) = make_float2(o[mk][2] * mul, o[mk][3] * mul);
+            }
+        }
+    }
+}
+
+// coalesced 16-byte staging of `L` row segments [col0, col0 + 4*W4) into a [.][Cp] tile with cp.async (no register staging,
+// all of a thread's requests in flight at once), one warp per row; and the store back (optionally rounded to tf32)
+__device__ __forceinline__ void mma_load_tile(float* tile, int Cp, const float* __restrict__ src, long long ld, const long long* rows, int L,
+                                              int W4, int col0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int l = warp; l < L; l += nw) {
+        const float* r = src + rows[l] * ld + col0;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + l * Cp);
+        for (int c = lane; c < W4; c += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(r + 4 * c) : "memory");
+    }
+}
+__device__ __forceinline__ void mma_load_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void mma_store_tile(const float* tile, int Cp, float* __restrict__ dst, long long ld, const long long* rows, int L,
+                                               int W4, int col0, int round_tf32) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int l = warp; l < L; l += nw) {
+        float4* r = reinterpret_cast<float4*>(dst + rows[l] * ld + col0);
+        const float4* sr = reinterpret_cast<const float4*>(tile + l * Cp);
+        for (int c = lane; c < W4; c += 32) {
+            float4 v = sr[c];
+            if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+            r[c] = v;
+        }
+    }
+}
+// dropout keep-scales of probabilities (b, h, i, j) and (b, h, i, j + 1), j even: one hash when both fall into one group of four
+__device__ __forceinline__ void prob_drop2(const AttnGeom& g, int b, int h, int i, int j, float& k0, float& k1) {
+    const unsigned long long idx = (((unsigned long long)b * g.nhead + h) * g.Lq + i) * g.Lk + j;
+    if (idx & 1) { k0 = vptr_drop_scale(g.drop_seed, idx, g.drop_p); k1 = vptr_drop_scale(g.drop_seed, idx + 1, g.drop_p); return; }
+    const unsigned z = (unsigned)(vptr_hash4(g.drop_seed, idx >> 2) >> (16 * (unsigned)(idx & 3)));
+    const unsigned thr = vptr_drop_threshold(g.drop_p);
+    const float inv = 1.f / (1.f - g.drop_p);
+    k0 = (z & 0xFFFFu) >= thr ? inv : 0.f;
+    k1 = ((z >> 16) & 0xFFFFu) >= thr ? inv : 0.f;
+}
+
+template <int MT, int NT, int HPC, bool BWD>
+__global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
+                                                            const float* __restrict__ V, long long ldv, const float* __restrict__ dO,
+                                                            float* __restrict__ O_or_dQ, long long ldo, float* __restrict__ dK, long long lddk,
+                                                            float* __restrict__ dV, long long lddv, long long lddo,
+                                                            const float* __restrict__ rpe_table, float* __restrict__ d_rpe_table,
+                                                            const AttnGeom g, int batches) {
+    using Cfg = MmaCfg<MT, NT, HPC>;
+    constexpr int LQP = Cfg::LQP, LKP = Cfg::LKP, LP = Cfg::LP;
+    extern __shared__ __align__(16) float sm[];
+    const int Cp = mma_pitch(HPC, g.d);
+    const int W4 = HPC * g.d / 4;
+    float* sq = sm;                                   // [LQP][Cp]   (forward: O is staged over it)
+    float* sk = sq + LQP * Cp;                        // [LKP][Cp]   (backward: dK over it)
+    float* sv = sk + LKP * Cp;                        // [LKP][Cp]   (backward: dV over it)
+    float* sgo = sv + LKP * Cp;                       // [LQP][Cp]   (backward only: dO, dQ over it)
+    float* spw = sgo + (BWD ? LQP * Cp : 0);          // per-warp PD and dS tiles [HPC][2][LQP][LP] (backward only)
+    float* sdb = spw + (BWD ? HPC * 2 * LQP * LP : 0);                   // [HPC][Lq][Lk] bias-gradient accumulator (backward, rpe)
+    float* sbias = sdb + ((BWD && d_rpe_table) ? ((HPC * g.Lq * g.Lk + 1) & ~1) : 0);   // [HPC][LQP][LKP] rpe bias of this CTA's heads
+    // + 8 zero floats: fragment loads of the last head's pad columns run a few floats past the last tile row
+    long long* rq = reinterpret_cast<long long*>(sbias + (rpe_table ? HPC * LQP * LKP : 0) + 8);
+    long long* rk = rq + LQP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+    const int hgroups = g.nhead / HPC;
+    // pad rows / columns are never loaded: zero them once so every product with them is finite (and zero)
+    for (int e = threadIdx.x; e < (int)(reinterpret_cast<float*>(rq) - sm); e += blockDim.x) sm[e] = 0.f;
+    __syncthreads();
+    if (rpe_table) {   // gridDim.x is a multiple of hgroups: all items of this CTA share one head group
+        const int hb = (blockIdx.x % hgroups) * HPC;
+        for (int e = threadIdx.x; e < HPC * g.Lq * g.Lk; e += blockDim.x) {
+            const int w = e / (g.Lq * g.Lk), r = e - w * g.Lq * g.Lk, i = r / g.Lk, j = r - i * g.Lk;
+            sbias[(w * LQP + i) * LKP + j] = __ldg(rpe_table + rel_pos_index(g.ws, i, j) * g.nhead + hb + w);
+        }
+    }
+    __syncthreads();
+    for (int item = blockIdx.x; item < batches * hgroups; item += gridDim.x) {
+        const int b = item / hgroups, h0 = (item - b * hgroups) * HPC;
+        for (int l = threadIdx.x; l < g.Lq; l += blockDim.x) rq[l] = q_row(g, b, l);
+        for (int l = threadIdx.x; l < g.Lk; l += blockDim.x) rk[l] = k_row(g, b, l);
+        __syncthreads();
+        mma_load_tile(sq, Cp, Q, ldq, rq, g.Lq, W4, h0 * g.d);
+        mma_load_tile(sk, Cp, K, ldk, rk, g.Lk, W4, h0 * g.d);
+        mma_load_tile(sv, Cp, V, ldv, rk, g.Lk, W4, h0 * g.d);
+        if (BWD) mma_load_tile(sgo, Cp, dO, lddo, rq, g.Lq, W4, h0 * g.d);
+        mma_load_wait();
+        __syncthreads();
+        {
+            const int h = h0 + warp, c0 = warp * g.d;
+            // ---- S = Q K^T, P = softmax(scale * S + bias) (undropped probabilities)
+            float P[MT][NT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0.f;
+            mma_rows_dot<MT, NT>(P, sq, sk, Cp, c0, g.d, gq, t);
+            float keep[MT][NT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int i = mt * 16 + gq + hh * 8, j = nt * 8 + 2 * t;
+                        float2 bias = make_float2(0.f, 0.f);
+                        if (rpe_table) bias = *reinterpret_cast<const float2*>(sbias + (warp * LQP + i) * LKP + j);   // pad entries are 0
+                        float s0 = fmaf(P[mt][nt][2 * hh], g.scale, bias.x), s1 = fmaf(P[mt][nt][2 * hh + 1], g.scale, bias.y);
+                        if (j >= g.Lk || (g.causal && j > i)) s0 = -INFINITY;
+                        if (j + 1 >= g.Lk || (g.causal && j + 1 > i)) s1 = -INFINITY;
+                        P[mt][nt][2 * hh] = s0;
+                        P[mt][nt][2 * hh + 1] = s1;
+                        mx[hh] = fmaxf(mx[hh], fmaxf(s0, s1));
+                        float k0 = 1.f, k1 = 1.f;
+                        if (g.drop_p > 0.f && i < g.Lq && j < g.Lk) {
+                            prob_drop2(g, b, h, i, j, k0, k1);
+                            if (j + 1 >= g.Lk) k1 = 1.f;
+                        }
+                        keep[mt][nt][2 * hh] = k0;
+                        keep[mt][nt][2 * hh + 1] = k1;
+                    }
+                float sum[2] = {0.f, 0.f};
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+                    mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float e = __expf(P[mt][nt][r] - mx[r >> 1]);
+                        P[mt][nt][r] = e;
+                        sum[r >> 1] += e;
+                    }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+                    sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+                    sum[hh] = 1.f / sum[hh];
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) P[mt][nt][r] *= sum[r >> 1];
+            }
+            if (!BWD) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) P[mt][nt][r] *= keep[mt][nt][r];
+                mma_regs_times_rows<MT, NT>(P, sv, sq, Cp, c0, g.d, 1.f, gq, t);        // O = PD V, staged over this head's Q columns
+            } else {
+                // ---- dP = (dO V^T) * keep ; dS = P * (dP - rowsum(P * dP)) ; PD = P * keep
+                float dS[MT][NT][4];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dS[mt][nt][0] = dS[mt][nt][1] = dS[mt][nt][2] = dS[mt][nt][3] = 0.f;
+                mma_rows_dot<MT, NT>(dS, sgo, sv, Cp, c0, g.d, gq, t);
+                float* PDw = spw + warp * 2 * LQP * LP;
+                float* dSw = PDw + LQP * LP;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    float tsum[2] = {0.f, 0.f};
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            dS[mt][nt][r] *= keep[mt][nt][r];
+                            tsum[r >> 1] = fmaf(P[mt][nt][r], dS[mt][nt][r], tsum[r >> 1]);
+                        }
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        tsum[hh] += __shfl_xor_sync(0xffffffffu, tsum[hh], 1);
+                        tsum[hh] += __shfl_xor_sync(0xffffffffu, tsum[hh], 2);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const float ds = P[mt][nt][r] * (dS[mt][nt][r] - tsum[r >> 1]);
+                            dS[mt][nt][r] = ds;
+                            P[mt][nt][r] *= keep[mt][nt][r];
+                            if (d_rpe_table) {
+                                const int i = mt * 16 + gq + (r >> 1) * 8, j = nt * 8 + 2 * t + (r & 1);
+                                if (i < g.Lq && j < g.Lk) sdb[(warp * g.Lq + i) * g.Lk + j] += ds;
+                            }
+                        }
+                        const int i0 = mt * 16 + gq, j0 = nt * 8 + 2 * t;
+                        *reinterpret_cast<float2*>(PDw + i0 * LP + j0) = make_float2(P[mt][nt][0], P[mt][nt][1]);
+                        *reinterpret_cast<float2*>(PDw + (i0 + 8) * LP + j0) = make_float2(P[mt][nt][2], P[mt][nt][3]);
+                        *reinterpret_cast<float2*>(dSw + i0 * LP + j0) = make_float2(dS[mt][nt][0], dS[mt][nt][1]);
+                        *reinterpret_cast<float2*>(dSw + (i0 + 8) * LP + j0) = make_float2(dS[mt][nt][2], dS[mt][nt][3]);
+                    }
+                }
+                __syncwarp();
+                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(PDw, LP, sgo, sv, Cp, c0, g.d, 1.f, gq, t);      // dV = PD^T dO  -> over V (dead)
+                __syncwarp();
+                mma_regs_times_rows<MT, NT>(dS, sk, sgo, Cp, c0, g.d, g.scale, gq, t);                   // dQ = dS K     -> over dO (dead)
+                __syncwarp();
+                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(dSw, LP, sq, sk, Cp, c0, g.d, g.scale, gq, t);   // dK = dS^T Q   -> over K (dead)
+            }
+        }
+        __syncthreads();
+        if (!BWD) {
+            mma_store_tile(sq, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * g.d, g.round_tf32);
+        } else {
+            mma_store_tile(sv, Cp, dV, lddv, rk, g.Lk, W4, h0 * g.d, g.round_tf32);
+            mma_store_tile(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * g.d, g.round_tf32);
+            mma_store_tile(sk, Cp, dK, lddk, rk, g.Lk, W4, h0 * g.d, g.round_tf32);
+        }
+        __syncthreads();
+    }
+    if (BWD && d_rpe_table) {
+        // the launch makes gridDim.x a multiple of hgroups, so all items of a CTA share one head group
+        // (item % hgroups == blockIdx.x % hgroups) and the accumulator can be flushed once, here
+        const int h0 = (blockIdx.x % hgroups) * HPC;
+        for (int e = threadIdx.x; e < HPC * g.Lq * g.Lk; e += blockDim.x) {
+            const int w = e / (g.Lq * g.Lk), r = e - w * g.Lq * g.Lk;
+            atomicAdd(d_rpe_table + rel_pos_index(g.ws, r / g.Lk, r % g.Lk) * g.nhead + h0 + w, sdb[e]);
+        }
+    }
+}
+
+template <int MT, int NT, int HPC, bool BWD>
+int launch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,
+                    long long ldo, float* dK, long long lddk, float* dV, long long lddv, long long lddo, const float* rpe_table,
+                    float* d_rpe_table, const AttnGeom& g, int batches, cudaStream_t stream) {
+    using Cfg = MmaCfg<MT, NT, HPC>;
+    const int Cp = mma_pitch(HPC, g.d);
+    size_t floats = (size_t)(Cfg::LQP + 2 * Cfg::LKP) * Cp;
+    if (BWD) floats += (size_t)Cfg::LQP * Cp + (size_t)HPC * 2 * Cfg::LQP * Cfg::LP + ((d_rpe_table ? (size_t)HPC * g.Lq * g.Lk + 1 : 0) & ~(size_t)1);
+    if (rpe_table) floats += (size_t)HPC * Cfg::LQP * Cfg::LKP;
+    const size_t smem = (floats + 8) * sizeof(float) + sizeof(long long) * (size_t)(Cfg::LQP + Cfg::LKP);
+    auto kern = attn_mma_kernel<MT, NT, HPC, BWD>;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(attn_mma, smem=%zu): %s", smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    const int hgroups = g.nhead / HPC;
+    const long long items = (long long)batches * hgroups;
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long grid = 148LL * per_sm;
+    grid -= grid % hgroups;                       // a CTA keeps one head group: item % hgroups == blockIdx.x % hgroups
+    if (grid > items) grid = items;               // (items is a multiple of hgroups)
+    kern<<<(int)grid, HPC * 32, smem, stream>>>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g,
+                                                batches);
+    return vptr_check_launch("attn_mma_kernel");
+}
+
+bool attn_mma_disabled() {
+    static const bool v = [] { const char* e = getenv("VPTR_ATTN_NO_MMA"); return e && e[0] == '1'; }();
+    return v;
+}
+// shapes the tensor-core path covers: Lq, Lk <= 32, head_dim in (64, 72] and even, an even number of heads, 16-byte aligned rows
+bool attn_mma_ok(const AttnGeom& g, int nhead, int d) {
+    return !attn_mma_disabled() && g.Lq <= 32 && g.Lk <= 32 && d > 64 && d <= 72 && d % 2 == 0 && nhead % 2 == 0 && (2 * d) % 4 == 0;
+}
+template <bool BWD>
+int dispatch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,
+                      long long ldo, float* dK, long long lddk, float* dV, long long lddv, long long lddo, const float* rpe_table,
+                      float* d_rpe_table, const AttnGeom& g, int batches, cudaStream_t stream) {
+    if (g.Lq <= 16 && g.Lk <= 16) {
+        if (g.nhead % 4 == 0)
+            return launch_attn_mma<1, 2, 4, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
+        return launch_attn_mma<1, 2, 2, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
+    }
+    return launch_attn_mma<2, 4, 2, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
+}
+
 // The lane-per-row "fast" kernels below are EXPERIMENTAL and currently slower than the generic ones at cfg1 sizes (their load /
 // compute / store phases are serialised per warp with too few resident warps to hide global latency: 664 vs 455 us forward,
 // tools/bench_attn.py), so they are opt-in (VPTR_ATTN_FAST=1) until they are software-pipelined.
@@ -807,7 +1234,10 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_fwd: empty problem");
-    {   // main path: one CTA per batch entry, all heads
+    if (attn_mma_ok(g, nhead, d) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)Q % 16 == 0) &&
+        ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0))   // tensor-core path (mma.sync, 3xTF32)
+        return dispatch_attn_mma<false>(Q, ldq, K, ldk, V, ldv, nullptr, O, ldo, nullptr, 0, nullptr, 0, 0, rpe_table, nullptr, g, batches, stream);
+    {   // one CTA per batch entry, all heads (scalar)
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (C + 2) + (((size_t)nhead * g.Lq * (g.Lk + 1) + 1) & ~(size_t)1)) +
                           sizeof(long long) * (size_t)(g.Lq + g.Lk);
@@ -865,7 +1295,11 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_bwd: empty problem");
-    {   // main path: one CTA per batch entry, all heads
+    if (attn_mma_ok(g, nhead, d) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 &&
+        lddv % 4 == 0 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)dO % 16 == 0) &&
+        ((uintptr_t)dQ % 16 == 0) && ((uintptr_t)dK % 16 == 0) && ((uintptr_t)dV % 16 == 0))   // tensor-core path (mma.sync, 3xTF32)
+        return dispatch_attn_mma<true>(Q, ldq, K, ldk, V, ldv, dO, dQ, lddq, dK, lddk, dV, lddv, ldo, rpe_table, d_rpe_table, g, batches, stream);
+    {   // one CTA per batch entry, all heads (scalar)
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (C + 2) + (size_t)2 * nhead * g.Lq * (g.Lk + 1) +
                                            (((size_t)nhead * g.Lq * g.Lk + 1) & ~(size_t)1)) + sizeof(long long) * (size_t)(g.Lq + g.Lk);

@@ -193,13 +193,13 @@ __device__ __forceinline__ float4 load_bias(const GemmParams& p, int lane, int n
     if (p.bias && n < p.N) return __ldg(reinterpret_cast<const float4*>(p.bias + n));
     return make_float4(0.f, 0.f, 0.f, 0.f);
 }
-template <int NCOLS>
+template <int NCOLS, bool PERM>
 __device__ __forceinline__ void load_residual(const GemmParams& p, int lane, int m_base, int n_base, float4 (&res)[8]) {
     using CM = ChunkMap<NCOLS>;
     const int r_in = lane / CM::LPR, n = n_base + (lane % CM::LPR) * 4;
 #pragma unroll
     for (int it = 0; it < CM::ITERS; ++it) {
-        const int m = epi_row(p, m_base, it * CM::RPI + r_in);
+        const int m = PERM ? epi_row(p, m_base, it * CM::RPI + r_in) : m_base + it * CM::RPI + r_in;
         res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.residual && n < p.N && m < p.M) res[it] = *reinterpret_cast<const float4*>(p.residual + (long long)m * p.ldr + n);
     }
@@ -224,7 +224,7 @@ __device__ __forceinline__ RowScale load_rowscale(const GemmParams& p, int m_bas
     }
     return r;
 }
-template <int NCOLS, int MODE>
+template <int NCOLS, int MODE, bool PERM>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* v, float* sT, int lane, int m_base, int n_base,
                                                const float4 bias, const float4 (&res)[8], const RowScale rsc) {
     using CM = ChunkMap<NCOLS>;
@@ -234,10 +234,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
     __syncwarp();
     const int r_in = lane / CM::LPR, c = (lane % CM::LPR) * 4;
     const int n = n_base + c;
+    // plain GEMM: rows are affine in `it` (pointer stepping, one bound); the permuted conv tile recomputes each row
+    const int rows_ok = (n < p.N) ? p.M - m_base - r_in : 0;          // rows of this lane's column group that exist (N % 4 == 0)
+    float* dcol = p.D + (long long)(m_base + r_in) * p.ldd + n;
+    const long long dstep = (long long)CM::RPI * p.ldd;
 #pragma unroll
     for (int it = 0; it < CM::ITERS; ++it) {
-        const int m = epi_row(p, m_base, it * CM::RPI + r_in);
-        if (n < p.N && m < p.M) {
+        const int m = PERM ? epi_row(p, m_base, it * CM::RPI + r_in) : m_base + it * CM::RPI + r_in;
+        if (PERM ? (n < p.N && m < p.M) : (it * CM::RPI < rows_ok)) {
             float4 o = *reinterpret_cast<const float4*>(sT + (it * CM::RPI + r_in) * EPI_PITCH + c);
             o.x += bias.x; o.y += bias.y; o.z += bias.z; o.w += bias.w;
             if (MODE == 3) o = epilogue_options(p, o, m, n);
@@ -254,7 +258,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
             if (MODE == 1 || (MODE >= 3 && (p.flags & 2))) {
                 o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
             }
-            float* d = p.D + (long long)m * p.ldd + n;
+            float* d = PERM ? p.D + (long long)m * p.ldd + n : dcol + it * dstep;
             if (MODE == 2)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             else
@@ -267,14 +271,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float*
 // Whole-tile epilogue of one warp (its 32 accumulator rows, BLOCK_N columns).  Global loads (bias, residual) have 1-3k cycles
 // of latency while TMA keeps the memory system busy, so they are issued early: for chunk 0 before the accumulator-ready wait,
 // for chunk c+1 while chunk c is stored.
-template <int BLOCK_N, int MODE, class WaitFn>
+template <int BLOCK_N, int MODE, bool PERM, class WaitFn>
 __device__ __forceinline__ void epilogue_tile_mode(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0,
                                                    WaitFn wait_full) {
     constexpr int NFULL = BLOCK_N / 32;
     constexpr bool TAIL = (BLOCK_N % 32) != 0;
     float4 res[8];
     float4 bias = load_bias<32>(p, lane, n0);
-    load_residual<32>(p, lane, m_base, n0, res);
+    load_residual<32, PERM>(p, lane, m_base, n0, res);
     const RowScale rsc = (MODE == 4 || MODE == 5) ? load_rowscale(p, m_base) : RowScale{1.f, 1.f, 0x7fffffff};
     wait_full();
 #pragma unroll 1
@@ -288,31 +292,36 @@ __device__ __forceinline__ void epilogue_tile_mode(const GemmParams& p, uint32_t
         for (int i = 0; i < 8; ++i) res_c[i] = res[i];
         if (c + 1 < NFULL) {
             bias = load_bias<32>(p, lane, n0 + (c + 1) * 32);
-            load_residual<32>(p, lane, m_base, n0 + (c + 1) * 32, res);
+            load_residual<32, PERM>(p, lane, m_base, n0 + (c + 1) * 32, res);
         } else if (TAIL) {
             bias = load_bias<16>(p, lane, n0 + (c + 1) * 32);
-            load_residual<16>(p, lane, m_base, n0 + (c + 1) * 32, res);
+            load_residual<16, PERM>(p, lane, m_base, n0 + (c + 1) * 32, res);
         }
-        epilogue_chunk<32, MODE>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c, rsc);
+        epilogue_chunk<32, MODE, PERM>(p, v, sT, lane, m_base, n0 + c * 32, bias_c, res_c, rsc);
     }
     if (TAIL) {
         float v[16];
         tmem_ld16(taddr + NFULL * 32, v);
         tmem_ld_wait();
-        epilogue_chunk<16, MODE>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res, rsc);
+        epilogue_chunk<16, MODE, PERM>(p, v, sT, lane, m_base, n0 + NFULL * 32, bias, res, rsc);
     }
 }
-template <int BLOCK_N, class WaitFn>
+template <int BLOCK_N, bool PERM, class WaitFn>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, float* sT, int lane, int m_base, int n0, WaitFn wait_full) {
     const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
-    const bool inline_ok = (p.act == 0 || p.act == 2) && (p.rowscale == nullptr || (p.rows_per_group >= 32 && !p.conv_w8));
-    if (p.flags & 1) epilogue_tile_mode<BLOCK_N, 2>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else if (fancy && inline_ok && p.drop_p > 0.f && p.act == 0) epilogue_tile_mode<BLOCK_N, 5>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else if (fancy && inline_ok && p.drop_p <= 0.f) epilogue_tile_mode<BLOCK_N, 4>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else if (fancy && inline_ok) epilogue_tile_mode<BLOCK_N, 4>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else if (fancy) epilogue_tile_mode<BLOCK_N, 3>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else if (p.flags & 2) epilogue_tile_mode<BLOCK_N, 1>(p, taddr, sT, lane, m_base, n0, wait_full);
-    else epilogue_tile_mode<BLOCK_N, 0>(p, taddr, sT, lane, m_base, n0, wait_full);
+    if (PERM) {   // W == 8 implicit conv: bias (+ ReLU) (+ residual) (+ tf32 rounding)
+        if (fancy) epilogue_tile_mode<BLOCK_N, (PERM ? 4 : 0), PERM>(p, taddr, sT, lane, m_base, n0, wait_full);
+        else if (p.flags & 2) epilogue_tile_mode<BLOCK_N, (PERM ? 1 : 0), PERM>(p, taddr, sT, lane, m_base, n0, wait_full);
+        else epilogue_tile_mode<BLOCK_N, 0, PERM>(p, taddr, sT, lane, m_base, n0, wait_full);
+        return;
+    }
+    const bool inline_ok = (p.act == 0 || p.act == 2) && (p.rowscale == nullptr || p.rows_per_group >= 32);
+    if (p.flags & 1) epilogue_tile_mode<BLOCK_N, 2, false>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok && p.drop_p > 0.f && p.act == 0) epilogue_tile_mode<BLOCK_N, 5, false>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok && p.drop_p <= 0.f) epilogue_tile_mode<BLOCK_N, 4, false>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (fancy) epilogue_tile_mode<BLOCK_N, 3, false>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else if (p.flags & 2) epilogue_tile_mode<BLOCK_N, 1, false>(p, taddr, sT, lane, m_base, n0, wait_full);
+    else epilogue_tile_mode<BLOCK_N, 0, false>(p, taddr, sT, lane, m_base, n0, wait_full);
 }
 
 template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
@@ -469,7 +478,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
             const bool stamp = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
             if (stamp) p.dbg[(tile / gridDim.x) * 8 + 3] = clock64();
-            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+            epilogue_tile<BLOCK_N, false>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 if (stamp) p.dbg[(tile / gridDim.x) * 8 + 4] = clock64();
                 tcgen05_fence_after();
@@ -729,7 +738,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
             const bool stamp = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
             if (stamp) p.dbg[(tile / n_clusters) * 8 + 3] = clock64();
-            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+            epilogue_tile<BLOCK_N, false>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 if (stamp) p.dbg[(tile / n_clusters) * 8 + 4] = clock64();
                 tcgen05_fence_after();
@@ -892,7 +901,7 @@ conv3x3_w8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const int m_base = (m_pair * 2 + (int)rank) * BLOCK_M + q * 32;
             float* sT = epi_tiles + (warp - 2) * 32 * EPI_PITCH;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
-            epilogue_tile<BLOCK_N>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+            epilogue_tile<BLOCK_N, true>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
             });
