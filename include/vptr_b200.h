@@ -116,6 +116,9 @@ int vptr_gelu_bwd(const float* dy, const float* x, float* dx, long long n, int r
  * tensor core's mantissa truncation is exact and unbiased */
 int vptr_round_copy(const float* x, float* y, long long n, int do_round, const float* rowscale, long long group_elems,
                     unsigned long long drop_seed, float drop_p, vptr_stream_t stream);
+/* one launch for all GEMM weights of a pass: table = n device source pointers (as int64) followed by n cumulative end
+ * offsets (float4 units) inside dst */
+int vptr_round_copy_multi(const long long* table, int n, float* dst, long long total4, vptr_stream_t stream);
 int vptr_droppath_scales(float* out, int n, unsigned long long seed, float p, vptr_stream_t stream);
 int vptr_relu_fwd(const float* x, float* y, long long n, vptr_stream_t stream);
 int vptr_relu_bwd(const float* dy, const float* y, float* dx, long long n, vptr_stream_t stream);

@@ -38,6 +38,7 @@ _SIGS = {
     "vptr_gelu_fwd": ([P, P, L, I, U, F, P], I),
     "vptr_gelu_bwd": ([P, P, P, L, I, U, F, P], I),
     "vptr_round_copy": ([P, P, L, I, P, L, U, F, P], I),
+    "vptr_round_copy_multi": ([P, I, P, L, P], I),
     "vptr_droppath_scales": ([P, I, U, F, P], I),
     "vptr_relu_fwd": ([P, P, L, P], I),
     "vptr_relu_bwd": ([P, P, P, L, P], I),

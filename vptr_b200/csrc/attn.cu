@@ -764,7 +764,7 @@ __global__ void causal_mask_kernel(int T, unsigned char* mask) {
 }
 
 // =============================================================================================
-// Tensor-core path (Lq, Lk <= 32, head_dim in (64, 72]): warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
+// Tensor-core path (Lq, Lk <= 32, head_dim 66): warp-level mma.sync m16n8k8 TF32 with the 3xTF32 split
 // (x = hi + lo, d += a_lo*b_hi + a_hi*b_lo + a_hi*b_hi), which keeps fp32-level accuracy -- the attention core is HBM-bound
 // (AI ~ 4 FLOP/B), so the extra MMAs are free, while the scalar kernels above are shared-memory-latency bound at 4-7x the HBM
 // floor.  One CTA = HPC heads of one batch entry (window / pixel sequence): the HPC*d-float row segments of Q, K, V (and dO) are
@@ -780,9 +780,12 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// x = hi + lo exactly: hi = x truncated to tf32 (one LOP3), lo = x - hi (<= 13 significant bits; the tensor core reads its top
+// 11, so the split is good to ~2^-21).  cvt.rna.tf32.f32 is EMULATED on sm_100 (VIADD + FSETP + SEL + LOP3): the rounding split
+// cost 9 ALU instructions per fragment element and dominated the kernel (ncu source page); truncation costs 2.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(x - __uint_as_float(hi)));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 struct Frag4 { uint32_t hi[4], lo[4]; };
 struct Frag2 { uint32_t hi[2], lo[2]; };
@@ -790,6 +793,12 @@ __device__ __forceinline__ void mma3(float (&d)[4], const Frag4& a, const Frag2&
     mma_tf32_16x8x8(d, a.lo, b.hi);
     mma_tf32_16x8x8(d, a.hi, b.lo);
     mma_tf32_16x8x8(d, a.hi, b.hi);
+}
+// same, with the small cross terms in their own accumulator (two independent dependency chains instead of one)
+__device__ __forceinline__ void mma3_split(float (&d)[4], float (&dc)[4], const Frag4& a, const Frag2& b) {
+    mma_tf32_16x8x8(dc, a.lo, b.hi);
+    mma_tf32_16x8x8(d, a.hi, b.hi);
+    mma_tf32_16x8x8(dc, a.hi, b.lo);
 }
 
 template <int MT, int NT, int HPC>
@@ -799,9 +808,9 @@ struct MmaCfg {
     static constexpr int MTK = (LKP + 15) / 16;        // m-tiles over the key index (dV, dK)
     static constexpr int LP = NT > 2 ? 36 : 20;        // pitch of the per-warp P / dS tiles ([LQP][LP])
 };
-__host__ __device__ inline int mma_pitch(int hpc, int d) {   // tile row pitch (floats): == 4 or 12 (mod 32), multiple of 4
-    int w = hpc * d;
-    w = (w + 3) & ~3;
+constexpr int MMA_D = 66;   // head dim of the tensor-core path (d_model 528 / 8 heads); compile time so fragment addresses fold
+__host__ __device__ constexpr int mma_pitch(int hpc, int d) {   // tile row pitch (floats): == 4 or 12 (mod 32), multiple of 4
+    int w = (hpc * d + 3) & ~3;
     while ((w & 31) != 4 && (w & 31) != 12) w += 4;
     return w;
 }
@@ -809,6 +818,11 @@ __host__ __device__ inline int mma_pitch(int hpc, int d) {   // tile row pitch (
 // C[i][j] += sum_c A[i][c0 + c] * B[j][c0 + c], c < d (contraction over the head dim; columns >= d are masked on the A side)
 template <int MT, int NT>
 __device__ __forceinline__ void mma_rows_dot(float (&acc)[MT][NT][4], const float* sA, const float* sB, int Cp, int c0, int d, int g, int t) {
+    float corr[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) corr[mt][nt][0] = corr[mt][nt][1] = corr[mt][nt][2] = corr[mt][nt][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < 9; ++ks) {
         const int c = ks * 8 + t;
@@ -830,9 +844,15 @@ __device__ __forceinline__ void mma_rows_dot(float (&acc)[MT][NT][4], const floa
             split_tf32(rb[0], b.hi[0], b.lo[0]);
             split_tf32(rb[4], b.hi[1], b.lo[1]);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) mma3(acc[mt][nt], a[mt], b);
+            for (int mt = 0; mt < MT; ++mt) mma3_split(acc[mt][nt], corr[mt][nt], a[mt], b);
         }
     }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[mt][nt][r] += corr[mt][nt][r];
 }
 // out[i][c0 + c] = mul * sum_j W[i][j] * T[j][c0 + c] with W in accumulator registers (k-slot permutation), T rows in shared
 // memory; the result is written to dst rows (this head's columns, c < d) as float2.
@@ -944,8 +964,7 @@ __device__ __forceinline__ void mma_store_tile(const float* tile, int Cp, float*
     }
 }
 // dropout keep-scales of probabilities (b, h, i, j) and (b, h, i, j + 1), j even: one hash when both fall into one group of four
-__device__ __forceinline__ void prob_drop2(const AttnGeom& g, int b, int h, int i, int j, float& k0, float& k1) {
-    const unsigned long long idx = (((unsigned long long)b * g.nhead + h) * g.Lq + i) * g.Lk + j;
+__device__ __forceinline__ void prob_drop2(const AttnGeom& g, unsigned long long idx, float& k0, float& k1) {
     if (idx & 1) { k0 = vptr_drop_scale(g.drop_seed, idx, g.drop_p); k1 = vptr_drop_scale(g.drop_seed, idx + 1, g.drop_p); return; }
     const unsigned z = (unsigned)(vptr_hash4(g.drop_seed, idx >> 2) >> (16 * (unsigned)(idx & 3)));
     const unsigned thr = vptr_drop_threshold(g.drop_p);
@@ -964,8 +983,9 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
     using Cfg = MmaCfg<MT, NT, HPC>;
     constexpr int LQP = Cfg::LQP, LKP = Cfg::LKP, LP = Cfg::LP;
     extern __shared__ __align__(16) float sm[];
-    const int Cp = mma_pitch(HPC, g.d);
-    const int W4 = HPC * g.d / 4;
+    constexpr int Cp = mma_pitch(HPC, MMA_D);
+    constexpr int W4 = HPC * MMA_D / 4;
+    constexpr int D = MMA_D;
     float* sq = sm;                                   // [LQP][Cp]   (forward: O is staged over it)
     float* sk = sq + LQP * Cp;                        // [LKP][Cp]   (backward: dK over it)
     float* sv = sk + LKP * Cp;                        // [LKP][Cp]   (backward: dV over it)
@@ -994,25 +1014,29 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
         for (int l = threadIdx.x; l < g.Lq; l += blockDim.x) rq[l] = q_row(g, b, l);
         for (int l = threadIdx.x; l < g.Lk; l += blockDim.x) rk[l] = k_row(g, b, l);
         __syncthreads();
-        mma_load_tile(sq, Cp, Q, ldq, rq, g.Lq, W4, h0 * g.d);
-        mma_load_tile(sk, Cp, K, ldk, rk, g.Lk, W4, h0 * g.d);
-        mma_load_tile(sv, Cp, V, ldv, rk, g.Lk, W4, h0 * g.d);
-        if (BWD) mma_load_tile(sgo, Cp, dO, lddo, rq, g.Lq, W4, h0 * g.d);
+        mma_load_tile(sq, Cp, Q, ldq, rq, g.Lq, W4, h0 * D);
+        mma_load_tile(sk, Cp, K, ldk, rk, g.Lk, W4, h0 * D);
+        mma_load_tile(sv, Cp, V, ldv, rk, g.Lk, W4, h0 * D);
+        if (BWD) mma_load_tile(sgo, Cp, dO, lddo, rq, g.Lq, W4, h0 * D);
         mma_load_wait();
         __syncthreads();
         {
-            const int h = h0 + warp, c0 = warp * g.d;
+            const int h = h0 + warp, c0 = warp * D;
             // ---- S = Q K^T, P = softmax(scale * S + bias) (undropped probabilities)
             float P[MT][NT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0.f;
-            mma_rows_dot<MT, NT>(P, sq, sk, Cp, c0, g.d, gq, t);
+            mma_rows_dot<MT, NT>(P, sq, sk, Cp, c0, D, gq, t);
             float keep[MT][NT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 float mx[2] = {-INFINITY, -INFINITY};
+                unsigned long long drop_row[2];      // index of probability (b, h, i, 0) for this lane's two rows
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+                    drop_row[hh] = (((unsigned long long)b * g.nhead + h) * g.Lq + (mt * 16 + gq + hh * 8)) * g.Lk;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -1028,7 +1052,7 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
                         mx[hh] = fmaxf(mx[hh], fmaxf(s0, s1));
                         float k0 = 1.f, k1 = 1.f;
                         if (g.drop_p > 0.f && i < g.Lq && j < g.Lk) {
-                            prob_drop2(g, b, h, i, j, k0, k1);
+                            prob_drop2(g, drop_row[hh] + j, k0, k1);
                             if (j + 1 >= g.Lk) k1 = 1.f;
                         }
                         keep[mt][nt][2 * hh] = k0;
@@ -1066,7 +1090,7 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int r = 0; r < 4; ++r) P[mt][nt][r] *= keep[mt][nt][r];
-                mma_regs_times_rows<MT, NT>(P, sv, sq, Cp, c0, g.d, 1.f, gq, t);        // O = PD V, staged over this head's Q columns
+                mma_regs_times_rows<MT, NT>(P, sv, sq, Cp, c0, D, 1.f, gq, t);        // O = PD V, staged over this head's Q columns
             } else {
                 // ---- dP = (dO V^T) * keep ; dS = P * (dP - rowsum(P * dP)) ; PD = P * keep
                 float dS[MT][NT][4];
@@ -1074,7 +1098,7 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dS[mt][nt][0] = dS[mt][nt][1] = dS[mt][nt][2] = dS[mt][nt][3] = 0.f;
-                mma_rows_dot<MT, NT>(dS, sgo, sv, Cp, c0, g.d, gq, t);
+                mma_rows_dot<MT, NT>(dS, sgo, sv, Cp, c0, D, gq, t);
                 float* PDw = spw + warp * 2 * LQP * LP;
                 float* dSw = PDw + LQP * LP;
 #pragma unroll
@@ -1112,30 +1136,48 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
                     }
                 }
                 __syncwarp();
-                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(PDw, LP, sgo, sv, Cp, c0, g.d, 1.f, gq, t);      // dV = PD^T dO  -> over V (dead)
+                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(PDw, LP, sgo, sv, Cp, c0, D, 1.f, gq, t);      // dV = PD^T dO  -> over V (dead)
                 __syncwarp();
-                mma_regs_times_rows<MT, NT>(dS, sk, sgo, Cp, c0, g.d, g.scale, gq, t);                   // dQ = dS K     -> over dO (dead)
+                mma_regs_times_rows<MT, NT>(dS, sk, sgo, Cp, c0, D, g.scale, gq, t);                   // dQ = dS K     -> over dO (dead)
                 __syncwarp();
-                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(dSw, LP, sq, sk, Cp, c0, g.d, g.scale, gq, t);   // dK = dS^T Q   -> over K (dead)
+                mma_smemT_times_rows<Cfg::MTK, 2 * MT>(dSw, LP, sq, sk, Cp, c0, D, g.scale, gq, t);   // dK = dS^T Q   -> over K (dead)
             }
         }
         __syncthreads();
         if (!BWD) {
-            mma_store_tile(sq, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * g.d, g.round_tf32);
+            mma_store_tile(sq, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * D, g.round_tf32);
         } else {
-            mma_store_tile(sv, Cp, dV, lddv, rk, g.Lk, W4, h0 * g.d, g.round_tf32);
-            mma_store_tile(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * g.d, g.round_tf32);
-            mma_store_tile(sk, Cp, dK, lddk, rk, g.Lk, W4, h0 * g.d, g.round_tf32);
+            mma_store_tile(sv, Cp, dV, lddv, rk, g.Lk, W4, h0 * D, g.round_tf32);
+            mma_store_tile(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * D, g.round_tf32);
+            mma_store_tile(sk, Cp, dK, lddk, rk, g.Lk, W4, h0 * D, g.round_tf32);
         }
         __syncthreads();
     }
     if (BWD && d_rpe_table) {
         // the launch makes gridDim.x a multiple of hgroups, so all items of a CTA share one head group
         // (item % hgroups == blockIdx.x % hgroups) and the accumulator can be flushed once, here
+        // reduce the (i, j) entries into the (2ws-1)^2 table bins in shared memory first (over the dead PD/dS tiles): 5x fewer,
+        // far less contended global atomics than one per (i, j)
         const int h0 = (blockIdx.x % hgroups) * HPC;
+        const int bins = (2 * g.ws - 1) * (2 * g.ws - 1);
+        const bool binned = BWD && HPC * bins <= HPC * 2 * LQP * LP;
+        __syncthreads();
+        if (binned) {
+            for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) spw[e] = 0.f;
+            __syncthreads();
+        }
         for (int e = threadIdx.x; e < HPC * g.Lq * g.Lk; e += blockDim.x) {
             const int w = e / (g.Lq * g.Lk), r = e - w * g.Lq * g.Lk;
-            atomicAdd(d_rpe_table + rel_pos_index(g.ws, r / g.Lk, r % g.Lk) * g.nhead + h0 + w, sdb[e]);
+            const int idx = rel_pos_index(g.ws, r / g.Lk, r % g.Lk);
+            if (binned) atomicAdd(spw + w * bins + idx, sdb[e]);
+            else atomicAdd(d_rpe_table + idx * g.nhead + h0 + w, sdb[e]);
+        }
+        if (binned) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) {
+                const int w = e / bins, idx = e - w * bins;
+                atomicAdd(d_rpe_table + idx * g.nhead + h0 + w, spw[e]);
+            }
         }
     }
 }
@@ -1145,7 +1187,7 @@ int launch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk
                     long long ldo, float* dK, long long lddk, float* dV, long long lddv, long long lddo, const float* rpe_table,
                     float* d_rpe_table, const AttnGeom& g, int batches, cudaStream_t stream) {
     using Cfg = MmaCfg<MT, NT, HPC>;
-    const int Cp = mma_pitch(HPC, g.d);
+    constexpr int Cp = mma_pitch(HPC, MMA_D);
     size_t floats = (size_t)(Cfg::LQP + 2 * Cfg::LKP) * Cp;
     if (BWD) floats += (size_t)Cfg::LQP * Cp + (size_t)HPC * 2 * Cfg::LQP * Cfg::LP + ((d_rpe_table ? (size_t)HPC * g.Lq * g.Lk + 1 : 0) & ~(size_t)1);
     if (rpe_table) floats += (size_t)HPC * Cfg::LQP * Cfg::LKP;
@@ -1174,9 +1216,9 @@ bool attn_mma_disabled() {
     static const bool v = [] { const char* e = getenv("VPTR_ATTN_NO_MMA"); return e && e[0] == '1'; }();
     return v;
 }
-// shapes the tensor-core path covers: Lq, Lk <= 32, head_dim in (64, 72] and even, an even number of heads, 16-byte aligned rows
+// shapes the tensor-core path covers: Lq, Lk <= 32, head_dim 66, an even number of heads, 16-byte aligned rows
 bool attn_mma_ok(const AttnGeom& g, int nhead, int d) {
-    return !attn_mma_disabled() && g.Lq <= 32 && g.Lk <= 32 && d > 64 && d <= 72 && d % 2 == 0 && nhead % 2 == 0 && (2 * d) % 4 == 0;
+    return !attn_mma_disabled() && g.Lq <= 32 && g.Lk <= 32 && d == MMA_D && nhead % 2 == 0;
 }
 template <bool BWD>
 int dispatch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,

@@ -34,10 +34,11 @@ __device__ __forceinline__ float vptr_gelu_grad(float x) {
     float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     return cdf + x * kInvSqrt2Pi * __expf(-0.5f * x * x);
 }
+// round to nearest tf32 (ties away from zero, like cvt.rna.tf32.f32): add half an ulp of the 10-bit mantissa and truncate.
+// cvt.rna.tf32.f32 itself is EMULATED on sm_100 with four instructions (VIADD, FSETP |x| < inf, SEL, LOP3); the two-instruction
+// form below differs only for NaN payloads and for finite values within half a tf32 ulp of FLT_MAX (which round to inf).
 __device__ __forceinline__ float vptr_round_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 // Counter-based RNG for dropout / DropPath: ONE splitmix64 hash per group of four consecutive elements, 16 random bits per
 // element (the fused sites are float4-vectorised, and a hash per element made the 4-warp GEMM epilogue compute-bound).

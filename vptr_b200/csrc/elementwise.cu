@@ -54,6 +54,26 @@ __global__ void __launch_bounds__(256) round_copy_kernel(const float* __restrict
     }
 }
 
+// Multi-tensor rounded copy: n source tensors (device table: src pointer, then the END offset of each tensor in the flat
+// destination, offsets in float4 units) -> one flat buffer.  One launch replaces the per-weight round_copy launches of a
+// forward / backward pass (372 launches, 4 ms per cfg1 step, all launch-latency).
+__global__ void __launch_bounds__(256) round_copy_multi_kernel(const long long* __restrict__ table, int n, float* __restrict__ dst,
+                                                               long long total4) {
+    const long long* ends = table + n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;                       // first tensor whose end offset is > i
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(ends + mid) > i) hi = mid; else lo = mid + 1;
+        }
+        const long long begin = lo ? __ldg(ends + lo - 1) : 0;
+        const float4* src = reinterpret_cast<const float4*>(__ldg(table + lo));
+        float4 v = src[i - begin];
+        v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w);
+        reinterpret_cast<float4*>(dst)[i] = v;
+    }
+}
+
 // out[r][0:K] = rna_tf32(w[r][:]) ; out[r][K:2K] = rna_tf32(w[r][:] - hi)   ("2xTF32" split of a weight matrix, rows of K)
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ out, long long rows, long long K) {
     const long long total = rows * K;
@@ -234,6 +254,13 @@ extern "C" int vptr_round_copy(const float* x, float* y, long long n, int do_rou
     VPTR_REQUIRE(rowscale == nullptr || (group_elems > 0 && group_elems % 4 == 0), VPTR_ERR_SHAPE, "vptr_round_copy: group_elems=%lld", group_elems);
     round_copy_kernel<<<ew_grid(n / 4, 256), 256, 0, stream>>>(x, y, n / 4, do_round, rowscale, group_elems, drop_seed, drop_p);
     return vptr_check_launch("round_copy_kernel");
+}
+// table: device array of 2n int64 -- n source pointers (16-byte aligned, element counts multiples of 4) followed by the n
+// cumulative end offsets (in float4) of the tensors inside dst; total4 = last end offset.
+extern "C" int vptr_round_copy_multi(const long long* table, int n, float* dst, long long total4, cudaStream_t stream) {
+    VPTR_REQUIRE(table != nullptr && n > 0 && dst != nullptr && total4 > 0, VPTR_ERR_SHAPE, "vptr_round_copy_multi: n=%d total4=%lld", n, total4);
+    round_copy_multi_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(table, n, dst, total4);
+    return vptr_check_launch("round_copy_multi_kernel");
 }
 extern "C" int vptr_split_tf32(const float* w, float* out, long long rows, long long K, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_split_tf32: rows=%lld K=%lld", rows, K);

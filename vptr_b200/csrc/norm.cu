@@ -138,6 +138,104 @@ __global__ void __launch_bounds__(128) layernorm_bwd_affine_kernel(const float* 
     atomicAdd(dbeta + c, ab);
 }
 
+// ------------------------------------------------------------------ LayerNorm(C) backward, fused (C <= 1024, C % 4 == 0)
+// One pass: a warp walks rows; the row's g = dy1 (+ dy2) and x live in registers (float4 per lane, up to 8), so dx needs no
+// second read, and every lane accumulates dgamma / dbeta of its own columns over all the warp's rows in registers -- the
+// separate affine kernel (which re-read dy1, dy2 and x) disappears.  Per-block partial sums are combined through shared memory
+// and flushed with one atomic per column and block.
+template <int NV>   // float4 per lane (C <= 128 * NV)
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(const float* __restrict__ dy1, const float* __restrict__ dy2,
+                                                                     const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, const float* __restrict__ mean_in,
+                                                                     const float* __restrict__ rstd_in, const float* __restrict__ dres,
+                                                                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                     long long rows, int C, int relu, int rows_per_block) {
+    extern __shared__ float red[];   // [2][C] block accumulators
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int C4 = C >> 2;
+    for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) red[e] = 0.f;
+    __syncthreads();
+    float4 ag[NV], ab[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ag[v] = ab[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* gm4 = reinterpret_cast<const float4*>(gamma);   // gamma / beta stay L1-resident: re-read per row, not held in registers
+    const float4* bt4 = reinterpret_cast<const float4*>(beta);
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    const float invC = 1.f / (float)C;
+    for (long long row = r0 + warp; row < r1; row += nw) {
+        const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+        float4 g[NV], xh[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {   // all of the row's loads first (independent, in flight together)
+            const int c4 = lane + 32 * v;
+            g[v] = xh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < C4) {
+                g[v] = reinterpret_cast<const float4*>(dy1 + row * C)[c4];
+                xh[v] = reinterpret_cast<const float4*>(x + row * C)[c4];
+            }
+        }
+        if (dy2) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c4 = lane + 32 * v;
+                if (c4 < C4) { const float4 t = reinterpret_cast<const float4*>(dy2 + row * C)[c4]; g[v].x += t.x; g[v].y += t.y; g[v].z += t.z; g[v].w += t.w; }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int c4 = lane + 32 * v;
+            if (c4 < C4) {
+                const float4 gm = __ldg(gm4 + c4);
+                xh[v] = make_float4((xh[v].x - mean) * rstd, (xh[v].y - mean) * rstd, (xh[v].z - mean) * rstd, (xh[v].w - mean) * rstd);
+                if (relu) {
+                    const float4 bt = __ldg(bt4 + c4);
+                    if (xh[v].x * gm.x + bt.x <= 0.f) g[v].x = 0.f;
+                    if (xh[v].y * gm.y + bt.y <= 0.f) g[v].y = 0.f;
+                    if (xh[v].z * gm.z + bt.z <= 0.f) g[v].z = 0.f;
+                    if (xh[v].w * gm.w + bt.w <= 0.f) g[v].w = 0.f;
+                }
+                ab[v].x += g[v].x; ab[v].y += g[v].y; ab[v].z += g[v].z; ab[v].w += g[v].w;
+                ag[v].x = fmaf(g[v].x, xh[v].x, ag[v].x); ag[v].y = fmaf(g[v].y, xh[v].y, ag[v].y);
+                ag[v].z = fmaf(g[v].z, xh[v].z, ag[v].z); ag[v].w = fmaf(g[v].w, xh[v].w, ag[v].w);
+                g[v].x *= gm.x; g[v].y *= gm.y; g[v].z *= gm.z; g[v].w *= gm.w;
+                s1 += (g[v].x + g[v].y) + (g[v].z + g[v].w);
+                s2 += (g[v].x * xh[v].x + g[v].y * xh[v].y) + (g[v].z * xh[v].z + g[v].w * xh[v].w);
+            }
+        }
+        if (dx) {
+            s1 = warp_sum(s1) * invC;
+            s2 = warp_sum(s2) * invC;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int c4 = lane + 32 * v;
+                if (c4 < C4) {
+                    float4 o = make_float4(rstd * (g[v].x - s1 - xh[v].x * s2), rstd * (g[v].y - s1 - xh[v].y * s2),
+                                           rstd * (g[v].z - s1 - xh[v].z * s2), rstd * (g[v].w - s1 - xh[v].w * s2));
+                    if (dres) { const float4 t = reinterpret_cast<const float4*>(dres + row * C)[c4]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                    reinterpret_cast<float4*>(dx + row * C)[c4] = o;
+                }
+            }
+        }
+    }
+    if (dgamma) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int c = (lane + 32 * v) * 4;
+            if (c < C) {
+                atomicAdd(red + c, ag[v].x); atomicAdd(red + c + 1, ag[v].y); atomicAdd(red + c + 2, ag[v].z); atomicAdd(red + c + 3, ag[v].w);
+                atomicAdd(red + C + c, ab[v].x); atomicAdd(red + C + c + 1, ab[v].y); atomicAdd(red + C + c + 2, ab[v].z); atomicAdd(red + C + c + 3, ab[v].w);
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(dgamma + c, red[c]);
+            atomicAdd(dbeta + c, red[C + c]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ statistics
 // per-column sum / sum of squares over rows (BatchNorm batch statistics), fp64 accumulators
 __global__ void __launch_bounds__(128) colstats_kernel(const float* __restrict__ x, double* __restrict__ sum, double* __restrict__ sumsq,
@@ -293,60 +391,63 @@ __global__ void __launch_bounds__(128) bn_act_bwd_pass_a_kernel(const float* __r
     atomicAdd(dgamma + c, a2.x); atomicAdd(dgamma + c + 1, a2.y); atomicAdd(dgamma + c + 2, a2.z); atomicAdd(dgamma + c + 3, a2.w);
 }
 
-// frame LayerNorm, pass A: one block per frame; g0 stored, P1 = sum g0*gamma, P2 = sum g0*gamma*xhat
-__global__ void __launch_bounds__(512) ln3_act_bwd_pass_a_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                 float* __restrict__ g0, float* __restrict__ p1, float* __restrict__ p2,
-                                                                 long long gsize, int ch, const DropArgs da) {
-    __shared__ float red[32];
-    const long long base = (long long)blockIdx.x * gsize;
-    const float m = mean[blockIdx.x], r = rstd[blockIdx.x];
-    const bool drop = da.p > 0.f || da.rowscale;
-    float a1 = 0.f, a2 = 0.f;
-    for (long long i = (long long)threadIdx.x * 4; i < gsize; i += (long long)blockDim.x * 4) {
-        const long long e = base + i;
-        const float4 xv = *reinterpret_cast<const float4*>(x + e);
-        float4 d = *reinterpret_cast<const float4*>(dy + e);
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i)), b = __ldg(reinterpret_cast<const float4*>(beta + i));
-        if (drop) {
-            const long long row = e / ch;   // 4 consecutive elements share a row (ch % 4 == 0)
-            const float4 k = drop_factor4(da, row, e);
-            d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
-        }
-        const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
-        d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
-        d.z *= vptr_gelu_grad(xh.z * g.z + b.z); d.w *= vptr_gelu_grad(xh.w * g.w + b.w);
-        *reinterpret_cast<float4*>(g0 + e) = d;
-        const float4 t = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-        a1 += t.x + t.y + t.z + t.w;
-        a2 += t.x * xh.x + t.y * xh.y + t.z * xh.z + t.w * xh.w;
-    }
-    a1 = block_sum(a1, red);
-    a2 = block_sum(a2, red);
-    if (threadIdx.x == 0) { p1[blockIdx.x] = a1; p2[blockIdx.x] = a2; }
-}
-
-// frame LayerNorm, pass B: dgamma[a] += sum_f g0*xhat ; dbeta[a] += sum_f g0   (4 affine indices per thread)
-__global__ void __launch_bounds__(128) ln3_act_bwd_affine_kernel(const float* __restrict__ g0, const float* __restrict__ x,
-                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, long long gsize,
-                                                                 int frames, int frames_per_block) {
+// frame LayerNorm, passes A + affine merged: a thread owns four (hw, ch) positions and walks a chunk of frames, so the affine
+// gradients dgamma / dbeta (sums over frames at fixed position) accumulate in registers and gamma / beta are read once, while
+// the per-frame sums P1 = sum g0*gamma, P2 = sum g0*gamma*xhat (needed by the dx pass) go warp-reduce -> shared -> one atomic
+// per frame and block.  Saves the separate affine kernel's re-read of g0 and x (692 MB per 2112-channel call at cfg1).
+constexpr int LN3_FPB = 64;   // frames per block
+__global__ void __launch_bounds__(256) ln3_act_bwd_pass_ab_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ g0, float* __restrict__ p1, float* __restrict__ p2,
+                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, long long gsize, int ch,
+                                                                  int frames, const DropArgs da) {
+    __shared__ float part[LN3_FPB][8][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (a >= gsize) return;
-    const int f0 = blockIdx.y * frames_per_block;
-    const int f1 = min(f0 + frames_per_block, frames);
-    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    const bool live = a < gsize;
+    const int f0 = blockIdx.y * LN3_FPB;
+    const int f1 = min(f0 + LN3_FPB, frames);
+    const bool drop = da.p > 0.f || da.rowscale;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = g, ag = g, ab = g;
+    if (live) { g = __ldg(reinterpret_cast<const float4*>(gamma + a)); b = __ldg(reinterpret_cast<const float4*>(beta + a)); }
     for (int f = f0; f < f1; ++f) {
-        const float m = __ldg(mean + f), r = __ldg(rstd + f);
-        const float4 xv = *reinterpret_cast<const float4*>(x + f * gsize + a);
-        const float4 d = *reinterpret_cast<const float4*>(g0 + f * gsize + a);
-        ag.x = fmaf(d.x, (xv.x - m) * r, ag.x); ag.y = fmaf(d.y, (xv.y - m) * r, ag.y);
-        ag.z = fmaf(d.z, (xv.z - m) * r, ag.z); ag.w = fmaf(d.w, (xv.w - m) * r, ag.w);
-        ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+        float a1 = 0.f, a2 = 0.f;
+        if (live) {
+            const float m = __ldg(mean + f), r = __ldg(rstd + f);
+            const long long e = (long long)f * gsize + a;
+            const float4 xv = *reinterpret_cast<const float4*>(x + e);
+            float4 d = *reinterpret_cast<const float4*>(dy + e);
+            if (drop) {
+                const float4 k = drop_factor4(da, e / ch, e);   // 4 consecutive elements share a row (ch % 4 == 0)
+                d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
+            }
+            const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
+            d.x *= vptr_gelu_grad(xh.x * g.x + b.x); d.y *= vptr_gelu_grad(xh.y * g.y + b.y);
+            d.z *= vptr_gelu_grad(xh.z * g.z + b.z); d.w *= vptr_gelu_grad(xh.w * g.w + b.w);
+            *reinterpret_cast<float4*>(g0 + e) = d;
+            ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+            ag.x = fmaf(d.x, xh.x, ag.x); ag.y = fmaf(d.y, xh.y, ag.y); ag.z = fmaf(d.z, xh.z, ag.z); ag.w = fmaf(d.w, xh.w, ag.w);
+            const float4 t = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            a1 = (t.x + t.y) + (t.z + t.w);
+            a2 = (t.x * xh.x + t.y * xh.y) + (t.z * xh.z + t.w * xh.w);
+        }
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane == 0) { part[f - f0][warp][0] = a1; part[f - f0][warp][1] = a2; }
     }
-    atomicAdd(dgamma + a, ag.x); atomicAdd(dgamma + a + 1, ag.y); atomicAdd(dgamma + a + 2, ag.z); atomicAdd(dgamma + a + 3, ag.w);
-    atomicAdd(dbeta + a, ab.x); atomicAdd(dbeta + a + 1, ab.y); atomicAdd(dbeta + a + 2, ab.z); atomicAdd(dbeta + a + 3, ab.w);
+    if (live) {
+        atomicAdd(dgamma + a, ag.x); atomicAdd(dgamma + a + 1, ag.y); atomicAdd(dgamma + a + 2, ag.z); atomicAdd(dgamma + a + 3, ag.w);
+        atomicAdd(dbeta + a, ab.x); atomicAdd(dbeta + a + 1, ab.y); atomicAdd(dbeta + a + 2, ab.z); atomicAdd(dbeta + a + 3, ab.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (f1 - f0) * 2; i += blockDim.x) {
+        const int fi = i >> 1, w = i & 1;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[fi][k][w];
+        atomicAdd((w ? p2 : p1) + f0 + fi, s);
+    }
 }
 
 // Final pass (in place on the g0 buffer): dx from g0 and the reduced sums.
@@ -411,6 +512,20 @@ extern "C" int vptr_layernorm_bwd(const float* dy1, const float* dy2, const floa
                                   const float* mean, const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
                                   long long rows, int C, int relu, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && C > 0, VPTR_ERR_SHAPE, "vptr_layernorm_bwd: rows=%lld C=%d", rows, C);
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    if (C % 4 == 0 && C <= 1024 && al16(dy1) && al16(dy2) && al16(x) && al16(gamma) && al16(beta) && al16(dres) && al16(dx)) {
+        // fused single pass (dx and the affine gradients from one read of dy / x)
+        int blocks = 148 * 4;
+        int rpb = (int)((rows + blocks - 1) / blocks);
+        if (rpb < 8) rpb = 8;
+        blocks = (int)((rows + rpb - 1) / rpb);
+        const size_t smem = sizeof(float) * 2 * C;
+        if (C <= 512) layernorm_bwd_fused_kernel<4><<<blocks, 256, smem, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, rows, C, relu, rpb);
+        else if (C <= 640) layernorm_bwd_fused_kernel<5><<<blocks, 256, smem, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, rows, C, relu, rpb);
+        else if (C <= 768) layernorm_bwd_fused_kernel<6><<<blocks, 256, smem, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, rows, C, relu, rpb);
+        else layernorm_bwd_fused_kernel<8><<<blocks, 256, smem, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, rows, C, relu, rpb);
+        return vptr_check_launch("layernorm_bwd_fused_kernel");
+    }
     if (dx) {
         layernorm_bwd_dx_kernel<<<vptr_cdiv(rows, 8), 256, 0, stream>>>(dy1, dy2, x, gamma, beta, mean, rstd, dres, dx, rows, C, relu);
         int rc = vptr_check_launch("layernorm_bwd_dx_kernel");
@@ -485,10 +600,9 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
-        ln3_act_bwd_pass_a_kernel<<<frames, 512, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, gsize, ch, da);
-        int fpb = 32;
-        dim3 g2(vptr_cdiv(gsize / 4, 128), vptr_cdiv(frames, fpb));
-        ln3_act_bwd_affine_kernel<<<g2, 128, 0, stream>>>(dx, x, mean, rstd, dgamma, dbeta, gsize, frames, fpb);
+        cudaMemsetAsync(ws, 0, sizeof(float) * 2 * frames, stream);
+        dim3 g2(vptr_cdiv(gsize / 4, 256), vptr_cdiv(frames, LN3_FPB));
+        ln3_act_bwd_pass_ab_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, dgamma, dbeta, gsize, ch, frames, da);
         norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, total4, ch, gsize, 1.0f / (float)gsize, round_tf32);
     }
     return vptr_check_launch("vptr_norm_act_bwd");

@@ -27,11 +27,21 @@ RT = ROUND_TF32
 class Params:
     """name -> parameter tensor / gradient buffer (views into one flat fp32 buffer when grads are wanted)."""
 
-    def __init__(self, named, want_grads):
+    GEMM_WEIGHTS = ("proj.weight", "in_proj_weight", "fc1.weight", "fc2.weight", "linear1.weight", "linear2.weight")
+
+    def __init__(self, named, want_grads, rounded=None):
         self.t = {k: v for k, v in named}
         self.gflat = None
         self.gv = {}
-        self.rounded = {}
+        # tf32-rounded GEMM weights: one multi-tensor launch per step (the backward reuses the forward's copies -- the
+        # optimizer only steps after it)
+        self.rounded = rounded if rounded is not None else {}
+        if ROUND_TF32 and rounded is None:
+            names = [k for k, v in self.t.items() if k.endswith(self.GEMM_WEIGHTS) and v.is_cuda and v.numel() % 4 == 0
+                     and v.data_ptr() % 16 == 0 and v.is_contiguous()]
+            if names:
+                for k, r in zip(names, ops.round_copy_multi([self.t[k] for k in names])):
+                    self.rounded[k] = r
         if want_grads:
             names = [k for k, v in self.t.items() if v.requires_grad]
             total = sum(self.t[k].numel() for k in names)

@@ -282,12 +282,14 @@ class _FARFunction(torch.autograd.Function):
         h = E.encoder_fwd(P, bufs, _tokens(x), g, mod.num_encoder_layers, True, mod.rpe, tpos, lw_tab, mod.training, save, D)
         y = E.final_norm_fwd(P, "transformer.encoder.norm", h, True, save)
         ctx.save, ctx.names, ctx.params, ctx.shape = save, names, params, (N, T, C, H, W)
+        ctx.rounded = P.rounded if (want and E.ROUND_TF32) else None
         return y.view(N, T, H, W, C).permute(0, 1, 4, 2, 3)
 
     @staticmethod
     def backward(ctx, dout):
         N, T, C, H, W = ctx.shape
-        P = E.Params(zip(ctx.names, ctx.params), want_grads=True)
+        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None)
+        ctx.rounded = None
         d = _tokens(dout)
         dx = E.backward_tape(P, ctx.save, d)
         ctx.save = None
@@ -320,13 +322,15 @@ class _NARFunction(torch.autograd.Function):
         tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D)
         y = E.final_norm_fwd(P, "transformer.decoder.norm", tgt, True, save)
         ctx.save, ctx.names, ctx.params, ctx.n_enc = save, names, params, n_enc
+        ctx.rounded = P.rounded if (want and E.ROUND_TF32) else None
         ctx.shape = (N, Tp, Tf, C, H, W)
         return y.view(N, Tf, H, W, C).permute(0, 1, 4, 2, 3)
 
     @staticmethod
     def backward(ctx, dout):
         N, Tp, Tf, C, H, W = ctx.shape
-        P = E.Params(zip(ctx.names, ctx.params), want_grads=True)
+        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None)
+        ctx.rounded = None
         dq = P.g("frame_queries")
         dqpos = dq.view(Tf * H * W, C) if dq is not None else None
         dmem = ops.zeros(N * Tp * H * W, C, like=dout)

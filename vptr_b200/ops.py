@@ -219,6 +219,36 @@ def round_copy(x, do_round=True, rowscale=None, group_elems=0, drop_seed=0, drop
     return y
 
 
+_ROUND_TABLES = {}
+
+
+def round_copy_multi(tensors):
+    """tf32-rounded copies of several tensors with ONE launch; returns views of one flat buffer (same shapes).  The device
+    pointer table is cached per set of source pointers (parameters keep their storage across steps)."""
+    key = tuple((t.data_ptr(), t.numel()) for t in tensors)
+    ent = _ROUND_TABLES.get(key)
+    if ent is None:
+        ends, acc = [], 0
+        for t in tensors:
+            _chk(t, "weight")
+            if t.numel() % 4 or t.data_ptr() % 16 or not t.is_contiguous():
+                raise RuntimeError("vptr_b200.round_copy_multi: tensors must be contiguous, 16-byte aligned, numel % 4 == 0")
+            acc += t.numel() // 4
+            ends.append(acc)
+        table = torch.tensor([t.data_ptr() for t in tensors] + ends, dtype=torch.int64).to(tensors[0].device)
+        if len(_ROUND_TABLES) > 64:
+            _ROUND_TABLES.clear()
+        ent = _ROUND_TABLES[key] = (table, ends)
+    table, ends = ent
+    flat = torch.empty(ends[-1] * 4, dtype=torch.float32, device=tensors[0].device)
+    _call("vptr_round_copy_multi", table.data_ptr(), len(tensors), _p(flat), ends[-1], _s())
+    out, b = [], 0
+    for t, e in zip(tensors, ends):
+        out.append(flat[b * 4:e * 4].view(t.shape))
+        b = e
+    return out
+
+
 def droppath_scales(n, seed, p, device):
     out = torch.empty(n, dtype=torch.float32, device=device)
     _call("vptr_droppath_scales", _p(out), n, int(seed), float(p), _s())
