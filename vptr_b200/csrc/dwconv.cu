@@ -23,45 +23,56 @@ __device__ __forceinline__ float4 ld_col(const float* __restrict__ x, long long 
 __device__ __forceinline__ void fma4(float4& a, const float4& k, const float4& v) {
     a.x = fmaf(k.x, v.x, a.x); a.y = fmaf(k.y, v.y, a.y); a.z = fmaf(k.z, v.z, a.z); a.w = fmaf(k.w, v.w, a.w);
 }
-__global__ void __launch_bounds__(128) dwconv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w9,
-                                                        const float* __restrict__ bias, float* __restrict__ y, int H, int W, int C4,
-                                                        int flip) {
+// Two output rows per thread: a 4-row x 3-column register window (every input row is loaded for 2 outputs instead of 1, and
+// the two accumulator chains are independent); the next column's loads are issued before the current column's FMAs.
+constexpr int DW_THREADS = 176;   // 528 float4 channel groups = 3 blocks exactly (128-thread blocks left the 5th 87 % idle)
+__global__ void __launch_bounds__(DW_THREADS) dwconv3x3_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+                                                               const float* __restrict__ bias, float* __restrict__ y, int H, int W, int C4,
+                                                               int flip) {
     const int c = blockIdx.y * blockDim.x + threadIdx.x;
     if (c >= C4) return;
-    const int f = blockIdx.x / H, h = blockIdx.x - f * H;
+    const int hp = (H + 1) >> 1;                      // row pairs per frame
+    const int f = blockIdx.x / hp, h = (blockIdx.x - f * hp) * 2;
     const long long fb = (long long)f * H * W;
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w9) + (flip ? 8 - t : t) * C4 + c);
     const float4 b = (bias && !flip) ? __ldg(reinterpret_cast<const float4*>(bias) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 win[3][3];
+    float4 win[4][3], nxt[4];
 #pragma unroll
-    for (int dh = 0; dh < 3; ++dh) {
-        win[dh][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        win[dh][1] = ld_col(x, fb, h + dh - 1, 0, H, W, C4, c);
-        win[dh][2] = ld_col(x, fb, h + dh - 1, 1, H, W, C4, c);
+    for (int r = 0; r < 4; ++r) {
+        win[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        win[r][1] = ld_col(x, fb, h + r - 1, 0, H, W, C4, c);
+        win[r][2] = ld_col(x, fb, h + r - 1, 1, H, W, C4, c);
     }
+    const bool two = h + 1 < H;
     for (int w = 0; w < W; ++w) {
-        float4 acc = b;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) nxt[r] = ld_col(x, fb, h + r - 1, w + 2, H, W, C4, c);
+        float4 a0 = b, a1 = b;
 #pragma unroll
         for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
-            for (int dw = 0; dw < 3; ++dw) fma4(acc, k[dh * 3 + dw], win[dh][dw]);
-        reinterpret_cast<float4*>(y)[(fb + (long long)h * W + w) * C4 + c] = acc;
+            for (int dw = 0; dw < 3; ++dw) {
+                fma4(a0, k[dh * 3 + dw], win[dh][dw]);
+                fma4(a1, k[dh * 3 + dw], win[dh + 1][dw]);
+            }
+        reinterpret_cast<float4*>(y)[(fb + (long long)h * W + w) * C4 + c] = a0;
+        if (two) reinterpret_cast<float4*>(y)[(fb + (long long)(h + 1) * W + w) * C4 + c] = a1;
 #pragma unroll
-        for (int dh = 0; dh < 3; ++dh) {
-            win[dh][0] = win[dh][1];
-            win[dh][1] = win[dh][2];
-            win[dh][2] = ld_col(x, fb, h + dh - 1, w + 2, H, W, C4, c);
+        for (int r = 0; r < 4; ++r) {
+            win[r][0] = win[r][1];
+            win[r][1] = win[r][2];
+            win[r][2] = nxt[r];
         }
     }
 }
 
 // dW9[t][c] += sum_{f,h,w} dy[f,h,w,c] * x[f,h+dh-1,w+dw-1,c] ; dbias[c] += sum dy.  Thread = float4 channel group, a chunk of
 // frames per blockIdx.y, same sliding window over x.
-__global__ void __launch_bounds__(128) dwconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                              float* __restrict__ dw9, float* __restrict__ dbias, int F, int H, int W,
-                                                              int C4, int frames_per_block) {
+__global__ void __launch_bounds__(DW_THREADS) dwconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     float* __restrict__ dw9, float* __restrict__ dbias, int F, int H, int W,
+                                                                     int C4, int frames_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C4) return;
     const int f0 = blockIdx.y * frames_per_block;
@@ -72,26 +83,34 @@ __global__ void __launch_bounds__(128) dwconv3x3_wgrad_kernel(const float* __res
     float4 ab = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int f = f0; f < f1; ++f) {
         const long long fb = (long long)f * H * W;
-        for (int h = 0; h < H; ++h) {
-            float4 win[3][3];
+        for (int h = 0; h < H; h += 2) {                    // two dy rows per pass over a 4-row x window
+            const bool two = h + 1 < H;
+            float4 win[4][3], nxt[4];
 #pragma unroll
-            for (int dh = 0; dh < 3; ++dh) {
-                win[dh][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                win[dh][1] = ld_col(x, fb, h + dh - 1, 0, H, W, C4, c);
-                win[dh][2] = ld_col(x, fb, h + dh - 1, 1, H, W, C4, c);
+            for (int r = 0; r < 4; ++r) {
+                win[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                win[r][1] = ld_col(x, fb, h + r - 1, 0, H, W, C4, c);
+                win[r][2] = ld_col(x, fb, h + r - 1, 1, H, W, C4, c);
             }
             for (int w = 0; w < W; ++w) {
-                const float4 g = reinterpret_cast<const float4*>(dy)[(fb + (long long)h * W + w) * C4 + c];
-                ab.x += g.x; ab.y += g.y; ab.z += g.z; ab.w += g.w;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) nxt[r] = ld_col(x, fb, h + r - 1, w + 2, H, W, C4, c);
+                const float4 g0 = reinterpret_cast<const float4*>(dy)[(fb + (long long)h * W + w) * C4 + c];
+                const float4 g1 = two ? reinterpret_cast<const float4*>(dy)[(fb + (long long)(h + 1) * W + w) * C4 + c]
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                ab.x += g0.x + g1.x; ab.y += g0.y + g1.y; ab.z += g0.z + g1.z; ab.w += g0.w + g1.w;
 #pragma unroll
                 for (int dh = 0; dh < 3; ++dh)
 #pragma unroll
-                    for (int dw = 0; dw < 3; ++dw) fma4(acc[dh * 3 + dw], g, win[dh][dw]);
+                    for (int dw = 0; dw < 3; ++dw) {
+                        fma4(acc[dh * 3 + dw], g0, win[dh][dw]);
+                        fma4(acc[dh * 3 + dw], g1, win[dh + 1][dw]);
+                    }
 #pragma unroll
-                for (int dh = 0; dh < 3; ++dh) {
-                    win[dh][0] = win[dh][1];
-                    win[dh][1] = win[dh][2];
-                    win[dh][2] = ld_col(x, fb, h + dh - 1, w + 2, H, W, C4, c);
+                for (int r = 0; r < 4; ++r) {
+                    win[r][0] = win[r][1];
+                    win[r][1] = win[r][2];
+                    win[r][2] = nxt[r];
                 }
             }
         }
@@ -112,8 +131,8 @@ extern "C" int vptr_dwconv3x3(const float* x, const float* w9, const float* bias
                               cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F=%d H=%d W=%d ch=%d", F, H, W, ch);
     VPTR_REQUIRE((long long)F * H < 2147483647LL, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F*H too large");
-    dim3 grid(F * H, vptr_cdiv(ch / 4, 128));
-    dwconv3x3_kernel<<<grid, 128, 0, stream>>>(x, w9, bias, y, H, W, ch / 4, flip);
+    dim3 grid(F * ((H + 1) / 2), vptr_cdiv(ch / 4, DW_THREADS));
+    dwconv3x3_kernel<<<grid, DW_THREADS, 0, stream>>>(x, w9, bias, y, H, W, ch / 4, flip);
     return vptr_check_launch("dwconv3x3_kernel");
 }
 
@@ -122,7 +141,7 @@ extern "C" int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9,
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3_wgrad: F=%d H=%d W=%d ch=%d", F, H, W, ch);
     int fpb = (256 + H * W - 1) / (H * W);  // ~256 pixels per block
     if (fpb < 1) fpb = 1;
-    dim3 grid(vptr_cdiv(ch / 4, 128), vptr_cdiv(F, fpb));
-    dwconv3x3_wgrad_kernel<<<grid, 128, 0, stream>>>(x, dy, dw9, dbias, F, H, W, ch / 4, fpb);
+    dim3 grid(vptr_cdiv(ch / 4, DW_THREADS), vptr_cdiv(F, fpb));
+    dwconv3x3_wgrad_kernel<<<grid, DW_THREADS, 0, stream>>>(x, dy, dw9, dbias, F, H, W, ch / 4, fpb);
     return vptr_check_launch("dwconv3x3_wgrad_kernel");
 }

@@ -310,47 +310,56 @@ __global__ void __launch_bounds__(512) groupstats_kernel(const float* __restrict
 // ------------------------------------------------------------------ norm + GELU (+ residual) forward
 // mode 0 (BatchNorm): stats and affine indexed by channel c.
 // mode 1 (frame LayerNorm): stats indexed by frame = row / hw, affine indexed by (row % hw)*ch + c.
+// Grid = (chunks of a frame, frames): every index below is 32-bit and relative to the frame -- the flat-index version spent two
+// 64-bit divisions (e / ch, row / hw) plus one more for DropPath per float4 and was ALU-bound at ~2x its HBM time.
 template <int MODE>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                            const float* __restrict__ res, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, long long total4, int ch, int hw,
+                                                           const float* __restrict__ beta, int frame4, int C4, int hw,
                                                            int round_tf32, const DropArgs da) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i * 4;
-        const long long row = e / ch;
-        const int c = (int)(e - row * ch);
-        float4 v = *reinterpret_cast<const float4*>(x + e);
+    const int f = blockIdx.y;
+    const long long fbase = (long long)f * frame4;                    // float4 index of the frame's first element
+    float mm = 0.f, rr = 0.f;
+    if (MODE == 1) { mm = __ldg(mean + f); rr = __ldg(rstd + f); }
+    const bool drop = da.p > 0.f;
+    float rs = 1.f;                                                   // DropPath: clips are whole frames (rows_per_group % hw == 0)
+    if (da.rowscale) rs = __ldg(da.rowscale + ((long long)f * hw) / da.rows_per_group);
+    // each block streams one contiguous chunk of the frame (DRAM-page friendly), 256 float4 per step
+    const int per = ((frame4 + (int)gridDim.x - 1) / (int)gridDim.x + 255) & ~255;
+    const int i_end = min((int)(blockIdx.x + 1) * per, frame4);
+#pragma unroll 2
+    for (int i = blockIdx.x * per + threadIdx.x; i < i_end; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(x)[fbase + i];
         float4 m, r, g, b;
         if (MODE == 0) {
-            m = __ldg(reinterpret_cast<const float4*>(mean + c));
-            r = __ldg(reinterpret_cast<const float4*>(rstd + c));
-            g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-            b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const int c4 = i % C4;
+            m = __ldg(reinterpret_cast<const float4*>(mean) + c4);
+            r = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+            g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            b = __ldg(reinterpret_cast<const float4*>(beta) + c4);
         } else {
-            const long long f = row / hw;
-            const long long a = (row - f * hw) * ch + c;
-            const float mm = __ldg(mean + f), rr = __ldg(rstd + f);
             m = make_float4(mm, mm, mm, mm);
             r = make_float4(rr, rr, rr, rr);
-            g = __ldg(reinterpret_cast<const float4*>(gamma + a));
-            b = __ldg(reinterpret_cast<const float4*>(beta + a));
+            g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+            b = __ldg(reinterpret_cast<const float4*>(beta) + i);
         }
         float4 o;
         o.x = vptr_gelu((v.x - m.x) * r.x * g.x + b.x);
         o.y = vptr_gelu((v.y - m.y) * r.y * g.y + b.y);
         o.z = vptr_gelu((v.z - m.z) * r.z * g.z + b.z);
         o.w = vptr_gelu((v.w - m.w) * r.w * g.w + b.w);
-        if (da.p > 0.f || da.rowscale) {
-            const float4 k = drop_factor4(da, row, e);
+        if (drop) {
+            const float4 k = vptr_drop_scale4(da.seed, (unsigned long long)(fbase + i), da.p);
             o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
         }
+        o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
         if (res) {
-            float4 q = *reinterpret_cast<const float4*>(res + e);
+            const float4 q = reinterpret_cast<const float4*>(res)[fbase + i];
             o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
         }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
-        *reinterpret_cast<float4*>(y + e) = o;
+        reinterpret_cast<float4*>(y)[fbase + i] = o;
     }
 }
 
@@ -411,6 +420,7 @@ __global__ void __launch_bounds__(256) ln3_act_bwd_pass_ab_kernel(const float* _
     const bool drop = da.p > 0.f || da.rowscale;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f), b = g, ag = g, ab = g;
     if (live) { g = __ldg(reinterpret_cast<const float4*>(gamma + a)); b = __ldg(reinterpret_cast<const float4*>(beta + a)); }
+#pragma unroll 2
     for (int f = f0; f < f1; ++f) {
         float a1 = 0.f, a2 = 0.f;
         if (live) {
@@ -419,7 +429,7 @@ __global__ void __launch_bounds__(256) ln3_act_bwd_pass_ab_kernel(const float* _
             const float4 xv = *reinterpret_cast<const float4*>(x + e);
             float4 d = *reinterpret_cast<const float4*>(dy + e);
             if (drop) {
-                const float4 k = drop_factor4(da, e / ch, e);   // 4 consecutive elements share a row (ch % 4 == 0)
+                const float4 k = drop_factor4(da, (long long)f * (int)(gsize / ch) + (int)a / ch, e);   // 32-bit in-frame row; 4 elements share a row
                 d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
             }
             const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
@@ -458,37 +468,48 @@ template <int MODE>
 __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(float* __restrict__ g0dx, const float* __restrict__ x,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma, const float* __restrict__ s1,
-                                                              const float* __restrict__ s2, long long total4, int ch, long long gsize,
-                                                              float inv_n, int round_tf32) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const long long e = i * 4;
-        const float4 d = *reinterpret_cast<const float4*>(g0dx + e);
-        const float4 xv = *reinterpret_cast<const float4*>(x + e);
+                                                              const float* __restrict__ s2, int frame4, int C4, float inv_n, int round_tf32) {
+    const int f = blockIdx.y;                                          // (chunk, frame) grid, 32-bit in-frame indices (see forward)
+    const long long fbase = (long long)f * frame4;
+    float mm = 0.f, rr = 0.f, t1 = 0.f, t2 = 0.f;
+    if (MODE == 1) { mm = __ldg(mean + f); rr = __ldg(rstd + f); t1 = __ldg(s1 + f) * inv_n; t2 = __ldg(s2 + f) * inv_n; }
+    // each block streams one contiguous chunk of the frame (DRAM-page friendly), 256 float4 per step
+    const int per = ((frame4 + (int)gridDim.x - 1) / (int)gridDim.x + 255) & ~255;
+    const int i_end = min((int)(blockIdx.x + 1) * per, frame4);
+#pragma unroll 2
+    for (int i = blockIdx.x * per + threadIdx.x; i < i_end; i += 256) {
+        const float4 d = reinterpret_cast<const float4*>(g0dx)[fbase + i];
+        const float4 xv = reinterpret_cast<const float4*>(x)[fbase + i];
         float4 o;
         if (MODE == 1) {
-            const long long f = e / gsize;
-            const long long a = e - f * gsize;
-            const float m = __ldg(mean + f), r = __ldg(rstd + f), t1 = __ldg(s1 + f) * inv_n, t2 = __ldg(s2 + f) * inv_n;
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + a));
-            o.x = r * (d.x * g.x - t1 - (xv.x - m) * r * t2); o.y = r * (d.y * g.y - t1 - (xv.y - m) * r * t2);
-            o.z = r * (d.z * g.z - t1 - (xv.z - m) * r * t2); o.w = r * (d.w * g.w - t1 - (xv.w - m) * r * t2);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+            o.x = rr * (d.x * g.x - t1 - (xv.x - mm) * rr * t2); o.y = rr * (d.y * g.y - t1 - (xv.y - mm) * rr * t2);
+            o.z = rr * (d.z * g.z - t1 - (xv.z - mm) * rr * t2); o.w = rr * (d.w * g.w - t1 - (xv.w - mm) * rr * t2);
         } else {
-            const int c = (int)(e % ch);
-            const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c)), r = __ldg(reinterpret_cast<const float4*>(rstd + c));
-            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const int c4 = i % C4;
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + c4), r = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
             if (MODE == 0) {
-                const float4 t1 = __ldg(reinterpret_cast<const float4*>(s1 + c)), t2 = __ldg(reinterpret_cast<const float4*>(s2 + c));
-                o.x = g.x * r.x * (d.x - t1.x * inv_n - (xv.x - m.x) * r.x * t2.x * inv_n);
-                o.y = g.y * r.y * (d.y - t1.y * inv_n - (xv.y - m.y) * r.y * t2.y * inv_n);
-                o.z = g.z * r.z * (d.z - t1.z * inv_n - (xv.z - m.z) * r.z * t2.z * inv_n);
-                o.w = g.w * r.w * (d.w - t1.w * inv_n - (xv.w - m.w) * r.w * t2.w * inv_n);
+                const float4 u1 = __ldg(reinterpret_cast<const float4*>(s1) + c4), u2 = __ldg(reinterpret_cast<const float4*>(s2) + c4);
+                o.x = g.x * r.x * (d.x - u1.x * inv_n - (xv.x - m.x) * r.x * u2.x * inv_n);
+                o.y = g.y * r.y * (d.y - u1.y * inv_n - (xv.y - m.y) * r.y * u2.y * inv_n);
+                o.z = g.z * r.z * (d.z - u1.z * inv_n - (xv.z - m.z) * r.z * u2.z * inv_n);
+                o.w = g.w * r.w * (d.w - u1.w * inv_n - (xv.w - m.w) * r.w * u2.w * inv_n);
             } else {
                 o.x = g.x * r.x * d.x; o.y = g.y * r.y * d.y; o.z = g.z * r.z * d.z; o.w = g.w * r.w * d.w;
             }
         }
         if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
-        *reinterpret_cast<float4*>(g0dx + e) = o;
+        reinterpret_cast<float4*>(g0dx)[fbase + i] = o;
     }
+}
+
+// blocks per frame for the (chunk, frame) grids: enough CTAs to fill the GPU a few times over, >= 2 float4 per thread
+int norm_chunks(int frame4, int frames) {
+    int chunks = (frame4 + 2 * 256 - 1) / (2 * 256);
+    const int want = (148 * 16 + frames - 1) / frames;
+    if (chunks > want) chunks = want;
+    return chunks < 1 ? 1 : chunks;
 }
 
 int ew_grid(long long n, int block) {
@@ -571,10 +592,12 @@ extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, con
                                  int rows_per_group, unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_fwd: rows=%lld ch=%d", rows, ch);
     const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
-    long long total4 = rows * ch / 4;
-    int grid = ew_grid(total4, 256);
-    if (mode == 0) norm_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32, da);
-    else norm_act_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, total4, ch, hw, round_tf32, da);
+    VPTR_REQUIRE(hw > 0 && rows % hw == 0 && rows / hw < 65536, VPTR_ERR_SHAPE, "vptr_norm_act_fwd: rows=%lld not whole frames of hw=%d", rows, hw);
+    VPTR_REQUIRE(rowscale == nullptr || rows_per_group % hw == 0, VPTR_ERR_SHAPE, "vptr_norm_act_fwd: DropPath groups must be whole frames");
+    const int frames = (int)(rows / hw), frame4 = hw * (ch / 4);
+    dim3 grid(norm_chunks(frame4, frames), frames);
+    if (mode == 0) norm_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, frame4, ch / 4, hw, round_tf32, da);
+    else norm_act_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, y, res, mean, rstd, gamma, beta, frame4, ch / 4, hw, round_tf32, da);
     return vptr_check_launch("norm_act_fwd_kernel");
 }
 
@@ -586,24 +609,25 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
                                  float drop_p, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d (ch %% 4 == 0 required)", rows, ch);
     const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
-    const long long total4 = rows * ch / 4;
-    const int grid = ew_grid(total4, 256);
+    VPTR_REQUIRE(hw > 0 && rows % hw == 0 && rows / hw < 65536, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld not whole frames of hw=%d", rows, hw);
+    const int frame4 = hw * (ch / 4);
+    const dim3 gdx(norm_chunks(frame4, (int)(rows / hw)), (unsigned)(rows / hw));
     if (mode == 0 || mode == 2) {
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * ch, stream);
         int rpb = 128;
         dim3 g2(vptr_cdiv(ch / 4, 128), vptr_cdiv(rows, rpb));
         bn_act_bwd_pass_a_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, ws, ws + ch, rows, ch, rpb, da);
         if (mode == 0)
-            norm_act_bwd_dx_kernel<0><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, total4, ch, 0, 1.0f / (float)rows, round_tf32);
+            norm_act_bwd_dx_kernel<0><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, frame4, ch / 4, 1.0f / (float)rows, round_tf32);
         else
-            norm_act_bwd_dx_kernel<2><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, total4, ch, 0, 0.f, round_tf32);
+            norm_act_bwd_dx_kernel<2><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, frame4, ch / 4, 0.f, round_tf32);
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * frames, stream);
         dim3 g2(vptr_cdiv(gsize / 4, 256), vptr_cdiv(frames, LN3_FPB));
         ln3_act_bwd_pass_ab_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, dgamma, dbeta, gsize, ch, frames, da);
-        norm_act_bwd_dx_kernel<1><<<grid, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, total4, ch, gsize, 1.0f / (float)gsize, round_tf32);
+        norm_act_bwd_dx_kernel<1><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, frame4, ch / 4, 1.0f / (float)gsize, round_tf32);
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }
