@@ -1263,6 +1263,15 @@ int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, i
 
 }  // namespace
 
+// tcgen05 / TMA forward (attn_tcgen05.cu); VPTR_ERR_UNSUPPORTED when the shape is outside its domain
+int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O, long long ldo,
+                          const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead, int d, int causal,
+                          float scale, int round_tf32, unsigned long long drop_seed, float drop_p, cudaStream_t stream);
+static bool attn_tc_enabled() {
+    static const bool v = [] { const char* e = getenv("VPTR_ATTN_TC"); return e && e[0] == '1'; }();
+    return v;
+}
+
 // mode 0: F_or_N = number of frames (N*T); mode 1: F_or_N = number of clips N.
 extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                              long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
@@ -1276,6 +1285,11 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_fwd: empty problem");
+    if (attn_tc_enabled()) {   // tcgen05 + TMA + TMEM forward
+        rc = vptr_attn_fwd_tcgen05(Q, ldq, K, ldk, V, ldv, O, ldo, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32,
+                                   drop_seed, drop_p, stream);
+        if (rc != VPTR_ERR_UNSUPPORTED) return rc;
+    }
     if (attn_mma_ok(g, nhead, d) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)Q % 16 == 0) &&
         ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0))   // tensor-core path (mma.sync, 3xTF32)
         return dispatch_attn_mma<false>(Q, ldq, K, ldk, V, ldv, nullptr, O, ldo, nullptr, 0, nullptr, 0, 0, rpe_table, nullptr, g, batches, stream);
