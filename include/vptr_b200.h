@@ -86,6 +86,13 @@ int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const 
 int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
                   long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead,
                   int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p, vptr_stream_t stream);
+/* tcgen05 / TMA / TMEM forward of the same core (head_dim 66, groups <= 32 tokens, 4x4 windows or temporal sequences): same
+ * arguments as vptr_attn_fwd; returns -3 (unsupported) outside its domain.  TF32 operands (~4e-4 relative when q/k/v were
+ * rounded to tf32 by their producers).  vptr_attn_fwd routes here when VPTR_ATTN_TC=1; the default is the 3xTF32 mma path. */
+int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
+                          long long ldo, const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead,
+                          int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p,
+                          vptr_stream_t stream);
 int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO,
                   long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV, long long lddv,
                   const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,

@@ -149,6 +149,54 @@ def test_temporal_attention_core(Tq, Tk, causal):
     assert rel_l2(dq, qr.grad) < 1e-4 and rel_l2(dkv, kvr.grad) < 1e-4
 
 
+@pytest.mark.parametrize("case", ["window", "window_tail", "temporal", "causal29", "cross"])
+def test_attention_tcgen05_forward(case):
+    """The tcgen05 / TMA / TMEM forward (vptr_attn_fwd_tcgen05, opt-in VPTR_ATTN_TC=1) against the fp32 oracle core.  Operands enter
+    the tensor core as TF32, so q/k/v are pre-rounded (as their producing GEMMs do) and the gate is 1e-3 instead of 2e-5."""
+    from vptr_b200 import ops
+    nhead, d = 8, 66
+    C, scale = nhead * d, d ** -0.5
+    if case.startswith("window"):
+        Fr, H, W, ws = (5 if case == "window_tail" else 4), 8, 8, 4
+        L, rows = ws * ws, Fr * H * W
+        qkv = ops.round_copy(rnd(rows, 3 * C, seed=1))
+        table = rnd((2 * ws - 1) ** 2, nhead, seed=2) * 0.5
+        o = torch.full((rows, C), float("nan"), device="cuda")
+        ops.attn_fwd_tcgen05(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, H, W, ws, 0, 0, nhead, d, False, scale)
+        tmap = O.window_token_map(Fr, H, W, ws).cuda()
+        g = lambda t: t[tmap.t()]
+        bias = table[O.relative_position_index(ws).cuda().reshape(-1)].reshape(L, L, nhead).permute(2, 0, 1)
+        ob = _attn_ref(g(qkv[:, :C]), g(qkv[:, C:2 * C]), g(qkv[:, 2 * C:]), nhead, scale, bias=bias)
+        oref = torch.zeros(rows, C, device="cuda").index_put((tmap.t().reshape(-1),), ob.reshape(-1, C))
+    else:
+        N, H, W = 2, 8, 8
+        Tq, Tk, causal = {"temporal": (10, 10, False), "causal29": (29, 29, True), "cross": (28, 2, False)}[case]
+        HW = H * W
+        q, kv = ops.round_copy(rnd(N * Tq * HW, C, seed=1)), ops.round_copy(rnd(N * Tk * HW, 2 * C, seed=2))
+        o = torch.full_like(q, float("nan"))
+        ops.attn_fwd_tcgen05(q, kv[:, :C], kv[:, C:], o, None, 1, N, H, W, 0, Tq, Tk, nhead, d, causal, scale)
+        seq = lambda t, T: t.view(N, T, HW, -1).permute(0, 2, 1, 3).reshape(N * HW, T, -1)
+        mask = O.causal_mask(Tq).cuda() if causal else None
+        ob = _attn_ref(seq(q, Tq), seq(kv[:, :C], Tk), seq(kv[:, C:], Tk), nhead, scale, mask=mask)
+        oref = ob.view(N, HW, Tq, C).permute(0, 2, 1, 3).reshape(N * Tq * HW, C)
+    assert torch.isfinite(o).all() and rel_l2(o, oref) < 1e-3
+
+
+def test_attention_tcgen05_rejects_unsupported_shapes():
+    from vptr_b200 import ops
+    q = torch.zeros(64, 48, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.attn_fwd_tcgen05(q, q, q, torch.empty_like(q), None, 1, 1, 2, 2, 0, 16, 16, 4, 12, False, 1.0)
+
+
+def test_round_copy_multi_matches_single():
+    from vptr_b200 import ops
+    ws = [rnd(528, 528, seed=1), rnd(2112, 528, seed=2), rnd(8, 4, seed=3)]
+    outs = ops.round_copy_multi(ws)
+    for w, o in zip(ws, outs):
+        assert o.shape == w.shape and torch.equal(o, ops.round_copy(w))
+
+
 def test_dwconv3x3():
     from vptr_b200 import ops
     Fr, H, W, ch = 5, 8, 6, 48

@@ -27,6 +27,7 @@ _SIGS = {
     "vptr_norm_act_fwd": ([P, P, P, P, P, P, P, L, I, I, I, I, P, I, U, F, P], I),
     "vptr_norm_act_bwd": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P, I, U, F, P], I),
     "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
+    "vptr_attn_fwd_tcgen05": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
     "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
     "vptr_window_index_maps": ([I, I, I, I, P, P, P], I),
     "vptr_causal_mask": ([I, P, P], I),

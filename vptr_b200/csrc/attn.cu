@@ -1264,7 +1264,7 @@ int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, i
 }  // namespace
 
 // tcgen05 / TMA forward (attn_tcgen05.cu); VPTR_ERR_UNSUPPORTED when the shape is outside its domain
-int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O, long long ldo,
+extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O, long long ldo,
                           const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead, int d, int causal,
                           float scale, int round_tf32, unsigned long long drop_seed, float drop_p, cudaStream_t stream);
 static bool attn_tc_enabled() {

@@ -14,12 +14,11 @@
 // applies the causal rule, and writes exp(s - max) as the K-major A operand of the second MMA, O = P V (N = 96, K = 128),
 // whose result is normalised by 1/rowsum in the epilogue and leaves through a TMA store.
 //
-//   * head slices are 66 floats at 264-byte offsets.  Each head gets its own tensor map with the SAME base and a width of
-//     66*(h+1) columns, so a 32-column box reaching past the head's last column is clipped by the map: TMA zero-fills (loads) /
-//     drops (stores) the excess and no junk enters the contraction over head_dim.
-//   * TMA needs 16-byte aligned box starts, which an odd head (offset 264*h = 8 mod 16) does not have: its boxes start two floats
-//     EARLY (66*h - 2).  The two leading columns (the previous head's tail) are zeroed in the Q tile by the issuing warp before
-//     the score MMA and are ignored in O (V's shift just moves the output columns by two).
+//   * head slices are 66 floats at 264-byte offsets, loaded as three 32-column boxes (96 columns, contraction over 72).  TMA
+//     needs 16-byte aligned box starts, which an odd head (offset 264*h = 8 mod 16) does not have: its boxes start two floats
+//     EARLY (66*h - 2).  Tile columns that belong to a neighbouring head (0..1 of an odd head, 66/68..71) are zeroed in the Q
+//     tile by the issuing warp before the score MMA, so whatever K holds there contributes nothing; in V they only produce
+//     output columns that are never stored.
 //   * O leaves as two aligned 32-column TMA boxes (head columns 0..63 of an even head, 2..65 of an odd one) plus one 8-byte
 //     generic store per row for the remaining pair: a clipped TMA STORE rewrites the whole 16-byte granule that the pair shares
 //     with the neighbouring head (measured: it zeroed the neighbour's two columns), so no store box may end inside a granule.
@@ -41,7 +40,8 @@ constexpr int TC_THREADS = 160;
 constexpr int TC_MAXHEADS = 8;
 
 struct TcMaps {
-    CUtensorMap q[TC_MAXHEADS], k[TC_MAXHEADS], v[TC_MAXHEADS], o[TC_MAXHEADS];
+    CUtensorMap q, k, v, o;   // ONE map per tensor: with a map per (tensor, head) the TMA unit re-fetched a descriptor for nearly
+                              // every copy (32 maps cycling through its small descriptor cache) and an item took ~23 us
 };
 struct TcGeom {
     int mode;                 // 0 window, 1 temporal
@@ -205,6 +205,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
         }
     }
     if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.o) : "memory");
         *abort_flag = 0;
         mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(o_ready, 1); mbar_init(v_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -231,12 +235,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     if (g.mode == 0) {
-                        tma_load_2d(&maps.q[h], qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
-                        tma_load_2d(&maps.k[h], qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
+                        tma_load_2d(&maps.q, qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
+                        tma_load_2d(&maps.k, qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_load_4d(&maps.q[h], qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
-                        tma_load_4d(&maps.k[h], qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
+                        tma_load_4d(&maps.q, qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
+                        tma_load_4d(&maps.k, qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
                     }
                 }
             }
@@ -249,10 +253,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     if (g.mode == 0) {
-                        tma_load_2d(&maps.v[h], v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
+                        tma_load_2d(&maps.v, v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_load_4d(&maps.v[h], v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
+                        tma_load_4d(&maps.v, v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
                     }
                 }
             }
@@ -264,9 +268,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
             const int next = item + gridDim.x;
             // ---- S = Q K^T : 9 k-steps of 8 over head_dim 72 (columns 66..71 are zero-filled by the clipped maps)
             mbar_wait(qk_full, ph, abort_flag, 1 + 10 * (warp == 4));
-            if ((item % g.nhead) & 1) {   // odd head: columns 0..1 of the tiles are the previous head's tail -> zero them in Q
+            {   // columns of the 72-wide contraction that do not belong to this head (the neighbours' data, or zero fill past the
+                // tensor) are zeroed in the Q tile: even head -> 66..71; odd head (tile starts 2 columns early) -> 0..1 and 68..71
+                const int odd_h = (item % g.nhead) & 1;
 #pragma unroll
-                for (int r = lane; r < TC_ROWS; r += 32) *reinterpret_cast<float2*>(sQ + sw128_offset(r, 0)) = make_float2(0.f, 0.f);
+                for (int r = lane; r < TC_ROWS; r += 32) {
+                    *reinterpret_cast<float2*>(sQ + sw128_offset(r, odd_h ? 0 : 66)) = make_float2(0.f, 0.f);
+                    *reinterpret_cast<float4*>(sQ + sw128_offset(r, 68)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 fence_async_smem();
                 __syncwarp();
             }
@@ -422,10 +431,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                 const int c0 = h * TC_D + 2 * odd;
                 for (int c = 0; c < 2; ++c) {
                     if (g.mode == 0) {
-                        tma_store_2d(&maps.o[h], sV + c * TC_CHUNK, c0 + c * 32, tile * TC_ROWS);
+                        tma_store_2d(&maps.o, sV + c * TC_CHUNK, c0 + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_store_4d(&maps.o[h], sV + c * TC_CHUNK, c0 + c * 32, p0, 0, n);
+                        tma_store_4d(&maps.o, sV + c * TC_CHUNK, c0 + c * 32, p0, 0, n);
                     }
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -458,11 +467,11 @@ EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// per-head map: same base, width clipped to the end of head h.  window: [rows][width]; temporal: [N][T][HW][width]
-int make_head_map(CUtensorMap* m, const float* base, long long ld, int h, const TcGeom& g, long long rows, int N, int T, CUtensorMapSwizzle sw) {
+// window: [rows][width]; temporal: [N][T][HW][width]  (width = nhead * 66 columns from `base`; boxes past it are zero-filled)
+int make_tensor_map(CUtensorMap* m, const float* base, long long ld, int width_cols, const TcGeom& g, long long rows, int N, int T, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = encode_fn();
     VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-    const cuuint64_t width = (cuuint64_t)TC_D * (h + 1);
+    const cuuint64_t width = (cuuint64_t)width_cols;
     CUresult r;
     if (g.mode == 0) {
         cuuint64_t dims[2] = {width, (cuuint64_t)rows};
@@ -477,7 +486,7 @@ int make_head_map(CUtensorMap* m, const float* base, long long ld, int h, const 
         r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(attention head map) failed (%d)", (int)r);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(attention map) failed (%d)", (int)r);
     return VPTR_OK;
 }
 
@@ -485,9 +494,10 @@ int make_head_map(CUtensorMap* m, const float* base, long long ld, int h, const 
 
 // Returns VPTR_ERR_UNSUPPORTED (without setting an error a caller must report) when the shape is outside the kernel's domain.
 // mode 0: F_or_N = frames; mode 1: F_or_N = clips.  Same argument meaning as vptr_attn_fwd.
-int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O, long long ldo,
+extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O, long long ldo,
                           const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead, int d, int causal,
                           float scale, int round_tf32, unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
+    vptr_set_error("vptr_attn_fwd_tcgen05: shape outside the kernel's domain (head_dim 66, <= 8 heads, groups of <= 32 tokens, windows of <= 16)");
     if (d != TC_D || nhead > TC_MAXHEADS || nhead < 1) return VPTR_ERR_UNSUPPORTED;
     if ((ldq | ldk | ldv | ldo) % 4 != 0 || ((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) % 16 != 0) return VPTR_ERR_UNSUPPORTED;
     TcGeom g{};
@@ -519,16 +529,14 @@ int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float* K, long lo
     }
     g.total_rows_q = rows_q;
     TcMaps maps;
-    for (int h = 0; h < nhead; ++h) {
-        int rc = make_head_map(&maps.q[h], Q, ldq, h, g, rows_q, F_or_N, Tq, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        rc = make_head_map(&maps.k[h], K, ldk, h, g, rows_k, F_or_N, Tk, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        rc = make_head_map(&maps.v[h], V, ldv, h, g, rows_k, F_or_N, Tk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-        if (rc) return rc;
-        rc = make_head_map(&maps.o[h], O, ldo, h, g, rows_q, F_or_N, Tq, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-    }
+    int rc = make_tensor_map(&maps.q, Q, ldq, nhead * TC_D, g, rows_q, F_or_N, Tq, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map(&maps.k, K, ldk, nhead * TC_D, g, rows_k, F_or_N, Tk, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = make_tensor_map(&maps.v, V, ldv, nhead * TC_D, g, rows_k, F_or_N, Tk, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+    rc = make_tensor_map(&maps.o, O, ldo, nhead * TC_D, g, rows_q, F_or_N, Tq, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
     const size_t smem = 13 * TC_CHUNK + 1024 + 512 + (rpe_table ? sizeof(float) * nhead * g.Lq * g.Lk : 0) + 64;
     static bool attr_set = false;
     if (!attr_set) {

@@ -149,6 +149,13 @@ def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, 
     return out
 
 
+def attn_fwd_tcgen05(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False, drop_seed=0, drop_p=0.0):
+    """the tcgen05 / TMA / TMEM forward (opt-in, VPTR_ATTN_TC=1 routes attn_fwd here); raises outside its shape domain"""
+    _call("vptr_attn_fwd_tcgen05", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode, F_or_N,
+          H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _s())
+    return out
+
+
 def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False,
              drop_seed=0, drop_p=0.0):
     _call("vptr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
