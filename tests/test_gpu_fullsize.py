@@ -24,6 +24,21 @@ def test_nar_cfg1_shape_one_clip():
     assert rel_l2(y, yo) < 1e-3
 
 
+def test_nar_cfg3_shape_one_clip():
+    """BAIR-shape 2 -> 28 (cfg3): temporal groups of 28 and enc-dec attention with 28 queries x 2 keys take the 32-row
+    instantiation of the tensor-core attention kernels"""
+    from vptr_b200.model import VPTRFormerNAR
+    torch.manual_seed(2021)
+    net = VPTRFormerNAR(2, 28, encH=8, encW=8, d_model=528, nhead=8, num_encoder_layers=4, num_decoder_layers=8, dropout=0.1,
+                        window_size=4, rpe=True).eval()
+    x = torch.rand(1, 2, 528, 8, 8, generator=torch.Generator().manual_seed(8))
+    with torch.no_grad():
+        yo = O.vptr_former_nar({k: v for k, v in net.state_dict().items()}, x, nhead=8, ws=4, rpe=True, training=False)
+        y = net.cuda()(x.cuda())
+    assert tuple(y.shape) == (1, 28, 528, 8, 8)
+    assert rel_l2(y, yo) < 1e-3
+
+
 def test_far_cfg2_shape_one_clip():
     from vptr_b200.model import VPTRFormerFAR
     torch.manual_seed(2021)

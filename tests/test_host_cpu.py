@@ -74,7 +74,14 @@ def _dp_worker(rank, world, port, q):
     x = torch.full((5, 6), float(rank + 1))
     lin(x).sum().backward()
     n = allreduce_mean_grads(list(lin.parameters()) + [extra], world)
-    q.put((rank, lin.weight.detach().clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), n))
+    # gradients that are consecutive views of one flat buffer (what the engine's backward returns) are reduced in place
+    flat = torch.full(((1 << 20) + 8,), float(rank + 1))
+    pa, pb = torch.nn.Parameter(torch.zeros(1 << 20)), torch.nn.Parameter(torch.zeros(2, 4))
+    pa.grad, pb.grad = flat[:1 << 20], flat[1 << 20:].view(2, 4)
+    ptr = flat.data_ptr()
+    allreduce_mean_grads([pa, pb, lin.weight], world)            # + one loose gradient in the same call
+    inplace_ok = pa.grad.data_ptr() == ptr and bool((flat == 1.5).all())
+    q.put((rank, lin.weight.detach().clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), n, inplace_ok))
     dist.destroy_process_group()
 
 
@@ -90,7 +97,8 @@ def test_flat_allreduce_mean_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, w0, gw0, gb0, n0), (_, w1, gw1, gb1, n1) = res
+    (_, w0, gw0, gb0, n0, ok0), (_, w1, gw1, gb1, n1, ok1) = res
+    assert ok0 and ok1                                           # flat views averaged in place (1.0 and 2.0 -> 1.5)
     assert torch.equal(w0, w1)                                   # rank-0 weights broadcast
     assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)       # identical after the mean
     assert torch.allclose(gw0, torch.full((4, 6), 5 * 1.5)) and torch.allclose(gb0, torch.full((4,), 5.0))

@@ -1224,8 +1224,9 @@ template <bool BWD>
 int dispatch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,
                       long long ldo, float* dK, long long lddk, float* dV, long long lddv, long long lddo, const float* rpe_table,
                       float* d_rpe_table, const AttnGeom& g, int batches, cudaStream_t stream) {
+    static const int hpc_env = [] { const char* e = getenv("VPTR_ATTN_HPC"); return e ? atoi(e) : 0; }();
     if (g.Lq <= 16 && g.Lk <= 16) {
-        if (g.nhead % 4 == 0)
+        if (g.nhead % 4 == 0 && hpc_env != 2)
             return launch_attn_mma<1, 2, 4, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
         return launch_attn_mma<1, 2, 2, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
     }

@@ -11,22 +11,74 @@ def broadcast_parameters(module, src=0):
         dist.broadcast(t.data, src)
 
 
+_CHECKED = set()
+
+
+def _covering_view(grads):
+    """If the gradients are consecutive views of ONE contiguous buffer (the engine hands out parameter gradients as views of a
+    flat fp32 buffer, vptr_b200.engine.Params), return a 1-D view covering them all; else None."""
+    if not grads or any(not g.is_contiguous() for g in grads):
+        return None
+    base = grads[0].untyped_storage().data_ptr()
+    esz = grads[0].element_size()
+    pos = grads[0].data_ptr()
+    for g in grads:
+        if g.untyped_storage().data_ptr() != base or g.dtype != grads[0].dtype or g.data_ptr() != pos:
+            return None
+        pos += g.numel() * esz
+    total = (pos - grads[0].data_ptr()) // esz
+    return torch.as_strided(grads[0], (total,), (1,), grads[0].storage_offset())
+
+
 def allreduce_mean_grads(params, world_size=None):
-    """In-place mean over ranks of every existing .grad, through one flat buffer.  Parameters whose grad is None
-    contribute nothing locally; if ranks disagree on which grads exist the call raises instead of hanging."""
+    """In-place mean over ranks of every existing .grad with ONE collective.  Gradients that already are consecutive views of a
+    flat buffer (the Transformer's, straight out of the engine's backward) are reduced in place -- no flatten / unflatten copies;
+    anything else goes through a temporary flat buffer.  NCCL averages inside the collective (ReduceOp.AVG); other backends sum
+    and divide.  Parameters whose grad is None contribute nothing locally; the first call for a given gradient set checks that
+    all ranks hold the same set and raises instead of hanging later."""
     world_size = dist.get_world_size() if world_size is None else world_size
     grads = [p.grad for p in params if p.grad is not None]
-    n_local = torch.tensor([len(grads), sum(g.numel() for g in grads)], dtype=torch.int64,
-                           device=grads[0].device if grads else "cpu")
-    n_max = n_local.clone()
-    dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
-    if not torch.equal(n_max, n_local):
-        raise RuntimeError("allreduce_mean_grads: ranks hold different gradient sets (%s vs max %s)" % (n_local.tolist(), n_max.tolist()))
+    sig = (len(grads), sum(g.numel() for g in grads))
+    if sig not in _CHECKED:
+        n_local = torch.tensor(list(sig), dtype=torch.int64, device=grads[0].device if grads else "cpu")
+        n_max = n_local.clone()
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+        n_min = n_local.clone()
+        dist.all_reduce(n_min, op=dist.ReduceOp.MIN)
+        if not (torch.equal(n_max, n_local) and torch.equal(n_min, n_local)):
+            raise RuntimeError("allreduce_mean_grads: ranks hold different gradient sets (%s vs min %s max %s)" %
+                               (n_local.tolist(), n_min.tolist(), n_max.tolist()))
+        _CHECKED.add(sig)
     if not grads:
         return 0
-    flat = torch._utils._flatten_dense_tensors(grads)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-    flat.div_(world_size)
-    for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-        g.copy_(s)
-    return flat.numel()
+    avg = dist.get_backend() == "nccl"
+
+    def reduce_(flat):
+        if avg:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.div_(world_size)
+
+    # split into maximal runs that are already flat in memory; the longest run (the Transformer) is reduced in place
+    runs, cur = [], [grads[0]]
+    for g in grads[1:]:
+        if _covering_view(cur + [g]) is not None:
+            cur.append(g)
+        else:
+            runs.append(cur)
+            cur = [g]
+    runs.append(cur)
+    loose = []
+    for r in runs:
+        v = _covering_view(r)
+        if v is not None and v.numel() >= (1 << 20):
+            reduce_(v)
+        else:
+            loose.extend(r)
+    if loose:
+        flat = torch._utils._flatten_dense_tensors(loose)
+        reduce_(flat)
+        for g, s_ in zip(loose, torch._utils._unflatten_dense_tensors(flat, loose)):
+            g.copy_(s_)
+    return sig[1]
