@@ -1080,9 +1080,11 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.total_chunks = vptr_cdiv(K, BLOCK_K);
     if (!(flags & 1)) k_splits = 1;
     const int workers = two_cta ? num_sms() / 2 : num_sms();
-    if (k_splits <= 0) {  // auto split-K for accumulate mode: aim for >= 2 tiles per worker
+    if (k_splits <= 0) {  // auto split-K for accumulate mode: fill exactly two rounds of the persistent grid
+        // (rounding UP gave e.g. 9 tiles x 17 splits = 153 items on 74 CTA pairs = 2.07 waves, i.e. a third, nearly empty round:
+        //  every weight-gradient GEMM of the path ran 3 rounds instead of 2)
         int tiles = p.m_tiles * p.n_tiles;
-        k_splits = (2 * workers + tiles - 1) / tiles;
+        k_splits = (2 * workers) / tiles;
         int max_splits = p.total_chunks / 8 > 0 ? p.total_chunks / 8 : 1;  // keep >= 8 chunks per split
         if (k_splits > max_splits) k_splits = max_splits;
         if (k_splits < 1) k_splits = 1;
