@@ -105,8 +105,11 @@ def cpu_step_rate(TS, torch, clips, steps, warmup):
     torch.manual_seed(2021)
     enc = VPTREnc(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3).eval()
     dec = VPTRDec(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3, out_layer="Sigmoid").eval()
-    init_weights(enc)
-    init_weights(dec)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):     # init_weights prints; stdout carries exactly one JSON line
+        init_weights(enc)
+        init_weights(dec)
     T = VPTRFormerNAR(CFG["Tp"], CFG["Tf"], encH=8, encW=8, d_model=CFG["d_model"], nhead=CFG["nhead"], num_encoder_layers=CFG["enc_layers"],
                       num_decoder_layers=CFG["dec_layers"], dropout=0.0, window_size=CFG["ws"], rpe=True)
     sd_T = {k: v.detach() for k, v in T.state_dict().items()}
