@@ -23,30 +23,35 @@ __device__ __forceinline__ int pad_index(int i, int n, int mode) {  // returns -
 }
 
 // col[(f,oh,ow)][(kh,kw,ci)] = x[f][oh*s+kh-p][ow*s+kw-p][ci] (* (mask > 0))
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ col,
-                                                     long long total4, int H, int W, int C4, int Ho, int Wo, int k, int stride, int pad,
-                                                     int pad_mode, int round_tf32) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long t = i / C4;
-        const int kw = (int)(t % k); t /= k;
-        const int kh = (int)(t % k); t /= k;
-        const int ow = (int)(t % Wo); t /= Wo;
-        const int oh = (int)(t % Ho);
-        const long long f = t / Ho;
+// Grid = (output rows (f, oh), chunks of ow); a thread owns one (tap, float4 channel group) slot of the k*k*C4-wide column row
+// and walks its block's output pixels, so the per-element index arithmetic is 32-bit adds (the flat-index version did six
+// 64-bit divisions per float4 and ran at a third of its HBM bound).
+__global__ void __launch_bounds__(288) im2col_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ col,
+                                                     int H, int W, int C4, int Ho, int Wo, int k, int stride, int pad, int pad_mode,
+                                                     int round_tf32, int ow_per_block) {
+    const int row4 = k * k * C4;                            // float4 per column row
+    const int f = blockIdx.x / Ho, oh = blockIdx.x - f * Ho;
+    const int ow0 = blockIdx.y * ow_per_block, ow1 = min(ow0 + ow_per_block, Wo);
+    for (int slot = threadIdx.x; slot < row4; slot += blockDim.x) {
+        const int tap = slot / C4, c = slot - tap * C4;
+        const int kh = tap / k, kw = tap - kh * k;
         const int ih = pad_index(oh * stride + kh - pad, H, pad_mode);
-        const int iw = pad_index(ow * stride + kw - pad, W, pad_mode);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ih >= 0 && iw >= 0) {
-            const long long src = ((f * H + ih) * W + iw) * C4 + c;
-            v = reinterpret_cast<const float4*>(x)[src];
-            if (mask) {
-                float4 m = reinterpret_cast<const float4*>(mask)[src];
-                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+        const long long src_row = ((long long)f * H + (ih >= 0 ? ih : 0)) * W;
+        float4* dst = reinterpret_cast<float4*>(col) + ((long long)blockIdx.x * Wo + ow0) * row4 + slot;
+        for (int ow = ow0; ow < ow1; ++ow, dst += row4) {
+            const int iw = pad_index(ow * stride + kw - pad, W, pad_mode);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ih >= 0 && iw >= 0) {
+                const long long src = (src_row + iw) * C4 + c;
+                v = reinterpret_cast<const float4*>(x)[src];
+                if (mask) {
+                    const float4 m = reinterpret_cast<const float4*>(mask)[src];
+                    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                }
             }
+            if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+            *dst = v;
         }
-        if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
-        reinterpret_cast<float4*>(col)[i] = v;
     }
 }
 
@@ -399,8 +404,15 @@ extern "C" int vptr_im2col(const float* x, const float* mask, float* col, int F,
                  "vptr_im2col: F=%d H=%d W=%d Cin=%d k=%d stride=%d", F, H, W, Cin, k, stride);
     VPTR_REQUIRE(pad_mode == 0 || (pad < H && pad < W), VPTR_ERR_SHAPE, "vptr_im2col: reflect/replicate pad %d too large for %dx%d", pad, H, W);
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    const long long total4 = (long long)F * Ho * Wo * k * k * (Cin / 4);
-    im2col_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, mask, col, total4, H, W, Cin / 4, Ho, Wo, k, stride, pad, pad_mode, round_tf32);
+    VPTR_REQUIRE((long long)F * Ho < 2147483647LL, VPTR_ERR_SHAPE, "vptr_im2col: F*Ho too large");
+    const int row4 = k * k * (Cin / 4);
+    const int threads = row4 < 288 ? ((row4 + 31) / 32) * 32 : 288;
+    // enough blocks to fill the GPU: split each output row into ow chunks when there are few rows
+    int chunks = 1;
+    while ((long long)F * Ho * chunks < 148 * 8 && chunks < Wo) chunks *= 2;
+    const int owpb = (Wo + chunks - 1) / chunks;
+    dim3 grid(F * Ho, (Wo + owpb - 1) / owpb);
+    im2col_kernel<<<grid, threads, 0, stream>>>(x, mask, col, H, W, Cin / 4, Ho, Wo, k, stride, pad, pad_mode, round_tf32, owpb);
     return vptr_check_launch("im2col_kernel");
 }
 
