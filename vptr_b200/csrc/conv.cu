@@ -57,15 +57,17 @@ __global__ void __launch_bounds__(288) im2col_kernel(const float* __restrict__ x
 
 // xpad[f][h][w][c] = x[f][pad_index(h - pad)][pad_index(w - pad)][c]  (zero / reflect / replicate), optionally rounded to tf32:
 // the explicit padded copy that the implicit-GEMM convolution's TMA boxes read (1.56x the activation instead of a 9x im2col)
+// IDX = unsigned when the element count fits 32 bits (always, at the path's sizes): 64-bit div/mod cost ~5x more instructions
+template <typename IDX>
 __global__ void __launch_bounds__(256) pad_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, long long total4, int H, int W,
                                                        int C4, int pad, int pad_mode, int round_tf32) {
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long t = i / C4;
-        const int w = (int)(t % Wp); t /= Wp;
-        const int h = (int)(t % Hp);
-        const long long f = t / Hp;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < (IDX)total4; i += (IDX)gridDim.x * blockDim.x) {
+        const int c = (int)(i % (IDX)C4);
+        IDX t = i / (IDX)C4;
+        const int w = (int)(t % (IDX)Wp); t /= (IDX)Wp;
+        const int h = (int)(t % (IDX)Hp);
+        const long long f = (long long)(t / (IDX)Hp);
         const int ih = pad_index(h - pad, H, pad_mode), iw = pad_index(w - pad, W, pad_mode);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ih >= 0 && iw >= 0) v = reinterpret_cast<const float4*>(x)[((f * H + ih) * W + iw) * C4 + c];
@@ -76,15 +78,16 @@ __global__ void __launch_bounds__(256) pad_nhwc_kernel(const float* __restrict__
 
 // ConvTranspose2d(k3,s2,p1,op1) output gather: out[f][oh][ow][co] = relu( sum_{kh,kw} col[(f,ih,iw)][(kh,kw,co)] + shift[co] )
 // with oh = 2*ih - 1 + kh.
+template <typename IDX>
 __global__ void __launch_bounds__(256) convT_gather_kernel(const float* __restrict__ col, const float* __restrict__ shift,
                                                            float* __restrict__ out, long long total4, int H, int W, int C4, int relu) {
     const int Ho = 2 * H, Wo = 2 * W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C4);
-        long long t = i / C4;
-        const int ow = (int)(t % Wo); t /= Wo;
-        const int oh = (int)(t % Ho);
-        const long long f = t / Ho;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < (IDX)total4; i += (IDX)gridDim.x * blockDim.x) {
+        const int c = (int)(i % (IDX)C4);
+        IDX t = i / (IDX)C4;
+        const int ow = (int)(t % (IDX)Wo); t /= (IDX)Wo;
+        const int oh = (int)(t % (IDX)Ho);
+        const long long f = (long long)(t / (IDX)Ho);
         float4 acc = shift ? __ldg(reinterpret_cast<const float4*>(shift) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
@@ -421,7 +424,8 @@ extern "C" int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, in
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && pad >= 0, VPTR_ERR_SHAPE, "vptr_pad_nhwc: F=%d H=%d W=%d C=%d pad=%d", F, H, W, C, pad);
     VPTR_REQUIRE(pad_mode == 0 || (pad < H && pad < W), VPTR_ERR_SHAPE, "vptr_pad_nhwc: reflect/replicate pad %d too large for %dx%d", pad, H, W);
     const long long total4 = (long long)F * (H + 2 * pad) * (W + 2 * pad) * (C / 4);
-    pad_nhwc_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
+    if (total4 < 0x7fffffffLL) pad_nhwc_kernel<unsigned><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
+    else pad_nhwc_kernel<long long><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
     return vptr_check_launch("pad_nhwc_kernel");
 }
 
@@ -429,7 +433,8 @@ extern "C" int vptr_convT_gather(const float* col, const float* shift, float* ou
                                  cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0, VPTR_ERR_SHAPE, "vptr_convT_gather: F=%d H=%d W=%d Cout=%d", F, H, W, Cout);
     const long long total4 = (long long)F * 4 * H * W * (Cout / 4);
-    convT_gather_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(col, shift, out, total4, H, W, Cout / 4, relu);
+    if (total4 < 0x7fffffffLL) convT_gather_kernel<unsigned><<<ew_grid(total4, 256), 256, 0, stream>>>(col, shift, out, total4, H, W, Cout / 4, relu);
+    else convT_gather_kernel<long long><<<ew_grid(total4, 256), 256, 0, stream>>>(col, shift, out, total4, H, W, Cout / 4, relu);
     return vptr_check_launch("convT_gather_kernel");
 }
 
