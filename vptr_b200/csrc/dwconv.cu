@@ -68,6 +68,82 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv3x3_kernel(const float* __re
     }
 }
 
+// Streaming variant for small frames (H*W*SLAB float4 <= ~100 KB, i.e. the 8x8 grid of every 64x64 config): persistent blocks,
+// work item = (frame, slab of SLAB float4 channel groups), the item's whole input tile [H*W][SLAB] is brought in with cp.async
+// into one of two shared buffers while the previous item is computed -- ~90 KB of loads in flight per SM instead of the
+// 4 float4 per thread of the register-window kernel above (which was memory-latency bound at 52 % of HBM peak).  A thread owns
+// one channel group and two output rows and slides the same 4x3 register window, now fed from shared memory.
+__global__ void __launch_bounds__(352, 1) dwconv3x3_stream_kernel(const float* __restrict__ x, const float* __restrict__ w9,
+                                                                  const float* __restrict__ bias, float* __restrict__ y, int F, int H, int W,
+                                                                  int C4, int slab, int nslab, int flip) {
+    extern __shared__ __align__(16) float4 dsm[];
+    const int HW = H * W, tile4 = HW * slab;
+    const int c = threadIdx.x % slab, rg = threadIdx.x / slab;       // channel group in slab, output row pair
+    const int items = F * nslab;
+    auto issue = [&](int item, float4* buf) {
+        const int f = item / nslab, s0 = (item - f * nslab) * slab;
+        const float4* src = reinterpret_cast<const float4*>(x) + (long long)f * HW * C4 + s0;
+        for (int e = threadIdx.x; e < tile4; e += blockDim.x) {
+            const int px = e / slab, cc = e - px * slab;
+            if (s0 + cc < C4) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + e);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (long long)px * C4 + cc) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if ((int)blockIdx.x < items) issue(blockIdx.x, dsm);
+    for (int item = blockIdx.x; item < items; item += gridDim.x, cur ^= 1) {
+        const int next = item + gridDim.x;
+        if (next < items) issue(next, dsm + (cur ^ 1) * tile4);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const int f = item / nslab, s0 = (item - f * nslab) * slab;
+        const int h = rg * 2;
+        if (s0 + c < C4 && h < H) {
+            const float4* tile = dsm + cur * tile4;
+            float4 k[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w9) + (flip ? 8 - t : t) * C4 + s0 + c);
+            const float4 b = (bias && !flip) ? __ldg(reinterpret_cast<const float4*>(bias) + s0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            auto ld = [&](int hh, int j) -> float4 {
+                if (hh < 0 || hh >= H || j < 0 || j >= W) return make_float4(0.f, 0.f, 0.f, 0.f);
+                return tile[(hh * W + j) * slab + c];
+            };
+            float4 win[4][3];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                win[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                win[r][1] = ld(h + r - 1, 0);
+                win[r][2] = ld(h + r - 1, 1);
+            }
+            const bool two = h + 1 < H;
+            float4* out = reinterpret_cast<float4*>(y) + ((long long)f * HW + (long long)h * W) * C4 + s0 + c;
+            for (int w = 0; w < W; ++w) {
+                float4 a0 = b, a1 = b;
+#pragma unroll
+                for (int dh = 0; dh < 3; ++dh)
+#pragma unroll
+                    for (int dw = 0; dw < 3; ++dw) {
+                        fma4(a0, k[dh * 3 + dw], win[dh][dw]);
+                        fma4(a1, k[dh * 3 + dw], win[dh + 1][dw]);
+                    }
+                out[(long long)w * C4] = a0;
+                if (two) out[(long long)(W + w) * C4] = a1;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    win[r][0] = win[r][1];
+                    win[r][1] = win[r][2];
+                    win[r][2] = ld(h + r - 1, w + 2);
+                }
+            }
+        }
+        __syncthreads();      // the buffer just read is the target of the prefetch issued in the next iteration
+    }
+}
+
 // dW9[t][c] += sum_{f,h,w} dy[f,h,w,c] * x[f,h+dh-1,w+dw-1,c] ; dbias[c] += sum dy.  Thread = float4 channel group, a chunk of
 // frames per blockIdx.y, same sliding window over x.
 __global__ void __launch_bounds__(DW_THREADS) dwconv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
@@ -131,6 +207,26 @@ extern "C" int vptr_dwconv3x3(const float* x, const float* w9, const float* bias
                               cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F=%d H=%d W=%d ch=%d", F, H, W, ch);
     VPTR_REQUIRE((long long)F * H < 2147483647LL, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F*H too large");
+    {   // streaming kernel: whole-frame tiles double-buffered in shared memory
+        static const bool off = [] { const char* e = getenv("VPTR_DWCONV_NOSTREAM"); return e && e[0] == '1'; }();
+        const int C4 = ch / 4, HW = H * W, pairs = (H + 1) / 2;
+        int slab = 352 / pairs;                                   // one thread per (channel group, row pair)
+        if (slab > C4) slab = C4;
+        const size_t smem = (size_t)2 * HW * slab * sizeof(float4);
+        if (!off && slab >= 32 && smem <= 200 * 1024 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
+            const int nslab = vptr_cdiv(C4, slab);
+            static size_t attr = 0;
+            if (smem > attr) {
+                cudaError_t e = cudaFuncSetAttribute(dwconv3x3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(dwconv3x3_stream, smem=%zu): %s", smem, cudaGetErrorString(e));
+                attr = smem;
+            }
+            long long items = (long long)F * nslab;
+            const int blocks = (int)(items < 148 ? items : 148);
+            dwconv3x3_stream_kernel<<<blocks, slab * pairs, smem, stream>>>(x, w9, bias, y, F, H, W, C4, slab, nslab, flip);
+            return vptr_check_launch("dwconv3x3_stream_kernel");
+        }
+    }
     dim3 grid(F * ((H + 1) / 2), vptr_cdiv(ch / 4, DW_THREADS));
     dwconv3x3_kernel<<<grid, DW_THREADS, 0, stream>>>(x, w9, bias, y, H, W, ch / 4, flip);
     return vptr_check_launch("dwconv3x3_kernel");
