@@ -936,31 +936,30 @@ __device__ __forceinline__ void mma_smemT_times_rows(const float* Wt, int lp, co
 
 // coalesced 16-byte staging of `L` row segments [col0, col0 + 4*W4) into a [.][Cp] tile with cp.async (no register staging,
 // all of a thread's requests in flight at once), one warp per row; and the store back (optionally rounded to tf32)
+template <int W4>
 __device__ __forceinline__ void mma_load_tile(float* tile, int Cp, const float* __restrict__ src, long long ld, const long long* rows, int L,
-                                              int W4, int col0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int l = warp; l < L; l += nw) {
-        const float* r = src + rows[l] * ld + col0;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + l * Cp);
-        for (int c = lane; c < W4; c += 32)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * c), "l"(r + 4 * c) : "memory");
+                                              int col0) {
+    // flat (row, float4) index with a compile-time row width: the division is a multiply-shift and every thread issues
+    // ceil(L * W4 / blockDim) copies (the one-warp-per-row form spent 3 iterations, the last 2 lanes wide, on 66 float4)
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(tile);
+    for (int e = threadIdx.x; e < L * W4; e += blockDim.x) {
+        const int l = e / W4, c = e - l * W4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(l * Cp + 4 * c) * 4u), "l"(src + rows[l] * ld + col0 + 4 * c)
+                     : "memory");
     }
 }
 __device__ __forceinline__ void mma_load_wait() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+template <int W4>
 __device__ __forceinline__ void mma_store_tile(const float* tile, int Cp, float* __restrict__ dst, long long ld, const long long* rows, int L,
-                                               int W4, int col0, int round_tf32) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int l = warp; l < L; l += nw) {
-        float4* r = reinterpret_cast<float4*>(dst + rows[l] * ld + col0);
-        const float4* sr = reinterpret_cast<const float4*>(tile + l * Cp);
-        for (int c = lane; c < W4; c += 32) {
-            float4 v = sr[c];
-            if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
-            r[c] = v;
-        }
+                                               int col0, int round_tf32) {
+    for (int e = threadIdx.x; e < L * W4; e += blockDim.x) {
+        const int l = e / W4, c = e - l * W4;
+        float4 v = *reinterpret_cast<const float4*>(tile + l * Cp + 4 * c);
+        if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+        *reinterpret_cast<float4*>(dst + rows[l] * ld + col0 + 4 * c) = v;
     }
 }
 // dropout keep-scales of probabilities (b, h, i, j) and (b, h, i, j + 1), j even: one hash when both fall into one group of four
@@ -1014,10 +1013,10 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
         for (int l = threadIdx.x; l < g.Lq; l += blockDim.x) rq[l] = q_row(g, b, l);
         for (int l = threadIdx.x; l < g.Lk; l += blockDim.x) rk[l] = k_row(g, b, l);
         __syncthreads();
-        mma_load_tile(sq, Cp, Q, ldq, rq, g.Lq, W4, h0 * D);
-        mma_load_tile(sk, Cp, K, ldk, rk, g.Lk, W4, h0 * D);
-        mma_load_tile(sv, Cp, V, ldv, rk, g.Lk, W4, h0 * D);
-        if (BWD) mma_load_tile(sgo, Cp, dO, lddo, rq, g.Lq, W4, h0 * D);
+        mma_load_tile<W4>(sq, Cp, Q, ldq, rq, g.Lq, h0 * D);
+        mma_load_tile<W4>(sk, Cp, K, ldk, rk, g.Lk, h0 * D);
+        mma_load_tile<W4>(sv, Cp, V, ldv, rk, g.Lk, h0 * D);
+        if (BWD) mma_load_tile<W4>(sgo, Cp, dO, lddo, rq, g.Lq, h0 * D);
         mma_load_wait();
         __syncthreads();
         {
@@ -1145,11 +1144,11 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
         }
         __syncthreads();
         if (!BWD) {
-            mma_store_tile(sq, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sq, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
         } else {
-            mma_store_tile(sv, Cp, dV, lddv, rk, g.Lk, W4, h0 * D, g.round_tf32);
-            mma_store_tile(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, W4, h0 * D, g.round_tf32);
-            mma_store_tile(sk, Cp, dK, lddk, rk, g.Lk, W4, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32);
         }
         __syncthreads();
     }
