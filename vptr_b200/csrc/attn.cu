@@ -827,22 +827,24 @@ __device__ __forceinline__ void mma_rows_dot(float (&acc)[MT][NT][4], const floa
     for (int ks = 0; ks < 9; ++ks) {
         const int c = ks * 8 + t;
         const bool ok0 = c < d, ok1 = c + 4 < d;
+        const int o0 = ok0 ? 0 : d - 1 - c, o1 = ok1 ? 4 : d - 1 - c;     // offsets from column c, clamped to the head's last column
         Frag4 a[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             const float* r0 = sA + (mt * 16 + g) * Cp + c0 + c;
             const float* r1 = r0 + 8 * Cp;
-            split_tf32(ok0 ? r0[0] : 0.f, a[mt].hi[0], a[mt].lo[0]);
-            split_tf32(ok0 ? r1[0] : 0.f, a[mt].hi[1], a[mt].lo[1]);
-            split_tf32(ok1 ? r0[4] : 0.f, a[mt].hi[2], a[mt].lo[2]);
-            split_tf32(ok1 ? r1[4] : 0.f, a[mt].hi[3], a[mt].lo[3]);
+            // masked columns are read from a clamped (in-head) address and discarded: no access ever leaves this head's columns
+            split_tf32(ok0 ? r0[o0] : 0.f, a[mt].hi[0], a[mt].lo[0]);
+            split_tf32(ok0 ? r1[o0] : 0.f, a[mt].hi[1], a[mt].lo[1]);
+            split_tf32(ok1 ? r0[o1] : 0.f, a[mt].hi[2], a[mt].lo[2]);
+            split_tf32(ok1 ? r1[o1] : 0.f, a[mt].hi[3], a[mt].lo[3]);
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const float* rb = sB + (nt * 8 + g) * Cp + c0 + c;
-            Frag2 b;
-            split_tf32(rb[0], b.hi[0], b.lo[0]);
-            split_tf32(rb[4], b.hi[1], b.lo[1]);
+            Frag2 b;   // columns >= d belong to the neighbouring head (whose warp may be overwriting them): never read
+            split_tf32(ok0 ? rb[o0] : 0.f, b.hi[0], b.lo[0]);
+            split_tf32(ok1 ? rb[o1] : 0.f, b.hi[1], b.lo[1]);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) mma3_split(acc[mt][nt], corr[mt][nt], a[mt], b);
         }
@@ -877,9 +879,11 @@ __device__ __forceinline__ void mma_regs_times_rows(const float (&W)[MT][NT][4],
 #pragma unroll
         for (int kt = 0; kt < NT; ++kt) {
             const float* rb = sT + (kt * 8 + 2 * t) * Cp + c0 + n9 * 8 + g;
+            const bool okn = n9 * 8 + g < d;      // output columns >= d are never stored; their inputs are another head's
+            const int on = okn ? 0 : d - 1 - (n9 * 8 + g);                     // clamped to the head's last column
             Frag2 b;
-            split_tf32(rb[0], b.hi[0], b.lo[0]);
-            split_tf32(rb[Cp], b.hi[1], b.lo[1]);
+            split_tf32(okn ? rb[on] : 0.f, b.hi[0], b.lo[0]);
+            split_tf32(okn ? rb[Cp + on] : 0.f, b.hi[1], b.lo[1]);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) mma3(o[mt], a[mt][kt], b);
         }
@@ -917,9 +921,11 @@ __device__ __forceinline__ void mma_smemT_times_rows(const float* Wt, int lp, co
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             const float* rb = sT + (ks * 8 + 2 * t) * Cp + c0 + n9 * 8 + g;
+            const bool okn = n9 * 8 + g < d;
+            const int on = okn ? 0 : d - 1 - (n9 * 8 + g);
             Frag2 b;
-            split_tf32(rb[0], b.hi[0], b.lo[0]);
-            split_tf32(rb[Cp], b.hi[1], b.lo[1]);
+            split_tf32(okn ? rb[on] : 0.f, b.hi[0], b.lo[0]);
+            split_tf32(okn ? rb[Cp + on] : 0.f, b.hi[1], b.lo[1]);
 #pragma unroll
             for (int mk = 0; mk < MTK; ++mk) mma3(o[mk], a[mk][ks], b);
         }
@@ -1028,6 +1034,7 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) P[mt][nt][0] = P[mt][nt][1] = P[mt][nt][2] = P[mt][nt][3] = 0.f;
             mma_rows_dot<MT, NT>(P, sq, sk, Cp, c0, D, gq, t);
+            __syncwarp();   // all lanes' reads of this head's Q / K columns precede the stores that later reuse them (O, dK)
             float keep[MT][NT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -1098,6 +1105,7 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) dS[mt][nt][0] = dS[mt][nt][1] = dS[mt][nt][2] = dS[mt][nt][3] = 0.f;
                 mma_rows_dot<MT, NT>(dS, sgo, sv, Cp, c0, D, gq, t);
+                __syncwarp();
                 float* PDw = spw + warp * 2 * LQP * LP;
                 float* dSw = PDw + LQP * LP;
 #pragma unroll
