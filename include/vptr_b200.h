@@ -107,6 +107,12 @@ int vptr_causal_mask(int T, unsigned char* mask, vptr_stream_t stream);
 /* ---- depthwise 3x3 of MlpDWBN (model/VidHRFormer_modules.py:405-410) ----------------------------------- */
 int vptr_dwconv3x3(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, int flip,
                    vptr_stream_t stream);
+/* forward depthwise conv + per-frame (sum, sum of squares) of its outputs into sums[0:F], sums[F:2F] (fp64, caller-zeroed): the
+ * statistics of the LayerNorm((ch,H,W)) that follows (MlpDWBN norm2) without another pass.  -3 outside the streaming kernel's domain. */
+int vptr_dwconv3x3_stats(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, double* sums,
+                         vptr_stream_t stream);
+/* mean / rstd per group from such (sum, sum of squares) pairs */
+int vptr_group_stats_finalize(const double* sums, int groups, long long gsize, float* mean, float* rstd, float eps, vptr_stream_t stream);
 int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9, float* dbias, int F, int H, int W, int ch,
                          vptr_stream_t stream);
 

@@ -208,6 +208,10 @@ def test_dwconv3x3(Fr, H, W, ch):
     xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     yr = F.conv2d(xr.view(Fr, H, W, ch).permute(0, 3, 1, 2), wr, br, padding=1, groups=ch).permute(0, 2, 3, 1).reshape(-1, ch)
     assert rel_l2(y, yr) < TOL
+    # fused statistics variant: same output, (mean, rstd) per frame equal to a separate pass
+    y2, (m2, r2) = ops.dwconv3x3_stats(x, w9, b, Fr, H, W)
+    m1, r1 = ops.group_stats(y, Fr)
+    assert torch.equal(y2, y) and rel_l2(m2, m1) < 1e-5 and rel_l2(r2, r1) < 1e-5
     dy = rnd(Fr * H * W, ch, seed=4)
     (yr * dy).sum().backward()
     dx = ops.dwconv3x3(dy, w9, None, Fr, H, W, flip=True)

@@ -32,6 +32,8 @@ _SIGS = {
     "vptr_window_index_maps": ([I, I, I, I, P, P, P], I),
     "vptr_causal_mask": ([I, P, P], I),
     "vptr_dwconv3x3": ([P, P, P, P, I, I, I, I, I, P], I),
+    "vptr_dwconv3x3_stats": ([P, P, P, P, I, I, I, I, P, P], I),
+    "vptr_group_stats_finalize": ([P, I, L, P, P, F, P], I),
     "vptr_dwconv3x3_wgrad": ([P, P, P, P, I, I, I, I, P], I),
     "vptr_axpby": ([P, P, P, L, F, F, P], I),
     "vptr_add_rows": ([P, P, P, L, I, I, I, I, P], I),

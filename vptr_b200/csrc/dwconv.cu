@@ -3,6 +3,7 @@
 // (ch,1,3,3) parameter is re-laid once per step).  HBM-bound: every element is read once from DRAM (the 9-tap
 // reuse is served by L1/L2) and written once.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv3x3_kernel(const float* __re
 // one channel group and two output rows and slides the same 4x3 register window, now fed from shared memory.
 __global__ void __launch_bounds__(352, 1) dwconv3x3_stream_kernel(const float* __restrict__ x, const float* __restrict__ w9,
                                                                   const float* __restrict__ bias, float* __restrict__ y, int F, int H, int W,
-                                                                  int C4, int slab, int nslab, int flip) {
+                                                                  int C4, int slab, int nslab, int flip, double* __restrict__ sums) {
     extern __shared__ __align__(16) float4 dsm[];
     const int HW = H * W, tile4 = HW * slab;
     const int c = threadIdx.x % slab, rg = threadIdx.x / slab;       // channel group in slab, output row pair
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(352, 1) dwconv3x3_stream_kernel(const float* _
         __syncthreads();
         const int f = item / nslab, s0 = (item - f * nslab) * slab;
         const int h = rg * 2;
+        float st_s = 0.f, st_q = 0.f;        // per-frame sum / sum of squares of the outputs (LayerNorm((ch,H,W)) statistics of the next op)
         if (s0 + c < C4 && h < H) {
             const float4* tile = dsm + cur * tile4;
             float4 k[9];
@@ -131,7 +133,13 @@ __global__ void __launch_bounds__(352, 1) dwconv3x3_stream_kernel(const float* _
                         fma4(a1, k[dh * 3 + dw], win[dh + 1][dw]);
                     }
                 out[(long long)w * C4] = a0;
-                if (two) out[(long long)(W + w) * C4] = a1;
+                st_s += (a0.x + a0.y) + (a0.z + a0.w);
+                st_q += (a0.x * a0.x + a0.y * a0.y) + (a0.z * a0.z + a0.w * a0.w);
+                if (two) {
+                    out[(long long)(W + w) * C4] = a1;
+                    st_s += (a1.x + a1.y) + (a1.z + a1.w);
+                    st_q += (a1.x * a1.x + a1.y * a1.y) + (a1.z * a1.z + a1.w * a1.w);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     win[r][0] = win[r][1];
@@ -139,6 +147,11 @@ __global__ void __launch_bounds__(352, 1) dwconv3x3_stream_kernel(const float* _
                     win[r][2] = ld(h + r - 1, w + 2);
                 }
             }
+        }
+        if (sums) {   // one pair of fp64 atomics per warp and item
+            st_s = warp_sum(st_s);
+            st_q = warp_sum(st_q);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(sums + f, (double)st_s); atomicAdd(sums + F + f, (double)st_q); }
         }
         __syncthreads();      // the buffer just read is the target of the prefetch issued in the next iteration
     }
@@ -203,33 +216,49 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv3x3_wgrad_kernel(const float
 
 }  // namespace
 
+// launches the streaming kernel when the shape allows it; returns 1 if it did not (caller falls back), <0 / >1 on error
+static int dwconv_stream_launch(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, int flip,
+                                double* sums, cudaStream_t stream) {
+    static const bool off = [] { const char* e = getenv("VPTR_DWCONV_NOSTREAM"); return e && e[0] == '1'; }();
+    const int C4 = ch / 4, HW = H * W, pairs = (H + 1) / 2;
+    int slab = 352 / pairs;                                   // one thread per (channel group, row pair)
+    if (slab > C4) slab = C4;
+    const size_t smem = (size_t)2 * HW * slab * sizeof(float4);
+    if (off || slab < 32 || smem > 200 * 1024 || ((uintptr_t)x % 16) || ((uintptr_t)y % 16)) return 1;
+    const int nslab = vptr_cdiv(C4, slab);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(dwconv3x3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(dwconv3x3_stream, smem=%zu): %s", smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    const long long items = (long long)F * nslab;
+    const int blocks = (int)(items < 148 ? items : 148);
+    dwconv3x3_stream_kernel<<<blocks, slab * pairs, smem, stream>>>(x, w9, bias, y, F, H, W, C4, slab, nslab, flip, sums);
+    return vptr_check_launch("dwconv3x3_stream_kernel");
+}
+
 extern "C" int vptr_dwconv3x3(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch, int flip,
                               cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F=%d H=%d W=%d ch=%d", F, H, W, ch);
     VPTR_REQUIRE((long long)F * H < 2147483647LL, VPTR_ERR_SHAPE, "vptr_dwconv3x3: F*H too large");
-    {   // streaming kernel: whole-frame tiles double-buffered in shared memory
-        static const bool off = [] { const char* e = getenv("VPTR_DWCONV_NOSTREAM"); return e && e[0] == '1'; }();
-        const int C4 = ch / 4, HW = H * W, pairs = (H + 1) / 2;
-        int slab = 352 / pairs;                                   // one thread per (channel group, row pair)
-        if (slab > C4) slab = C4;
-        const size_t smem = (size_t)2 * HW * slab * sizeof(float4);
-        if (!off && slab >= 32 && smem <= 200 * 1024 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0)) {
-            const int nslab = vptr_cdiv(C4, slab);
-            static size_t attr = 0;
-            if (smem > attr) {
-                cudaError_t e = cudaFuncSetAttribute(dwconv3x3_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(dwconv3x3_stream, smem=%zu): %s", smem, cudaGetErrorString(e));
-                attr = smem;
-            }
-            long long items = (long long)F * nslab;
-            const int blocks = (int)(items < 148 ? items : 148);
-            dwconv3x3_stream_kernel<<<blocks, slab * pairs, smem, stream>>>(x, w9, bias, y, F, H, W, C4, slab, nslab, flip);
-            return vptr_check_launch("dwconv3x3_stream_kernel");
-        }
-    }
+    const int rc = dwconv_stream_launch(x, w9, bias, y, F, H, W, ch, flip, nullptr, stream);
+    if (rc != 1) return rc;
     dim3 grid(F * ((H + 1) / 2), vptr_cdiv(ch / 4, DW_THREADS));
     dwconv3x3_kernel<<<grid, DW_THREADS, 0, stream>>>(x, w9, bias, y, H, W, ch / 4, flip);
     return vptr_check_launch("dwconv3x3_kernel");
+}
+
+// Forward depthwise conv that also accumulates, per frame, the sum and the sum of squares of its outputs into
+// sums[0:F] / sums[F:2F] (fp64, zeroed by the caller): the statistics of the LayerNorm((ch,H,W)) that follows (MlpDWBN norm2,
+// VidHRFormer_modules.py:436) without a separate pass over the tensor.  Returns -3 when the shape is outside the streaming
+// kernel's domain (callers then use vptr_dwconv3x3 + vptr_group_stats).  vptr_group_stats_finalize turns sums into mean / rstd.
+extern "C" int vptr_dwconv3x3_stats(const float* x, const float* w9, const float* bias, float* y, int F, int H, int W, int ch,
+                                    double* sums, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H > 0 && W > 0 && ch > 0 && ch % 4 == 0 && sums != nullptr, VPTR_ERR_SHAPE, "vptr_dwconv3x3_stats: F=%d H=%d W=%d ch=%d", F, H, W, ch);
+    const int rc = dwconv_stream_launch(x, w9, bias, y, F, H, W, ch, 0, sums, stream);
+    if (rc == 1) { vptr_set_error("vptr_dwconv3x3_stats: shape outside the streaming kernel's domain"); return VPTR_ERR_UNSUPPORTED; }
+    return rc;
 }
 
 extern "C" int vptr_dwconv3x3_wgrad(const float* x, const float* dy, float* dw9, float* dbias, int F, int H, int W, int ch,

@@ -307,6 +307,18 @@ __global__ void __launch_bounds__(512) groupstats_kernel(const float* __restrict
     }
 }
 
+// mean / rstd of `groups` groups from fp64 (sum, sum of squares) pairs accumulated by a producer (vptr_dwconv3x3_stats)
+__global__ void groupstats_finalize_kernel(const double* __restrict__ sums, int groups, double gsize, float* __restrict__ mean,
+                                           float* __restrict__ rstd, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups) return;
+    const double m = sums[i] / gsize;
+    double var = sums[groups + i] / gsize - m * m;
+    if (var < 0) var = 0;
+    mean[i] = (float)m;
+    rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 // ------------------------------------------------------------------ norm + GELU (+ residual) forward
 // mode 0 (BatchNorm): stats and affine indexed by channel c.
 // mode 1 (frame LayerNorm): stats indexed by frame = row / hw, affine indexed by (row % hw)*ch + c.
@@ -583,6 +595,13 @@ extern "C" int vptr_group_stats(const float* x, int groups, long long gsize, flo
     VPTR_REQUIRE(groups > 0 && gsize > 0 && gsize % 4 == 0, VPTR_ERR_SHAPE, "vptr_group_stats: groups=%d gsize=%lld", groups, gsize);
     groupstats_kernel<<<groups, 512, 0, stream>>>(x, mean, rstd, gsize, eps);
     return vptr_check_launch("groupstats_kernel");
+}
+
+extern "C" int vptr_group_stats_finalize(const double* sums, int groups, long long gsize, float* mean, float* rstd, float eps,
+                                         cudaStream_t stream) {
+    VPTR_REQUIRE(sums != nullptr && groups > 0 && gsize > 0, VPTR_ERR_SHAPE, "vptr_group_stats_finalize: groups=%d gsize=%lld", groups, gsize);
+    groupstats_finalize_kernel<<<vptr_cdiv(groups, 128), 128, 0, stream>>>(sums, groups, (double)gsize, mean, rstd, eps);
+    return vptr_check_launch("groupstats_finalize_kernel");
 }
 
 // y = GELU(norm(x)) (+ res).  mode 0: BatchNorm (per-channel stats/affine); mode 1: LayerNorm((ch,H,W)) per frame with

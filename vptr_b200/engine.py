@@ -283,8 +283,11 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     g1, b1 = _ffn_norm_params(P, pre, "norm1", g.HW, layer_norm)
     u1 = ops.norm_act_fwd(h1, st1[0], st1[1], g1, b1, g.HW, mode)
     w9 = ops.transpose(P.w(pre + ".dw3x3.weight"), 1, Ch, 9)
-    h2 = ops.dwconv3x3(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
-    st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
+    if layer_norm:   # frame-LayerNorm statistics of the conv output come out of the conv kernel itself
+        h2, st2 = ops.dwconv3x3_stats(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
+    else:
+        h2 = ops.dwconv3x3(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
+        st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
     g2, b2 = _ffn_norm_params(P, pre, "norm2", g.HW, layer_norm)
     s2, s3, dp = D.seed(), D.seed(), D.path()
     rpg = g.T * g.HW

@@ -185,6 +185,25 @@ def dwconv3x3(x, w9, bias, F, H, W, flip=False):
     return y
 
 
+def dwconv3x3_stats(x, w9, bias, F, H, W, eps=1e-5):
+    """forward depthwise conv that also returns the per-frame (mean, rstd) of its output -- one pass when the streaming kernel
+    applies, else dwconv3x3 + group_stats"""
+    y = torch.empty_like(x)
+    sums = torch.zeros(2 * F, dtype=torch.float64, device=x.device)
+    l = _lib.lib()
+    rc = l.vptr_dwconv3x3_stats(_p(x), _p(w9), _p(bias), _p(y), F, H, W, x.shape[-1], _p(sums), _s())
+    _lib.launch_count += 1
+    if rc == -3:
+        y = dwconv3x3(x, w9, bias, F, H, W)
+        return y, group_stats(y, F, eps)
+    if rc != 0:
+        raise RuntimeError("vptr_dwconv3x3_stats failed (status %d): %s" % (rc, l.vptr_last_error().decode("utf-8", "replace")))
+    mean = torch.empty(F, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    _call("vptr_group_stats_finalize", _p(sums), F, x.numel() // F, _p(mean), _p(rstd), float(eps), _s())
+    return y, (mean, rstd)
+
+
 def dwconv3x3_wgrad(x, dy, dw9, dbias, F, H, W):
     _call("vptr_dwconv3x3_wgrad", _p(x), _p(dy), _p(dw9), _p(dbias), F, H, W, x.shape[-1], _s())
 
