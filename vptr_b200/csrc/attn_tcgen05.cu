@@ -335,6 +335,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
         for (int c = 0; c < 4; ++c) need |= (__ballot_sync(0xffffffffu, vm[c] != 0) ? 1u : 0u) << c;
         const uint32_t lane_taddr = (uint32_t)(warp * 32) << 16;
         const float* brow = sbias + pos_i * g.Lk;             // + h * Lq * Lk per head
+        // Fast path for THE window shape of the path (8x8 grid, 4x4 windows, tile = two frames): the 16 keys of a row's window are
+        // four runs of four columns inside the warp's own 32-column chunk (image row r -> columns r*8 + xoff .. +3), so the whole
+        // softmax is straight-line code on 16 registers -- no per-column bit tests, position look-ups or second TMEM pass.
+        const bool fast_win = g.mode == 0 && g.HW == 64 && g.W == 8 && g.ws == 4;
+        const bool xhi = ((row & 7) >> 2) != 0;               // my window is the right-hand one of its image rows
+        const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        const uint32_t r7 = (uint32_t)(row & 7);
         uint32_t ph = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ph ^= 1) {
             const int tile = item / g.nhead, h = item - tile * g.nhead;
@@ -345,46 +352,83 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
             const unsigned long long drop_row = (((unsigned long long)batch * g.nhead + h) * g.Lq + pos_i) * g.Lk;
             mbar_wait(s_ready, ph, abort_flag, 2 + 10 * (warp == 4));
             tcgen05_fence_after();
-            // pass 1: row maximum over the attended columns
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (!((need >> c) & 1)) continue;
-                float v[32];
-                tmem_ld32(tmem_S + lane_taddr + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if ((vm[c] >> j) & 1) {
-                        float s = v[j] * g.scale;
-                        if (rpe_table) s += brow[h * g.Lq * g.Lk + colpos[c * 32 + j]];
-                        mx = fmaxf(mx, s);
-                    }
-                }
-            }
-            // pass 2: p = exp(s - max) (x dropout keep-scale), row sum, P tile
             float sum = 0.f;
+            if (fast_win) {
+                float v[32], sc[16];
+                tmem_ld32(tmem_S + lane_taddr + warp * 32, v);
+                float4 bq[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (!((need >> c) & 1)) continue;
-                float v[32];
-                tmem_ld32(tmem_S + lane_taddr + c * 32, v);
+                for (int r = 0; r < 4; ++r)
+                    bq[r] = rpe_table ? *reinterpret_cast<const float4*>(brow + h * 256 + r * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 tmem_ld_wait();
+                float mx = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float p = 0.f;
-                    if ((vm[c] >> j) & 1) {
-                        float s = v[j] * g.scale;
-                        if (rpe_table) s += brow[h * g.Lq * g.Lk + colpos[c * 32 + j]];
-                        p = __expf(s - mx);
-                        sum += p;
-                        if (g.drop_p > 0.f) p *= vptr_drop_scale(g.drop_seed, drop_row + colpos[c * 32 + j], g.drop_p);
-                    }
-                    v[j] = vptr_round_tf32(p);
+                for (int r = 0; r < 4; ++r) {
+                    sc[r * 4 + 0] = fmaf(xhi ? v[r * 8 + 4] : v[r * 8 + 0], g.scale, bq[r].x);
+                    sc[r * 4 + 1] = fmaf(xhi ? v[r * 8 + 5] : v[r * 8 + 1], g.scale, bq[r].y);
+                    sc[r * 4 + 2] = fmaf(xhi ? v[r * 8 + 6] : v[r * 8 + 2], g.scale, bq[r].z);
+                    sc[r * 4 + 3] = fmaf(xhi ? v[r * 8 + 7] : v[r * 8 + 3], g.scale, bq[r].w);
+                    mx = fmaxf(fmaxf(mx, fmaxf(sc[r * 4], sc[r * 4 + 1])), fmaxf(sc[r * 4 + 2], sc[r * 4 + 3]));
                 }
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4)
-                    *reinterpret_cast<float4*>(sP + sw128_offset(row, c * 32 + q4 * 4)) = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+                for (int j = 0; j < 16; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+                if (g.drop_p > 0.f) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {       // probabilities (row, 4r .. 4r+3): one hash per four (drop_row % 16 == 0)
+                        const float4 k = vptr_drop_scale4(g.drop_seed, (drop_row >> 2) + r, g.drop_p);
+                        sc[r * 4] *= k.x; sc[r * 4 + 1] *= k.y; sc[r * 4 + 2] *= k.z; sc[r * 4 + 3] *= k.w;
+                    }
+                }
+                uint8_t* prow = sP + warp * TC_CHUNK + row_off;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 p4 = make_float4(vptr_round_tf32(sc[r * 4]), vptr_round_tf32(sc[r * 4 + 1]), vptr_round_tf32(sc[r * 4 + 2]),
+                                                  vptr_round_tf32(sc[r * 4 + 3]));
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r) ^ r7) << 4)) = xhi ? z4 : p4;
+                    *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r + 1) ^ r7) << 4)) = xhi ? p4 : z4;
+                }
+            } else {
+                // pass 1: row maximum over the attended columns
+                float mx = -INFINITY;
+    #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!((need >> c) & 1)) continue;
+                    float v[32];
+                    tmem_ld32(tmem_S + lane_taddr + c * 32, v);
+                    tmem_ld_wait();
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if ((vm[c] >> j) & 1) {
+                            float s = v[j] * g.scale;
+                            if (rpe_table) s += brow[h * g.Lq * g.Lk + colpos[c * 32 + j]];
+                            mx = fmaxf(mx, s);
+                        }
+                    }
+                }
+                // pass 2: p = exp(s - max) (x dropout keep-scale), row sum, P tile
+    #pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!((need >> c) & 1)) continue;
+                    float v[32];
+                    tmem_ld32(tmem_S + lane_taddr + c * 32, v);
+                    tmem_ld_wait();
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float p = 0.f;
+                        if ((vm[c] >> j) & 1) {
+                            float s = v[j] * g.scale;
+                            if (rpe_table) s += brow[h * g.Lq * g.Lk + colpos[c * 32 + j]];
+                            p = __expf(s - mx);
+                            sum += p;
+                            if (g.drop_p > 0.f) p *= vptr_drop_scale(g.drop_seed, drop_row + colpos[c * 32 + j], g.drop_p);
+                        }
+                        v[j] = vptr_round_tf32(p);
+                    }
+    #pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4)
+                        *reinterpret_cast<float4*>(sP + sw128_offset(row, c * 32 + q4 * 4)) = make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]);
+                }
             }
             const float inv = valid_i ? 1.f / sum : 0.f;
             tcgen05_fence_before();
@@ -401,26 +445,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                 const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
                 if (valid_i && p0 + gid_i < g.HW) grow = ((long long)n * g.Tq + pos_i) * g.HW + p0 + gid_i;
             }
+            // 64 of the head's 66 columns leave through two aligned TMA boxes; the remaining pair (whose 16-byte granule is shared
+            // with the neighbouring head -- a clipped TMA store rewrites the whole granule) is one generic store.  Accumulator
+            // column of head column c: c (even head) or c + 2 (odd head, tiles start two columns early).
+            uint8_t* orow = sV + row_off;
+            auto stage = [&](int G, float4 o) {     // staged columns 4G .. 4G+3 of this row (K-major SWIZZLE_128B)
+                *reinterpret_cast<float4*>(orow + (uint32_t)(G >> 3) * TC_CHUNK + ((((uint32_t)G & 7u) ^ r7) << 4)) = o;
+            };
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 float v[32];
-                tmem_ld32(tmem_O + lane_taddr + c * 32, v);
+                if (c < 2) tmem_ld32(tmem_O + lane_taddr + c * 32, v);
+                else {   // only accumulator columns 64..67 are needed from the last chunk
+                    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(tmem_O + lane_taddr + 64));
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
+                for (int q4 = 0; q4 < (c < 2 ? 8 : 1); ++q4) {
                     float4 o = make_float4(v[q4 * 4] * inv, v[q4 * 4 + 1] * inv, v[q4 * 4 + 2] * inv, v[q4 * 4 + 3] * inv);
                     if (g.round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
                     const int G = c * 8 + q4;                       // accumulator columns 4G..4G+3
-                    // 64 of the head's 66 columns leave through two aligned TMA boxes; the remaining pair (whose 16-byte granule
-                    // is shared with the neighbouring head -- a clipped TMA store rewrites the whole granule) is one generic store
                     if (!odd) {
-                        if (G < 16) *reinterpret_cast<float4*>(sV + sw128_offset(row, G * 4)) = o;          // head columns 0..63
-                        else if (G == 16 && grow >= 0)                                                       // head columns 64..65
-                            *reinterpret_cast<float2*>(g.O + grow * g.ldo + h * TC_D + 64) = make_float2(o.x, o.y);
+                        if (G < 16) stage(G, o);                                                             // head columns 0..63
+                        else if (grow >= 0) *reinterpret_cast<float2*>(g.O + grow * g.ldo + h * TC_D + 64) = make_float2(o.x, o.y);   // 64..65
                     } else if (G == 0) {                            // head columns 0..1 sit in accumulator columns 2..3
                         if (grow >= 0) *reinterpret_cast<float2*>(g.O + grow * g.ldo + h * TC_D) = make_float2(o.z, o.w);
-                    } else if (G <= 16) {                           // head columns 2..65 -> staged columns 0..63
-                        *reinterpret_cast<float4*>(sV + sw128_offset(row, (G - 1) * 4)) = o;
+                    } else {                                        // head columns 2..65 -> staged columns 0..63
+                        stage(G - 1, o);
                     }
                 }
             }
