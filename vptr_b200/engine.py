@@ -178,24 +178,27 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
         aq_in = ops.add_rows(aq_in, lw_tab, 1, lw_tab.shape[0], round_tf32=RT)
     Rp = a_in.shape[0]
     qkv = ops.empty(Rp, 3 * C, like=x)
+    o = ops.empty(Rp, C, like=x)
     at = pre + ".attn."
+    # tcgen05 / TMA / TMEM forward for the path's window shape: its operands enter the tensor core as TF32, so q / k / v are
+    # rounded to nearest tf32 by the projections' epilogues (then the hardware's mantissa truncation is exact and unbiased)
+    use_tc = RT and ops.attn_tc_window_ok(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, g.Hp, g.Wp, g.ws, g.nhead, g.d)
     if rpe:
-        ops.gemm(aq_in, P.wr(at + "q_proj.weight"), out=qkv[:, :C], bias=P.w(at + "q_proj.bias"))
-        ops.gemm(aq_in, P.wr(at + "k_proj.weight"), out=qkv[:, C:2 * C], bias=P.w(at + "k_proj.bias"))
-        ops.gemm(a_in, P.wr(at + "v_proj.weight"), out=qkv[:, 2 * C:], bias=P.w(at + "v_proj.bias"))
+        ops.gemm(aq_in, P.wr(at + "q_proj.weight"), out=qkv[:, :C], bias=P.w(at + "q_proj.bias"), round_tf32=use_tc)
+        ops.gemm(aq_in, P.wr(at + "k_proj.weight"), out=qkv[:, C:2 * C], bias=P.w(at + "k_proj.bias"), round_tf32=use_tc)
+        ops.gemm(a_in, P.wr(at + "v_proj.weight"), out=qkv[:, 2 * C:], bias=P.w(at + "v_proj.bias"), round_tf32=use_tc)
         table = P.w(at + "relative_position_bias_table")
         wo, bo = P.wr(at + "out_proj.weight"), P.w(at + "out_proj.bias")
     else:
         Wi, bi = P.wr(at + "in_proj_weight"), P.w(at + "in_proj_bias")
-        ops.gemm(aq_in, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
-        ops.gemm(a_in, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
+        ops.gemm(aq_in, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C], round_tf32=use_tc)
+        ops.gemm(a_in, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:], round_tf32=use_tc)
         table = None
         wo, bo = P.wr(at + "out_proj.weight"), P.w(at + "out_proj.bias")
-    o = ops.empty(Rp, C, like=x)
     s_attn, dp = D.seed(), D.path()
     rpg = g.T * g.Hp * g.Wp                      # rows per clip (DropPath is per clip)
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale,
-                 round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
+    (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, table, 0, Fr, g.Hp, g.Wp, g.ws, 0, 0,
+                                                       g.nhead, g.d, False, g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     if g.padded:
         yp = ops.gemm(o, wo, bias=bo, rowscale=dp, rows_per_group=rpg)
         y = ops.crop_hw(yp, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0)

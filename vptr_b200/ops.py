@@ -1,5 +1,7 @@
 """Thin torch-tensor wrappers over the C-ABI (include/vptr_b200.h).  torch is used here only for device memory and
 the current CUDA stream; every computation is a kernel of libvptr_b200.so."""
+import os
+
 import torch
 
 from . import _lib
@@ -147,6 +149,17 @@ def attn_fwd(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, 
     _call("vptr_attn_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode,
           F_or_N, H, W, ws, Tq, Tk, nhead, d, int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _s())
     return out
+
+
+# the engine routes the window-attention forward of the path's shape (8x8 grid, 4x4 windows, 8 heads of 66) to the tcgen05 / TMA /
+# TMEM kernel; VPTR_ATTN_TC=0 keeps everything on the warp-level 3xTF32 kernels
+ATTN_TC = os.environ.get("VPTR_ATTN_TC", "") != "0"
+
+
+def attn_tc_window_ok(q, k, v, out, H, W, ws, nhead, d):
+    """shape / alignment domain of the tcgen05 window-attention fast path"""
+    return (ATTN_TC and not FORCE_SIMT and H == 8 and W == 8 and ws == 4 and d == 66 and 1 <= nhead <= 8
+            and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
 
 
 def attn_fwd_tcgen05(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False, drop_seed=0, drop_p=0.0):
