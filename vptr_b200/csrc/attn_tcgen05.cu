@@ -6,7 +6,7 @@
 //
 // Work item = (tile of up to 128 token rows, head).  A tile is a set of WHOLE attention groups in their natural memory order:
 //   window mode   : 128 consecutive tokens = whole frames (H*W <= 128) or whole bands of ws image rows -> 2-D TMA boxes;
-//   temporal mode : P pixels x all T frames of one clip, rows ordered (t, p)                              -> 4-D TMA boxes.
+//   temporal mode : P pixels x all T frames of one clip, rows ordered (pixel, t)                          -> 4-D TMA boxes.
 // The window gather / scatter and the per-pixel temporal regrouping therefore cost nothing: TMA lands the rows where the
 // tensor core wants them and attention structure becomes a MASK on the 128 x 128 score tile: S = Q K^T is computed for all
 // row pairs (tcgen05.mma M=128, N=128, K=72), and a thread (= TMEM lane = query row) keeps only the columns of its own group
@@ -153,8 +153,8 @@ __device__ __forceinline__ void row_info(const TcGeom& g, int r, bool is_q, int&
         valid = r < g.rows_q;
     } else {
         const int T = is_q ? g.Tq : g.Tk;
-        gid = r % g.P;
-        pos = r / g.P;
+        gid = r / T;                 // rows ordered (pixel, t): a sequence's keys are T CONTIGUOUS columns of the score tile
+        pos = r - gid * T;
         valid = r < T * g.P;
     }
 }
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                         tma_load_2d(&maps.k, qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_load_4d(&maps.q, qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
-                        tma_load_4d(&maps.k, qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
+                        tma_load_4d(&maps.q, qk_full, sQ + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, 0, p0, n);
+                        tma_load_4d(&maps.k, qk_full, sK + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, 0, p0, n);
                     }
                 }
             }
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                         tma_load_2d(&maps.v, v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_load_4d(&maps.v, v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, p0, 0, n);
+                        tma_load_4d(&maps.v, v_full, sV + c * TC_CHUNK, h * TC_D - 2 * (h & 1) + c * 32, 0, p0, n);
                     }
                 }
             }
@@ -339,6 +339,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
         // four runs of four columns inside the warp's own 32-column chunk (image row r -> columns r*8 + xoff .. +3), so the whole
         // softmax is straight-line code on 16 registers -- no per-column bit tests, position look-ups or second TMEM pass.
         const bool fast_win = g.mode == 0 && g.HW == 64 && g.W == 8 && g.ws == 4;
+        // Fast path for the temporal shape of cfg1 (T = 10 queries and keys, 12 pixel sequences per tile): a row's 10 keys are the
+        // contiguous columns [10 p, 10 p + 10); a warp's rows span at most 4 sequences = 40 columns from 10 * (32 w / 10).
+        const bool fast_t10 = g.mode == 1 && g.Tq == 10 && g.Tk == 10 && g.P == 12;
+        const int t10_plo = (warp * 32) / 10, t10_k = gid_i - t10_plo;
         const bool xhi = ((row & 7) >> 2) != 0;               // my window is the right-hand one of its image rows
         const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
         const uint32_t r7 = (uint32_t)(row & 7);
@@ -387,6 +391,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r) ^ r7) << 4)) = xhi ? z4 : p4;
                     *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r + 1) ^ r7) << 4)) = xhi ? p4 : z4;
+                }
+            } else if (fast_t10) {
+                float v0[32], v1[8], sc[10];
+                tmem_ld32(tmem_S + lane_taddr + t10_plo * 10, v0);
+                {
+                    uint32_t* r = reinterpret_cast<uint32_t*>(v1);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                                 : "r"(tmem_S + lane_taddr + t10_plo * 10 + 32));
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const float a0 = v0[j], a1 = v0[10 + j], a2 = v0[20 + j], a3 = (30 + j < 32) ? v0[(30 + j) & 31] : v1[(30 + j - 32) & 7];
+                    sc[j] = (t10_k == 0 ? a0 : t10_k == 1 ? a1 : t10_k == 2 ? a2 : a3) * g.scale;
+                    if (g.causal && j > pos_i) sc[j] = -INFINITY;
+                }
+                float mx = sc[0];
+#pragma unroll
+                for (int j = 1; j < 10; ++j) mx = fmaxf(mx, sc[j]);
+#pragma unroll
+                for (int j = 0; j < 10; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+                if (g.drop_p > 0.f) {
+                    const unsigned thr = vptr_drop_threshold(g.drop_p);
+                    const float keep = 1.f / (1.f - g.drop_p);
+#pragma unroll
+                    for (int jj = 0; jj < 5; ++jj) {           // drop_row is a multiple of 10: indices drop_row + 2jj are even -> pairs share a hash
+                        const unsigned long long idx = drop_row + 2 * jj;
+                        const unsigned z = (unsigned)(vptr_hash4(g.drop_seed, idx >> 2) >> (16 * (unsigned)(idx & 3)));
+                        sc[2 * jj] *= (z & 0xFFFFu) >= thr ? keep : 0.f;
+                        sc[2 * jj + 1] *= ((z >> 16) & 0xFFFFu) >= thr ? keep : 0.f;
+                    }
+                }
+                if (valid_i) {
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) *reinterpret_cast<float*>(sP + sw128_offset(row, gid_i * 10 + j)) = vptr_round_tf32(sc[j]);
                 }
             } else {
                 // pass 1: row maximum over the attended columns
@@ -487,7 +527,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                         tma_store_2d(&maps.o, sV + c * TC_CHUNK, c0 + c * 32, tile * TC_ROWS);
                     } else {
                         const int n = tile / g.chunks_per_clip, p0 = (tile - n * g.chunks_per_clip) * g.P;
-                        tma_store_4d(&maps.o, sV + c * TC_CHUNK, c0 + c * 32, p0, 0, n);
+                        tma_store_4d(&maps.o, sV + c * TC_CHUNK, c0 + c * 32, 0, p0, n);
                     }
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -533,9 +573,10 @@ int make_tensor_map(CUtensorMap* m, const float* base, long long ld, int width_c
         r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
-        cuuint64_t dims[4] = {width, (cuuint64_t)g.HW, (cuuint64_t)T, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)g.HW * ld * 4, (cuuint64_t)T * g.HW * ld * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)g.P, (cuuint32_t)T, 1}, es[4] = {1, 1, 1, 1};
+        // dims ordered (column, t, pixel, clip): the box {32, T, P, 1} lands with t fastest, i.e. tile row = pixel * T + t
+        cuuint64_t dims[4] = {width, (cuuint64_t)T, (cuuint64_t)g.HW, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.HW * ld * 4, (cuuint64_t)ld * 4, (cuuint64_t)T * g.HW * ld * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)T, (cuuint32_t)g.P, 1}, es[4] = {1, 1, 1, 1};
         r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }

@@ -356,12 +356,13 @@ def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save, D=NO_DROP):
     z, zp, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), add=pos, add_div=g.HW, add_mod=g.T, round_tf32=RT)
     Wi, bi = P.wr(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
     qkv = ops.empty(g.R, 3 * C, like=x)
-    ops.gemm(zp, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C])
-    ops.gemm(z, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
+    use_tc = RT and ops.attn_tc_temporal_ok(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, g.T, g.T, g.nhead, g.d)   # tcgen05 forward
+    ops.gemm(zp, Wi[:2 * C], out=qkv[:, :2 * C], bias=bi[:2 * C], round_tf32=use_tc)
+    ops.gemm(z, Wi[2 * C:], out=qkv[:, 2 * C:], bias=bi[2 * C:], round_tf32=use_tc)
     s_attn, s1 = D.seed(), D.seed()
-    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T, g.nhead, g.d, causal, g.scale,
-                 round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
+    (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, None, 1, g.N, g.H, g.W, 0, g.T, g.T,
+                                                       g.nhead, g.d, causal, g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, drop_seed=s1, drop_p=D.p)
     if save is not None:
         save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g, s_attn=s_attn, s1=s1, p=D.p)))
@@ -424,15 +425,16 @@ def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save, D=NO_DROP):
     C = g.C
     _, zq, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=qadd, add_div=1, add_mod=qadd.shape[0], round_tf32=RT)
     Wi, bi = P.wr(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
-    q = ops.gemm(zq, Wi[:C], bias=bi[:C])
     kv = ops.empty(gm.R, 2 * C, like=x)
-    ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C])
-    ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:])
     o = ops.empty(g.R, C, like=x)
+    use_tc = RT and ops.attn_tc_temporal_ok(o, kv[:, :C], kv[:, C:], o, g.T, gm.T, g.nhead, g.d)   # tcgen05 forward (q has o's layout)
+    q = ops.gemm(zq, Wi[:C], bias=bi[:C], round_tf32=use_tc)
+    ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C], round_tf32=use_tc)
+    ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:], round_tf32=use_tc)
     s_attn, dp = D.seed(), D.path()
     rpg = g.T * g.HW
-    ops.attn_fwd(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False, g.scale, round_tf32=RT,
-                 drop_seed=s_attn, drop_p=D.p)
+    (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False,
+                                                       g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
         save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))

@@ -162,6 +162,12 @@ def attn_tc_window_ok(q, k, v, out, H, W, ws, nhead, d):
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
 
 
+def attn_tc_temporal_ok(q, k, v, out, Tq, Tk, nhead, d):
+    """domain of the tcgen05 temporal fast path (the T = 10 self- and enc-dec attention of cfg1)"""
+    return (ATTN_TC and not FORCE_SIMT and Tq == 10 and Tk == 10 and d == 66 and 1 <= nhead <= 8
+            and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
+
+
 def attn_fwd_tcgen05(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False, drop_seed=0, drop_p=0.0):
     """the tcgen05 / TMA / TMEM forward (opt-in, VPTR_ATTN_TC=1 routes attn_fwd here); raises outside its shape domain"""
     _call("vptr_attn_fwd_tcgen05", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), _p(rpe_table), mode, F_or_N,
