@@ -278,7 +278,10 @@ def run_cuda(args):
                      "traffic_sample": {"launch": "M=40960 N=2112 K=528 (fc1 / linear1 shape)", "dram_bytes": 388915456,
                                         "algorithmic_bytes": 437000000, "tensor_pipe_active_pct": 52.4,
                                         "source": "profiles/r01_ncu_gemm_fc1_s3.txt (ncu --set full; achieved above is the aggregate over all GEMM shapes of a step, so a single per-launch traffic figure does not exist)",
-                                        "conv3x3_w8": {"tensor_pipe_active_pct": 89.0, "dram_bytes": 230455808, "source": "profiles/r01_ncu_conv3x3_w8.txt"}},
+                                        "conv3x3_w8": {"tensor_pipe_active_pct": 89.0, "dram_bytes": 230455808, "source": "profiles/r01_ncu_conv3x3_w8.txt"},
+                                        "attn_tc_fwd (window attention, tcgen05)": {"tensor_pipe_active_pct": 14.4, "dram_bytes": 323859968, "algorithmic_bytes": 346030080,
+                                                                                    "hbm_gbs": 3280, "hbm_frac_of_measured": 0.50,
+                                                                                    "source": "profiles/r01_ncu_attn_tcgen05.txt"}},
                      "peak_note": "tf32 dense = half of the %s bf16 sustained %.1f TFLOP/s (MEASURED_PEAKS.json has no tf32 entry)" % (pk["src"], pk["bf16"]),
                      "launches_per_step": gemm_stats["launches"], "gemm_ms_per_step": round(gemm_stats["ms"], 3),
                      "gemm_share_of_step": round(gemm_stats["ms"] / ms_dev, 3), "gemm_tflop_per_step": round(gemm_stats["flop"] / 1e12, 3)},
