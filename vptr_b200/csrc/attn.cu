@@ -486,268 +486,6 @@ __global__ void __launch_bounds__(256) attn_bwd_allheads_kernel(const float* __r
     }
 }
 
-// =============================================================================================
-// Fast path for small problems (Lq, Lk <= 32: 4x4 windows, T <= 32 temporal / enc-dec): one LANE per query row.
-// A warp handles P = 32 / Lq problems (batch entries) of one head at a time; K and V tiles sit in shared memory and are read
-// as warp-broadcast float4 (one wavefront feeds 32 lanes x 4 FMAs), each lane keeps its score row in registers (softmax
-// needs no shuffles) and streams its Q (dO) row from global memory.  Outputs are staged through shared memory so global
-// stores are whole rows.  The kernel is HBM-bound by construction: q,k,v read once, o written once.
-template <int LKMAX>
-__device__ __forceinline__ void fast_scores(const AttnGeom& g, int b, int h, int i, const float* __restrict__ qrow, const float* sKs,
-                                            int dpad, const float* __restrict__ rpe_table, float (&s)[LKMAX], float (&m)[LKMAX]) {
-#pragma unroll
-    for (int j = 0; j < LKMAX; ++j) s[j] = 0.f;
-    for (int c = 0; c < g.d; c += 4) {
-        const float2 qa = *reinterpret_cast<const float2*>(qrow + c);          // global (forward) or shared (backward) row
-        float2 qb = make_float2(0.f, 0.f);
-        if (c + 2 < g.d) qb = *reinterpret_cast<const float2*>(qrow + c + 2);
-#pragma unroll
-        for (int j = 0; j < LKMAX; ++j) {
-            if (j < g.Lk) {
-                const float4 k = *reinterpret_cast<const float4*>(sKs + j * dpad + c);
-                s[j] = fmaf(qa.x, k.x, s[j]); s[j] = fmaf(qa.y, k.y, s[j]);
-                s[j] = fmaf(qb.x, k.z, s[j]); s[j] = fmaf(qb.y, k.w, s[j]);   // pad columns of K are zero-filled
-            }
-        }
-    }
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < LKMAX; ++j) {
-        if (j < g.Lk) {
-            float v = s[j] * g.scale;
-            if (rpe_table) v += __ldg(rpe_table + rel_pos_index(g.ws, i, j) * g.nhead + h);
-            if (g.causal && j > i) v = -INFINITY;
-            s[j] = v;
-            mx = fmaxf(mx, v);
-        }
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < LKMAX; ++j) {
-        if (j < g.Lk) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-    }
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int j = 0; j < LKMAX; ++j) {
-        if (j < g.Lk) {
-            s[j] *= inv;                                             // undropped probability
-            m[j] = g.drop_p > 0.f ? prob_drop(g, b, h, i, j) : 1.f;  // dropout keep-scale
-        }
-    }
-}
-
-// loads rows [0, L) x d of a token-major tensor (head h) into a [L][dpad] shared tile, zero-filling the pad columns
-__device__ __forceinline__ void fast_load_tile(float* dst, const float* __restrict__ src, long long ld, const AttnGeom& g, int b, int L,
-                                               bool is_q, int h, int dpad, int lane) {
-    const int half = dpad >> 1;
-    for (int e = lane; e < L * half; e += 32) {
-        const int j = e / half, c2 = e - j * half;
-        float2 v = make_float2(0.f, 0.f);
-        if (2 * c2 < g.d) v = __ldg(reinterpret_cast<const float2*>(src + (is_q ? q_row(g, b, j) : k_row(g, b, j)) * ld + h * g.d + 2 * c2));
-        *reinterpret_cast<float2*>(dst + j * dpad + 2 * c2) = v;
-    }
-}
-__device__ __forceinline__ void fast_store_tile(const float* src, float* __restrict__ dst, long long ld, const AttnGeom& g, int b, int L,
-                                                bool is_q, int h, int dpad, int lane, float mul) {
-    const int half = g.d >> 1;
-    for (int e = lane; e < L * half; e += 32) {
-        const int j = e / half, c2 = e - j * half;
-        float2 v = *reinterpret_cast<const float2*>(src + j * dpad + 2 * c2);
-        v.x *= mul; v.y *= mul;
-        if (g.round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); }
-        *reinterpret_cast<float2*>(dst + (is_q ? q_row(g, b, j) : k_row(g, b, j)) * ld + h * g.d + 2 * c2) = v;
-    }
-}
-
-template <int LKMAX>
-__global__ void __launch_bounds__(128) attn_fwd_fast_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
-                                                            long long ldk, const float* __restrict__ V, long long ldv,
-                                                            float* __restrict__ O, long long ldo, const float* __restrict__ rpe_table,
-                                                            const AttnGeom g, int batches) {
-    extern __shared__ __align__(16) float sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int h = blockIdx.y;
-    const int dpad = (g.d + 3) & ~3;
-    const int P = 32 / g.Lq;
-    const int slot = lane / g.Lq, i = lane - slot * g.Lq;
-    const int rowsK = max(g.Lq, g.Lk);                      // the K tile is reused as the output staging tile [Lq][dpad]
-    const int per_slot = (rowsK + g.Lk) * dpad;
-    float* base = sm + (size_t)warp * P * per_slot;
-    const int packs = (batches + P - 1) / P;
-    for (int pack = blockIdx.x * nwarps + warp; pack < packs; pack += gridDim.x * nwarps) {
-        const int b0 = pack * P;
-        for (int s = 0; s < P && b0 + s < batches; ++s) {
-            fast_load_tile(base + s * per_slot, K, ldk, g, b0 + s, g.Lk, false, h, dpad, lane);
-            fast_load_tile(base + s * per_slot + rowsK * dpad, V, ldv, g, b0 + s, g.Lk, false, h, dpad, lane);
-        }
-        __syncwarp();
-        const int b = b0 + slot;
-        const bool active = slot < P && b < batches;
-        float p[LKMAX], m[LKMAX];
-        float* sKs = base + slot * per_slot;
-        const float* sVs = sKs + rowsK * dpad;
-        if (active) fast_scores<LKMAX>(g, b, h, i, Q + q_row(g, b, i) * ldq + h * g.d, sKs, dpad, rpe_table, p, m);
-        __syncwarp();                                       // every lane is done with K before it becomes the O staging tile
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < LKMAX; ++j)
-                if (j < g.Lk) p[j] *= m[j];
-            for (int c = 0; c < g.d; c += 4) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < LKMAX; ++j) {
-                    if (j < g.Lk) {
-                        const float4 v = *reinterpret_cast<const float4*>(sVs + j * dpad + c);
-                        o.x = fmaf(p[j], v.x, o.x); o.y = fmaf(p[j], v.y, o.y); o.z = fmaf(p[j], v.z, o.z); o.w = fmaf(p[j], v.w, o.w);
-                    }
-                }
-                *reinterpret_cast<float4*>(sKs + i * dpad + c) = o;
-            }
-        }
-        __syncwarp();
-        for (int s = 0; s < P && b0 + s < batches; ++s)
-            fast_store_tile(base + s * per_slot, O, ldo, g, b0 + s, g.Lq, true, h, dpad, lane, 1.f);
-        __syncwarp();
-    }
-}
-
-// Backward fast path.  Shared tiles per problem: Q, dO [Lq][dpad], K, V [Lk][dpad], PD = P*keep and dS [Lq][Lk+1].
-// Phase 1 (lane = query row): recompute P, dP = dO V^T, dS, dQ = scale * dS K (staged over the Q tile... after phase 2 needs Q,
-// so dQ is staged in its own pass at the end).  Phase 2 (lane = key row): dV = PD^T dO, dK = scale * dS^T Q.
-template <int LKMAX>
-__global__ void __launch_bounds__(64) attn_bwd_fast_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K,
-                                                           long long ldk, const float* __restrict__ V, long long ldv,
-                                                           const float* __restrict__ dO, long long ldo, float* __restrict__ dQ,
-                                                           long long lddq, float* __restrict__ dK, long long lddk,
-                                                           float* __restrict__ dV, long long lddv, const float* __restrict__ rpe_table,
-                                                           float* __restrict__ d_rpe_table, const AttnGeom g, int batches) {
-    extern __shared__ __align__(16) float sm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int h = blockIdx.y;
-    const int dpad = (g.d + 3) & ~3;
-    const int Lmax = max(g.Lq, g.Lk);
-    const int P = 32 / Lmax;
-    const int lp = g.Lk + 1;
-    const int per_slot = (2 * g.Lq * dpad + 2 * g.Lk * dpad + 2 * g.Lq * lp + 3) & ~3;
-    float* base = sm + (size_t)warp * P * per_slot;
-    const int slot = lane / Lmax, r = lane - slot * Lmax;       // r = query row in phase 1, key row in phase 2
-    float dsacc[LKMAX];                                         // bias-gradient accumulator of query row r over this warp's batches
-#pragma unroll
-    for (int j = 0; j < LKMAX; ++j) dsacc[j] = 0.f;
-    const int packs = (batches + P - 1) / P;
-    for (int pack = blockIdx.x * nwarps + warp; pack < packs; pack += gridDim.x * nwarps) {
-        const int b0 = pack * P;
-        for (int s = 0; s < P && b0 + s < batches; ++s) {
-            float* t = base + s * per_slot;
-            fast_load_tile(t, Q, ldq, g, b0 + s, g.Lq, true, h, dpad, lane);
-            fast_load_tile(t + g.Lq * dpad, dO, ldo, g, b0 + s, g.Lq, true, h, dpad, lane);
-            fast_load_tile(t + 2 * g.Lq * dpad, K, ldk, g, b0 + s, g.Lk, false, h, dpad, lane);
-            fast_load_tile(t + 2 * g.Lq * dpad + g.Lk * dpad, V, ldv, g, b0 + s, g.Lk, false, h, dpad, lane);
-        }
-        __syncwarp();
-        const int b = b0 + slot;
-        const bool in_range = slot < P && b < batches;
-        float* sQ = base + slot * per_slot;
-        float* sdO = sQ + g.Lq * dpad;
-        float* sK = sdO + g.Lq * dpad;
-        float* sV = sK + g.Lk * dpad;
-        float* sPD = sV + g.Lk * dpad;
-        float* sdS = sPD + g.Lq * lp;
-        float ds[LKMAX];
-        // ---- phase 1: lane = query row
-        if (in_range && r < g.Lq) {
-            const int i = r;
-            float p[LKMAX], m[LKMAX], dp[LKMAX];
-            fast_scores<LKMAX>(g, b, h, i, sQ + i * dpad, sK, dpad, rpe_table, p, m);
-#pragma unroll
-            for (int j = 0; j < LKMAX; ++j) dp[j] = 0.f;
-            for (int c = 0; c < g.d; c += 4) {
-                const float4 go = *reinterpret_cast<const float4*>(sdO + i * dpad + c);
-#pragma unroll
-                for (int j = 0; j < LKMAX; ++j) {
-                    if (j < g.Lk) {
-                        const float4 v = *reinterpret_cast<const float4*>(sV + j * dpad + c);
-                        dp[j] = fmaf(go.x, v.x, dp[j]); dp[j] = fmaf(go.y, v.y, dp[j]);
-                        dp[j] = fmaf(go.z, v.z, dp[j]); dp[j] = fmaf(go.w, v.w, dp[j]);
-                    }
-                }
-            }
-            float t = 0.f;
-#pragma unroll
-            for (int j = 0; j < LKMAX; ++j)
-                if (j < g.Lk) { dp[j] *= m[j]; t = fmaf(p[j], dp[j], t); }
-#pragma unroll
-            for (int j = 0; j < LKMAX; ++j) {
-                if (j < g.Lk) {
-                    ds[j] = p[j] * (dp[j] - t);
-                    dsacc[j] += ds[j];
-                    sPD[i * lp + j] = p[j] * m[j];
-                    sdS[i * lp + j] = ds[j];
-                }
-            }
-        }
-        __syncwarp();
-        // ---- phase 2: lane = key row: dV = PD^T dO, staged in place over this lane's V row (V is no longer needed)
-        if (in_range && r < g.Lk) {
-            const int j = r;
-            for (int c = 0; c < g.d; c += 4) {
-                float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = 0; i < g.Lq; ++i) {
-                    const float pd = sPD[i * lp + j];
-                    const float4 go = *reinterpret_cast<const float4*>(sdO + i * dpad + c);
-                    dv.x = fmaf(pd, go.x, dv.x); dv.y = fmaf(pd, go.y, dv.y); dv.z = fmaf(pd, go.z, dv.z); dv.w = fmaf(pd, go.w, dv.w);
-                }
-                *reinterpret_cast<float4*>(sV + j * dpad + c) = dv;
-            }
-        }
-        __syncwarp();
-        for (int s = 0; s < P && b0 + s < batches; ++s)
-            fast_store_tile(base + s * per_slot + 2 * g.Lq * dpad + g.Lk * dpad, dV, lddv, g, b0 + s, g.Lk, false, h, dpad, lane, 1.f);
-        __syncwarp();
-        // ---- phase 2b: dK (lane = key row) staged over the V tile (dV already stored)
-        if (in_range && r < g.Lk) {
-            const int j = r;
-            for (int c = 0; c < g.d; c += 4) {
-                float4 dk = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = 0; i < g.Lq; ++i) {
-                    const float dsv = sdS[i * lp + j];
-                    const float4 q = *reinterpret_cast<const float4*>(sQ + i * dpad + c);
-                    dk.x = fmaf(dsv, q.x, dk.x); dk.y = fmaf(dsv, q.y, dk.y); dk.z = fmaf(dsv, q.z, dk.z); dk.w = fmaf(dsv, q.w, dk.w);
-                }
-                *reinterpret_cast<float4*>(sV + j * dpad + c) = dk;
-            }
-        }
-        __syncwarp();
-        for (int s = 0; s < P && b0 + s < batches; ++s)
-            fast_store_tile(base + s * per_slot + 2 * g.Lq * dpad + g.Lk * dpad, dK, lddk, g, b0 + s, g.Lk, false, h, dpad, lane, g.scale);
-        __syncwarp();
-        // ---- phase 3: dQ = scale * dS K (lane = query row), staged over the dO tile (no longer needed)
-        if (in_range && r < g.Lq) {
-            const int i = r;
-            for (int c = 0; c < g.d; c += 4) {
-                float4 dq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < LKMAX; ++j) {
-                    if (j < g.Lk) {
-                        const float4 k = *reinterpret_cast<const float4*>(sK + j * dpad + c);
-                        dq.x = fmaf(ds[j], k.x, dq.x); dq.y = fmaf(ds[j], k.y, dq.y); dq.z = fmaf(ds[j], k.z, dq.z); dq.w = fmaf(ds[j], k.w, dq.w);
-                    }
-                }
-                *reinterpret_cast<float4*>(sdO + i * dpad + c) = dq;
-            }
-        }
-        __syncwarp();
-        for (int s = 0; s < P && b0 + s < batches; ++s)
-            fast_store_tile(base + s * per_slot + g.Lq * dpad, dQ, lddq, g, b0 + s, g.Lq, true, h, dpad, lane, g.scale);
-        __syncwarp();
-    }
-    if (d_rpe_table && slot < P && r < g.Lq) {
-#pragma unroll
-        for (int j = 0; j < LKMAX; ++j)
-            if (j < g.Lk) atomicAdd(d_rpe_table + rel_pos_index(g.ws, r, j) * g.nhead + h, dsacc[j]);
-    }
-}
-
 __global__ void index_maps_kernel(int F, int H, int W, int ws, long long* rpi, long long* wmap) {
     AttnGeom g{};
     g.mode = 0; g.H = H; g.W = W; g.ws = ws; g.nwh = H / ws; g.nww = W / ws;
@@ -1240,14 +978,6 @@ int dispatch_attn_mma(const float* Q, long long ldq, const float* K, long long l
     return launch_attn_mma<2, 4, 2, BWD>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches, stream);
 }
 
-// The lane-per-row "fast" kernels below are EXPERIMENTAL and currently slower than the generic ones at cfg1 sizes (their load /
-// compute / store phases are serialised per warp with too few resident warps to hide global latency: 664 vs 455 us forward,
-// tools/bench_attn.py), so they are opt-in (VPTR_ATTN_FAST=1) until they are software-pipelined.
-bool attn_generic_only() {
-    static const bool v = [] { const char* e = getenv("VPTR_ATTN_FAST"); return !(e && e[0] == '1'); }();
-    return v;
-}
-
 bool attn_no_allheads() {
     static const bool v = [] { const char* e = getenv("VPTR_ATTN_PERHEAD"); return e && e[0] == '1'; }();
     return v;
@@ -1313,27 +1043,6 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
             return vptr_check_launch("attn_fwd_allheads_kernel");
         }
     }
-    if (!attn_generic_only() && g.Lq <= 32 && g.Lk <= 32 && d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 &&
-        ((uintptr_t)Q % 8 == 0) && ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) && ((uintptr_t)O % 8 == 0)) {
-        const int dpad = (d + 3) & ~3, P = 32 / g.Lq;
-        const size_t per_warp = sizeof(float) * (size_t)P * ((g.Lq > g.Lk ? g.Lq : g.Lk) + g.Lk) * dpad;
-        const int nwarps = 4;
-        const size_t fsmem = per_warp * nwarps;
-        if (fsmem <= 100 * 1024) {
-            const int packs = (batches + P - 1) / P;
-            int gx = (packs + nwarps - 1) / nwarps;
-            if (gx > 148 * 8) gx = 148 * 8;
-            dim3 fgrid(gx, nhead);
-            if (g.Lk <= 16) {
-                if (fsmem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-                attn_fwd_fast_kernel<16><<<fgrid, 32 * nwarps, fsmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, rpe_table, g, batches);
-            } else {
-                if (fsmem > 48 * 1024) cudaFuncSetAttribute(attn_fwd_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-                attn_fwd_fast_kernel<32><<<fgrid, 32 * nwarps, fsmem, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, rpe_table, g, batches);
-            }
-            return vptr_check_launch("attn_fwd_fast_kernel");
-        }
-    }
     VPTR_REQUIRE(d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && ((uintptr_t)Q % 8 == 0) &&
                      ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) && ((uintptr_t)O % 8 == 0),
                  VPTR_ERR_ALIGN, "vptr_attn_fwd: head_dim and pitches must be even, pointers 8-byte aligned");
@@ -1376,31 +1085,6 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
             attn_bwd_allheads_kernel<<<gx, 256, ah, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, rpe_table,
                                                               d_rpe_table, g, batches);
             return vptr_check_launch("attn_bwd_allheads_kernel");
-        }
-    }
-    if (!attn_generic_only() && g.Lq <= 32 && g.Lk <= 32 && d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && lddq % 2 == 0 &&
-        lddk % 2 == 0 && lddv % 2 == 0 && ((uintptr_t)Q % 8 == 0) && ((uintptr_t)K % 8 == 0) && ((uintptr_t)V % 8 == 0) &&
-        ((uintptr_t)dO % 8 == 0) && ((uintptr_t)dQ % 8 == 0) && ((uintptr_t)dK % 8 == 0) && ((uintptr_t)dV % 8 == 0)) {
-        const int dpad = (d + 3) & ~3, Lmax = g.Lq > g.Lk ? g.Lq : g.Lk, P = 32 / Lmax;
-        const size_t per_warp = sizeof(float) * (size_t)P * ((2 * g.Lq * dpad + 2 * g.Lk * dpad + 2 * g.Lq * (g.Lk + 1) + 3) & ~3);
-        const int nwarps = 2;
-        const size_t fsmem = per_warp * nwarps;
-        if (fsmem <= 110 * 1024) {
-            const int packs = (batches + P - 1) / P;
-            int gx = (packs + nwarps - 1) / nwarps;
-            const int cap = d_rpe_table ? 148 * 4 : 148 * 16;     // bound the number of bias-gradient flushes
-            if (gx > cap) gx = cap;
-            dim3 fgrid(gx, nhead);
-            if (g.Lk <= 16) {
-                if (fsmem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-                attn_bwd_fast_kernel<16><<<fgrid, 32 * nwarps, fsmem, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv,
-                                                                              rpe_table, d_rpe_table, g, batches);
-            } else {
-                if (fsmem > 48 * 1024) cudaFuncSetAttribute(attn_bwd_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
-                attn_bwd_fast_kernel<32><<<fgrid, 32 * nwarps, fsmem, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv,
-                                                                              rpe_table, d_rpe_table, g, batches);
-            }
-            return vptr_check_launch("attn_bwd_fast_kernel");
         }
     }
     VPTR_REQUIRE(d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 &&

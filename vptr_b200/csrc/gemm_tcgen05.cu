@@ -41,7 +41,7 @@ struct GemmParams {
     unsigned long long drop_seed;  // elementwise nn.Dropout on the branch (drop1/drop3, VidHRFormer_modules.py:53-55)
     float drop_p;
     // implicit-GEMM 3x3 convolution (A = 4-D TMA view of the padded NHWC activation): 0 = plain GEMM
-    int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C, conv_a3d, conv_hp;
+    int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C;
     int conv_w8;       // W == 8 implicit conv (conv3x3_w8_kernel): tile rows are ordered (oh, frame, ow) -- see epi_row()
     int conv_planes;
     long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
@@ -435,16 +435,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t b_base = a_base + Cfg::A_BYTES;
                     if (elect_one()) {
-                    if (BLOCK_N == 256 && STAGES == 3 && !A_MN && !B_MN) {
-                        // experiment: two independent 128-column accumulators interleaved (dependency-latency test)
-                        constexpr uint32_t idesc_h = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(128 >> 3) << 17) | (uint32_t(BLOCK_M >> 4) << 24);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024, 2);
-                            umma_tf32(d_tmem, da, make_smem_desc(b_base + k * 32, 16, 1024, 2), idesc_h, (kc > k0 || k > 0) ? 1u : 0u);
-                            umma_tf32(d_tmem + 128, da, make_smem_desc(b_base + 16384 + k * 32, 16, 1024, 2), idesc_h, (kc > k0 || k > 0) ? 1u : 0u);
-                        }
-                    } else {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         const uint64_t da = A_MN ? make_smem_desc(a_base + k * 1024, 4096, 512, 1)
@@ -452,7 +442,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         const uint64_t db = B_MN ? make_smem_desc(b_base + k * 1024, 4096, 512, 1)
                                                  : make_smem_desc(b_base + k * 32, 16, 1024, 2);
                         umma_tf32(d_tmem, da, db, idesc, (kc > k0 || k > 0) ? 1u : 0u);
-                    }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
                     }
@@ -540,14 +529,6 @@ __device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* map, uint64_
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
             smem_u32(dst)),
         "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2cta(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-    const uint32_t leader_bar = smem_u32(bar) & 0xFEFFFFFFu;
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
@@ -651,11 +632,6 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                         const int t = m_pair * 2 + (int)rank;                   // 128-pixel tile index
                         const int f0 = p.conv_bf > 1 ? t * p.conv_bf : t / p.conv_tiles_per_frame;
                         const int oh0 = p.conv_bf > 1 ? 0 : (t - f0 * p.conv_tiles_per_frame) * p.conv_bh;
-                        if (p.conv_a3d) {   // experiment: bf 3-D boxes {32 ch, W, bh} over [C][Wp][F*Hp] instead of one 4-D box
-                            for (int i = 0; i < p.conv_bf; ++i)
-                                tma_load_3d_2cta(&tma_a, &full_bar[stage], sA + i * (Cfg::A_BYTES / p.conv_bf), cs * BLOCK_K, kw,
-                                                 (f0 + i) * p.conv_hp + oh0 + kh);
-                        } else
                         tma_load_4d_2cta(&tma_a, &full_bar[stage], sA, cs * BLOCK_K, kw, oh0 + kh, f0);
                     } else if (!A_MN) {
                         tma_load_2d_2cta(&tma_a, &full_bar[stage], sA, kc * BLOCK_K, m0);
@@ -959,8 +935,7 @@ int make_map_2d(CUtensorMap* map, const float* ptr, long long inner, long long o
 }
 
 // 4-D fp32 tensor map over a padded NHWC activation [F][Hp][Wp][C]: box {32 channels, bw, bh, bf}
-int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, int bf,
-                  bool no_promo = false) {
+int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, int bf) {
     EncodeTiledFn enc = get_encode_fn();
     VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)F};
@@ -968,27 +943,12 @@ int make_map_nhwc(CUtensorMap* map, const float* ptr, long long F, long long Hp,
     cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bf};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     no_promo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): F=%lld Hp=%lld Wp=%lld C=%lld box=%dx%dx%d", (int)r,
                  F, Hp, Wp, C, bw, bh, bf);
     return VPTR_OK;
 }
-// 3-D variant: [C][Wp][F*Hp], box {32 channels, bw, bh}
-int make_map_nhwc3(CUtensorMap* map, const float* ptr, long long F, long long Hp, long long Wp, long long C, int bw, int bh, bool no_promo) {
-    EncodeTiledFn enc = get_encode_fn();
-    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)(Hp * F)};
-    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)Wp * C * 4};
-    cuuint32_t box[3] = {32, (cuuint32_t)bw, (cuuint32_t)bh};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     no_promo ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
-    return VPTR_OK;
-}
-
 // W == 8 raw-tile map: dims ordered (c, w, frame, h) so the box {32, 10, 2, 10} lands in shared memory as [h][frame][w][32 ch]
 int make_map_nhwc_w8(CUtensorMap* map, const float* ptr, long long F, long long C) {
     EncodeTiledFn enc = get_encode_fn();
@@ -1071,8 +1031,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     static const int mode_env = [] { const char* e = getenv("VPTR_GEMM_1CTA"); return (e && e[0] == '1') ? 1 : 0; }();
     const bool two_cta = !mode_env && M > BLOCK_M;          // CTA pairs (cta_group::2) unless the problem has a single M tile
     constexpr int BN1 = 176;                                 // 1-CTA N tile
-    static const int exp_bn = [] { const char* e = getenv("VPTR_GEMM_BN"); return e ? atoi(e) : 0; }();
-    const int BN = two_cta ? (b_mn ? 192 : 176) : ((exp_bn && !a_mn && !b_mn) ? (exp_bn == 257 ? 256 : exp_bn) : BN1);   // MN-major B halves: whole 32-column groups -> 192
+    const int BN = two_cta ? (b_mn ? 192 : 176) : BN1;   // MN-major B halves: whole 32-column groups -> 192
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = vptr_cdiv(M, two_cta ? 2 * BLOCK_M : BLOCK_M);
@@ -1097,7 +1056,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 0; p.conv_cpt = 1; p.conv_kw = 1; p.conv_bh = 1; p.conv_tiles_per_frame = 1; p.conv_bf = 1; p.conv_C = 0;
-    p.conv_a3d = 0; p.conv_hp = 0; p.conv_w8 = 0; p.conv_planes = 1;
+    p.conv_w8 = 0; p.conv_planes = 1;
 
     CUtensorMap ma, mb;
     int rc;
@@ -1116,12 +1075,6 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
         return launch_gemm_2cta<176, 1, 0, ST2>(ma, mb, p, stream);
     }
     constexpr int ST = 5;
-    if (exp_bn && !a_mn && !b_mn) {   // experiment: MMA cost vs N (tools/gemm_timeline.py)
-        if (exp_bn == 128) return launch_gemm<128, 0, 0, 5>(ma, mb, p, stream);
-        if (exp_bn == 192) return launch_gemm<192, 0, 0, 4>(ma, mb, p, stream);
-        if (exp_bn == 256) return launch_gemm<256, 0, 0, 4>(ma, mb, p, stream);
-        if (exp_bn == 257) return launch_gemm<256, 0, 0, 3>(ma, mb, p, stream);   // split into two interleaved N=128 accumulators
-    }
     if (!a_mn && !b_mn) return launch_gemm<BN1, 0, 0, ST>(ma, mb, p, stream);
     if (!a_mn && b_mn) return launch_gemm<BN1, 0, 1, ST>(ma, mb, p, stream);
     if (a_mn && b_mn) return launch_gemm<BN1, 1, 1, ST>(ma, mb, p, stream);
@@ -1167,12 +1120,12 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = bh; p.conv_tiles_per_frame = tiles_per_frame; p.conv_bf = bf; p.conv_C = C;
-    p.conv_a3d = 0; p.conv_hp = H + 2; p.conv_w8 = 0; p.conv_planes = w_planes;
+    p.conv_w8 = 0; p.conv_planes = w_planes;
     // rows of a tile beyond F*H*W (frames past the end) are zero-filled by TMA and masked by the epilogue (m < M) only when tiles
     // map to whole frames in order, which holds for both tilings above.
     CUtensorMap ma, mb;
-    static const int a_mode = [] { const char* e = getenv("VPTR_CONV_A"); return e ? atoi(e) : 0; }();
-    if (H == 8 && W == 8 && !(a_mode & 8)) {   // raw-tile kernel: one TMA box per channel slice serves all 9 taps (and both planes)
+    static const bool generic_only = [] { const char* e = getenv("VPTR_CONV_GENERIC"); return e && e[0] == '1'; }();
+    if (H == 8 && W == 8 && !generic_only) {   // raw-tile kernel: one TMA box per channel slice serves all 9 taps (and both planes)
         p.conv_w8 = 1; p.conv_planes = w_planes;
         p.m_tiles = vptr_cdiv(F, 4);           // pair tile = 4 frames = 256 output pixels
         int rc = make_map_nhwc_w8(&ma, xpad, F, C);
@@ -1191,9 +1144,7 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
         conv3x3_w8_kernel<<<2 * clusters, NUM_THREADS, CW_SMEM_BYTES, stream>>>(ma, mb, p);
         return vptr_check_launch("conv3x3_w8_kernel");
     }
-    p.conv_a3d = (a_mode & 1); p.conv_hp = H + 2;
-    int rc = p.conv_a3d ? make_map_nhwc3(&ma, xpad, F, H + 2, W + 2, C, bw, bh, (a_mode & 2) != 0)
-                        : make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf, (a_mode & 2) != 0);
+    int rc = make_map_nhwc(&ma, xpad, F, H + 2, W + 2, C, bw, bh, bf);
     if (rc) return rc;
     rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
