@@ -180,6 +180,18 @@ def test_attention_tcgen05_forward(case):
         ob = _attn_ref(seq(q, Tq), seq(kv[:, :C], Tk), seq(kv[:, C:], Tk), nhead, scale, mask=mask)
         oref = ob.view(N, HW, Tq, C).permute(0, 2, 1, 3).reshape(N * Tq * HW, C)
     assert torch.isfinite(o).all() and rel_l2(o, oref) < 1e-3
+    # probability dropout: the tcgen05 forward must draw exactly the masks the warp-level kernels (forward and backward) regenerate
+    # from (seed, batch, head, i, j) -- compare both forwards under the same seed
+    o1, o2 = torch.empty_like(o), torch.empty_like(o)
+    if case.startswith("window"):
+        args = (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])
+        tail = (table, 0, Fr, H, W, ws, 0, 0, nhead, d, False, scale)
+    else:
+        args = (q, kv[:, :C], kv[:, C:])
+        tail = (None, 1, N, H, W, 0, Tq, Tk, nhead, d, causal, scale)
+    ops.attn_fwd_tcgen05(*args, o1, *tail, drop_seed=4242, drop_p=0.3)
+    ops.attn_fwd(*args, o2, *tail, drop_seed=4242, drop_p=0.3)
+    assert rel_l2(o1, o2) < 1e-3 and rel_l2(o1, o) > 0.05
 
 
 def test_attention_tcgen05_rejects_unsupported_shapes():
