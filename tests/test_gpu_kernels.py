@@ -246,6 +246,12 @@ def test_elementwise_helpers():
     out = torch.ones(48, device="cuda")
     ops.colsum(x, out)
     assert rel_l2(out, x.sum(0) + 1) < 1e-5
+    # widths that are multiples of 528 take the tiled kernel, also on a column slice of a wider buffer and a ragged row count
+    big = rnd(4099, 1584, seed=9)
+    for sl in (slice(0, 528), slice(528, 1584), slice(0, 1584)):
+        o = torch.full((sl.stop - sl.start,), 2.0, device="cuda")
+        ops.colsum(big[:, sl], o)
+        assert rel_l2(o, big[:, sl].double().sum(0) + 2) < 1e-5
     t = ops.transpose(x.view(3, 100, 48), 3, 100, 48).view(3, 48, 100)
     assert torch.equal(t, x.view(3, 100, 48).transpose(1, 2).contiguous())
     add = rnd(5, 48, seed=3)
