@@ -165,6 +165,20 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
            ((((uint32_t)(col & 31) >> 2) ^ (uint32_t)(row & 7)) << 4) + (uint32_t)(col & 3) * 4u;
 }
 
+// sequences a warp's 32 rows (tile rows 32w .. 32w+31, ordered (pixel, t)) can touch, maximum over the four warps
+__host__ __device__ constexpr int seq_span(int TQ) {
+    int m = 0;
+    for (int w = 0; w < 4; ++w) {
+        const int n = (32 * w + 31) / TQ - (32 * w) / TQ + 1;
+        m = n > m ? n : m;
+    }
+    return m;
+}
+// FQ = FK = 0: window fast path (8x8 grid, 4x4 windows) or the generic mask path, chosen at run time.
+// FQ, FK > 0 : temporal / enc-dec attention with compile-time query / key counts (T = 10 of cfg1, 29 of cfg2, 28 and 28 x 2 of
+//              cfg3): a row's keys are the FK contiguous columns of its own pixel sequence, picked out of a window of
+//              seq_span(FQ) * FK columns the warp loads once from TMEM.
+template <int FQ, int FK>
 __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ rpe_table,
                                                                     const TcGeom g) {
     extern __shared__ uint8_t smem_raw[];
@@ -338,11 +352,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
         // Fast path for THE window shape of the path (8x8 grid, 4x4 windows, tile = two frames): the 16 keys of a row's window are
         // four runs of four columns inside the warp's own 32-column chunk (image row r -> columns r*8 + xoff .. +3), so the whole
         // softmax is straight-line code on 16 registers -- no per-column bit tests, position look-ups or second TMEM pass.
-        const bool fast_win = g.mode == 0 && g.HW == 64 && g.W == 8 && g.ws == 4;
-        // Fast path for the temporal shape of cfg1 (T = 10 queries and keys, 12 pixel sequences per tile): a row's 10 keys are the
-        // contiguous columns [10 p, 10 p + 10); a warp's rows span at most 4 sequences = 40 columns from 10 * (32 w / 10).
-        const bool fast_t10 = g.mode == 1 && g.Tq == 10 && g.Tk == 10 && g.P == 12;
-        const int t10_plo = (warp * 32) / 10, t10_k = gid_i - t10_plo;
+        const bool fast_win = FQ == 0 && g.mode == 0 && g.HW == 64 && g.W == 8 && g.ws == 4;
+        // sequence fast path (FQ > 0): first sequence of this warp's rows and my sequence's rank among them
+        constexpr int SEQ_Q = FQ > 0 ? FQ : 1, SEQ_K = FK > 0 ? FK : 1;
+        constexpr int NSEQ = seq_span(SEQ_Q), NLD = (NSEQ * SEQ_K + 31) / 32;
+        const int seq_plo = (warp * 32) / SEQ_Q, seq_k = gid_i - seq_plo;
         const bool xhi = ((row & 7) >> 2) != 0;               // my window is the right-hand one of its image rows
         const uint32_t row_off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
         const uint32_t r7 = (uint32_t)(row & 7);
@@ -392,43 +406,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid
                     *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r) ^ r7) << 4)) = xhi ? z4 : p4;
                     *reinterpret_cast<float4*>(prow + (((uint32_t)(2 * r + 1) ^ r7) << 4)) = xhi ? p4 : z4;
                 }
-            } else if (fast_t10) {
-                float v0[32], v1[8], sc[10];
-                tmem_ld32(tmem_S + lane_taddr + t10_plo * 10, v0);
-                {
-                    uint32_t* r = reinterpret_cast<uint32_t*>(v1);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                                 : "r"(tmem_S + lane_taddr + t10_plo * 10 + 32));
-                }
+            } else if (FQ > 0) {
+                float win[NLD * 32], sc[SEQ_K];
+#pragma unroll
+                for (int l = 0; l < NLD; ++l) tmem_ld32(tmem_S + lane_taddr + seq_plo * SEQ_K + l * 32, win + l * 32);
                 tmem_ld_wait();
+                float mx = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 10; ++j) {
-                    const float a0 = v0[j], a1 = v0[10 + j], a2 = v0[20 + j], a3 = (30 + j < 32) ? v0[(30 + j) & 31] : v1[(30 + j - 32) & 7];
-                    sc[j] = (t10_k == 0 ? a0 : t10_k == 1 ? a1 : t10_k == 2 ? a2 : a3) * g.scale;
-                    if (g.causal && j > pos_i) sc[j] = -INFINITY;
+                for (int j = 0; j < SEQ_K; ++j) {
+                    float a = win[j];
+#pragma unroll
+                    for (int kk = 1; kk < NSEQ; ++kk)
+                        if (seq_k == kk) a = win[kk * SEQ_K + j];
+                    a *= g.scale;
+                    if (g.causal && j > pos_i) a = -INFINITY;
+                    sc[j] = a;
+                    mx = fmaxf(mx, a);
                 }
-                float mx = sc[0];
 #pragma unroll
-                for (int j = 1; j < 10; ++j) mx = fmaxf(mx, sc[j]);
-#pragma unroll
-                for (int j = 0; j < 10; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+                for (int j = 0; j < SEQ_K; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
                 if (g.drop_p > 0.f) {
                     const unsigned thr = vptr_drop_threshold(g.drop_p);
                     const float keep = 1.f / (1.f - g.drop_p);
+                    if ((drop_row & 1) == 0) {                   // even start: elements (2jj, 2jj+1) share one hash group
 #pragma unroll
-                    for (int jj = 0; jj < 5; ++jj) {           // drop_row is a multiple of 10: indices drop_row + 2jj are even -> pairs share a hash
-                        const unsigned long long idx = drop_row + 2 * jj;
-                        const unsigned z = (unsigned)(vptr_hash4(g.drop_seed, idx >> 2) >> (16 * (unsigned)(idx & 3)));
-                        sc[2 * jj] *= (z & 0xFFFFu) >= thr ? keep : 0.f;
-                        sc[2 * jj + 1] *= ((z >> 16) & 0xFFFFu) >= thr ? keep : 0.f;
+                        for (int jj = 0; jj < (SEQ_K + 1) / 2; ++jj) {
+                            const unsigned long long idx = drop_row + 2 * jj;
+                            const unsigned z = (unsigned)(vptr_hash4(g.drop_seed, idx >> 2) >> (16 * (unsigned)(idx & 3)));
+                            sc[2 * jj] *= (z & 0xFFFFu) >= thr ? keep : 0.f;
+                            if (2 * jj + 1 < SEQ_K) sc[2 * jj + 1] *= ((z >> 16) & 0xFFFFu) >= thr ? keep : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < SEQ_K; ++j) sc[j] *= vptr_drop_scale(g.drop_seed, drop_row + j, g.drop_p);
                     }
                 }
                 if (valid_i) {
 #pragma unroll
-                    for (int j = 0; j < 10; ++j) *reinterpret_cast<float*>(sP + sw128_offset(row, gid_i * 10 + j)) = vptr_round_tf32(sc[j]);
+                    for (int j = 0; j < SEQ_K; ++j) *reinterpret_cast<float*>(sP + sw128_offset(row, gid_i * SEQ_K + j)) = vptr_round_tf32(sc[j]);
                 }
-            } else {
+            } else if (FQ == 0) {
                 // pass 1: row maximum over the attended columns
                 float mx = -INFINITY;
     #pragma unroll
@@ -632,12 +649,6 @@ extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float*
     rc = make_tensor_map(&maps.o, O, ldo, nhead * TC_D, g, rows_q, F_or_N, Tq, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     const size_t smem = 13 * TC_CHUNK + 1024 + 512 + (rpe_table ? sizeof(float) * nhead * g.Lq * g.Lk : 0) + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(attn_tc_fwd): %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
     VPTR_REQUIRE(smem <= 227 * 1024, VPTR_ERR_UNSUPPORTED, "vptr_attn_fwd_tcgen05: shared memory %zu", smem);
     int sms = 148;
     {
@@ -648,7 +659,16 @@ extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float*
     }
     const long long items = (long long)g.tiles * nhead;
     const int grid = (int)(items < sms ? items : sms);
-    attn_tc_fwd_kernel<<<grid, TC_THREADS, smem, stream>>>(maps, rpe_table, g);
+    void (*kern)(const TcMaps, const float*, const TcGeom) = attn_tc_fwd_kernel<0, 0>;
+    if (mode == 1 && g.P == TC_ROWS / (Tq > Tk ? Tq : Tk)) {   // full-width pixel chunks: the compile-time sequence fast paths
+        if (Tq == 10 && Tk == 10) kern = attn_tc_fwd_kernel<10, 10>;
+        else if (Tq == 29 && Tk == 29) kern = attn_tc_fwd_kernel<29, 29>;
+        else if (Tq == 28 && Tk == 28) kern = attn_tc_fwd_kernel<28, 28>;
+        else if (Tq == 28 && Tk == 2) kern = attn_tc_fwd_kernel<28, 2>;
+    }
+    cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    VPTR_REQUIRE(ea == cudaSuccess, (int)ea, "cudaFuncSetAttribute(attn_tc_fwd): %s", cudaGetErrorString(ea));
+    kern<<<grid, TC_THREADS, smem, stream>>>(maps, rpe_table, g);
     static const bool debug = [] { const char* e = getenv("VPTR_ATTN_TC_DEBUG"); return e && e[0] == '1'; }();
     if (debug) {
         int err[4] = {0, 0, 0, 0};

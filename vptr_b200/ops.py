@@ -162,9 +162,12 @@ def attn_tc_window_ok(q, k, v, out, H, W, ws, nhead, d):
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
 
 
+ATTN_TC_SEQ_SHAPES = ((10, 10), (29, 29), (28, 28), (28, 2))   # (Tq, Tk) with compile-time fast paths: cfg1, cfg2 (FAR), cfg3
+
+
 def attn_tc_temporal_ok(q, k, v, out, Tq, Tk, nhead, d):
-    """domain of the tcgen05 temporal fast path (the T = 10 self- and enc-dec attention of cfg1)"""
-    return (ATTN_TC and not FORCE_SIMT and Tq == 10 and Tk == 10 and d == 66 and 1 <= nhead <= 8
+    """domain of the tcgen05 temporal / enc-dec fast paths"""
+    return (ATTN_TC and not FORCE_SIMT and (Tq, Tk) in ATTN_TC_SEQ_SHAPES and d == 66 and 1 <= nhead <= 8
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
 
 
