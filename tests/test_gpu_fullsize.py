@@ -39,6 +39,22 @@ def test_nar_cfg3_shape_one_clip():
     assert rel_l2(y, yo) < 1e-3
 
 
+def test_nar_cfg4_geometry_one_clip():
+    """the stress geometry of cfg4 (16x16 feature grid, 8x8 windows = 64-token groups, 10 -> 30 frames, LayerNorm((2112,16,16))) at
+    d_model 528 with one encoder and one decoder layer: exercises the fallback kernels (scalar window attention, generic
+    temporal shapes, register-window depthwise conv) at the real dimensions"""
+    from vptr_b200.model import VPTRFormerNAR
+    torch.manual_seed(2021)
+    net = VPTRFormerNAR(10, 30, encH=16, encW=16, d_model=528, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.1,
+                        window_size=8, rpe=True).eval()
+    x = torch.rand(1, 10, 528, 16, 16, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        yo = O.vptr_former_nar({k: v for k, v in net.state_dict().items()}, x, nhead=8, ws=8, rpe=True, training=False)
+        y = net.cuda()(x.cuda())
+    assert tuple(y.shape) == (1, 30, 528, 16, 16)
+    assert rel_l2(y, yo) < 1e-3
+
+
 def test_far_cfg2_shape_one_clip():
     from vptr_b200.model import VPTRFormerFAR
     torch.manual_seed(2021)
