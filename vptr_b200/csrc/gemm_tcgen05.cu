@@ -1031,7 +1031,12 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     static const int mode_env = [] { const char* e = getenv("VPTR_GEMM_1CTA"); return (e && e[0] == '1') ? 1 : 0; }();
     const bool two_cta = !mode_env && M > BLOCK_M;          // CTA pairs (cta_group::2) unless the problem has a single M tile
     constexpr int BN1 = 176;                                 // 1-CTA N tile
-    const int BN = two_cta ? (b_mn ? 192 : 176) : BN1;   // MN-major B halves: whole 32-column groups -> 192
+    // wide outputs (fc1 / linear1, N = 2112): 256 x 256 pair tiles move 25 % fewer operand bytes per FLOP than 256 x 176 -- the TF32
+    // main loop is operand-delivery bound -- when the column count tiles into 256 with <= 10 % waste (528 -> 2112: 181 -> 157 us)
+    static const bool narrow_env = [] { const char* e = getenv("VPTR_GEMM_NARROW"); return e && e[0] == '1'; }();
+    // (no gain measured for MN-major B, whose 192-column tiles already stage whole 32-column groups: dgrad 158 vs 160 us)
+    const bool wide = !narrow_env && two_cta && !b_mn && N >= 1024 && (long long)vptr_cdiv(N, 256) * 256 * 10 <= (long long)N * 11;
+    const int BN = two_cta ? (wide ? 256 : (b_mn ? 192 : 176)) : BN1;   // MN-major B halves: whole 32-column groups -> 192
     GemmParams p;
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = vptr_cdiv(M, two_cta ? 2 * BLOCK_M : BLOCK_M);
@@ -1069,6 +1074,10 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
 
     if (two_cta) {
         constexpr int ST2 = 7;
+        if (wide) {
+            if (!a_mn) return launch_gemm_2cta<256, 0, 0, 6>(ma, mb, p, stream);
+            return launch_gemm_2cta<256, 1, 0, 6>(ma, mb, p, stream);
+        }
         if (!a_mn && !b_mn) return launch_gemm_2cta<176, 0, 0, ST2>(ma, mb, p, stream);
         if (!a_mn && b_mn) return launch_gemm_2cta<192, 0, 1, ST2>(ma, mb, p, stream);
         if (a_mn && b_mn) return launch_gemm_2cta<192, 1, 1, ST2>(ma, mb, p, stream);
