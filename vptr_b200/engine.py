@@ -69,6 +69,20 @@ class Params:
         return r
 
 
+def _stacked(*ws):
+    """[sum of rows][cols] view over weight matrices that sit back to back in memory (the tf32-rounded copies of one attention
+    module's q / k / v projections do: Params rounds all GEMM weights into one flat buffer in parameter order), else None."""
+    w0 = ws[0]
+    if any(w.dim() != 2 or not w.is_contiguous() or w.shape[1] != w0.shape[1] or w.dtype != w0.dtype for w in ws):
+        return None
+    ptr = w0.data_ptr()
+    for w in ws:
+        if w.data_ptr() != ptr or w.untyped_storage().data_ptr() != w0.untyped_storage().data_ptr():
+            return None
+        ptr += w.numel() * w.element_size()
+    return torch.as_strided(w0, (sum(w.shape[0] for w in ws), w0.shape[1]), (w0.shape[1], 1), w0.storage_offset())
+
+
 def _rc(x, rowscale=None, group_elems=0, seed=0, p=0.0):
     """GEMM-operand copy of x: tf32-rounded and, for the backward of a regularised branch, masked / DropPath-scaled"""
     if not ROUND_TF32 and rowscale is None and p <= 0.0:
@@ -234,9 +248,14 @@ def window_attn_bwd(P, s, dout, dqpos):
             src = a_in if nm == "v_proj" else aq_in
             _wgrad(P, at + nm + ".weight", dqkv[:, i * C:(i + 1) * C], src)
             _bgrad(P, at + nm + ".bias", dqkv[:, i * C:(i + 1) * C])
-        d_aq = ops.gemm(dqkv[:, :C], P.wr(at + "q_proj.weight"), b_mn=True)
-        ops.gemm(dqkv[:, C:2 * C], P.wr(at + "k_proj.weight"), b_mn=True, out=d_aq, residual=d_aq)
-        d_a = ops.gemm(dqkv[:, 2 * C:], P.wr(at + "v_proj.weight"), b_mn=True)
+        wq, wk, wv = P.wr(at + "q_proj.weight"), P.wr(at + "k_proj.weight"), P.wr(at + "v_proj.weight")
+        wqk = _stacked(wq, wk)
+        if wqk is not None:      # d(aq) = [dq | dk] [Wq ; Wk]: one contraction over 2C instead of two GEMMs chained through a residual
+            d_aq = ops.gemm(dqkv[:, :2 * C], wqk, b_mn=True)
+        else:
+            d_aq = ops.gemm(dqkv[:, :C], wq, b_mn=True)
+            ops.gemm(dqkv[:, C:2 * C], wk, b_mn=True, out=d_aq, residual=d_aq)
+        d_a = ops.gemm(dqkv[:, 2 * C:], wv, b_mn=True)
     else:
         Wi = P.wr(at + "in_proj_weight")
         gW, gb = P.g(at + "in_proj_weight"), P.g(at + "in_proj_bias")
@@ -461,8 +480,7 @@ def cross_attn_bwd(P, s, dout, dqpos, dmem):
         ops.colsum(dq, gb[:C])
         ops.colsum(dkv, gb[C:])
     dzq = ops.gemm(dq, Wi[:C], b_mn=True)
-    ops.gemm(dkv[:, :C], Wi[C:2 * C], b_mn=True, out=dmem, residual=dmem)
-    ops.gemm(dkv[:, C:], Wi[2 * C:], b_mn=True, out=dmem, residual=dmem)
+    ops.gemm(dkv, Wi[C:], b_mn=True, out=dmem, residual=dmem)     # d(mem) += [dk | dv] [Wk ; Wv]  (memory + pos_past and memory share it)
     if dqpos is not None:
         ops.rowgroup_sum(dzq, dqpos, g.N)
     return ops.layernorm_bwd(dzq, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
