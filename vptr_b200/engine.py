@@ -39,6 +39,17 @@ class Params:
         if ROUND_TF32 and rounded is None:
             names = [k for k, v in self.t.items() if k.endswith(self.GEMM_WEIGHTS) and v.is_cuda and v.numel() % 4 == 0
                      and v.data_ptr() % 16 == 0 and v.is_contiguous()]
+            # q before k before v inside each attention module (registration order is k, v, q), so that [Wq ; Wk] and
+            # [Wk ; Wv] are contiguous row blocks of the flat buffer (_stacked)
+            rank = {"q_proj.weight": 0, "k_proj.weight": 1, "v_proj.weight": 2}
+            pos = {k: i for i, k in enumerate(names)}
+            first = {}
+            for k in names:
+                mod, _, leaf = k.rpartition(".attn.")
+                if leaf in rank:
+                    first[mod] = min(first.get(mod, pos[k]), pos[k])
+            names.sort(key=lambda k: (first.get(k.rpartition(".attn.")[0], pos[k]) if k.rpartition(".attn.")[2] in rank else pos[k],
+                                      rank.get(k.rpartition(".attn.")[2], 0)))
             if names:
                 for k, r in zip(names, ops.round_copy_multi([self.t[k] for k in names])):
                     self.rounded[k] = r
