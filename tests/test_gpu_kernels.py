@@ -97,6 +97,39 @@ def test_norm_act(mode):
     assert rel_l2(dx, xr.grad) < 1e-4 and rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("ch", [528, 2112])
+def test_norm_act_bwd_cluster_path(ch):
+    """Frame LayerNorm + GELU backward at the path's frame sizes (64 tokens x 528 / 2112 channels, >= 16 frames): the single-pass
+    thread-block-cluster kernel, with DropPath row scales + dropout regenerated from the seed, in place and out of place."""
+    from vptr_b200 import ops
+    Fr, hw, P, seed = 21, 64, 0.25, 424242
+    rows = Fr * hw
+    x = rnd(rows, ch, seed=1) * 2 + 0.3
+    dy = rnd(rows, ch, seed=3)
+    gm, bt = rnd(hw, ch, seed=4) * 0.2 + 1, rnd(hw, ch, seed=5) * 0.1
+    xr, gr, br = x.clone().requires_grad_(True), gm.clone().requires_grad_(True), bt.clone().requires_grad_(True)
+    mean, rstd = ops.group_stats(x, Fr)
+    z = F.layer_norm(xr.view(Fr, hw, ch), (hw, ch), gr, br).view(rows, ch)
+    rs = ops.droppath_scales(7, 99, 0.3, "cuda")                                    # 3 frames per clip
+    mask = ops.round_copy(torch.ones_like(x), False, rs, 3 * hw * ch, seed, P)      # keep-scale of every element (dropout x DropPath)
+    (F.gelu(z) * mask * dy).sum().backward()
+    drop = dict(rowscale=rs, rows_per_group=3 * hw, drop_seed=seed, drop_p=P)
+    dg, db = torch.zeros_like(gm), torch.zeros_like(bt)
+    dx = ops.norm_act_bwd(dy, x, mean, rstd, gm, bt, dg, db, hw, 1, **drop)
+    assert rel_l2(dx, xr.grad) < 1e-4 and rel_l2(dg, gr.grad) < 1e-4 and rel_l2(db, br.grad) < 1e-4
+    # in place + tf32-rounded output, accumulating into the same affine gradients
+    buf = dy.clone()
+    out = ops.norm_act_bwd(buf, x, mean, rstd, gm, bt, dg, db, hw, 1, round_tf32=True, inplace=True, **drop)
+    assert out.data_ptr() == buf.data_ptr() and rel_l2(out, dx) < 5e-4
+    assert (out.view(torch.int32) & 0x1fff).abs().max().item() == 0
+    assert rel_l2(dg, 2 * gr.grad) < 1e-4 and rel_l2(db, 2 * br.grad) < 1e-4
+    # no regularisation
+    xr.grad = None
+    (F.gelu(F.layer_norm(xr.view(Fr, hw, ch), (hw, ch), gm, bt)).view(rows, ch) * dy).sum().backward()
+    dx0 = ops.norm_act_bwd(dy, x, mean, rstd, gm, bt, torch.zeros_like(gm), torch.zeros_like(bt), hw, 1)
+    assert rel_l2(dx0, xr.grad) < 1e-4
+
+
 def _attn_ref(q, k, v, nhead, scale, bias=None, mask=None):
     """(B,L,C) oracle core with q scaled first, as the reference does"""
     return O._mha_core(q * scale, k, v, nhead, bias=bias, mask=mask)
