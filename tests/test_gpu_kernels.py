@@ -98,9 +98,9 @@ def test_norm_act(mode):
 
 
 @pytest.mark.parametrize("ch", [528, 2112])
-def test_norm_act_bwd_cluster_path(ch):
-    """Frame LayerNorm + GELU backward at the path's frame sizes (64 tokens x 528 / 2112 channels, >= 16 frames): the single-pass
-    thread-block-cluster kernel, with DropPath row scales + dropout regenerated from the seed, in place and out of place."""
+def test_norm_act_bwd_path_frame_sizes(ch):
+    """Frame LayerNorm + GELU backward at the path's frame sizes (64 tokens x 528 / 2112 channels): DropPath row scales + dropout
+    regenerated from the seed, in place (tf32-rounded, accumulating affine gradients) and out of place."""
     from vptr_b200 import ops
     Fr, hw, P, seed = 21, 64, 0.25, 424242
     rows = Fr * hw

@@ -472,196 +472,6 @@ __global__ void __launch_bounds__(256) ln3_act_bwd_pass_ab_kernel(const float* _
     }
 }
 
-// frame LayerNorm backward, single pass over HBM: one 8-CTA thread-block cluster owns a frame at a time.  Each CTA streams its
-// eighth of the frame ONCE (dy, x), keeps t = g0*gamma and xhat in shared memory, the eight CTAs exchange their two partial sums
-// through distributed shared memory across one cluster barrier, and dx is written from the stash -- 3 tensor passes over HBM
-// instead of the two-kernel path's 6 (g0 written and re-read, x re-read).  Clusters are persistent (a cluster walks frames
-// cluster_id, cluster_id + n_clusters, ...), so the affine gradients of a thread's fixed positions accumulate in registers over
-// all its frames and leave as one vector reduction per position.  NV = float4 per thread and frame (frame = 8 * 352 * NV float4).
-constexpr int LNC_CLUSTER = 8;
-__device__ __forceinline__ void lnc_cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void lnc_cp16(float4* smem_dst, const float4* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void lnc_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void lnc_wait_pending(int n) {   // n is a constant after unrolling: the switch folds to one instruction
-    switch (n) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        case 7: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-        case 8: asm volatile("cp.async.wait_group 8;" ::: "memory"); break;
-        case 9: asm volatile("cp.async.wait_group 9;" ::: "memory"); break;
-        case 10: asm volatile("cp.async.wait_group 10;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 11;" ::: "memory"); break;
-    }
-}
-__device__ __forceinline__ void lnc_st_remote(float* local, unsigned rank, float v) {
-    unsigned ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned)__cvta_generic_to_shared(local)), "r"(rank));
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
-}
-// Loads are cp.async straight into the thread's own stash slots, one commit group per slot pair: the whole frame slice is in
-// flight at once with no registers held, slot i is consumed when its group lands, and the NEXT frame's slot i is requested as
-// soon as the dx phase has drained it -- HBM reads overlap the cluster barrier, the stores and the GELU' arithmetic of the other
-// slots.  Frame constants (mean, rstd, DropPath scale) are fetched one frame ahead; the partial sums are PUSHED into every
-// peer's shared memory before the barrier so that nothing remote is read after it.
-template <int NV, int LNC_THREADS>
-__global__ void __launch_bounds__(LNC_THREADS, 1) ln3_act_bwd_cluster_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                             float* __restrict__ dx, float* __restrict__ dgamma,
-                                                                             float* __restrict__ dbeta, int frames, int hw, float inv_n,
-                                                                             int round_tf32, const DropArgs da) {
-    static_assert(NV <= 12, "lnc_wait_pending covers 12 groups");
-    extern __shared__ float4 lnc_stash[];                 // [NV][2][LNC_THREADS]: thread-private slots (dy -> t, x -> xhat)
-    __shared__ float sred[LNC_THREADS / 32][2];
-    __shared__ __align__(16) float cl_all[2][LNC_CLUSTER][2];   // [frame parity][peer][P1, P2]: written by the peers
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int cluster_id = blockIdx.x / LNC_CLUSTER, n_clusters = gridDim.x / LNC_CLUSTER;
-    constexpr int E4 = LNC_CLUSTER * LNC_THREADS * NV;   // float4 per frame
-    const int q0 = (int)rank * NV * LNC_THREADS + tid;    // this thread's float4 index for i = 0 (stride LNC_THREADS in i)
-    const float4* __restrict__ gam4 = reinterpret_cast<const float4*>(gamma) + q0;
-    const float4* __restrict__ bet4 = reinterpret_cast<const float4*>(beta) + q0;
-    const float4* __restrict__ dy4 = reinterpret_cast<const float4*>(dy) + q0;
-    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x) + q0;
-    float4* __restrict__ dx4 = reinterpret_cast<float4*>(dx) + q0;
-    float4* const slot = lnc_stash + tid;
-    auto frame_scale = [&](int f) {                        // DropPath groups are whole frames
-        return da.rowscale ? __ldg(da.rowscale + (int)(((long long)f * hw) / da.rows_per_group)) : 1.f;
-    };
-    float4 ag[NV], ab[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float m_n = 0.f, r_n = 0.f, rs_n = 1.f;
-    if (cluster_id < frames) {
-        const long long fb = (long long)cluster_id * E4;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            lnc_cp16(slot + (i * 2 + 0) * LNC_THREADS, dy4 + fb + i * LNC_THREADS);
-            lnc_cp16(slot + (i * 2 + 1) * LNC_THREADS, x4 + fb + i * LNC_THREADS);
-            lnc_commit();
-        }
-        m_n = __ldg(mean + cluster_id); r_n = __ldg(rstd + cluster_id); rs_n = frame_scale(cluster_id);
-    }
-    int parity = 0;
-    for (int f = cluster_id; f < frames; f += n_clusters, parity ^= 1) {
-        const float m = m_n, r = r_n, rs = rs_n;
-        const int fn = f + n_clusters;
-        if (fn < frames) { m_n = __ldg(mean + fn); r_n = __ldg(rstd + fn); rs_n = frame_scale(fn); }
-        const long long fb = (long long)f * E4;
-        float a1 = 0.f, a2 = 0.f;
-        float4 g_n = __ldg(gam4), b_n = __ldg(bet4);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float4 g = g_n, b = b_n;
-            if (i + 1 < NV) { g_n = __ldg(gam4 + (i + 1) * LNC_THREADS); b_n = __ldg(bet4 + (i + 1) * LNC_THREADS); }
-            lnc_wait_pending(NV - 1 - i);
-            float4 d = slot[(i * 2 + 0) * LNC_THREADS];
-            const float4 xv = slot[(i * 2 + 1) * LNC_THREADS];
-            if (da.p > 0.f) {
-                const float4 k = vptr_drop_scale4(da.seed, (unsigned long long)(fb + q0 + i * LNC_THREADS), da.p);
-                d.x *= k.x; d.y *= k.y; d.z *= k.z; d.w *= k.w;
-            }
-            const float4 xh = make_float4((xv.x - m) * r, (xv.y - m) * r, (xv.z - m) * r, (xv.w - m) * r);
-            d.x *= rs * vptr_gelu_grad(xh.x * g.x + b.x); d.y *= rs * vptr_gelu_grad(xh.y * g.y + b.y);
-            d.z *= rs * vptr_gelu_grad(xh.z * g.z + b.z); d.w *= rs * vptr_gelu_grad(xh.w * g.w + b.w);
-            ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
-            ag[i].x = fmaf(d.x, xh.x, ag[i].x); ag[i].y = fmaf(d.y, xh.y, ag[i].y);
-            ag[i].z = fmaf(d.z, xh.z, ag[i].z); ag[i].w = fmaf(d.w, xh.w, ag[i].w);
-            const float4 t = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-            a1 += (t.x + t.y) + (t.z + t.w);
-            a2 += (t.x * xh.x + t.y * xh.y) + (t.z * xh.z + t.w * xh.w);
-            slot[(i * 2 + 0) * LNC_THREADS] = t;
-            slot[(i * 2 + 1) * LNC_THREADS] = xh;
-        }
-        a1 = warp_sum(a1);
-        a2 = warp_sum(a2);
-        if (lane == 0) { sred[warp][0] = a1; sred[warp][1] = a2; }
-        __syncthreads();
-        if (warp == 0) {
-            float s1 = lane < LNC_THREADS / 32 ? sred[lane][0] : 0.f, s2 = lane < LNC_THREADS / 32 ? sred[lane][1] : 0.f;
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            if (lane < LNC_CLUSTER) {   // lane c hands this CTA's partials to peer c
-                lnc_st_remote(&cl_all[parity][rank][0], (unsigned)lane, s1);
-                lnc_st_remote(&cl_all[parity][rank][1], (unsigned)lane, s2);
-            }
-        }
-        lnc_cluster_barrier();          // all eight partials have landed here (and a CTA barrier for the reuse of sred / cl_all)
-        float p1 = 0.f, p2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < LNC_CLUSTER; c += 2) {
-            const float4 v = *reinterpret_cast<const float4*>(&cl_all[parity][c][0]);
-            p1 += v.x + v.z;
-            p2 += v.y + v.w;
-        }
-        const float t1 = p1 * inv_n, t2 = p2 * inv_n;
-        const long long fbn = (long long)fn * E4;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const float4 t = slot[(i * 2 + 0) * LNC_THREADS], xh = slot[(i * 2 + 1) * LNC_THREADS];
-            if (fn < frames) {          // the slot is drained: request the next frame's data into it
-                lnc_cp16(slot + (i * 2 + 0) * LNC_THREADS, dy4 + fbn + i * LNC_THREADS);
-                lnc_cp16(slot + (i * 2 + 1) * LNC_THREADS, x4 + fbn + i * LNC_THREADS);
-                lnc_commit();
-            }
-            float4 o = make_float4(r * (t.x - t1 - xh.x * t2), r * (t.y - t1 - xh.y * t2), r * (t.z - t1 - xh.z * t2), r * (t.w - t1 - xh.w * t2));
-            if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
-            dx4[fb + i * LNC_THREADS] = o;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        float* pg = dgamma + 4ll * (q0 + i * LNC_THREADS);
-        float* pb = dbeta + 4ll * (q0 + i * LNC_THREADS);
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pg), "f"(ag[i].x), "f"(ag[i].y), "f"(ag[i].z), "f"(ag[i].w) : "memory");
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pb), "f"(ab[i].x), "f"(ab[i].y), "f"(ab[i].z), "f"(ab[i].w) : "memory");
-    }
-    lnc_cluster_barrier();              // no CTA leaves while a peer may still write its cl_all
-}
-
-// launch of the cluster path; returns false when the shape / device does not admit it (caller falls back to the two-kernel path)
-template <int NV, int LNC_THREADS>
-bool ln3_cluster_launch(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                        float* dx, float* dgamma, float* dbeta, int frames, int hw, long long gsize, int round_tf32, const DropArgs& da,
-                        cudaStream_t stream) {
-    static int n_clusters = -1;                           // max co-resident clusters (0: unavailable)
-    auto kern = ln3_act_bwd_cluster_kernel<NV, LNC_THREADS>;
-    const size_t smem = sizeof(float4) * NV * 2 * LNC_THREADS;
-    cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = LNC_CLUSTER; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    cfg.blockDim = dim3(LNC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cfg.attrs = &at;
-    cfg.numAttrs = 1;
-    if (n_clusters < 0) {
-        n_clusters = 0;
-        int n = 0;
-        cfg.gridDim = dim3(LNC_CLUSTER * 64);
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-            cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 8)
-            n_clusters = n;
-        cudaGetLastError();
-        if (getenv("VPTR_NORM_DEBUG")) fprintf(stderr, "ln3_act_bwd_cluster_kernel<%d,%d>: %d co-resident clusters of %d CTAs\n", NV, LNC_THREADS, n, LNC_CLUSTER);
-    }
-    if (n_clusters <= 0) return false;
-    cfg.gridDim = dim3(LNC_CLUSTER * (unsigned)(frames < n_clusters ? frames : n_clusters));
-    return cudaLaunchKernelEx(&cfg, kern, dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, frames, hw, 1.0f / (float)gsize, round_tf32, da) == cudaSuccess;
-}
-
 // Final pass (in place on the g0 buffer): dx from g0 and the reduced sums.
 //  MODE 0: dx = gamma*rstd*(g0 - S1/n - xhat*S2/n)        (S indexed by channel, n = rows)
 //  MODE 1: dx = rstd_f*(g0*gamma - P1_f/n - xhat*P2_f/n)   (P indexed by frame,  n = hw*ch)
@@ -833,18 +643,6 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
     } else {
         const long long gsize = (long long)hw * ch;
         const int frames = (int)(rows / hw);
-        // experimental single-pass cluster path for 64 tokens x 2112 channels (VPTR_NORM_CLUSTER=1)
-        static const bool no_cluster = getenv("VPTR_NORM_CLUSTER") == nullptr;    // opt-in: slower than the two-kernel path inside the step
-        auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-        const long long e4 = gsize / 4;
-        if (!no_cluster && dgamma && dbeta && frames >= 16 && (rowscale == nullptr || da.rows_per_group % hw == 0) && al16(dy) && al16(x) &&
-            al16(gamma) && al16(beta) && al16(dx) && al16(dgamma) && al16(dbeta)) {
-            bool done = false;
-            if (e4 == 8ll * 704 * 6)              // 64 tokens x 2112 channels
-                done = ln3_cluster_launch<6, 704>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, frames, hw, gsize, round_tf32, da, stream);
-            if (done) return vptr_check_launch("ln3_act_bwd_cluster_kernel");
-            cudaGetLastError();
-        }
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * frames, stream);
         dim3 g2(vptr_cdiv(gsize / 4, 256), vptr_cdiv(frames, LN3_FPB));
         ln3_act_bwd_pass_ab_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, dgamma, dbeta, gsize, ch, frames, da);
