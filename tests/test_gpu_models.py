@@ -157,6 +157,36 @@ def test_autoencoder_matches_reference_golden(name):
         assert rel_l2(fin.grad, z["dfeat"]) < 2e-4
 
 
+def test_packed_frozen_weights_follow_the_parameters():
+    """The eval-mode autoencoder keeps kernel-layout copies of its weights on the modules; they must be rebuilt when a
+    parameter or BatchNorm statistic changes (optimizer-style in-place update, load_state_dict), and on request."""
+    from vptr_b200.model import clear_packed_weights
+    enc, dec, x, c = build_ae("ae_reflect", "cuda")
+    convs = [m for m in enc.modules() if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in enc.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    with torch.no_grad():
+        f0 = enc(x)
+        assert any("_vptr_packed" in m.__dict__ for m in convs)
+        assert rel_l2(enc(x), f0) < 1e-6                                 # cached copies: same result
+        state = {k: v.clone() for k, v in enc.state_dict().items()}
+        convs[3].weight.mul_(1.5)                                        # in-place parameter update (bumps the version counter)
+        f1 = enc(x)
+        assert rel_l2(f1, f0) > 1e-3
+        bns[2].running_var.mul_(2.0)                                     # BatchNorm statistic update
+        f2 = enc(x)
+        assert rel_l2(f2, f1) > 1e-3
+        enc.load_state_dict(state)
+        assert rel_l2(enc(x), f0) < 1e-6
+        convs[5].weight.data.mul_(0.5)                                   # a .data write is invisible to the version counter ...
+        clear_packed_weights(enc)                                        # ... so the copies are dropped by hand
+        assert rel_l2(enc(x), f0) > 1e-3
+        enc.load_state_dict(state)
+        r0 = dec(f0)
+        head = [m for m in dec.modules() if isinstance(m, torch.nn.Conv2d)][-1]
+        head.weight.mul_(4.0)
+        assert rel_l2(dec(f0), r0) > 1e-3
+
+
 def test_modules_fail_loudly_off_gpu():
     net, x, c = build_former("far_rpe", "cuda")
     with pytest.raises(RuntimeError):

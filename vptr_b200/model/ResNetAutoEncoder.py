@@ -8,6 +8,7 @@ indices of the ResnetBlocks) is the reference's; compute is li
                           im2col of the ReLU-masked output gradient times the same packed weight.
 BatchNorm runs with running statistics (stage 2 keeps both modules in .eval(), train_NAR.py:190-191)."""
 import functools
+import os
 
 import torch
 import torch.nn as nn
@@ -119,23 +120,62 @@ def init_weights(net, init_type='normal', init_gain=0.02):
 
 
 # ----------------------------------------------------------------------------------------------- functional compute
+_NO_WEIGHT_CACHE = os.environ.get("VPTR_NO_WEIGHT_CACHE", "") not in ("", "0")
+
+
+def _packed(mod, tag, norm, tensors, build):
+    """Kernel-layout copy of a frozen layer's weights (BatchNorm folded in, tap-major packing, tf32 hi/lo planes), kept on the
+    module across calls.  Stage 2 runs the autoencoder in eval mode with constant weights (train_NAR.py:190-191), so packing them
+    again every step only costs launches.  The copy is rebuilt whenever a source tensor is replaced or modified in place
+    (data_ptr / autograd version counter of the weights and BatchNorm statistics: optimizer steps, load_state_dict, .to()),
+    when the precision mode changes, and always while the norm layer is in training mode.  Writes through `.data` bypass the
+    version counter: call `vptr_b200.model.clear_packed_weights(module)` after those (or set VPTR_NO_WEIGHT_CACHE=1)."""
+    if _NO_WEIGHT_CACHE or (norm is not None and norm.training):
+        return build()
+    key = (tag, E.ROUND_TF32, ops.FORCE_SIMT) + tuple((t.data_ptr(), t._version) for t in tensors)
+    ent = mod.__dict__.get("_vptr_packed")
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    val = build()
+    mod.__dict__["_vptr_packed"] = (key, val)
+    return val
+
+
+def clear_packed_weights(module):
+    """Drop the cached kernel-layout weights of every layer under `module` (see _packed)."""
+    for m in module.modules():
+        m.__dict__.pop("_vptr_packed", None)
+
+
+def _bn_tensors(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
+
 def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_after_residual=False):
     """x (F*H*W, Cin) channel-last -> (F*Ho*Wo, Cout).  y = act(conv(x)*scale + shift) (+ residual)."""
     Cout, Cin = conv.weight.shape[:2]
-    scale, shift = ops.bn_fold(bn)
-    wraw = ops.pack_conv_weight(conv.weight.data, scale, 0).view(Cout, 9 * Cin)
-    if stride == 1 and not ops.FORCE_SIMT and ops.conv3x3_implicit_ok(H, W) and Cin % 4 == 0 and Cout % 4 == 0:
+    implicit = stride == 1 and not ops.FORCE_SIMT and ops.conv3x3_implicit_ok(H, W) and Cin % 4 == 0 and Cout % 4 == 0
+
+    def build():
+        scale, shift = ops.bn_fold(bn)
+        wraw = ops.pack_conv_weight(conv.weight.data, scale, 0).view(Cout, 9 * Cin)
+        if implicit:
+            return (ops.split_tf32(wraw) if E.ROUND_TF32 else wraw), shift
+        return E._rc(wraw), shift
+
+    wk, shift = _packed(conv, "conv3x3-implicit" if implicit else "conv3x3-gemm", bn, (conv.weight,) + _bn_tensors(bn), build)
+    if implicit:
         # implicit GEMM: 4-D TMA boxes of the padded activation feed the tcgen05 kernel directly (no im2col matrix)
         # The frozen encoder chains 21 convolutions; with plain tf32 weights its features land at 1.16e-3 relative (just outside
         # the 1e-3 gate), so the weights enter as two tf32 planes [hi|lo] (2x MMA work, weight rounding error removed).
         xpad = ops.pad_nhwc(x, F_, H, W, Cin, 1, pad_mode, round_tf32=E.ROUND_TF32)
-        w2 = ops.split_tf32(wraw) if E.ROUND_TF32 else wraw
+        w2 = wk
         y = ops.conv3x3_tf32(xpad, w2, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE,
                              w_planes=2 if E.ROUND_TF32 else 1)
         if residual is not None and act_after_residual:
             y = ops.relu_fwd(y, out=y)
         return y, H, W
-    wpk = E._rc(wraw)
+    wpk = wk
     col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode, round_tf32=E.ROUND_TF32)
     if residual is not None and act_after_residual:
         y = ops.gemm(col, wpk, bias=shift, residual=residual)
@@ -152,8 +192,11 @@ def encoder_forward(enc, x):
     x = x.contiguous()
     F_, Ci, H, W = x.shape
     m = enc.model
-    scale, shift = ops.bn_fold(m[2])
-    wpk = ops.pack_conv_weight(m[1].weight.data, scale, 2)
+    def build_stem():
+        scale, shift = ops.bn_fold(m[2])
+        return ops.pack_conv_weight(m[1].weight.data, scale, 2), shift
+
+    wpk, shift = _packed(m[1], "stem7x7", m[2], (m[1].weight,) + _bn_tensors(m[2]), build_stem)
     h = ops.stem_conv7x7(x, wpk, shift, F_, Ci, H, W, m[1].weight.shape[0])
     idx = 4
     for _ in range(enc.n_downsampling):
@@ -179,8 +222,11 @@ def decoder_forward(dec, feat, F_, H, W, save):
     for _ in range(dec.n_downsampling):
         convT, bn = m[idx], m[idx + 1]
         Cin, Cout = convT.weight.shape[:2]
-        scale, shift = ops.bn_fold(bn)
-        wpk = E._rc(ops.pack_conv_weight(convT.weight.data, scale, 1)).view(9 * Cout, Cin)
+        def build_up(convT=convT, bn=bn, Cin=Cin, Cout=Cout):
+            scale, shift = ops.bn_fold(bn)
+            return E._rc(ops.pack_conv_weight(convT.weight.data, scale, 1)).view(9 * Cout, Cin), shift
+
+        wpk, shift = _packed(convT, "convT3x3", bn, (convT.weight,) + _bn_tensors(bn), build_up)
         col = ops.gemm(E._rc(h), wpk)      # operands of the tf32 GEMM are pre-rounded (engine.ROUND_TF32)
         y = ops.convT_gather(col, shift, F_, H, W, Cout, relu=True)
         if save:
@@ -189,7 +235,7 @@ def decoder_forward(dec, feat, F_, H, W, save):
         idx += 3
     head = m[idx + 1]
     Co, Ci = head.weight.shape[:2]
-    wpk = ops.pack_conv_weight(head.weight.data, None, 3)
+    wpk = _packed(head, "head7x7", None, (head.weight,), lambda: ops.pack_conv_weight(head.weight.data, None, 3))
     act = _ACT[dec.out_layer]
     out = ops.head_conv7x7_fwd(h, wpk, head.bias.data, F_, Ci, Co, H, W, act)
     return out, ((saved, out, head, act, F_, H, W) if save else None)
