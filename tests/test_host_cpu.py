@@ -103,3 +103,65 @@ def test_flat_allreduce_mean_two_ranks_gloo():
     assert torch.equal(gw0, gw1) and torch.equal(gb0, gb1)       # identical after the mean
     assert torch.allclose(gw0, torch.full((4, 6), 5 * 1.5)) and torch.allclose(gb0, torch.full((4,), 5.0))
     assert n0 == n1 == 4 * 6 + 4
+
+
+def test_rounded_weight_order_and_stacked_views():
+    """Host logic of the stacked-weight input-gradient GEMMs: q, k, v are adjacent (in that order) in the flat rounded buffer,
+    and a stacked view exists exactly when the matrices sit back to back in one storage."""
+    from vptr_b200 import engine
+    names = ["enc.0.SLMHSA.attn.k_proj.weight", "enc.0.SLMHSA.attn.v_proj.weight", "enc.0.SLMHSA.attn.q_proj.weight",
+             "enc.0.SLMHSA.attn.out_proj.weight", "enc.0.temporal_MHSA.in_proj_weight", "enc.0.temporal_MHSA.out_proj.weight",
+             "enc.0.SpatialFFN.fc1.weight", "enc.1.SLMHSA.attn.k_proj.weight", "enc.1.SLMHSA.attn.v_proj.weight",
+             "enc.1.SLMHSA.attn.q_proj.weight"]
+    order = engine._rounding_order(names)
+    assert sorted(order) == sorted(names)
+    assert order[:4] == ["enc.0.SLMHSA.attn.q_proj.weight", "enc.0.SLMHSA.attn.k_proj.weight", "enc.0.SLMHSA.attn.v_proj.weight",
+                         "enc.0.SLMHSA.attn.out_proj.weight"]
+    assert order[4:7] == names[4:7]
+    assert order[7:] == ["enc.1.SLMHSA.attn.q_proj.weight", "enc.1.SLMHSA.attn.k_proj.weight", "enc.1.SLMHSA.attn.v_proj.weight"]
+    flat = torch.arange(3 * 6 * 4, dtype=torch.float32)
+    wq, wk, wv = (flat[i * 24:(i + 1) * 24].view(6, 4) for i in range(3))
+    qk = engine._stacked(wq, wk)
+    assert qk is not None and qk.shape == (12, 4) and torch.equal(qk, torch.cat([wq, wk])) and qk.data_ptr() == wq.data_ptr()
+    kv = engine._stacked(wk, wv)
+    assert kv is not None and torch.equal(kv, torch.cat([wk, wv]))
+    assert torch.equal(engine._stacked(wq, wk, wv), flat.view(18, 4))
+    assert engine._stacked(wq, wv) is None                      # a gap between them
+    assert engine._stacked(wk, wq) is None                      # wrong order
+    assert engine._stacked(wq, wk.clone()) is None              # different storage
+    assert engine._stacked(wq, flat[24:48].view(4, 6)) is None  # different row length
+
+
+def test_packed_weight_copies_are_keyed_on_pointer_version_and_mode():
+    """Host logic of the frozen-autoencoder weight cache (no kernels: the builder is a stub)."""
+    from vptr_b200 import engine
+    from vptr_b200.model import ResNetAutoEncoder as R, clear_packed_weights
+    conv, bn = torch.nn.Conv2d(4, 4, 3), torch.nn.BatchNorm2d(4).eval()
+    calls = []
+
+    def build():
+        calls.append(1)
+        return len(calls)
+
+    get = lambda: R._packed(conv, "t", bn, (conv.weight,) + R._bn_tensors(bn), build)
+    assert get() == 1 and get() == 1
+    with torch.no_grad():
+        conv.weight.mul_(2.0)                                   # in-place update bumps the version counter
+    assert get() == 2 and get() == 2
+    with torch.no_grad():
+        bn.running_mean.add_(1.0)
+    assert get() == 3
+    conv.weight.data = conv.weight.data.clone()                 # new storage
+    assert get() == 4 and get() == 4
+    old = engine.ROUND_TF32
+    try:
+        engine.ROUND_TF32 = not old                             # precision mode is part of the key
+        assert get() == 5
+    finally:
+        engine.ROUND_TF32 = old
+    assert get() == 6 and get() == 6
+    assert R._packed(conv, "other-layout", bn, (conv.weight,) + R._bn_tensors(bn), build) == 7
+    clear_packed_weights(torch.nn.Sequential(conv, bn))
+    assert get() == 8
+    bn.train()                                                  # batch statistics: never cached
+    assert get() == 9 and get() == 10

@@ -39,17 +39,7 @@ class Params:
         if ROUND_TF32 and rounded is None:
             names = [k for k, v in self.t.items() if k.endswith(self.GEMM_WEIGHTS) and v.is_cuda and v.numel() % 4 == 0
                      and v.data_ptr() % 16 == 0 and v.is_contiguous()]
-            # q before k before v inside each attention module (registration order is k, v, q), so that [Wq ; Wk] and
-            # [Wk ; Wv] are contiguous row blocks of the flat buffer (_stacked)
-            rank = {"q_proj.weight": 0, "k_proj.weight": 1, "v_proj.weight": 2}
-            pos = {k: i for i, k in enumerate(names)}
-            first = {}
-            for k in names:
-                mod, _, leaf = k.rpartition(".attn.")
-                if leaf in rank:
-                    first[mod] = min(first.get(mod, pos[k]), pos[k])
-            names.sort(key=lambda k: (first.get(k.rpartition(".attn.")[0], pos[k]) if k.rpartition(".attn.")[2] in rank else pos[k],
-                                      rank.get(k.rpartition(".attn.")[2], 0)))
+            names = _rounding_order(names)
             if names:
                 for k, r in zip(names, ops.round_copy_multi([self.t[k] for k in names])):
                     self.rounded[k] = r
@@ -78,6 +68,25 @@ class Params:
         if r is None:
             r = self.rounded[name] = ops.round_copy(self.t[name])
         return r
+
+
+def _rounding_order(names):
+    """Order of the weights inside the flat tf32-rounded buffer: parameter order, except that q comes before k before v
+    inside each window-attention module (registration order is k, v, q), so that [Wq ; Wk] and [Wk ; Wv] are contiguous row
+    blocks of the buffer (_stacked)."""
+    rank = {"q_proj.weight": 0, "k_proj.weight": 1, "v_proj.weight": 2}
+    pos = {k: i for i, k in enumerate(names)}
+    first = {}
+    for k in names:
+        mod, _, leaf = k.rpartition(".attn.")
+        if leaf in rank:
+            first[mod] = min(first.get(mod, pos[k]), pos[k])
+
+    def key(k):
+        mod, _, leaf = k.rpartition(".attn.")
+        return (first[mod], rank[leaf]) if leaf in rank else (pos[k], 0)
+
+    return sorted(names, key=key)
 
 
 def _stacked(*ws):
