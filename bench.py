@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(Tp=10, Tf=10, img=64, Cimg=1, d_model=528, nhead=8, enc_layers=4, dec_layers=8, ws=4, clips_per_gpu=64)
 METRIC = "predicted frames/sec (NAR 10->10, 64x64)"
+WORKLOAD = "VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers, d_model 528, window 4 (cfg1)"   # both arms
 
 
 def peaks():
@@ -91,7 +92,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": res["steps"],
             "warmup": 1, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers (cfg1)", "clips_per_step": 2,
+            "config": {"workload": WORKLOAD, "clips_per_step": 2,
                        "note": "CPU port of the reference algorithm (oracle/), dropout 0"},
             "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "%d full training steps at 2 clips (of the 64-clip workload) after 1 warm-up" % res["steps"]},
@@ -264,7 +265,7 @@ def run_cuda(args):
         "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": "VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers, d_model 528, window 4 (cfg1)",
+        "config": {"workload": WORKLOAD,
                    "clips_per_gpu": n, "global_clips": n * world, "dropout": args.dropout, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (>60 GB of activations) far exceeds the 126 MB L2; L2 flushed once before timing",
                    "loss": "MSE + GDL + 0.1*BiPatchNCE", "optimizer": "AdamW lr 1e-4, clip_grad_norm 1.0",
