@@ -1,15 +1,22 @@
-"""bench.py -- predicted frames / second of one full stage-2 VPTR-NAR training iteration (BASELINE.json metric),
-workload cfg1: MovingMNIST-shape 10->10, 64x64x1, 64 synthetic clips per GPU, 4 encoder + 8 decoder layers.
+"""bench.py -- predicted frames / second of one full stage-2 VPTR training iteration (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores (rank 0 only)
+    python bench.py --gpus N --steps K --warmup W [--config cfg1|cfg2|cfg3|cfg4]     # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the UNMODIFIED reference's single_iter on the host CPU cores (rank 0 only)
 
-A step = everything train_NAR.single_iter does (reference train_NAR.py:49-107): ResNet-encode past and future clips
-(no_grad), Transformer forward, ResNet decoder, NCE projector, MSE + GDL + 0.1*BiPatchNCE, backward, [gradient all-reduce
-when N > 1], clip_grad_norm_(1.0), AdamW step.  `value` times it with the clips already resident in HBM; `e2e` times the
-same step through the public nn.Module API with the clips copied from pinned host memory and the loss read back every
-step.  Prints ONE JSON line on rank 0."""
+Workloads (BASELINE.json:configs; default cfg1 = the configuration the metric is quoted on):
+  cfg1  VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers, window 4, 64 clips / GPU   (train_NAR.py)
+  cfg2  VPTR-FAR KTH-shape 10->20 (T = 29), 64x64x1, 12 layers, causal temporal attention, 16 clips / GPU (train_FAR.py)
+  cfg3  VPTR-NAR BAIR-shape 2->28, 64x64x3, zero-padded ResNet, 4 + 8 layers, 32 clips / GPU             (train_NAR_mp.py)
+  cfg4  VPTR-NAR stress 10->30, 128x128x3, 16x16 grid, 8x8 windows, 4 + 12 layers, 16 clips / GPU        (train_NAR_mp.py)
+
+A step = everything `single_iter` does (reference train_NAR.py:49-107 / train_FAR.py:48-101): ResNet-encode the clips (no_grad),
+Transformer forward, ResNet decoder, [NCE projector], MSE + GDL [+ 0.1*BiPatchNCE in the single-GPU NAR script], backward,
+[gradient mean over ranks when N > 1, overlapped with the backward], clip_grad_norm_(1.0), AdamW step -- vptr_b200.trainer.
+`value` times it with the clips already resident in HBM; `e2e` times the same step through the public API with the clips copied
+from pinned host memory and the loss read back every step.  Prints ONE JSON line on rank 0."""
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -20,9 +27,30 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(Tp=10, Tf=10, img=64, Cimg=1, d_model=528, nhead=8, enc_layers=4, dec_layers=8, ws=4, clips_per_gpu=64)
-METRIC = "predicted frames/sec (NAR 10->10, 64x64)"
-WORKLOAD = "VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers, d_model 528, window 4 (cfg1)"   # both arms
+CONFIGS = {
+    "cfg1": dict(kind="nar", Tp=10, Tf=10, img=64, Cimg=1, enc_layers=4, dec_layers=8, ws=4, clips_per_gpu=64, out_layer="Sigmoid",
+                 padding="reflect", bpnce=True, gflop_per_clip=553.9, cpu_clips=2, script="train_NAR",
+                 metric="predicted frames/sec (NAR 10->10, 64x64)",
+                 workload="VPTR-NAR MovingMNIST-shape 10->10, 64x64x1, 4 enc + 8 dec layers, d_model 528, window 4 (cfg1)"),
+    "cfg2": dict(kind="far", Tp=10, Tf=20, img=64, Cimg=1, enc_layers=12, dec_layers=0, ws=4, clips_per_gpu=16, out_layer="Tanh",
+                 padding="reflect", bpnce=False, gflop_per_clip=1126.7, cpu_clips=1, script="train_FAR",
+                 metric="predicted frames/sec (FAR 10->20, 64x64; 29 predicted frames per clip)",
+                 workload="VPTR-FAR KTH-shape 10->20 (T = 29), 64x64x1, 12 layers, d_model 528, window 4, causal temporal attention (cfg2)"),
+    "cfg3": dict(kind="nar", Tp=2, Tf=28, img=64, Cimg=3, enc_layers=4, dec_layers=8, ws=4, clips_per_gpu=32, out_layer="Tanh",
+                 padding="zero", bpnce=False, gflop_per_clip=1081.3, cpu_clips=1, script="train_NAR",
+                 metric="predicted frames/sec (NAR 2->28, 64x64x3)",
+                 workload="VPTR-NAR BAIR-shape 2->28, 64x64x3, zero-padded ResNet, 4 enc + 8 dec layers, d_model 528, window 4 (cfg3)"),
+    "cfg4": dict(kind="nar", Tp=10, Tf=30, img=128, Cimg=3, enc_layers=4, dec_layers=12, ws=8, clips_per_gpu=16, out_layer="Tanh",
+                 padding="reflect", bpnce=False, gflop_per_clip=7045.9, cpu_clips=1, script="train_NAR",
+                 metric="predicted frames/sec (NAR 10->30, 128x128x3)",
+                 workload="VPTR-NAR stress 10->30, 128x128x3, 16x16 grid, 8x8 windows (L=64), 4 enc + 12 dec layers, d_model 528 (cfg4)"),
+}
+D_MODEL, NHEAD = 528, 8
+
+
+def frames_per_clip(c):
+    """NAR: Tf decoded frames; FAR: Tp+Tf-1 next-frame predictions"""
+    return c["Tf"] if c["kind"] == "nar" else c["Tp"] + c["Tf"] - 1
 
 
 def peaks():
@@ -70,110 +98,164 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def step_flops(n_clips):
-    """algorithmic FLOPs of one training step (SURVEY.md 8d / BASELINE.md 3): 553.9 GFLOP per clip for cfg1"""
-    return 553.9e9 * n_clips
+def clip_tensors(torch, c, n, rank):
+    """synthetic clips: uniform [0,1) for the Sigmoid decoder, [-1,1) for Tanh; seed 2021 + rank"""
+    g = torch.Generator().manual_seed(2021 + rank)
+    past = torch.rand(n, c["Tp"], c["Cimg"], c["img"], c["img"], generator=g)
+    fut = torch.rand(n, c["Tf"], c["Cimg"], c["img"], c["img"], generator=g)
+    if c["out_layer"] == "Tanh":
+        past, fut = past * 2 - 1, fut * 2 - 1
+    return past, fut
 
 
-# ======================================================================================================== reference arm
-def run_reference(args):
-    """The reference algorithm on the host CPU: oracle/train_step.py (a port -- /root/reference does not travel to the GPU
-    box), all host threads, batch 2 of the 64-clip workload per step."""
-    import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def build_modules(model, torch, c, device, dropout):
+    """Enc / Dec / Transformer of a workload from a `model` package (ours or the reference's: same constructors)"""
+    torch.manual_seed(2021)
+    grid = c["img"] // 8
+    enc = model.VPTREnc(c["Cimg"], feat_dim=D_MODEL, n_downsampling=3, padding_type=c["padding"]).to(device).eval()
+    dec = model.VPTRDec(c["Cimg"], feat_dim=D_MODEL, n_downsampling=3, out_layer=c["out_layer"], padding_type=c["padding"]).to(device).eval()
+    with contextlib.redirect_stdout(io.StringIO()):     # init_weights prints; stdout carries exactly one JSON line
+        model.init_weights(enc)
+        model.init_weights(dec)
+    if c["kind"] == "nar":
+        T = model.VPTRFormerNAR(c["Tp"], c["Tf"], encH=grid, encW=grid, d_model=D_MODEL, nhead=NHEAD, num_encoder_layers=c["enc_layers"],
+                                num_decoder_layers=c["dec_layers"], dropout=dropout, window_size=c["ws"], Spatial_FFN_hidden_ratio=4,
+                                TSLMA_flag=False, rpe=True).to(device)
+    else:
+        T = model.VPTRFormerFAR(c["Tp"], c["Tf"], encH=grid, encW=grid, d_model=D_MODEL, nhead=NHEAD, num_encoder_layers=c["enc_layers"],
+                                dropout=dropout, window_size=c["ws"], Spatial_FFN_hidden_ratio=4, rpe=True).to(device)
+    return enc, dec, T
+
+
+# ======================================================================================================== reference arm (host CPU)
+def cpu_reference_rate(torch, c, steps, warmup, dropout):
+    """The reference's own CPU implementation of the path: the UNMODIFIED train_NAR.single_iter / train_FAR.single_iter
+    (oracle/_ref, staged by oracle/make_ref.sh) on all host threads, a bounded sample of `cpu_clips` clips per step.
+    Falls back to the oracle port (oracle/train_step.py, dropout 0, cfg1 only) when the tree is not staged."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import train_step as TS
+    import ref_loader as RL
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    res = cpu_step_rate(TS, torch, clips=2, steps=max(1, min(args.steps, 3)), warmup=1)
-    line = {"impl": "reference", "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": res["steps"],
-            "warmup": 1, "ms_per_step": res["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+    n = c["cpu_clips"]
+    past, fut = clip_tensors(torch, c, n, 0)
+    dev = torch.device("cpu")
+    if RL.ref_root() is not None:
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            tr, model = RL.load_train_script(c["script"], dropin=False, device="cpu")
+        enc, dec, T = build_modules(model, torch, c, dev, dropout)
+        opt = torch.optim.AdamW(params=T.parameters(), lr=1e-4)
+        grid = c["img"] // 8
+        glob = dict(mse_loss=model.MSELoss(), gdl_loss=model.GDL(alpha=1), lam_gan=None, max_grad_norm=1.0)
+        if c["kind"] == "nar":
+            glob.update(bpnce=model.BiPatchNCE(n, c["Tf"], grid, grid, 1.0), lam_pc=0.1)
+            if not c["bpnce"]:      # train_NAR_mp.py:68-69: the multi-GPU script replaces the BiPatchNCE term by zeros
+                glob.update(bpnce=lambda a, b: (a.sum() + b.sum()) * 0.0)
+        for k, v in glob.items():
+            setattr(tr, k, v)
+
+        def one():
+            if c["kind"] == "nar":
+                return tr.single_iter(enc, dec, None, T, opt, None, (past, fut), dev, train_flag=True)
+            return tr.single_iter(enc, dec, None, T, opt, None, (past, fut), dev, None, train_flag=True)
+        kind = "reference"
+        what = "unmodified %s.single_iter (oracle/_ref), dropout %.1f" % (c["script"], dropout)
+    else:
+        if c["kind"] != "nar" or c["Cimg"] != 1:
+            raise RuntimeError("reference tree not staged (run oracle/make_ref.sh) and the oracle port covers cfg1 only")
+        import train_step as TS
+        import vptr_b200.model as model
+        enc, dec, T = build_modules(model, torch, c, dev, 0.0)
+        sd_T = {k: v.detach() for k, v in T.state_dict().items()}
+        params = {k: v.detach().clone().requires_grad_(True) for k, v in T.named_parameters()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-4)
+        sde = {k: v.detach() for k, v in enc.state_dict().items()}
+        sdd = {k: v.detach() for k, v in dec.state_dict().items()}
+
+        def one():
+            return TS.nar_step(sde, sdd, sd_T, params, opt, past, fut)
+        kind = "port"
+        what = "oracle port of train_NAR.single_iter (oracle/train_step.py), dropout 0"
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    try:
+        RL.unload()
+    except Exception:
+        pass
+    fpc = frames_per_clip(c)
+    return {"fps": n * fpc / dt, "ms": dt * 1e3, "steps": steps, "warmup": warmup, "cores": cores, "kind": kind, "clips": n,
+            "sample": "%d full training steps at %d clip(s) (of the %d-clip workload) after %d warm-up: %s" % (steps, n, c["clips_per_gpu"], warmup, what)}
+
+
+def run_reference(args):
+    import torch
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    c = CONFIGS[args.config]
+    heavy = args.config == "cfg4"
+    res = cpu_reference_rate(torch, c, steps=max(1, min(args.steps, 1 if heavy else 3)), warmup=0 if heavy else 1, dropout=args.dropout)
+    line = {"impl": "reference", "metric": c["metric"], "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": res["steps"],
+            "warmup": res["warmup"], "ms_per_step": res["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clips_per_step": 2,
-                       "note": "CPU port of the reference algorithm (oracle/), dropout 0"},
-            "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d full training steps at 2 clips (of the 64-clip workload) after 1 warm-up" % res["steps"]},
+            "config": {"workload": c["workload"], "clips_per_step": res["clips"], "dropout": args.dropout if res["kind"] == "reference" else 0.0,
+                       "note": "reference's own CPU path on the host cores; per-clip time is batch-independent on the CPU, so the "
+                               "bounded sample extrapolates linearly to the full batch"},
+            "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
             "e2e": {"value": res["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_step_rate(TS, torch, clips, steps, warmup):
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from vptr_b200.model import VPTRDec, VPTREnc, VPTRFormerNAR, init_weights
-    torch.manual_seed(2021)
-    enc = VPTREnc(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3).eval()
-    dec = VPTRDec(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3, out_layer="Sigmoid").eval()
-    import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):     # init_weights prints; stdout carries exactly one JSON line
-        init_weights(enc)
-        init_weights(dec)
-    T = VPTRFormerNAR(CFG["Tp"], CFG["Tf"], encH=8, encW=8, d_model=CFG["d_model"], nhead=CFG["nhead"], num_encoder_layers=CFG["enc_layers"],
-                      num_decoder_layers=CFG["dec_layers"], dropout=0.0, window_size=CFG["ws"], rpe=True)
-    sd_T = {k: v.detach() for k, v in T.state_dict().items()}
-    params = {k: v.detach().clone().requires_grad_(True) for k, v in T.named_parameters()}
-    opt = torch.optim.AdamW(list(params.values()), lr=1e-4)
-    g = torch.Generator().manual_seed(2021)
-    past = torch.rand(clips, CFG["Tp"], CFG["Cimg"], CFG["img"], CFG["img"], generator=g)
-    fut = torch.rand(clips, CFG["Tf"], CFG["Cimg"], CFG["img"], CFG["img"], generator=g)
-    sde = {k: v.detach() for k, v in enc.state_dict().items()}
-    sdd = {k: v.detach() for k, v in dec.state_dict().items()}
-    for _ in range(warmup):
-        TS.nar_step(sde, sdd, sd_T, params, opt, past, fut)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        TS.nar_step(sde, sdd, sd_T, params, opt, past, fut)
-    dt = (time.perf_counter() - t0) / steps
-    return {"fps": clips * CFG["Tf"] / dt, "ms": dt * 1e3, "steps": steps}
-
-
 # ======================================================================================================== CUDA arm
-def build_models(torch, device, dropout):
-    from vptr_b200.model import BiPatchNCE, GDL, MSELoss, VPTRDec, VPTREnc, VPTRFormerNAR, init_weights
-    torch.manual_seed(2021)
-    enc = VPTREnc(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3, padding_type="reflect").to(device).eval()
-    dec = VPTRDec(CFG["Cimg"], feat_dim=CFG["d_model"], n_downsampling=3, out_layer="Sigmoid", padding_type="reflect").to(device).eval()
-    import contextlib
-    import io
-    with contextlib.redirect_stdout(io.StringIO()):
-        init_weights(enc)
-        init_weights(dec)
-    T = VPTRFormerNAR(CFG["Tp"], CFG["Tf"], encH=8, encW=8, d_model=CFG["d_model"], nhead=CFG["nhead"], num_encoder_layers=CFG["enc_layers"],
-                      num_decoder_layers=CFG["dec_layers"], dropout=dropout, window_size=CFG["ws"], rpe=True).to(device)
-    losses = dict(mse=MSELoss(), gdl=GDL(alpha=1), bpnce=BiPatchNCE(CFG["clips_per_gpu"], CFG["Tf"], 8, 8, 1.0).to(device))
-    opt = torch.optim.AdamW(params=T.parameters(), lr=1e-4)
-    return enc, dec, T, losses, opt
+def measure_tf32_peak(torch, ops):
+    """Dense TF32 tensor-core throughput of THIS box, measured in the same run: (a) cuBLAS through torch.matmul with
+    allow_tf32 (the independent yardstick), (b) this library's own tcgen05 GEMM on a large well-shaped problem.  The roofline
+    denominator is the larger of the two, sustained (back to back for ~0.5 s), as MEASURED_PEAKS.json does for bf16."""
+    n = 8192
+    a = torch.randn(n, n, device="cuda")
+    b = torch.randn(n, n, device="cuda")
+    out = torch.empty(n, n, device="cuda")
+    flop = 2.0 * n ** 3
+
+    def rate(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 40
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return flop * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        cublas = rate(lambda: torch.matmul(a, b, out=out))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    ar, br = ops.round_copy(a), ops.round_copy(b)
+    own = rate(lambda: ops.gemm(ar, br, out=out))
+    del a, b, out, ar, br
+    return {"cublas_tf32_tflops": round(cublas, 1), "own_gemm_tf32_tflops": round(own, 1), "peak": max(cublas, own)}
 
 
-def train_step(torch, F, dist, world, enc, dec, T, losses, opt, past, future, flat_params):
-    """train_NAR.single_iter (reference train_NAR.py:49-107) on the drop-in modules"""
-    with torch.no_grad():
-        past_f = enc(past)
-        fut_f = enc(future)
-    T.train()
-    T.zero_grad(set_to_none=True)
-    dec.zero_grad(set_to_none=True)
-    pred_f = T(past_f)
-    pred = dec(pred_f)
-    pf = T.NCE_projector(pred_f.permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
-    gf = T.NCE_projector(fut_f.permute(0, 1, 3, 4, 2)).permute(0, 1, 4, 2, 3)
-    loss = losses["mse"](pred, future) + losses["gdl"](future, pred) + 0.1 * losses["bpnce"](F.normalize(gf, p=2.0, dim=2), F.normalize(pf, p=2.0, dim=2))
-    loss.backward()
-    if world > 1:   # data-parallel gradient mean over NVLink: replaces DistributedDataParallel (train_NAR_mp.py:118,167)
-        from vptr_b200.parallel import allreduce_mean_grads
-        allreduce_mean_grads(flat_params, world)
-    torch.nn.utils.clip_grad_norm_(T.parameters(), max_norm=1.0, norm_type=2)
-    opt.step()
-    return loss
+def gemm_traffic():
+    """per-launch DRAM bytes of the dominant kernel from the committed ncu capture of one step (profiles/r02_gemm_traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def run_cuda(args):
     import torch
     import torch.distributed as dist
-    import torch.nn.functional as F
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,21 +266,18 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from vptr_b200 import _lib, ops
+    from vptr_b200 import model as M
+    from vptr_b200.trainer import Stage2Trainer
     _lib.lib()
-    enc, dec, T, losses, opt = build_models(torch, device, args.dropout)
-    flat_params = list(T.parameters())
+    c = CONFIGS[args.config]
+    enc, dec, T = build_modules(M, torch, c, device, args.dropout)
     if world > 1:   # identical replicas: broadcast rank 0's initial weights (DDP constructor semantics)
-        for p in flat_params:
+        for p in T.parameters():
             dist.broadcast(p.data, 0)
-    n = args.batch or CFG["clips_per_gpu"]
-    if n != CFG["clips_per_gpu"]:
-        from vptr_b200.model import BiPatchNCE
-        losses["bpnce"] = BiPatchNCE(n, CFG["Tf"], 8, 8, 1.0).to(device)
-    g = torch.Generator().manual_seed(2021 + rank)
-    shape_p = (n, CFG["Tp"], CFG["Cimg"], CFG["img"], CFG["img"])
-    shape_f = (n, CFG["Tf"], CFG["Cimg"], CFG["img"], CFG["img"])
-    host_p = torch.rand(*shape_p, generator=g).pin_memory()
-    host_f = torch.rand(*shape_f, generator=g).pin_memory()
+    trainer = Stage2Trainer(c["kind"], enc, dec, T, lr=1e-4, max_grad_norm=1.0, lam_pc=0.1, use_bpnce=c["bpnce"], world=world,
+                            fused_tail=not args.torch_tail)
+    n = args.batch or c["clips_per_gpu"]
+    host_p, host_f = (t.pin_memory() for t in clip_tensors(torch, c, n, rank))
     dev_p, dev_f = host_p.to(device), host_f.to(device)
     l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
 
@@ -217,7 +296,7 @@ def run_cuda(args):
                 p, f = host_p.to(device, non_blocking=True), host_f.to(device, non_blocking=True)
             else:
                 p, f = dev_p, dev_f
-            loss = train_step(torch, F, dist, world, enc, dec, T, losses, opt, p, f, flat_params)
+            loss = trainer.step(p, f)
             if from_host:
                 last = loss.item()      # device -> host read of the step's result
         ev1.record()
@@ -230,12 +309,12 @@ def run_cuda(args):
         return ms / k, last
 
     for _ in range(args.warmup):
-        train_step(torch, F, dist, world, enc, dec, T, losses, opt, dev_p, dev_f, flat_params)
+        trainer.step(dev_p, dev_f)
     l2_flush.zero_()
     if args.ncu_step:   # one step between cudaProfilerStart/Stop for `ncu --profile-from-start off`; prints nothing
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        train_step(torch, F, dist, world, enc, dec, T, losses, opt, dev_p, dev_f, flat_params)
+        trainer.step(dev_p, dev_f)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -250,59 +329,65 @@ def run_cuda(args):
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
     # --- dominant kernel (tcgen05 TF32 GEMM): CUDA-event time of every launch of one more step -> achieved TFLOP/s
-    gemm_stats = profile_gemms(torch, ops, lambda: train_step(torch, F, dist, world, enc, dec, T, losses, opt, dev_p, dev_f, flat_params))
+    gemm_stats = profile_gemms(torch, ops, lambda: trainer.step(dev_p, dev_f))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    del trainer
+    torch.cuda.empty_cache()
     pk = peaks()
-    frames = n * CFG["Tf"] * world
+    tf32 = measure_tf32_peak(torch, ops)
+    fpc = frames_per_clip(c)
+    frames = n * fpc * world
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
-    tf32_peak = pk["bf16"] / 2.0
+    step_flop = c["gflop_per_clip"] * 1e9 * n
+    traffic = gemm_traffic() if args.config == "cfg1" and n == c["clips_per_gpu"] else None
     line = {
-        "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": c["metric"], "value": round(value, 2), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
+        "config": {"workload": c["workload"], "config": args.config,
                    "clips_per_gpu": n, "global_clips": n * world, "dropout": args.dropout, "parallelism": "dp%d" % world,
-                   "l2": "per-step working set (>60 GB of activations) far exceeds the 126 MB L2; L2 flushed once before timing",
-                   "loss": "MSE + GDL + 0.1*BiPatchNCE", "optimizer": "AdamW lr 1e-4, clip_grad_norm 1.0",
-                   "step_tflop_algorithmic": round(step_flops(n) / 1e12, 2), "peak_mem_gib": round(peak_mem, 1)},
+                   "l2": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2; L2 flushed once before timing",
+                   "loss": "MSE + GDL" + (" + 0.1*BiPatchNCE" if c["bpnce"] else ""), "optimizer": "AdamW lr 1e-4, clip_grad_norm 1.0",
+                   "tail": "torch" if args.torch_tail else "fused (vptr_b200.tail)",
+                   "step_tflop_algorithmic": round(step_flop / 1e12, 2), "peak_mem_gib": round(peak_mem, 1),
+                   "frames_per_clip": fpc},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
                 "h2d_bytes_per_step": int(host_p.numel() + host_f.numel()) * 4, "d2h_bytes_per_step": 4, "loss": loss_val},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "gemm_tf32_2cta_kernel (tcgen05.mma cta_group::2 kind::tf32, TMA operands, TMEM accumulators; all Linear/1x1/3x3-conv contractions, fwd+dgrad+wgrad)", "bound": "tensor", "achieved": round(gemm_stats["tflops"], 1),
-                     "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_stats["tflops"] / tf32_peak, 4), "traffic": None,
-                     "traffic_sample": {"launch": "M=40960 N=2112 K=528 (fc1 / linear1 shape)", "dram_bytes": 388915456,
-                                        "algorithmic_bytes": 437000000, "tensor_pipe_active_pct": 52.4,
-                                        "source": "profiles/r01_ncu_gemm_fc1_s3.txt (ncu --set full; achieved above is the aggregate over all GEMM shapes of a step, so a single per-launch traffic figure does not exist)",
-                                        "conv3x3_w8": {"tensor_pipe_active_pct": 89.0, "dram_bytes": 230455808, "source": "profiles/r01_ncu_conv3x3_w8.txt"},
-                                        "attn_tc_fwd (window attention, tcgen05)": {"tensor_pipe_active_pct": 14.4, "dram_bytes": 323859968, "algorithmic_bytes": 346030080,
-                                                                                    "hbm_gbs": 3280, "hbm_frac_of_measured": 0.50,
-                                                                                    "source": "profiles/r01_ncu_attn_tcgen05.txt"}},
-                     "peak_note": "tf32 dense = half of the %s bf16 sustained %.1f TFLOP/s (MEASURED_PEAKS.json has no tf32 entry)" % (pk["src"], pk["bf16"]),
+        "roofline": {"kernel": "gemm_tf32_2cta_kernel (tcgen05.mma cta_group::2 kind::tf32, TMA operands, TMEM accumulators; all Linear/1x1/3x3-conv contractions, fwd+dgrad+wgrad)",
+                     "bound": "tensor", "achieved": round(gemm_stats["tflops"], 1), "peak": round(tf32["peak"], 1), "unit": "TFLOP/s",
+                     "frac": round(gemm_stats["tflops"] / tf32["peak"], 4),
+                     "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                     "traffic_note": None if traffic is None else traffic.get("note"),
+                     "algorithmic_bytes_per_launch": round(gemm_stats["bytes"] / max(gemm_stats["launches"], 1)),
+                     "algorithmic_flop_per_launch": round(gemm_stats["flop"] / max(gemm_stats["launches"], 1)),
+                     "avg_launch_us": round(1e3 * gemm_stats["ms"] / max(gemm_stats["launches"], 1), 2),
+                     "peak_note": "dense TF32 measured on this box in this run, sustained: max(cuBLAS torch.matmul allow_tf32 %.1f, own tcgen05 GEMM %.1f) TFLOP/s at 8192^3; "
+                                  "MEASURED_PEAKS.json (%s) bf16 sustained %.1f" % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], pk["src"], pk["bf16"]),
                      "launches_per_step": gemm_stats["launches"], "gemm_ms_per_step": round(gemm_stats["ms"], 3),
                      "gemm_share_of_step": round(gemm_stats["ms"] / ms_dev, 3), "gemm_tflop_per_step": round(gemm_stats["flop"] / 1e12, 3)},
-        "model_flops_utilisation": {"achieved_tflops": round(step_flops(n) / (ms_dev * 1e-3) / 1e12, 1), "of_tf32_peak": round(step_flops(n) / (ms_dev * 1e-3) / 1e12 / tf32_peak, 4)},
+        "model_flops_utilisation": {"achieved_tflops": round(step_flop / (ms_dev * 1e-3) / 1e12, 1),
+                                    "of_tf32_peak": round(step_flop / (ms_dev * 1e-3) / 1e12 / tf32["peak"], 4)},
     }
+    if c["kind"] == "far":
+        line["config"]["future_frames_only_per_s"] = round(n * c["Tf"] * world / (ms_dev * 1e-3), 2)
     if not args.no_cpu_baseline and world == 1:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import train_step as TS
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        res = cpu_step_rate(TS, torch, clips=2, steps=2, warmup=1)
-        line["cpu_baseline"] = {"value": round(res["fps"], 3), "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": "2 full training steps at 2 clips (of the 64-clip workload) after 1 warm-up, oracle port, dropout 0"}
+        heavy = args.config == "cfg4"
+        res = cpu_reference_rate(torch, c, steps=1 if heavy else 2, warmup=0 if heavy else 1, dropout=args.dropout)
+        line["cpu_baseline"] = {"value": round(res["fps"], 3), "unit": "frames/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def profile_gemms(torch, ops, step_fn):
-    """re-runs one step with a CUDA-event pair around every vptr_gemm_tf32 launch (same stream)"""
+    """re-runs one step with a CUDA-event pair around every vptr_gemm_tf32 / implicit-conv launch (same stream)"""
     records = []
     orig = ops.gemm
 
@@ -313,17 +398,19 @@ def profile_gemms(torch, ops, step_fn):
         e1.record()
         K, M = (A.shape if a_mn else A.shape[::-1])
         N = B.shape[1] if b_mn else B.shape[0]
-        records.append((e0, e1, 2.0 * M * N * K))
+        nbytes = 4.0 * (M * K + N * K + M * N * (2 if kw.get("residual") is not None or kw.get("accumulate") else 1))
+        records.append((e0, e1, 2.0 * M * N * K, nbytes))
         return r
 
     orig_conv = ops.conv3x3_tf32
 
-    def wrapped_conv(xpad, w, F_, H, W, C, Cout, **kw):      # implicit-GEMM convolution: same kernel, A via 4-D TMA
+    def wrapped_conv(xpad, w, F_, H, W, C, Cout, **kw):      # implicit-GEMM convolution: same kernel family, A via 4-D TMA
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = orig_conv(xpad, w, F_, H, W, C, Cout, **kw)
         e1.record()
-        records.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * C))
+        nbytes = 4.0 * (xpad.numel() + w.numel() + F_ * H * W * Cout * (2 if kw.get("residual") is not None else 1))
+        records.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * C, nbytes))
         return r
 
     ops.gemm = wrapped
@@ -334,9 +421,10 @@ def profile_gemms(torch, ops, step_fn):
     finally:
         ops.gemm = orig
         ops.conv3x3_tf32 = orig_conv
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in records)
-    flop = sum(f for _, _, f in records)
-    return {"ms": ms, "flop": flop, "launches": len(records), "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
+    flop = sum(f for _, _, f, _ in records)
+    nbytes = sum(b for _, _, _, b in records)
+    return {"ms": ms, "flop": flop, "bytes": nbytes, "launches": len(records), "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
 
 
 def main():
@@ -345,8 +433,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the 64 of cfg1)")
+    ap.add_argument("--config", default="cfg1", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's own)")
     ap.add_argument("--dropout", type=float, default=0.1, help="Transformer dropout / DropPath rate (reference default 0.1, train_NAR.py:199)")
+    ap.add_argument("--torch-tail", action="store_true", help="losses / clip / AdamW as the reference's literal PyTorch sequence instead of the fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (use under ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -170,6 +170,24 @@ int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const float* bias, f
 int vptr_head_conv7x7_bwd(const float* dout, const float* out, const float* w, float* dx, int F, int Ci, int Co, int H, int W,
                           int act, float* ws, vptr_stream_t stream);
 
+/* ---- tail of the iteration: losses, global-norm clip, AdamW ---------------------------------- */
+/* MSELoss + GDL(alpha=1) of cal_lossT (model/criterion.py:105-204, train_NAR.py:33-36; train_FAR.py:32-34) over `planes` = N*T*C
+ * image planes of H x W.  sums: 3 device doubles zeroed by the caller; loss3 = {total, mse, gdl}. */
+int vptr_mse_gdl_fwd(const float* pred, const float* target, long long planes, int H, int W, double* sums, float* loss3,
+                     vptr_stream_t stream);
+/* dpred = dloss * d(mse + gdl)/d(pred); dloss: device scalar or NULL (= 1) */
+int vptr_mse_gdl_bwd(const float* pred, const float* target, const float* dloss, float* dpred, long long planes, int H, int W,
+                     vptr_stream_t stream);
+/* sum of squares over n tensors with one launch (torch.nn.utils.clip_grad_norm_, train_NAR.py:85).  table: device int64
+ * [n pointers][n cumulative unit ends]; vec != 0: units are float4 (16-byte aligned tensors, numel % 4 == 0), else floats */
+int vptr_sqnorm_multi(const long long* table, int n, long long total_units, int vec, double* out, vptr_stream_t stream);
+/* one AdamW step (torch.optim.AdamW semantics: decoupled weight decay, bias correction; optimizer_T.step(), train_NAR.py:86) over
+ * n tensors with one launch.  table: device int64 [param][grad][exp_avg][exp_avg_sq][cumulative unit ends], n entries each.
+ * sqnorm != NULL: the clip_grad_norm_(max_norm) coefficient min(1, max_norm/(sqrt(*sqnorm)+1e-6)) is applied to the gradients on
+ * the fly, so the clip costs no pass of its own. */
+int vptr_adamw_multi(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
+                     float weight_decay, long long step, const double* sqnorm, float max_norm, vptr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

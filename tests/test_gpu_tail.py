@@ -1,0 +1,89 @@
+"""GPU: the fused tail of the iteration (csrc/tail.cu, vptr_b200/tail.py) against the reference's literal PyTorch sequence --
+MSELoss + GDL (model/criterion.py:105-204), clip_grad_norm_ + AdamW (train_NAR.py:85-86) -- and the trainer built on it."""
+import copy
+
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 1, 64, 64), (2, 2, 3, 16, 24), (1, 2, 1, 5, 7)])
+def test_mse_gdl_matches_reference_losses(shape):
+    from vptr_b200.model import GDL, MSELoss
+    from vptr_b200.tail import mse_gdl_loss
+    g = torch.Generator().manual_seed(4)
+    pred = torch.rand(*shape, generator=g).cuda().requires_grad_(True)
+    tgt = torch.rand(*shape, generator=g).cuda()
+    ref = MSELoss()(pred, tgt) + GDL(alpha=1)(tgt, pred)
+    (ref * 1.7).backward()
+    gref = pred.grad.clone()
+    pred.grad = None
+    loss, parts = mse_gdl_loss(pred, tgt, parts=True)
+    (loss * 1.7).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert abs(float(parts[1]) - float(MSELoss()(pred, tgt))) <= 2e-6
+    assert rel_l2(pred.grad, gref) < 1e-6
+
+
+def test_fused_adamw_and_clip_match_torch():
+    from vptr_b200.tail import FusedAdamW, grad_sqnorm
+    torch.manual_seed(0)
+    shapes = [(528, 528), (2112,), (49, 8), (7,), (3, 5, 2), (528, 2112)]
+    ps_a = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    oa = torch.optim.AdamW(ps_a, lr=1e-3, weight_decay=0.01)
+    ob = FusedAdamW(ps_b, lr=1e-3, weight_decay=0.01)
+    for it in range(4):
+        for pa, pb in zip(ps_a, ps_b):
+            g = torch.randn_like(pa) * (3.0 if it % 2 else 0.01)           # alternately clipped / not clipped
+            pa.grad, pb.grad = g.clone(), g.clone()
+        if it == 2:
+            ps_a[3].grad = ps_b[3].grad = None                              # a parameter that skips a step
+        tn = torch.nn.utils.clip_grad_norm_(ps_a, max_norm=1.0, norm_type=2)
+        oa.step()
+        sq = grad_sqnorm(ps_b)
+        assert abs(float(sq.sqrt()) - float(tn)) <= 1e-5 * float(tn)
+        ob.step(grad_sqnorm=sq, max_norm=1.0)
+        for pa, pb in zip(ps_a, ps_b):
+            assert rel_l2(pb, pa) < 1e-6
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["param_groups"][0]["lr"] == sb["param_groups"][0]["lr"] and set(sa["state"]) == set(sb["state"])
+    for k in sa["state"]:
+        assert rel_l2(sb["state"][k]["exp_avg"], sa["state"][k]["exp_avg"]) < 1e-5
+        assert rel_l2(sb["state"][k]["exp_avg_sq"], sa["state"][k]["exp_avg_sq"]) < 1e-5
+        assert float(sb["state"][k]["step"]) == float(sa["state"][k]["step"])
+    # the state_dict is interchangeable with torch.optim.AdamW's (checkpoints: utils/train_summary.py:22-31,139)
+    oc = FusedAdamW([torch.nn.Parameter(p.detach().clone()) for p in ps_b], lr=1e-3)
+    oc.load_state_dict(copy.deepcopy(sa))
+    od = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in ps_b], lr=1e-3)
+    od.load_state_dict(copy.deepcopy(sb))
+
+
+@pytest.mark.parametrize("kind", ["nar", "far"])
+def test_trainer_fused_tail_matches_torch_tail(kind):
+    """two iterations of vptr_b200.trainer with the fused tail vs the reference's literal PyTorch tail: same losses, same weights"""
+    from vptr_b200.model import VPTRDec, VPTREnc, VPTRFormerFAR, VPTRFormerNAR
+    from vptr_b200.trainer import Stage2Trainer
+    dev = torch.device("cuda")
+    res = []
+    for fused in (False, True):
+        torch.manual_seed(11)
+        enc = VPTREnc(1, feat_dim=528, n_downsampling=3).to(dev).eval()
+        dec = VPTRDec(1, feat_dim=528, n_downsampling=3, out_layer="Sigmoid").to(dev).eval()
+        if kind == "nar":
+            T = VPTRFormerNAR(3, 3, encH=8, encW=8, d_model=528, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.0, window_size=4, rpe=True).to(dev)
+        else:
+            T = VPTRFormerFAR(3, 3, encH=8, encW=8, d_model=528, nhead=8, num_encoder_layers=2, dropout=0.0, window_size=4, rpe=True).to(dev)
+        tr = Stage2Trainer(kind, enc, dec, T, lr=1e-4, use_bpnce=True, fused_tail=fused)
+        g = torch.Generator().manual_seed(2)
+        past, fut = torch.rand(2, 3, 1, 64, 64, generator=g).to(dev), torch.rand(2, 3, 1, 64, 64, generator=g).to(dev)
+        losses = [float(tr.step(past, fut)) for _ in range(2)]
+        res.append((losses, {k: v.detach().clone() for k, v in T.named_parameters()}))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) <= 1e-4 * abs(a), (res[0][0], res[1][0])
+    for k in res[0][1]:
+        # AdamW's first steps move every weight by ~lr * sign(g): compare the displacement-insensitive way, on the values
+        assert rel_l2(res[1][1][k], res[0][1][k]) < 2e-4, k

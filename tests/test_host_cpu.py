@@ -81,6 +81,22 @@ def _dp_worker(rank, world, port, q):
     ptr = flat.data_ptr()
     allreduce_mean_grads([pa, pb, lin.weight], world)            # + one loose gradient in the same call
     inplace_ok = pa.grad.data_ptr() == ptr and bool((flat == 1.5).all())
+    # overlapped reduction: slices announced through the engine hook while "backward" runs, the rest at finish(); every
+    # element must be averaged exactly once
+    from vptr_b200 import engine
+    from vptr_b200.parallel import GradReducer
+    flat2 = torch.full((3 * 4096 + 8,), float(rank + 1))
+    ps = [torch.nn.Parameter(torch.zeros(4096)) for _ in range(3)] + [torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(5))]
+    for i in range(3):
+        ps[i].grad = flat2[i * 4096:(i + 1) * 4096]
+    ps[3].grad = flat2[3 * 4096:]
+    ps[4].grad = torch.full((5,), float(rank + 1))                  # a gradient outside the flat buffer
+    red = GradReducer(ps, world, min_chunk=1024)
+    red.arm()
+    engine.GRAD_READY(flat2, 2 * 4096, 3 * 4096)                    # "layer 2" finishes first, then "layer 1"
+    engine.GRAD_READY(flat2, 4096, 2 * 4096)
+    red.finish()
+    inplace_ok = inplace_ok and engine.GRAD_READY is None and bool((flat2 == 1.5).all()) and bool((ps[4].grad == 1.5).all())
     q.put((rank, lin.weight.detach().clone(), lin.weight.grad.clone(), lin.bias.grad.clone(), n, inplace_ok))
     dist.destroy_process_group()
 

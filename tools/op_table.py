@@ -1,4 +1,4 @@
-"""Per-entry-point timing table of one cfg1 training step: wraps the C-ABI call site with CUDA events (same stream) and
+"""Per-entry-point timing table of one training step (any bench.py --config): wraps the C-ABI call site with CUDA events (same stream) and
 aggregates by (entry point, shape signature).  Usage: python tools/op_table.py [--batch N] [--out gpurun_out/op_table.txt]"""
 import argparse
 import os
@@ -29,24 +29,24 @@ def gemm_flops(name, a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--config", default="cfg1")
+    ap.add_argument("--torch-tail", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "op_table.txt"))
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    enc, dec, T, losses, opt = bench.build_models(torch, dev, args.dropout)
-    n = args.batch
-    if n != bench.CFG["clips_per_gpu"]:
-        from vptr_b200.model import BiPatchNCE
-        losses["bpnce"] = BiPatchNCE(n, bench.CFG["Tf"], 8, 8, 1.0).to(dev)
-    g = torch.Generator().manual_seed(2021)
-    past = torch.rand(n, 10, 1, 64, 64, generator=g).to(dev)
-    fut = torch.rand(n, 10, 1, 64, 64, generator=g).to(dev)
-    params = list(T.parameters())
+    from vptr_b200 import model as M
+    from vptr_b200.trainer import Stage2Trainer
+    c = bench.CONFIGS[args.config]
+    enc, dec, T = bench.build_modules(M, torch, c, dev, args.dropout)
+    n = args.batch or c["clips_per_gpu"]
+    trainer = Stage2Trainer(c["kind"], enc, dec, T, use_bpnce=c["bpnce"], fused_tail=not args.torch_tail)
+    past, fut = (t.to(dev) for t in bench.clip_tensors(torch, c, n, 0))
 
     def step():
-        return bench.train_step(torch, F, None, 1, enc, dec, T, losses, opt, past, fut, params)
+        return trainer.step(past, fut)
 
     for _ in range(3):
         step()
@@ -62,13 +62,16 @@ def main():
         rec.append((name, signature(name, a), gemm_flops(name, a), e0, e1))
         return r
 
+    from vptr_b200 import tail
     ops._call = wrapped
+    tail._call = wrapped
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     step()
     t1.record()
     torch.cuda.synchronize()
     ops._call = orig
+    tail._call = orig
     total = t0.elapsed_time(t1)
     by_name, by_sig = defaultdict(lambda: [0.0, 0, 0.0]), defaultdict(lambda: [0.0, 0, 0.0])
     for name, sig, fl, e0, e1 in rec:

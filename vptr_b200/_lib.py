@@ -60,6 +60,10 @@ _SIGS = {
     "vptr_stem_conv7x7": ([P, P, P, P, I, I, I, I, I, P], I),
     "vptr_head_conv7x7_fwd": ([P, P, P, P, I, I, I, I, I, I, P], I),
     "vptr_head_conv7x7_bwd": ([P, P, P, P, I, I, I, I, I, I, P, P], I),
+    "vptr_mse_gdl_fwd": ([P, P, L, I, I, P, P, P], I),
+    "vptr_mse_gdl_bwd": ([P, P, P, P, L, I, I, P], I),
+    "vptr_sqnorm_multi": ([P, I, L, I, P, P], I),
+    "vptr_adamw_multi": ([P, I, L, I, F, F, F, F, F, L, P, F, P], I),
 }
 
 EXPORTS = tuple(_SIGS) + ("vptr_last_error",)

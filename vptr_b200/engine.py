@@ -24,15 +24,46 @@ ROUND_TF32 = True
 RT = ROUND_TF32
 
 
+# Activation-memory mode.  "fast" keeps every GEMM operand of the forward for the backward (LayerNorm outputs, GELU outputs);
+# "lean" keeps only the pre-activation tensors and re-derives those operands in the backward with one extra elementwise pass each
+# (LayerNorm / norm+GELU / GELU forward: HBM-bound, ~6 % of a cfg1 step) -- 58 % of the "fast" bytes per decoder block, which is
+# what lets cfg4 (16 clips of 10 -> 30 frames at 128x128 per GPU; the reference needs 353 GiB there) fit 180 GB.
+# "auto" (default) picks lean when the fast-mode estimate would not fit the device.
+MEMORY_MODE = "auto"
+FAST_FLOATS_PER_TOKEN = {"enc": 22176, "dec": 35376}      # saved fp32 values per token and block in fast mode
+
+
+def set_memory_mode(mode):
+    global MEMORY_MODE
+    if mode not in ("auto", "fast", "lean"):
+        raise ValueError("vptr_b200.engine.set_memory_mode: mode must be 'auto', 'fast' or 'lean'")
+    MEMORY_MODE = mode
+
+
+def lean_for(enc_tokens, n_enc, dec_tokens, n_dec, device):
+    """decide the mode of one forward pass"""
+    if MEMORY_MODE != "auto":
+        return MEMORY_MODE == "lean"
+    need = 4.0 * (enc_tokens * n_enc * FAST_FLOATS_PER_TOKEN["enc"] + dec_tokens * n_dec * FAST_FLOATS_PER_TOKEN["dec"])
+    free, total = torch.cuda.mem_get_info(device)
+    reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return need > 0.85 * (free + reusable) - 8e9          # 8 GB of head room for transients (decoder, loss, workspaces)
+
+
 class Params:
     """name -> parameter tensor / gradient buffer (views into one flat fp32 buffer when grads are wanted)."""
 
     GEMM_WEIGHTS = ("proj.weight", "in_proj_weight", "fc1.weight", "fc2.weight", "linear1.weight", "linear2.weight")
 
-    def __init__(self, named, want_grads, rounded=None):
+    def __init__(self, named, want_grads, rounded=None, holder=None):
+        """holder: the owning nn.Module.  Its flat gradient buffer is kept across steps (`holder._vptr_gflat`) and re-zeroed
+        instead of re-allocated, so gradient addresses are stable from step to step (the multi-tensor optimizer keeps its pointer
+        table, the all-reduce its chunk views) -- but only when no parameter's current .grad still aliases it (i.e. the caller
+        did zero_grad(set_to_none=True), as train_NAR.py:60 does); gradient accumulation gets a fresh buffer."""
         self.t = {k: v for k, v in named}
         self.gflat = None
         self.gv = {}
+        self.goff = {}
         # tf32-rounded GEMM weights: one multi-tensor launch per step (the backward reuses the forward's copies -- the
         # optimizer only steps after it)
         self.rounded = rounded if rounded is not None else {}
@@ -47,11 +78,20 @@ class Params:
             names = [k for k, v in self.t.items() if v.requires_grad]
             total = sum(self.t[k].numel() for k in names)
             dev = next(iter(self.t.values())).device
-            self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+            cached = getattr(holder, "_vptr_gflat", None) if holder is not None else None
+            if cached is not None and cached.numel() == total and cached.device == dev:
+                base = cached.untyped_storage().data_ptr()
+                if all(self.t[k].grad is None or self.t[k].grad.untyped_storage().data_ptr() != base for k in names):
+                    self.gflat = cached.zero_()
+            if self.gflat is None:
+                self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+                if holder is not None:
+                    holder._vptr_gflat = self.gflat
             off = 0
             for k in names:
                 n = self.t[k].numel()
                 self.gv[k] = self.gflat[off:off + n].view(self.t[k].shape)
+                self.goff[k] = (off, off + n)
                 off += n
 
     def w(self, name):
@@ -112,7 +152,9 @@ def _rc(x, rowscale=None, group_elems=0, seed=0, p=0.0):
 
 class Drop:
     """Dropout / DropPath state of one forward call (train mode, p > 0).  Every site draws its own 64-bit seed; masks are
-    regenerated from (seed, element index) in the backward.  drop_path rate == dropout rate (VPTR_modules.py:114,170)."""
+    regenerated from (seed, element index) in the backward.  drop_path rate == dropout rate (VPTR_modules.py:114,170).
+    DropPath granularity follows the reference site by site: per clip where it is applied to (N,T,H,W,C) tensors (window attention,
+    conv FFNs), per future-frame index where it is applied to the seq-first (T2, N*H*W, C) tensor (encoder-decoder attention)."""
 
     def __init__(self, p, n_clips, device):
         self.p, self.n_clips, self.device = float(p), n_clips, device
@@ -131,6 +173,15 @@ class Drop:
             return None
         return ops.droppath_scales(self.n_clips, self.seed(), self.p_path, self.device)
 
+    def path_per_t(self, T):
+        """(n_clips*T,) per-frame keep-scales for the encoder-decoder attention: the reference applies drop_path1 to the
+        (T2, N*H*W, C) seq-first tensor there (VidHRFormer_modules.py:200-205), and drop_path draws along dim 0
+        (:563-575) -- i.e. ONE Bernoulli per future-frame index t, shared by every clip and pixel.  Reproduced as such."""
+        if self.p_path <= 0.0:
+            self.seed()
+            return None
+        return ops.droppath_scales(T, self.seed(), self.p_path, self.device).repeat(self.n_clips)
+
 
 class _NoDrop:
     p = 0.0
@@ -139,6 +190,9 @@ class _NoDrop:
         return 0
 
     def path(self):
+        return None
+
+    def path_per_t(self, T):
         return None
 
 
@@ -165,8 +219,9 @@ class exact_fp32:
 
 
 class Geom:
-    def __init__(self, N, T, H, W, C, nhead, ws):
+    def __init__(self, N, T, H, W, C, nhead, ws, lean=False):
         self.N, self.T, self.H, self.W, self.C, self.nhead, self.ws = N, T, H, W, C, nhead, ws
+        self.lean = lean
         self.d = C // nhead
         self.HW = H * W
         self.F = N * T
@@ -193,9 +248,8 @@ def _bgrad(P, name, dY):
 
 
 # =================================================================================================== window attention
-def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
-    """x (R,C) -> x + SLMHSA(LN(x)).  qpos (T*H*W, C) or None: q/k source = LN(x)+qpos (decoder)."""
-    C = g.C
+def _win_inputs(P, ln, x, g, rpe, qpos, lw_tab):
+    """(v source, q/k source, mean, rstd): LN(x) [+ query_pos] [padded] [+ lw_pos]; also re-run by the lean-mode backward"""
     lnw, lnb = P.w(ln + ".weight"), P.w(ln + ".bias")
     if qpos is not None:
         a, aq, mean, rstd = ops.layernorm_fwd(x, lnw, lnb, add=qpos, add_div=1, add_mod=qpos.shape[0], round_tf32=RT)
@@ -210,6 +264,14 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
         a_in, aq_in = a, aq
     if not rpe:   # VidHRFormer_modules.py:341: q = k = x + lw_pos (per in-window position), v = x
         aq_in = ops.add_rows(aq_in, lw_tab, 1, lw_tab.shape[0], round_tf32=RT)
+    return a_in, aq_in, mean, rstd
+
+
+def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
+    """x (R,C) -> x + SLMHSA(LN(x)).  qpos (T*H*W, C) or None: q/k source = LN(x)+qpos (decoder)."""
+    C = g.C
+    Fr = g.F
+    a_in, aq_in, mean, rstd = _win_inputs(P, ln, x, g, rpe, qpos, lw_tab)
     Rp = a_in.shape[0]
     qkv = ops.empty(Rp, 3 * C, like=x)
     o = ops.empty(Rp, C, like=x)
@@ -240,8 +302,10 @@ def window_attn_fwd(P, pre, ln, x, g, rpe, qpos, lw_tab, save, D=NO_DROP):
     else:
         out = ops.gemm(o, wo, bias=bo, residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
-        save.append(("win", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, a_in=a_in, aq_in=aq_in, qkv=qkv, o=o, rpe=rpe,
-                                 has_qpos=qpos is not None, g=g, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
+        keep = not g.lean
+        save.append(("win", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, a_in=a_in if keep else None, aq_in=aq_in if keep else None,
+                                 qkv=qkv, o=o, rpe=rpe, qpos=qpos, lw_tab=lw_tab, has_qpos=qpos is not None, g=g, s_attn=s_attn, dp=dp,
+                                 rpg=rpg, p=D.p)))
     return out
 
 
@@ -263,6 +327,8 @@ def window_attn_bwd(P, s, dout, dqpos):
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtable, 0, Fr,
                  g.Hp, g.Wp, g.ws, 0, 0, g.nhead, g.d, False, g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
     a_in, aq_in = s["a_in"], s["aq_in"]
+    if a_in is None:      # lean mode: the projections' operands are re-derived from the block input
+        a_in, aq_in, _, _ = _win_inputs(P, ln, s["x"], g, s["rpe"], s["qpos"], s["lw_tab"])
     if s["rpe"]:
         for i, nm in enumerate(("q_proj", "k_proj", "v_proj")):
             src = a_in if nm == "v_proj" else aq_in
@@ -341,6 +407,8 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     out = ops.norm_act_fwd(h3, st3[0], st3[1], g3, b3, g.HW, mode, res=x, rowscale=dp, rows_per_group=rpg, drop_seed=s3, drop_p=D.p)
     if save is not None:
         bwd_mode = mode if (layer_norm or training) else 2
+        if g.lean:
+            b_ = u1 = u2 = None
         save.append(("ffn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, b=b_, h1=h1, st1=st1, u1=u1, h2=h2, st2=st2, u2=u2, h3=h3,
                                  st3=st3, g=g, layer_norm=layer_norm, mode=bwd_mode, w9=w9, aff=((g1, b1), (g2, b2), (g3, b3)),
                                  s2=s2, s3=s3, dp=dp, rpg=rpg, p=D.p)))
@@ -369,7 +437,12 @@ def conv_ffn_bwd(P, s, dout):
     Ch = s["h1"].shape[1]
     dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT,
                         drop=dict(rowscale=s["dp"], rows_per_group=s["rpg"], drop_seed=s["s3"], drop_p=s["p"]))
-    _wgrad(P, pre + ".fc2.weight", dh3, s["u2"])
+    u2 = s["u2"]
+    if u2 is None:        # lean mode: u2 = drop(GELU(norm2(h2))) again, same dropout seed
+        u2 = ops.norm_act_fwd(s["h2"], s["st2"][0], s["st2"][1], s["aff"][1][0], s["aff"][1][1], g.HW, 1 if lnm else 0,
+                              round_tf32=ROUND_TF32, drop_seed=s["s2"], drop_p=s["p"])
+    _wgrad(P, pre + ".fc2.weight", dh3, u2)
+    del u2
     _bgrad(P, pre + ".fc2.bias", dh3)
     du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
     dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]),
@@ -377,11 +450,19 @@ def conv_ffn_bwd(P, s, dout):
     gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
     if gdw is not None:
         dw9 = ops.zeros(9 * Ch, like=dh2)
-        ops.dwconv3x3_wgrad(s["u1"], dh2, dw9, gdb, g.F, g.H, g.W)
+        u1 = s["u1"]
+        if u1 is None:    # lean mode
+            u1 = ops.norm_act_fwd(s["h1"], s["st1"][0], s["st1"][1], s["aff"][0][0], s["aff"][0][1], g.HW, 1 if lnm else 0)
+        ops.dwconv3x3_wgrad(u1, dh2, dw9, gdb, g.F, g.H, g.W)
+        del u1
         ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
     du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
     dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT, inplace=True)
-    _wgrad(P, pre + ".fc1.weight", dh1, s["b"])
+    b_ = s["b"]
+    if b_ is None:        # lean mode
+        b_ = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT, save_stats=False)[0]
+    _wgrad(P, pre + ".fc1.weight", dh1, b_)
+    del b_
     _bgrad(P, pre + ".fc1.bias", dh1)
     db = ops.gemm(dh1, P.wr(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)
     return ops.layernorm_bwd(db, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
@@ -404,7 +485,10 @@ def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save, D=NO_DROP):
                                                        g.nhead, g.d, causal, g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, drop_seed=s1, drop_p=D.p)
     if save is not None:
-        save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, qkv=qkv, o=o, causal=causal, g=g, s_attn=s_attn, s1=s1, p=D.p)))
+        if g.lean:
+            z = zp = None
+        save.append(("tattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, z=z, zp=zp, pos=pos, qkv=qkv, o=o, causal=causal, g=g,
+                                   s_attn=s_attn, s1=s1, p=D.p)))
     return out
 
 
@@ -421,8 +505,13 @@ def temporal_attn_bwd(P, s, dout):
     Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
-        ops.gemm(dqkv[:, :2 * C], s["zp"], out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
-        ops.gemm(dqkv[:, 2 * C:], s["z"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        z, zp = s["z"], s["zp"]
+        if z is None:     # lean mode
+            z, zp, _, _ = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), add=s["pos"], add_div=g.HW, add_mod=g.T,
+                                            round_tf32=RT, save_stats=False)
+        ops.gemm(dqkv[:, :2 * C], zp, out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dqkv[:, 2 * C:], z, out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        del z, zp
         ops.colsum(dqkv, gb)
     dzp = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
     dz = ops.gemm(dqkv[:, 2 * C:], Wi[2 * C:], b_mn=True)
@@ -439,6 +528,8 @@ def mlp_fwd(P, pre, ln, x, g, save, D=NO_DROP):
     u = ops.gelu_fwd(h, round_tf32=ROUND_TF32, drop_seed=s2, drop_p=D.p)
     out = ops.gemm(u, P.wr(pre + ".linear2.weight"), bias=P.w(pre + ".linear2.bias"), residual=x, drop_seed=s3, drop_p=D.p)
     if save is not None:
+        if g.lean:
+            y = u = None
         save.append(("mlp", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, y=y, h=h, u=u, g=g, s2=s2, s3=s3, p=D.p)))
     return out
 
@@ -446,11 +537,19 @@ def mlp_fwd(P, pre, ln, x, g, save, D=NO_DROP):
 def mlp_bwd(P, s, dout):
     pre, ln = s["pre"], s["ln"]
     dres, dout = dout, _rc(dout, seed=s["s3"], p=s["p"])
-    _wgrad(P, pre + ".linear2.weight", dout, s["u"])
+    u = s["u"]
+    if u is None:         # lean mode
+        u = ops.gelu_fwd(s["h"], round_tf32=ROUND_TF32, drop_seed=s["s2"], drop_p=s["p"])
+    _wgrad(P, pre + ".linear2.weight", dout, u)
+    del u
     _bgrad(P, pre + ".linear2.bias", dout)
     du = ops.gemm(dout, P.wr(pre + ".linear2.weight"), b_mn=True)
     dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT, drop_seed=s["s2"], drop_p=s["p"])
-    _wgrad(P, pre + ".linear1.weight", dh, s["y"])
+    y = s["y"]
+    if y is None:         # lean mode
+        y = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT, save_stats=False)[0]
+    _wgrad(P, pre + ".linear1.weight", dh, y)
+    del y
     _bgrad(P, pre + ".linear1.bias", dh)
     dy = ops.gemm(dh, P.wr(pre + ".linear1.weight"), b_mn=True)
     return ops.layernorm_bwd(dy, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
@@ -470,13 +569,16 @@ def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save, D=NO_DROP):
     q = ops.gemm(zq, Wi[:C], bias=bi[:C], round_tf32=use_tc)
     ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C], round_tf32=use_tc)
     ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:], round_tf32=use_tc)
-    s_attn, dp = D.seed(), D.path()
-    rpg = g.T * g.HW
+    s_attn, dp = D.seed(), D.path_per_t(g.T)
+    rpg = g.HW                                   # DropPath per future-frame index here (see Drop.path_per_t)
     (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False,
                                                        g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
-        save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem, mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
+        if g.lean:
+            zq = None
+        save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, qadd=qadd, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem,
+                                   mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
     return out
 
 
@@ -494,7 +596,12 @@ def cross_attn_bwd(P, s, dout, dqpos, dmem):
     Wi = P.wr(pre + ".in_proj_weight")
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
-        ops.gemm(dq, s["zq"], out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
+        zq = s["zq"]
+        if zq is None:    # lean mode
+            zq = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=s["qadd"], add_div=1,
+                                   add_mod=s["qadd"].shape[0], round_tf32=RT, save_stats=False)[1]
+        ops.gemm(dq, zq, out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
+        del zq
         ops.gemm(dkv[:, :C], s["mem_k"], out=gW[C:2 * C], a_mn=True, b_mn=True, accumulate=True)
         ops.gemm(dkv[:, C:], s["mem"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dq, gb[:C])
@@ -552,6 +659,23 @@ def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem
     return tgt
 
 
+# Called as GRAD_READY(flat, lo, hi) from the backward thread each time a Transformer layer's parameter gradients are final (they
+# are one contiguous slice of the flat gradient buffer); vptr_b200.parallel.GradReducer uses it to start that slice's all-reduce
+# while the rest of the backward still runs.
+GRAD_READY = None
+
+
+def _layer_done(P, pre):
+    """pre = '<...>.layers.<i>.SLMHSA' of the layer whose backward just finished (its window attention is the first sub-block of
+    a layer, so the last one of its backward)"""
+    if GRAD_READY is None or P.gflat is None:
+        return
+    layer = pre.rsplit(".", 1)[0] + "."
+    span = [P.goff[k] for k in P.goff if k.startswith(layer)]
+    if span:
+        GRAD_READY(P.gflat, min(a for a, _ in span), max(b for _, b in span))
+
+
 def backward_tape(P, save, dout, dqpos=None, dmem=None, stop=0):
     """Walks the saved sub-blocks in reverse down to index `stop`; returns the gradient at that point."""
     d = dout
@@ -559,6 +683,7 @@ def backward_tape(P, save, dout, dqpos=None, dmem=None, stop=0):
         kind, s = save.pop()
         if kind == "win":
             d = window_attn_bwd(P, s, d, dqpos)
+            _layer_done(P, s["pre"])
         elif kind == "ffn":
             d = conv_ffn_bwd(P, s, d)
         elif kind == "tattn":

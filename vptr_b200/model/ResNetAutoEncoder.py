@@ -117,6 +117,7 @@ def init_weights(net, init_type='normal', init_gain=0.02):
 
     print('initialize network with %s' % init_type)
     net.apply(init_func)
+    clear_packed_weights(net)      # the writes above go through .data and bypass the version counters _packed keys on
 
 
 # ----------------------------------------------------------------------------------------------- functional compute

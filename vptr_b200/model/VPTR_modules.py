@@ -269,44 +269,46 @@ def _tokens(x):
 
 class _FARFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, x, names, *params):
+    def forward(ctx, mod, x, names, record, *params):
         N, T, C, H, W = x.shape
-        want = any(ctx.needs_input_grad)
+        want = record and any(ctx.needs_input_grad)      # grad mode is always off in here: the module's forward passes it in
         P = E.Params(zip(names, params), want_grads=False)
         bufs = dict(mod.named_buffers())
-        g = E.Geom(N, T, H, W, C, mod.nhead, mod.window_size)
+        lean = want and E.lean_for(N * T * H * W, mod.num_encoder_layers, 0, 0, x.device)
+        g = E.Geom(N, T, H, W, C, mod.nhead, mod.window_size, lean=lean)
         save = [] if want else None
         lw_tab = None if mod.rpe else E.lw_table(mod.lw_pos, g)
         tpos = mod.temporal_pos[:T].contiguous()
         D = _drop_ctx(mod, N, x.device)
         h = E.encoder_fwd(P, bufs, _tokens(x), g, mod.num_encoder_layers, True, mod.rpe, tpos, lw_tab, mod.training, save, D)
         y = E.final_norm_fwd(P, "transformer.encoder.norm", h, True, save)
-        ctx.save, ctx.names, ctx.params, ctx.shape = save, names, params, (N, T, C, H, W)
+        ctx.save, ctx.names, ctx.params, ctx.shape, ctx.mod = save, names, params, (N, T, C, H, W), mod
         ctx.rounded = P.rounded if (want and E.ROUND_TF32) else None
         return y.view(N, T, H, W, C).permute(0, 1, 4, 2, 3)
 
     @staticmethod
     def backward(ctx, dout):
         N, T, C, H, W = ctx.shape
-        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None)
+        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None, holder=ctx.mod)
         ctx.rounded = None
         d = _tokens(dout)
         dx = E.backward_tape(P, ctx.save, d)
         ctx.save = None
         grads = tuple(P.g(n) for n in ctx.names)
-        return (None, dx.view(N, T, H, W, C).permute(0, 1, 4, 2, 3), None) + grads
+        return (None, dx.view(N, T, H, W, C).permute(0, 1, 4, 2, 3), None, None) + grads
 
 
 class _NARFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod, x, names, *params):
+    def forward(ctx, mod, x, names, record, *params):
         N, Tp, C, H, W = x.shape
         Tf = mod.num_future_frames
-        want = any(ctx.needs_input_grad)
+        want = record and any(ctx.needs_input_grad)
         P = E.Params(zip(names, params), want_grads=False)
         bufs = dict(mod.named_buffers())
-        ge = E.Geom(N, Tp, H, W, C, mod.nhead, mod.window_size)
-        gd = E.Geom(N, Tf, H, W, C, mod.nhead, mod.window_size)
+        lean = want and E.lean_for(N * Tp * H * W, mod.num_encoder_layers, N * Tf * H * W, mod.num_decoder_layers, x.device)
+        ge = E.Geom(N, Tp, H, W, C, mod.nhead, mod.window_size, lean=lean)
+        gd = E.Geom(N, Tf, H, W, C, mod.nhead, mod.window_size, lean=lean)
         save = [] if want else None
         lw_tab = None if mod.rpe else E.lw_table(mod.lw_pos, ge)
         tpos_p = mod.temporal_pos[:Tp].contiguous()
@@ -321,7 +323,7 @@ class _NARFunction(torch.autograd.Function):
         tgt = ops.zeros(gd.R, C, like=x)                                         # init_tgt = zeros (VidHRFormer.py:48)
         tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D)
         y = E.final_norm_fwd(P, "transformer.decoder.norm", tgt, True, save)
-        ctx.save, ctx.names, ctx.params, ctx.n_enc = save, names, params, n_enc
+        ctx.save, ctx.names, ctx.params, ctx.n_enc, ctx.mod = save, names, params, n_enc, mod
         ctx.rounded = P.rounded if (want and E.ROUND_TF32) else None
         ctx.shape = (N, Tp, Tf, C, H, W)
         return y.view(N, Tf, H, W, C).permute(0, 1, 4, 2, 3)
@@ -329,7 +331,7 @@ class _NARFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         N, Tp, Tf, C, H, W = ctx.shape
-        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None)
+        P = E.Params(zip(ctx.names, ctx.params), want_grads=True, rounded=ctx.rounded if E.ROUND_TF32 else None, holder=ctx.mod)
         ctx.rounded = None
         dq = P.g("frame_queries")
         dqpos = dq.view(Tf * H * W, C) if dq is not None else None
@@ -338,7 +340,7 @@ class _NARFunction(torch.autograd.Function):
         dx = E.backward_tape(P, ctx.save, dmem)                                                # encoder norm + encoder
         ctx.save = None
         grads = tuple(P.g(n) for n in ctx.names)
-        return (None, dx.view(N, Tp, H, W, C).permute(0, 1, 4, 2, 3), None) + grads
+        return (None, dx.view(N, Tp, H, W, C).permute(0, 1, 4, 2, 3), None, None) + grads
 
 
 def _fwd_params(mod):
@@ -382,7 +384,7 @@ class VPTRFormerNAR(nn.Module):
         """past_gt_feat (N, Tp, C, H, W) -> predicted future features (N, Tf, C, H, W)."""
         _check_input(past_gt_feat, "VPTRFormerNAR")
         names, params = _fwd_params(self)
-        return _NARFunction.apply(self, past_gt_feat, names, *params)
+        return _NARFunction.apply(self, past_gt_feat, names, torch.is_grad_enabled(), *params)
 
     def _reset_parameters(self):
         for p in self.parameters():
@@ -411,7 +413,7 @@ class VPTRFormerFAR(nn.Module):
         """input_feats (N, T, C, H, W), any T <= Tp+Tf -> same shape; output t predicts frame t+1 (causal in time)."""
         _check_input(input_feats, "VPTRFormerFAR")
         names, params = _fwd_params(self)
-        return _FARFunction.apply(self, input_feats, names, *params)
+        return _FARFunction.apply(self, input_feats, names, torch.is_grad_enabled(), *params)
 
     def _reset_parameters(self):
         for p in self.parameters():

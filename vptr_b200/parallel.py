@@ -60,14 +60,19 @@ def allreduce_mean_grads(params, world_size=None):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             flat.div_(world_size)
 
-    # split into maximal runs that are already flat in memory; the longest run (the Transformer) is reduced in place
-    runs, cur = [], [grads[0]]
-    for g in grads[1:]:
-        if _covering_view(cur + [g]) is not None:
+    # split into maximal runs that are already flat in memory (one linear pass: a gradient extends the current run iff it starts
+    # where the previous one ended, in the same storage); the longest run (the Transformer) is reduced in place
+    runs, cur, nxt = [], [], None
+    for g in grads:
+        ok = g.is_contiguous()
+        if cur and ok and g.data_ptr() == nxt and g.dtype == cur[0].dtype and \
+                g.untyped_storage().data_ptr() == cur[0].untyped_storage().data_ptr():
             cur.append(g)
         else:
-            runs.append(cur)
+            if cur:
+                runs.append(cur)
             cur = [g]
+        nxt = g.data_ptr() + g.numel() * g.element_size() if ok else None
     runs.append(cur)
     loose = []
     for r in runs:
@@ -82,3 +87,60 @@ def allreduce_mean_grads(params, world_size=None):
         for g, s_ in zip(loose, torch._utils._unflatten_dense_tensors(flat, loose)):
             g.copy_(s_)
     return sig[1]
+
+
+class GradReducer:
+    """Data-parallel gradient mean overlapped with the backward pass (the role of DistributedDataParallel's bucketed hooks,
+    train_NAR_mp.py:118,167): the engine finishes the Transformer's layers in reverse order and each layer's parameter gradients
+    are one contiguous slice of the flat gradient buffer, so every finished slice is handed to NCCL at once (`arm()` installs the
+    engine hook; asynchronous all-reduce on the process group's own stream, ordered after the kernels that produced the slice)
+    while the remaining layers' backward keeps the SMs busy.  `finish()` reduces whatever is left (frame queries, final norms,
+    gradients outside the flat buffer) with the one-collective path and makes the compute stream wait for all of it."""
+
+    def __init__(self, params, world_size=None, min_chunk=1 << 20):
+        self.params = list(params)
+        self.world = dist.get_world_size() if world_size is None else world_size
+        self.min_chunk = min_chunk
+        self.works, self.done, self.flat = [], [], None
+        self.avg = dist.get_backend() == "nccl"
+
+    def arm(self):
+        from . import engine
+        self.works, self.done, self.flat = [], [], None
+        engine.GRAD_READY = self._ready
+
+    def _ready(self, flat, lo, hi):
+        if hi - lo < self.min_chunk:
+            return
+        self.flat = flat
+        chunk = flat[lo:hi]
+        if self.avg:
+            w = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, async_op=True)
+        else:
+            w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True)
+        self.works.append((w, chunk))
+        self.done.append((lo, hi))
+
+    def finish(self):
+        from . import engine
+        engine.GRAD_READY = None
+        for w, chunk in self.works:
+            w.wait()
+            if not self.avg:
+                chunk.div_(self.world)
+        rest = []
+        if self.flat is not None and self.done:
+            base, esz, n = self.flat.data_ptr(), self.flat.element_size(), self.flat.numel()
+            spans = sorted(self.done)
+            for p in self.params:
+                g = p.grad
+                if g is None:
+                    continue
+                off = (g.data_ptr() - base) // esz
+                inside = 0 <= off < n and any(lo <= off and off + g.numel() <= hi for lo, hi in spans)
+                if not inside:
+                    rest.append(p)
+        else:
+            rest = self.params
+        allreduce_mean_grads(rest, self.world)
+        self.works, self.done = [], []
