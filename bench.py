@@ -241,7 +241,15 @@ def measure_tf32_peak(torch, ops):
     ar, br = ops.round_copy(a), ops.round_copy(b)
     own = rate(lambda: ops.gemm(ar, br, out=out))
     del a, b, out, ar, br
-    return {"cublas_tf32_tflops": round(cublas, 1), "own_gemm_tf32_tflops": round(own, 1), "peak": max(cublas, own)}
+    # (c) the raw-tile implicit-GEMM 3x3 convolution of the ResNet blocks (A operand reused from shared memory: the least
+    # operand-delivery-bound tcgen05 kernel in the library), counting the MMA work it executes (two tf32 weight planes)
+    F_, H, W, C = 640, 8, 8, 528
+    xp = ops.pad_nhwc(torch.randn(F_ * H * W, C, device="cuda"), F_, H, W, C, 1, 1)
+    w2 = ops.split_tf32(torch.randn(C, 9 * C, device="cuda") * 0.02)
+    flop = 2.0 * 2.0 * F_ * H * W * C * 9 * C
+    conv = rate(lambda: ops.conv3x3_tf32(xp, w2, F_, H, W, C, C, w_planes=2))
+    return {"cublas_tf32_tflops": round(cublas, 1), "own_gemm_tf32_tflops": round(own, 1), "own_conv3x3_tf32_tflops_executed": round(conv, 1),
+            "peak": max(cublas, own, conv)}
 
 
 def gemm_traffic():
@@ -368,8 +376,9 @@ def run_cuda(args):
                      "algorithmic_bytes_per_launch": round(gemm_stats["bytes"] / max(gemm_stats["launches"], 1)),
                      "algorithmic_flop_per_launch": round(gemm_stats["flop"] / max(gemm_stats["launches"], 1)),
                      "avg_launch_us": round(1e3 * gemm_stats["ms"] / max(gemm_stats["launches"], 1), 2),
-                     "peak_note": "dense TF32 measured on this box in this run, sustained: max(cuBLAS torch.matmul allow_tf32 %.1f, own tcgen05 GEMM %.1f) TFLOP/s at 8192^3; "
-                                  "MEASURED_PEAKS.json (%s) bf16 sustained %.1f" % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], pk["src"], pk["bf16"]),
+                     "peak_note": "dense TF32 measured on this box in this run, sustained: max(cuBLAS torch.matmul allow_tf32 %.1f at 8192^3, own tcgen05 GEMM %.1f at 8192^3, "
+                                  "own raw-tile 3x3 conv kernel %.1f executed) TFLOP/s; MEASURED_PEAKS.json (%s) bf16 sustained %.1f"
+                                  % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], tf32["own_conv3x3_tf32_tflops_executed"], pk["src"], pk["bf16"]),
                      "launches_per_step": gemm_stats["launches"], "gemm_ms_per_step": round(gemm_stats["ms"], 3),
                      "gemm_share_of_step": round(gemm_stats["ms"] / ms_dev, 3), "gemm_tflop_per_step": round(gemm_stats["flop"] / 1e12, 3)},
         "model_flops_utilisation": {"achieved_tflops": round(step_flop / (ms_dev * 1e-3) / 1e12, 1),

@@ -2,13 +2,18 @@
 FFN 2112), train mode (dropout 0, BatchNorm batch statistics), against autograd through the CPU oracle (oracle/vptr_oracle.py,
 pinned to the unmodified reference by tests/golden).  Reference path: train_NAR.py:63-85 / train_FAR.py:62-82.
 
-Cotangent: L = sum(0.5 * y^2 * probe), i.e. dL/dy = y * probe, which vanishes where the final ReLU has its kink -- the gradient
-is then a continuous function of the forward values, so a ~5e-4 forward perturbation cannot flip a mask into an O(1) gradient
-difference (with a linear cotangent ~4e-4 of the ReLU outputs flip and move every gradient by ~3 % regardless of kernel accuracy).
+Cotangent: the SAME fixed tensor c = y_oracle * probe is fed to both sides (L = sum(c * y)).  It vanishes where the final ReLU has
+its kink, so a ~5e-4 forward perturbation cannot flip a mask into an O(1) gradient difference (with a plain linear cotangent
+~4e-4 of the ReLU outputs flip and move every gradient by ~3 % regardless of kernel accuracy), and being identical on both sides it
+does not feed the forward error straight into the comparison.
+
+Two modes per case: the PRODUCT path (default engine, TF32 operands) and `engine.precise_3xtf32()` -- the same tcgen05 GEMM kernel fed
+3xTF32 operand planes -- which shows that what separates the product from the fp32 reference is operand rounding, not the kernels.
 
 For every case the per-tensor table (rel-L2 of dx and of each parameter gradient, product path vs oracle) is written to
 gpurun_out/bwd_parity_<case>.txt and summarised in profiles/; the gates below are the ones BASELINE.md 5 states (1e-3 on
 outputs) and, for gradients, the measured TF32 envelope stated next to each assert."""
+import contextlib
 import os
 
 import pytest
@@ -23,7 +28,7 @@ pytestmark = pytest.mark.gpu
 OUT_DIR = os.path.join(ROOT, "gpurun_out")
 
 
-def _run_case(case, kind, Tp, Tf, enc_layers, dec_layers, encH, ws, n_clips, T_in=None, seed=5):
+def _run_case(case, kind, Tp, Tf, enc_layers, dec_layers, encH, ws, n_clips, T_in=None, seed=5, modes=("tf32",)):
     from vptr_b200.model import VPTRFormerFAR, VPTRFormerNAR
     torch.manual_seed(2021)
     if kind == "nar":
@@ -43,31 +48,40 @@ def _run_case(case, kind, Tp, Tf, enc_layers, dec_layers, encH, ws, n_clips, T_i
         yo = O.vptr_former_nar(sd, xo, nhead=8, ws=ws, rpe=True, training=True, bn_updates={})
     else:
         yo = O.vptr_former_far(sd, xo, nhead=8, ws=ws, rpe=True, training=True)
-    pr = probe(yo.shape, 2)
-    (0.5 * yo * yo * pr).sum().backward()
-    # --- product path (TF32 tcgen05 GEMMs, tensor-core attention): the default engine mode, nothing switched
-    net = net.cuda().train()
-    xin = x.cuda().requires_grad_(True)
-    y = net(xin)
-    (0.5 * y * y * pr.cuda()).sum().backward()
-    rows = [("<output y>", rel_l2(y, yo), float(yo.norm())), ("<dx>", rel_l2(xin.grad, xo.grad), float(xo.grad.norm()))]
-    gmax = max(float(p.grad.norm()) for p in params.values() if p.grad is not None)
-    for k, p in net.named_parameters():
-        if k.startswith("NCE_projector"):
-            continue
-        go = params[k].grad
-        if go is None:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
-            continue
-        rows.append((k, rel_l2(p.grad, go), float(go.norm())))
-    os.makedirs(OUT_DIR, exist_ok=True)
-    with open(os.path.join(OUT_DIR, "bwd_parity_%s.txt" % case), "w") as f:
-        f.write("# %s: rel-L2(product TF32 path, CPU oracle autograd); train mode, dropout 0; %d clip(s); cotangent y*probe\n" % (case, n_clips))
-        f.write("# largest parameter-gradient norm %.4e; tensors whose gradient norm is < 1e-4 of it are rounding noise of a mathematical zero\n" % gmax)
-        for k, e, n in sorted(rows, key=lambda r: -r[1]):
-            f.write("%-72s rel_l2 %.3e   |ref| %.3e%s\n" % (k, e, n, "   (noise-level gradient)" if n < 1e-4 * gmax else ""))
-    sig = [(k, e) for k, e, n in rows[2:] if n >= 1e-4 * gmax]
-    return rows[0][1], rows[1][1], sig
+    cot = (yo.detach() * probe(yo.shape, 2))
+    (yo * cot).sum().backward()
+    out = {}
+    for mode in modes:
+        # --- product path (TF32 tcgen05 GEMMs, tensor-core attention): the default engine mode, nothing switched;
+        #     "3xtf32": same kernels, 3xTF32 operand planes
+        from vptr_b200 import engine
+        net = net.cuda().train()
+        net.zero_grad(set_to_none=True)
+        for k, v in net.named_buffers():               # BatchNorm running statistics back to their initial values
+            v.copy_(sd[k].to(v.device))
+        xin = x.cuda().requires_grad_(True)
+        with (engine.precise_3xtf32() if mode == "3xtf32" else contextlib.nullcontext()):
+            y = net(xin)
+            (y * cot.cuda()).sum().backward()
+        rows = [("<output y>", rel_l2(y, yo), float(yo.norm())), ("<dx>", rel_l2(xin.grad, xo.grad), float(xo.grad.norm()))]
+        gmax = max(float(p.grad.norm()) for p in params.values() if p.grad is not None)
+        for k, p in net.named_parameters():
+            if k.startswith("NCE_projector"):
+                continue
+            go = params[k].grad
+            if go is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+                continue
+            rows.append((k, rel_l2(p.grad, go), float(go.norm())))
+        os.makedirs(OUT_DIR, exist_ok=True)
+        with open(os.path.join(OUT_DIR, "bwd_parity_%s_%s.txt" % (case, mode)), "w") as f:
+            f.write("# %s [%s]: rel-L2(CUDA path, CPU oracle autograd); train mode, dropout 0; %d clip(s); cotangent y_oracle*probe\n" % (case, mode, n_clips))
+            f.write("# largest parameter-gradient norm %.4e; tensors whose gradient norm is < 1e-4 of it are rounding noise of a mathematical zero\n" % gmax)
+            for k, e, n in sorted(rows, key=lambda r: -r[1]):
+                f.write("%-72s rel_l2 %.3e   |ref| %.3e%s\n" % (k, e, n, "   (noise-level gradient)" if n < 1e-4 * gmax else ""))
+        sig = [(k, e) for k, e, n in rows[2:] if n >= 1e-4 * gmax]
+        out[mode] = (rows[0][1], rows[1][1], sig)
+    return out
 
 
 def _summ(sig):
@@ -75,39 +89,38 @@ def _summ(sig):
     return es[len(es) // 2], es[-1], max(sig, key=lambda t: t[1])[0]
 
 
-# Gates.  Outputs: 1e-3.  Gradients: every GEMM operand is rounded to tf32 (2^-11 relative) and the backward chains
-# 3 GEMMs per sub-block through up to 12 + 8 blocks; the measured envelope of the product path is recorded in
-# profiles/r02_bwd_parity.md and the gates sit ~1.5x above it.
-def test_nar_cfg1_full_depth_backward():
-    ey, edx, sig = _run_case("cfg1_nar_4enc_8dec", "nar", 10, 10, 4, 8, 8, 4, n_clips=2)
+# Gates.  Outputs: 1e-3.  Gradients of the product path: every GEMM operand is rounded to tf32 (2^-11 relative)
+# and a gradient has passed the forward chain AND the backward chain (3 GEMMs per sub-block, up to 12 + 8 blocks), so it carries
+# about twice the forward's ~8e-4: measured medians 1.1e-3 - 1.8e-3, worst tensor 4.4e-3 (window-attention q/k projections, whose
+# gradients flow through the softmax Jacobian) -- profiles/r02_bwd_parity.md holds the per-tensor tables.  Gates sit ~1.5x above
+# the measured envelope.  In 3xTF32 mode the same kernels must meet BASELINE.md's 1e-3 on every gradient.
+def _check(res, case):
+    ey, edx, sig = res["tf32"]
     med, worst, who = _summ(sig)
-    print("cfg1: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (ey, edx, med, worst, who))
+    print("%s [tf32]: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (case, ey, edx, med, worst, who))
     assert ey < 1e-3
-    assert edx < 5e-3 and med < 3e-3 and worst < 2e-2, (edx, med, worst, who)
+    assert edx < 4.5e-3 and med < 2.7e-3 and worst < 7e-3, (edx, med, worst, who)
+    if "3xtf32" in res:
+        ey, edx, sig = res["3xtf32"]
+        med, worst, who = _summ(sig)
+        print("%s [3xtf32]: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (case, ey, edx, med, worst, who))
+        assert ey < 1e-4 and edx < 1e-3 and worst < 1e-3, (ey, edx, med, worst, who)
+
+
+def test_nar_cfg1_full_depth_backward():
+    _check(_run_case("cfg1_nar_4enc_8dec", "nar", 10, 10, 4, 8, 8, 4, n_clips=2, modes=("tf32", "3xtf32")), "cfg1")
 
 
 def test_far_cfg2_full_depth_backward():
-    ey, edx, sig = _run_case("cfg2_far_12enc_T29", "far", 10, 20, 12, 0, 8, 4, n_clips=1, T_in=29)
-    med, worst, who = _summ(sig)
-    print("cfg2: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (ey, edx, med, worst, who))
-    assert ey < 1e-3
-    assert edx < 5e-3 and med < 3e-3 and worst < 2e-2, (edx, med, worst, who)
+    _check(_run_case("cfg2_far_12enc_T29", "far", 10, 20, 12, 0, 8, 4, n_clips=1, T_in=29, modes=("tf32", "3xtf32")), "cfg2")
 
 
 def test_nar_cfg3_slice_backward():
-    ey, edx, sig = _run_case("cfg3_nar_2to28_1enc_2dec", "nar", 2, 28, 1, 2, 8, 4, n_clips=2)
-    med, worst, who = _summ(sig)
-    print("cfg3: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (ey, edx, med, worst, who))
-    assert ey < 1e-3
-    assert edx < 5e-3 and med < 3e-3 and worst < 2e-2, (edx, med, worst, who)
+    _check(_run_case("cfg3_nar_2to28_1enc_2dec", "nar", 2, 28, 1, 2, 8, 4, n_clips=2), "cfg3")
 
 
 def test_nar_cfg4_slice_backward():
-    ey, edx, sig = _run_case("cfg4_nar_10to30_grid16_ws8_1enc_1dec", "nar", 10, 30, 1, 1, 16, 8, n_clips=1)
-    med, worst, who = _summ(sig)
-    print("cfg4: y %.2e dx %.2e grads median %.2e worst %.2e (%s)" % (ey, edx, med, worst, who))
-    assert ey < 1e-3
-    assert edx < 5e-3 and med < 3e-3 and worst < 2e-2, (edx, med, worst, who)
+    _check(_run_case("cfg4_nar_10to30_grid16_ws8_1enc_1dec", "nar", 10, 30, 1, 1, 16, 8, n_clips=1, modes=("tf32", "3xtf32")), "cfg4")
 
 
 def test_lean_memory_mode_matches_fast():
@@ -133,5 +146,8 @@ def test_lean_memory_mode_matches_fast():
             engine.set_memory_mode("auto")
     assert torch.equal(res[0][0], res[1][0]) and rel_l2(res[1][1], res[0][1]) < 1e-5
     assert len(res[0][2]) == len(res[1][2])
+    gmax = max(float(a.norm()) for a in res[0][2])
     for a, b in zip(res[0][2], res[1][2]):
-        assert rel_l2(b, a) < 1e-5
+        # relative to the tensor's own norm, floored at 1e-3 of the largest gradient: gradients that are mathematically zero
+        # (k_proj.bias: softmax is shift invariant; fc1.bias in front of a norm) are cancellation noise of O(1) atomics
+        assert float((a - b).norm()) < 1e-5 * max(float(a.norm()), 1e-3 * gmax)

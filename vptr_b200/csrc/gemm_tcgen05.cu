@@ -26,6 +26,10 @@ constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + 
 
 struct GemmParams {
     int M, N, K;
+    // Work item `tile` = (ks, mn) with mn fastest: the (m, n) tiles of one K-slice run concurrently on neighbouring CTAs (pairs), so an
+    // operand slab shared by several of them is fetched from HBM once and re-read from L2.  With ks fastest (round 1) the second
+    // round of the persistent grid re-read every B slab from HBM: ncu showed 445 MB per weight-gradient launch against 269 MB
+    // algorithmic, at 4.7 TB/s -- those GEMMs were HBM-bound by their own re-reads (profiles/r02_launches_step_cfg1_summary.txt).
     int m_tiles, n_tiles, k_splits, chunks_per_split, total_chunks;
     float* D;
     long long ldd;
@@ -380,8 +384,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ks = tile % p.k_splits;
-                const int mn = tile / p.k_splits;
+                const int ks = tile / (p.m_tiles * p.n_tiles);   // ks-major order: see GemmParams::k_splits
+                const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int n_tile = mn % p.n_tiles;
                 const int m_tile = mn / p.n_tiles;
                 const int k0 = ks * p.chunks_per_split;
@@ -421,7 +425,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int ks = tile % p.k_splits;
+                const int ks = tile / (p.m_tiles * p.n_tiles);   // ks-major order: see GemmParams::k_splits
                 const int k0 = ks * p.chunks_per_split;
                 const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
                 if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / gridDim.x) * 8 + 0] = clock64();
@@ -459,7 +463,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mn = tile / p.k_splits;
+            const int mn = tile % (p.m_tiles * p.n_tiles);
             const int n_tile = mn % p.n_tiles;
             const int m_tile = mn / p.n_tiles;
             const int m_base = m_tile * BLOCK_M + q * 32;
@@ -609,8 +613,8 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-                const int ks = tile % p.k_splits;
-                const int mn = tile / p.k_splits;
+                const int ks = tile / (p.m_tiles * p.n_tiles);   // ks-major order: see GemmParams::k_splits
+                const int mn = tile % (p.m_tiles * p.n_tiles);
                 const int n_tile = mn % p.n_tiles;
                 const int m_pair = mn / p.n_tiles;
                 const int k0 = ks * p.chunks_per_split;
@@ -668,7 +672,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-                const int ks = tile % p.k_splits;
+                const int ks = tile / (p.m_tiles * p.n_tiles);   // ks-major order: see GemmParams::k_splits
                 const int k0 = ks * p.chunks_per_split;
                 const int k1 = min(k0 + p.chunks_per_split, p.total_chunks);
                 if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 0] = clock64();
@@ -706,7 +710,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-            const int mn = tile / p.k_splits;
+            const int mn = tile % (p.m_tiles * p.n_tiles);
             const int n_tile = mn % p.n_tiles;
             const int m_pair = mn / p.n_tiles;
             const int m_base = (m_pair * 2 + (int)rank) * BLOCK_M + q * 32;

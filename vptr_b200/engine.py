@@ -218,6 +218,26 @@ class exact_fp32:
         return False
 
 
+class precise_3xtf32:
+    """Verification mode (tests only): every contraction still runs on the product's tcgen05 GEMM kernel, but with 3xTF32 operand
+    precision (ops._gemm_3xtf32: hi/lo tf32 planes concatenated along K), nothing is pre-rounded to tf32, and the attention cores
+    run on the 3xTF32 mma.sync kernels.  Isolates operand rounding from everything else the product path does."""
+
+    def __enter__(self):
+        global ROUND_TF32, RT
+        self.prev = (ROUND_TF32, ops.GEMM_3XTF32, ops.ATTN_TC)
+        ROUND_TF32 = RT = False
+        ops.GEMM_3XTF32 = True
+        ops.ATTN_TC = False
+        return self
+
+    def __exit__(self, *a):
+        global ROUND_TF32, RT
+        ROUND_TF32 = RT = self.prev[0]
+        ops.GEMM_3XTF32, ops.ATTN_TC = self.prev[1], self.prev[2]
+        return False
+
+
 class Geom:
     def __init__(self, N, T, H, W, C, nhead, ws, lean=False):
         self.N, self.T, self.H, self.W, self.C, self.nhead, self.ws = N, T, H, W, C, nhead, ws

@@ -73,9 +73,37 @@ def gemm(A, B, out=None, a_mn=False, b_mn=False, bias=None, residual=None, alpha
     aligned = (lda % 4 == 0 and ldb % 4 == 0 and ldd % 4 == 0 and ldr % 4 == 0 and N % 4 == 0 and pa % 16 == 0 and pb % 16 == 0
                and pd % 16 == 0 and pr % 16 == 0 and _p(bias) % 16 == 0)             # TMA / float4 epilogue: 16-byte rules
     name = "vptr_gemm_tf32" if (aligned and not FORCE_SIMT) else "vptr_gemm_simt"
+    if GEMM_3XTF32 and name == "vptr_gemm_tf32" and K % 4 == 0:
+        return _gemm_3xtf32(A, B, out, a_mn, b_mn, bias, residual, alpha, act, accumulate, round_tf32, rowscale, rows_per_group, drop_seed, drop_p)
     _call(name, pa, lda, int(a_mn), pb, ldb, int(b_mn), pd, ldd, M, N, K, _p(bias), pr, ldr, float(alpha), int(act), flags,
           int(k_splits), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
     return out
+
+
+GEMM_3XTF32 = False   # verification mode (engine.precise_3xtf32): see _gemm_3xtf32
+
+
+def _gemm_3xtf32(A, B, out, a_mn, b_mn, bias, residual, alpha, act, accumulate, round_tf32, rowscale, rows_per_group, drop_seed, drop_p):
+    """The SAME tcgen05 kernel with 3xTF32 operand precision: A = Ah + Al, B = Bh + Bl (tf32 planes), A.B ~ Ah.Bh + Ah.Bl + Al.Bh
+    as ONE contraction over 3K on the concatenated operands [Ah | Ah | Al] . [Bh | Bl | Bh]^T.  Tests use it to show that what
+    separates the shipped TF32 path from the fp32 reference is operand rounding, not the kernels (tile shapes, pipelines, epilogues,
+    split-K reductions are exactly the product's)."""
+    def planes(X, mn):
+        X = X.contiguous()
+        hi = round_copy(X)
+        lo = round_copy(X - hi)
+        return hi, lo, (0 if mn else 1)
+    Ah, Al, da = planes(A, a_mn)
+    Bh, Bl, db = planes(B, b_mn)
+    A3 = torch.cat([Ah, Ah, Al], dim=da)
+    B3 = torch.cat([Bh, Bl, Bh], dim=db)
+    global GEMM_3XTF32
+    GEMM_3XTF32 = False
+    try:
+        return gemm(A3, B3, out=out, a_mn=a_mn, b_mn=b_mn, bias=bias, residual=residual, alpha=alpha, act=act, accumulate=accumulate,
+                    round_tf32=round_tf32, rowscale=rowscale, rows_per_group=rows_per_group, drop_seed=drop_seed, drop_p=drop_p)
+    finally:
+        GEMM_3XTF32 = True
 
 
 # --------------------------------------------------------------------------------------------------- norms

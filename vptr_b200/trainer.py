@@ -62,9 +62,11 @@ class Stage2Trainer:
             pred = dec(T(feats))
             loss = self._pixel_loss(pred, torch.cat([past[:, 1:], future], dim=1))   # :80
         else:
-            with torch.no_grad():
-                past_f = enc(past)
-                fut_f = enc(future)                                             # train_NAR.py:54-56
+            with torch.no_grad():                                               # train_NAR.py:54-56: Enc(past), Enc(future) -- frames
+                n, tp, tf = past.shape[0], past.shape[1], future.shape[1]       # are independent, so both go through ONE encoder pass
+                f = enc(torch.cat([past.flatten(0, 1), future.flatten(0, 1)], dim=0).unsqueeze(0))[0]
+                past_f = f[:n * tp].unflatten(0, (n, tp))
+                fut_f = f[n * tp:].unflatten(0, (n, tf))
             T.train()
             T.zero_grad(set_to_none=True)
             dec.zero_grad(set_to_none=True)
