@@ -62,6 +62,38 @@ def test_attention_probability_dropout():
     assert float((o - 1).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("ws,H,W,nhead,d", [(4, 8, 8, 8, 66), (8, 16, 16, 8, 66)])
+def test_attention_backward_regenerates_the_forward_dropout_mask(ws, H, W, nhead, d):
+    """tensor-core window attention (16-token and 64-token groups) with probability dropout: the backward's dq must be the
+    derivative of the forward run with the same seed (central finite difference along a random direction)"""
+    from vptr_b200 import ops
+    Fr, C, rows = 2, nhead * d, 2 * H * W
+    g = torch.Generator().manual_seed(9)
+    qkv = torch.randn(rows, 3 * C, generator=g).cuda()
+    table = (torch.randn((2 * ws - 1) ** 2, nhead, generator=g) * 0.5).cuda()
+    do = torch.randn(rows, C, generator=g).cuda()
+    v = torch.randn(rows, 3 * C, generator=g).cuda()
+    args = (table, 0, Fr, H, W, ws, 0, 0, nhead, d, False, d ** -0.5)
+
+    def f(x):
+        o = torch.empty(rows, C, device="cuda")
+        ops.attn_fwd(x[:, :C], x[:, C:2 * C], x[:, 2 * C:], o, *args, drop_seed=123, drop_p=0.25)
+        return float((o.double() * do.double()).sum())
+
+    dqkv, dtab = torch.empty_like(qkv), torch.zeros_like(table)
+    ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], table, dtab, *args[1:],
+                 drop_seed=123, drop_p=0.25)
+    eps = 1e-2
+    fd = (f(qkv + eps * v) - f(qkv - eps * v)) / (2 * eps)
+    an = float((dqkv.double() * v.double()).sum())
+    assert abs(fd - an) <= 5e-3 * abs(an) + 1e-3, (fd, an)
+    o0 = torch.empty(rows, C, device="cuda")
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o0, *args)
+    o1 = torch.empty(rows, C, device="cuda")
+    ops.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o1, *args, drop_seed=123, drop_p=0.25)
+    assert rel_l2(o1, o0) > 0.05                                           # dropout really active
+
+
 @pytest.mark.parametrize("name", ["far_rpe", "nar_rpe"])
 def test_transformer_gradient_finite_difference_with_dropout(name):
     from vptr_b200 import engine

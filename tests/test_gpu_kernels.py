@@ -135,7 +135,7 @@ def _attn_ref(q, k, v, nhead, scale, bias=None, mask=None):
     return O._mha_core(q * scale, k, v, nhead, bias=bias, mask=mask)
 
 
-@pytest.mark.parametrize("ws,H,W,nhead,d", [(4, 8, 8, 8, 66), (2, 4, 6, 4, 12), (8, 8, 8, 2, 20)])
+@pytest.mark.parametrize("ws,H,W,nhead,d", [(4, 8, 8, 8, 66), (2, 4, 6, 4, 12), (8, 8, 8, 2, 20), (8, 16, 16, 8, 66), (6, 12, 6, 4, 66)])
 def test_window_attention_core(ws, H, W, nhead, d):
     from vptr_b200 import ops
     Fr, C, L = 3, nhead * d, ws * ws
@@ -160,7 +160,8 @@ def test_window_attention_core(ws, H, W, nhead, d):
     assert rel_l2(dqkv, qr.grad) < 1e-4 and rel_l2(dtab, tr.grad) < 1e-4
 
 
-@pytest.mark.parametrize("Tq,Tk,causal", [(10, 10, False), (29, 29, True), (5, 2, False), (1, 1, True)])
+@pytest.mark.parametrize("Tq,Tk,causal", [(10, 10, False), (29, 29, True), (5, 2, False), (1, 1, True), (40, 40, True), (64, 33, False),
+                                          (3, 50, False)])
 def test_temporal_attention_core(Tq, Tk, causal):
     from vptr_b200 import ops
     N, H, W, nhead, d = 2, 4, 4, 8, 66

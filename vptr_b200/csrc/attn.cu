@@ -957,6 +957,242 @@ int launch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk
     return vptr_check_launch("attn_mma_kernel");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Wide tensor-core path: groups of 33..64 tokens (the 8x8 windows of the 16x16 grid, cfg4; temporal sequences of up to 64 frames).
+// Same 3xTF32 mma.sync arithmetic and shared-memory tiles as attn_mma_kernel, but a head no longer fits one warp's registers
+// (S alone is 64 x 64), so FOUR warps share a head: warp (hw, mt) owns the 16 query rows of m-tile mt -- S, softmax, dP, dS, O and
+// dQ are row-local -- and, for the products that contract over the query index (dV = PD^T dO, dK = dS^T Q), the 16 key rows of
+// slice mt, reading the whole head's PD / dS tiles from shared memory after a 128-thread named barrier.  Two heads per CTA.
+// The relative-position bias is looked up through a [64][64] uint8 index table built once per CTA ((2 ws - 1)^2 <= 255 bins) and
+// its gradient accumulates in registers across the CTA's items (the (i, j) ownership of a thread never changes).
+// The scalar kernels this replaces ran the cfg4 window attention at 6.3 ms per backward call (30 % of the step).
+constexpr int W64_L = 64, W64_HPC = 2, W64_LP = 68, W64_THREADS = W64_HPC * 4 * 32;
+__device__ __forceinline__ void bar_head(int hw) { asm volatile("bar.sync %0, 128;" ::"r"(hw + 1) : "memory"); }
+
+template <bool BWD>
+__global__ void __launch_bounds__(W64_THREADS, 1) attn_mma64_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
+                                                                    const float* __restrict__ V, long long ldv, const float* __restrict__ dO,
+                                                                    float* __restrict__ O_or_dQ, long long ldo, float* __restrict__ dK, long long lddk,
+                                                                    float* __restrict__ dV, long long lddv, long long lddo,
+                                                                    const float* __restrict__ rpe_table, float* __restrict__ d_rpe_table,
+                                                                    const AttnGeom g, int batches) {
+    constexpr int L = W64_L, HPC = W64_HPC, LP = W64_LP, D = MMA_D, NT = 8;
+    constexpr int Cp = mma_pitch(HPC, MMA_D);
+    constexpr int W4 = HPC * MMA_D / 4;
+    extern __shared__ __align__(16) float sm[];
+    float* sq = sm;                                   // [64][Cp]   (forward: O staged over it)
+    float* sk = sq + L * Cp;                          // [64][Cp]   (backward: dK over it)
+    float* sv = sk + L * Cp;                          // [64][Cp]   (backward: dV over it)
+    float* sgo = sv + L * Cp;                         // [64][Cp]   (backward only: dO, dQ over it)
+    float* spw = sgo + (BWD ? L * Cp : 0);            // [HPC][2][64][LP] PD and dS tiles of each head (backward only)
+    const int bins = (2 * g.ws - 1) * (2 * g.ws - 1);
+    float* stab = spw + (BWD ? HPC * 2 * L * LP : 0);                    // [HPC][bins] bias table of this CTA's heads
+    float* sbin = stab + (rpe_table ? HPC * bins : 0);                   // [HPC][bins] bias-gradient bins (flush)
+    float* tail = sbin + ((BWD && d_rpe_table) ? HPC * bins : 0);
+    tail += (4 - ((tail - sm) & 3)) & 3;
+    long long* rq = reinterpret_cast<long long*>(tail + 8);             // + 8 zero floats (fragment loads run a little past the last row)
+    long long* rk = rq + L;
+    unsigned char* lut = reinterpret_cast<unsigned char*>(rk + L);      // [64][64] relative-position index of (i, j)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+    const int hw = warp >> 2, mt = warp & 3, row0 = mt * 16;
+    const int hgroups = g.nhead / HPC;
+    for (int e = threadIdx.x; e < (int)(reinterpret_cast<float*>(rq) - sm); e += blockDim.x) sm[e] = 0.f;
+    __syncthreads();
+    if (rpe_table) {   // gridDim.x is a multiple of hgroups: all items of this CTA share one head group
+        const int hb = (blockIdx.x % hgroups) * HPC;
+        for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) stab[e] = __ldg(rpe_table + (e % bins) * g.nhead + hb + e / bins);
+        for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+            const int i = e >> 6, j = e & 63;
+            lut[e] = (i < g.Lq && j < g.Lk) ? (unsigned char)rel_pos_index(g.ws, i, j) : 0;
+        }
+    }
+    float dbacc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) dbacc[nt][0] = dbacc[nt][1] = dbacc[nt][2] = dbacc[nt][3] = 0.f;
+    __syncthreads();
+    for (int item = blockIdx.x; item < batches * hgroups; item += gridDim.x) {
+        const int b = item / hgroups, h0 = (item - b * hgroups) * HPC;
+        for (int l = threadIdx.x; l < g.Lq; l += blockDim.x) rq[l] = q_row(g, b, l);
+        for (int l = threadIdx.x; l < g.Lk; l += blockDim.x) rk[l] = k_row(g, b, l);
+        __syncthreads();
+        mma_load_tile<W4>(sq, Cp, Q, ldq, rq, g.Lq, h0 * D);
+        mma_load_tile<W4>(sk, Cp, K, ldk, rk, g.Lk, h0 * D);
+        mma_load_tile<W4>(sv, Cp, V, ldv, rk, g.Lk, h0 * D);
+        if (BWD) mma_load_tile<W4>(sgo, Cp, dO, lddo, rq, g.Lq, h0 * D);
+        mma_load_wait();
+        __syncthreads();
+        {
+            const int h = h0 + hw, c0 = hw * D;
+            // ---- S = Q_mt K^T, P = softmax(scale * S + bias) for the 16 query rows of this warp
+            float P[1][NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) P[0][nt][0] = P[0][nt][1] = P[0][nt][2] = P[0][nt][3] = 0.f;
+            mma_rows_dot<1, NT>(P, sq + row0 * Cp, sk, Cp, c0, D, gq, t);
+            uint32_t keepm = 0xffffffffu;                 // bit nt*4 + r: probability kept by dropout
+            float mx[2] = {-INFINITY, -INFINITY};
+            unsigned long long drop_row[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) drop_row[hh] = (((unsigned long long)b * g.nhead + h) * g.Lq + (row0 + gq + hh * 8)) * g.Lk;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int i = row0 + gq + hh * 8, j = nt * 8 + 2 * t;
+                    float b0 = 0.f, b1 = 0.f;
+                    if (rpe_table) { b0 = stab[hw * bins + lut[i * L + j]]; b1 = stab[hw * bins + lut[i * L + j + 1]]; }
+                    float s0 = fmaf(P[0][nt][2 * hh], g.scale, b0), s1 = fmaf(P[0][nt][2 * hh + 1], g.scale, b1);
+                    if (j >= g.Lk || (g.causal && j > i)) s0 = -INFINITY;
+                    if (j + 1 >= g.Lk || (g.causal && j + 1 > i)) s1 = -INFINITY;
+                    P[0][nt][2 * hh] = s0;
+                    P[0][nt][2 * hh + 1] = s1;
+                    mx[hh] = fmaxf(mx[hh], fmaxf(s0, s1));
+                    if (g.drop_p > 0.f && i < g.Lq && j < g.Lk) {
+                        float k0, k1;
+                        prob_drop2(g, drop_row[hh] + j, k0, k1);
+                        if (j + 1 >= g.Lk) k1 = 1.f;
+                        if (k0 == 0.f) keepm &= ~(1u << (nt * 4 + 2 * hh));
+                        if (k1 == 0.f) keepm &= ~(1u << (nt * 4 + 2 * hh + 1));
+                    }
+                }
+            const float keep_scale = g.drop_p > 0.f ? 1.f / (1.f - g.drop_p) : 1.f;
+            float sum[2] = {0.f, 0.f};
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
+                mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float e = __expf(P[0][nt][r] - mx[r >> 1]);
+                    P[0][nt][r] = e;
+                    sum[r >> 1] += e;
+                }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 1);
+                sum[hh] += __shfl_xor_sync(0xffffffffu, sum[hh], 2);
+                sum[hh] = 1.f / sum[hh];
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) P[0][nt][r] *= sum[r >> 1];
+            if (!BWD) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) P[0][nt][r] *= ((keepm >> (nt * 4 + r)) & 1u) ? keep_scale : 0.f;
+                __syncwarp();
+                mma_regs_times_rows<1, NT>(P, sv, sq + row0 * Cp, Cp, c0, D, 1.f, gq, t);      // O_mt = PD V, staged over this warp's own Q rows
+            } else {
+                // ---- dP = (dO_mt V^T) * keep ; dS = P o (dP - rowsum(P o dP)) ; PD = P o keep
+                float dS[1][NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dS[0][nt][0] = dS[0][nt][1] = dS[0][nt][2] = dS[0][nt][3] = 0.f;
+                mma_rows_dot<1, NT>(dS, sgo + row0 * Cp, sv, Cp, c0, D, gq, t);
+                float* PDh = spw + hw * 2 * L * LP;
+                float* dSh = PDh + L * LP;
+                float tsum[2] = {0.f, 0.f};
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        dS[0][nt][r] *= ((keepm >> (nt * 4 + r)) & 1u) ? keep_scale : 0.f;
+                        tsum[r >> 1] = fmaf(P[0][nt][r], dS[0][nt][r], tsum[r >> 1]);
+                    }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    tsum[hh] += __shfl_xor_sync(0xffffffffu, tsum[hh], 1);
+                    tsum[hh] += __shfl_xor_sync(0xffffffffu, tsum[hh], 2);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float ds = P[0][nt][r] * (dS[0][nt][r] - tsum[r >> 1]);
+                        dS[0][nt][r] = ds;
+                        P[0][nt][r] *= ((keepm >> (nt * 4 + r)) & 1u) ? keep_scale : 0.f;
+                        dbacc[nt][r] += ds;                 // (entries outside Lq x Lk are exact zeros: P is 0 there)
+                    }
+                    const int i0 = row0 + gq, j0 = nt * 8 + 2 * t;
+                    *reinterpret_cast<float2*>(PDh + i0 * LP + j0) = make_float2(P[0][nt][0], P[0][nt][1]);
+                    *reinterpret_cast<float2*>(PDh + (i0 + 8) * LP + j0) = make_float2(P[0][nt][2], P[0][nt][3]);
+                    *reinterpret_cast<float2*>(dSh + i0 * LP + j0) = make_float2(dS[0][nt][0], dS[0][nt][1]);
+                    *reinterpret_cast<float2*>(dSh + (i0 + 8) * LP + j0) = make_float2(dS[0][nt][2], dS[0][nt][3]);
+                }
+                bar_head(hw);            // the head's PD / dS tiles are complete; every warp is done reading V
+                mma_smemT_times_rows<1, 8>(PDh + row0, LP, sgo, sv + row0 * Cp, Cp, c0, D, 1.f, gq, t);       // dV[slice mt] = PD^T dO -> over V
+                bar_head(hw);            // every warp is done reading dO
+                mma_regs_times_rows<1, NT>(dS, sk, sgo + row0 * Cp, Cp, c0, D, g.scale, gq, t);              // dQ_mt = dS K -> over dO
+                bar_head(hw);            // every warp is done reading K
+                mma_smemT_times_rows<1, 8>(dSh + row0, LP, sq, sk + row0 * Cp, Cp, c0, D, g.scale, gq, t);   // dK[slice mt] = dS^T Q -> over K
+            }
+        }
+        __syncthreads();
+        if (!BWD) {
+            mma_store_tile<W4>(sq, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
+        } else {
+            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32);
+        }
+        __syncthreads();
+    }
+    if (BWD && d_rpe_table) {
+        for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) sbin[e] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = row0 + gq + (r >> 1) * 8, j = nt * 8 + 2 * t + (r & 1);
+                if (i < g.Lq && j < g.Lk) atomicAdd(sbin + hw * bins + lut[i * L + j], dbacc[nt][r]);
+            }
+        __syncthreads();
+        const int hb = (blockIdx.x % hgroups) * HPC;
+        for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) atomicAdd(d_rpe_table + (e % bins) * g.nhead + hb + e / bins, sbin[e]);
+    }
+}
+
+template <bool BWD>
+int launch_attn_mma64(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,
+                      long long ldo, float* dK, long long lddk, float* dV, long long lddv, long long lddo, const float* rpe_table,
+                      float* d_rpe_table, const AttnGeom& g, int batches, cudaStream_t stream) {
+    constexpr int Cp = mma_pitch(W64_HPC, MMA_D);
+    const int bins = (2 * g.ws - 1) * (2 * g.ws - 1);
+    size_t floats = (size_t)(BWD ? 4 : 3) * W64_L * Cp + (BWD ? (size_t)W64_HPC * 2 * W64_L * W64_LP : 0);
+    if (rpe_table) floats += (size_t)W64_HPC * bins;
+    if (BWD && d_rpe_table) floats += (size_t)W64_HPC * bins;
+    const size_t smem = (floats + 16) * sizeof(float) + sizeof(long long) * 2 * W64_L + (size_t)W64_L * W64_L;
+    VPTR_REQUIRE(smem <= 227 * 1024, VPTR_ERR_UNSUPPORTED, "attn_mma64: %zu bytes of shared memory", smem);
+    auto kern = attn_mma64_kernel<BWD>;
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(attn_mma64, smem=%zu): %s", smem, cudaGetErrorString(e));
+        attr = smem;
+    }
+    const int hgroups = g.nhead / W64_HPC;
+    const long long items = (long long)batches * hgroups;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    long long grid = 148LL * per_sm;
+    grid -= grid % hgroups;                       // a CTA keeps one head group: item % hgroups == blockIdx.x % hgroups
+    if (grid > items) grid = items;
+    kern<<<(int)grid, W64_THREADS, smem, stream>>>(Q, ldq, K, ldk, V, ldv, dO, O_or_dQ, ldo, dK, lddk, dV, lddv, lddo, rpe_table, d_rpe_table, g, batches);
+    return vptr_check_launch("attn_mma64_kernel");
+}
+// shapes of the wide path: some side in 33..64, head_dim 66, an even number of heads, (2 ws - 1)^2 <= 255 relative positions
+bool attn_mma64_ok(const AttnGeom& g, int nhead, int d, bool rpe) {
+    static const bool off = [] { const char* e = getenv("VPTR_ATTN_NO_MMA64"); return e && e[0] == '1'; }();
+    return !off && g.Lq <= 64 && g.Lk <= 64 && (g.Lq > 32 || g.Lk > 32) && d == MMA_D && nhead % 2 == 0 &&
+           (!rpe || (g.mode == 0 && (2 * g.ws - 1) * (2 * g.ws - 1) <= 255));
+}
+
 bool attn_mma_disabled() {
     static const bool v = [] { const char* e = getenv("VPTR_ATTN_NO_MMA"); return e && e[0] == '1'; }();
     return v;
@@ -1031,6 +1267,9 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
     if (attn_mma_ok(g, nhead, d) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)Q % 16 == 0) &&
         ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0))   // tensor-core path (mma.sync, 3xTF32)
         return dispatch_attn_mma<false>(Q, ldq, K, ldk, V, ldv, nullptr, O, ldo, nullptr, 0, nullptr, 0, 0, rpe_table, nullptr, g, batches, stream);
+    if (!attn_mma_disabled() && attn_mma64_ok(g, nhead, d, rpe_table != nullptr) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 &&
+        ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0))   // wide tensor-core path
+        return launch_attn_mma64<false>(Q, ldq, K, ldk, V, ldv, nullptr, O, ldo, nullptr, 0, nullptr, 0, 0, rpe_table, nullptr, g, batches, stream);
     {   // one CTA per batch entry, all heads (scalar)
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (C + 2) + (((size_t)nhead * g.Lq * (g.Lk + 1) + 1) & ~(size_t)1)) +
@@ -1072,6 +1311,10 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
         lddv % 4 == 0 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)dO % 16 == 0) &&
         ((uintptr_t)dQ % 16 == 0) && ((uintptr_t)dK % 16 == 0) && ((uintptr_t)dV % 16 == 0))   // tensor-core path (mma.sync, 3xTF32)
         return dispatch_attn_mma<true>(Q, ldq, K, ldk, V, ldv, dO, dQ, lddq, dK, lddk, dV, lddv, ldo, rpe_table, d_rpe_table, g, batches, stream);
+    if (!attn_mma_disabled() && attn_mma64_ok(g, nhead, d, rpe_table != nullptr) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 &&
+        lddq % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) &&
+        ((uintptr_t)dO % 16 == 0) && ((uintptr_t)dQ % 16 == 0) && ((uintptr_t)dK % 16 == 0) && ((uintptr_t)dV % 16 == 0))   // wide tensor-core path
+        return launch_attn_mma64<true>(Q, ldq, K, ldk, V, ldv, dO, dQ, lddq, dK, lddk, dV, lddv, ldo, rpe_table, d_rpe_table, g, batches, stream);
     {   // one CTA per batch entry, all heads (scalar)
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (C + 2) + (size_t)2 * nhead * g.Lq * (g.Lk + 1) +
