@@ -188,6 +188,19 @@ int vptr_sqnorm_multi(const long long* table, int n, long long total_units, int 
 int vptr_adamw_multi(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
                      float weight_decay, long long step, const double* sqnorm, float max_norm, vptr_stream_t stream);
 
+/* ---- data-parallel gradient reduction (replaces DistributedDataParallel, train_NAR_mp.py:118,167-168) ------------ */
+/* NCCL is bound at run time (dlopen of the process's libnccl.so.2).  A communicator is created from a 128-byte unique id made on
+ * one rank (vptr_nccl_unique_id) and shipped to the others by the host (torch.distributed broadcast, MPI, a file ...). */
+int vptr_nccl_unique_id(unsigned char* out128);
+int vptr_nccl_comm_init(void** comm, int world, int rank, const unsigned char* id128);
+int vptr_nccl_comm_destroy(void* comm);
+/* flat[0..n) <- mean over ranks, in place (ncclAvg); then *sqnorm_out (device double, may be NULL) += sum of squares of the reduced
+ * values on the same stream: the all-reduce of a finished gradient slice and its share of clip_grad_norm_'s norm in one call */
+int vptr_allreduce_grads(void* comm, float* flat, long long n, double* sqnorm_out, vptr_stream_t stream);
+/* scratch bytes of the entry points that take a caller-provided workspace: op 0 vptr_norm_act_bwd, 1 vptr_bn_stats,
+ * 2 vptr_head_conv7x7_bwd (rows = F, ch = Ci, hw = H = W, mode = Co) */
+long long vptr_workspace_bytes(int op, long long rows, int ch, int hw, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,11 @@ _SIGS = {
     "vptr_mse_gdl_bwd": ([P, P, P, P, L, I, I, P], I),
     "vptr_sqnorm_multi": ([P, I, L, I, P, P], I),
     "vptr_adamw_multi": ([P, I, L, I, F, F, F, F, F, L, P, F, P], I),
+    "vptr_nccl_unique_id": ([P], I),
+    "vptr_nccl_comm_init": ([P, I, I, P], I),
+    "vptr_nccl_comm_destroy": ([P], I),
+    "vptr_allreduce_grads": ([P, P, L, P, P], I),
+    "vptr_workspace_bytes": ([I, L, I, I, I], L),
 }
 
 EXPORTS = tuple(_SIGS) + ("vptr_last_error",)

@@ -89,24 +89,73 @@ def allreduce_mean_grads(params, world_size=None):
     return sig[1]
 
 
+class NativeComm:
+    """NCCL communicator owned by libvptr_b200.so (vptr_nccl_comm_init): the 128-byte unique id is made on rank 0 and shipped with
+    torch.distributed (whatever backend is up); after that the gradient reduction needs no torch collective."""
+
+    def __init__(self, device):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.lib()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            rc = self.lib.vptr_nccl_unique_id(uid.data_ptr())
+            if rc != 0:
+                raise RuntimeError("vptr_nccl_unique_id failed (%d): %s" % (rc, self.lib.vptr_last_error().decode("utf-8", "replace")))
+        if dist.get_backend() == "nccl":
+            u = uid.to(device)
+            dist.broadcast(u, 0)
+            uid = u.cpu()
+        else:
+            dist.broadcast(uid, 0)
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.vptr_nccl_comm_init(ctypes.byref(comm), world, rank, uid.data_ptr())
+        if rc != 0:
+            raise RuntimeError("vptr_nccl_comm_init failed (%d): %s" % (rc, self.lib.vptr_last_error().decode("utf-8", "replace")))
+        self.comm, self.world = comm, world
+
+    def allreduce_mean_(self, flat, sqnorm, stream):
+        from . import _lib
+        _lib.call("vptr_allreduce_grads", self.comm, flat.data_ptr(), flat.numel(), 0 if sqnorm is None else sqnorm.data_ptr(), stream.cuda_stream)
+
+
 class GradReducer:
     """Data-parallel gradient mean overlapped with the backward pass (the role of DistributedDataParallel's bucketed hooks,
     train_NAR_mp.py:118,167): the engine finishes the Transformer's layers in reverse order and each layer's parameter gradients
     are one contiguous slice of the flat gradient buffer, so every finished slice is handed to NCCL at once (`arm()` installs the
-    engine hook; asynchronous all-reduce on the process group's own stream, ordered after the kernels that produced the slice)
-    while the remaining layers' backward keeps the SMs busy.  `finish()` reduces whatever is left (frame queries, final norms,
-    gradients outside the flat buffer) with the one-collective path and makes the compute stream wait for all of it."""
+    engine hook) while the remaining layers' backward keeps the SMs busy.  `finish()` reduces whatever is left (frame queries, final
+    norms, gradients outside the flat buffer) and makes the compute stream wait for all of it.
 
-    def __init__(self, params, world_size=None, min_chunk=1 << 20):
+    On CUDA with the NCCL backend the collectives go through the library's own communicator (vptr_allreduce_grads) on a side
+    stream, each followed by the squared-norm accumulation of the reduced slice -- so the norm clip_grad_norm_ needs (`sqnorm`)
+    is ready when the reduction is, without a pass of its own.  Other backends (gloo in the CPU tests) use torch.distributed."""
+
+    def __init__(self, params, world_size=None, min_chunk=1 << 20, native=None):
         self.params = list(params)
         self.world = dist.get_world_size() if world_size is None else world_size
         self.min_chunk = min_chunk
         self.works, self.done, self.flat = [], [], None
         self.avg = dist.get_backend() == "nccl"
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.native = None
+        if native is None:
+            native = self.avg and dev.type == "cuda"
+        if native:
+            self.native = NativeComm(dev)
+            self.side = torch.cuda.Stream(device=dev)
+            self.sq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.sqnorm = None          # after finish(): (1,) float64 device tensor = sum of squares of ALL reduced gradients, or None
+        self.rest = None
 
     def arm(self):
         from . import engine
-        self.works, self.done, self.flat = [], [], None
+        self.works, self.done, self.flat, self.sqnorm = [], [], None, None
+        if self.native is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                self.sq.zero_()
         engine.GRAD_READY = self._ready
 
     def _ready(self, flat, lo, hi):
@@ -114,11 +163,13 @@ class GradReducer:
             return
         self.flat = flat
         chunk = flat[lo:hi]
-        if self.avg:
-            w = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, async_op=True)
+        if self.native is not None:
+            self.side.wait_stream(torch.cuda.current_stream())      # the slice's producers have been enqueued on the compute stream
+            self.native.allreduce_mean_(chunk, self.sq, self.side)
+        elif self.avg:
+            self.works.append((dist.all_reduce(chunk, op=dist.ReduceOp.AVG, async_op=True), chunk))
         else:
-            w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True)
-        self.works.append((w, chunk))
+            self.works.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, async_op=True), chunk))
         self.done.append((lo, hi))
 
     def finish(self):
@@ -143,4 +194,9 @@ class GradReducer:
         else:
             rest = self.params
         allreduce_mean_grads(rest, self.world)
+        self.rest = rest
+        if self.native is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            if self.done:
+                self.sqnorm = self.sq
         self.works, self.done = [], []

@@ -83,11 +83,15 @@ def _check(ts, what):
 _SQ_TABLES = {}
 
 
-def grad_sqnorm(params, out=None):
-    """(1,) float64 device tensor: sum of squares of every existing .grad -- the square of clip_grad_norm_'s total_norm"""
+def grad_sqnorm(params, out=None, accumulate=False):
+    """(1,) float64 device tensor: sum of squares of every existing .grad -- the square of clip_grad_norm_'s total_norm.
+    accumulate: add to `out` instead of overwriting it (part of the norm came from the gradient reducer)"""
     grads = [p.grad for p in params if p.grad is not None]
     dev = grads[0].device if grads else torch.device("cuda")
-    out = torch.zeros(1, dtype=torch.float64, device=dev) if out is None else out.zero_()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=dev)
+    elif not accumulate:
+        out.zero_()
     if not grads:
         return out
     _check(grads, "gradients")
@@ -157,8 +161,13 @@ class FusedTail:
         self.opt = FusedAdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self._sq = None
 
-    def clip_and_step(self):
-        self._sq = grad_sqnorm(self.params, self._sq)
+    def clip_and_step(self, reduced_sqnorm=None, rest=None):
+        """reduced_sqnorm / rest: from parallel.GradReducer -- the squared norm of the slices it already reduced (accumulated behind
+        each all-reduce) and the parameters it did not cover; only those still need a norm pass"""
+        if reduced_sqnorm is not None and rest is not None:
+            self._sq = grad_sqnorm(rest, reduced_sqnorm, accumulate=True)
+        else:
+            self._sq = grad_sqnorm(self.params, self._sq if self._sq is not reduced_sqnorm else None)
         self.opt.step(grad_sqnorm=self._sq, max_norm=self.max_grad_norm)
         return self._sq
 

@@ -84,7 +84,10 @@ class Stage2Trainer:
         if self.reducer is not None:   # data-parallel gradient mean over NVLink: replaces DistributedDataParallel
             self.reducer.finish()
         if self.fused_tail:
-            self.tail.clip_and_step()
+            if self.reducer is not None and self.reducer.sqnorm is not None:
+                self.tail.clip_and_step(self.reducer.sqnorm, self.reducer.rest)
+            else:
+                self.tail.clip_and_step()
         else:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm, norm_type=2)   # :85
             self.opt.step()                                                                          # :86
