@@ -98,6 +98,13 @@ int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, 
                   const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
                   int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p,
                   vptr_stream_t stream);
+/* same, and dbq / dbk / dbv ([nhead*d], any may be NULL) += column sums of dQ / dK / dV: the bias gradients of the q / k / v
+ * projections (in_proj_bias, q/k/v_proj.bias) come out of the attention backward itself instead of a pass over dq / dk / dv */
+int vptr_attn_bwd_bias(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO,
+                  long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV, long long lddv,
+                  const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk,
+                  int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed, float drop_p,
+                  float* dbq, float* dbk, float* dbv, vptr_stream_t stream);
 /* integer artefacts from the kernels' own index functions (bit-exact contract): relative_position_index
  * (model/MultiHeadAttentionRPE.py:373-387) as int64 [L][L]; window token map (model/VidHRFormer_modules.py:503-513)
  * as int64 [L][B]; causal mask (model/VidHRFormer_modules.py:78) as uint8 [T][T] */
@@ -140,6 +147,16 @@ int vptr_transpose(const float* in, float* out, int batch, int R, int C, int acc
 /* PadBlock (model/VidHRFormer_modules.py:527-561): dir 0 centre zero-pad, dir 1 crop */
 int vptr_pad_crop(const float* in, float* out, int F, int H, int W, int Hp, int Wp, int ph0, int pw0, int C, int dir,
                   vptr_stream_t stream);
+/* Producers of dY that also emit its column sums (= the bias gradient of the Linear / 1x1 conv consuming dY), so that no separate
+ * pass re-reads dY: colsum[c] += sum_r out[r][c] (caller provides an accumulator; the flat gradient buffer's bias slice). */
+int vptr_round_copy_colsum(const float* x, float* y, long long rows, int C, int do_round, const float* rowscale, int group_rows,
+                           unsigned long long drop_seed, float drop_p, float* colsum, vptr_stream_t stream);
+int vptr_gelu_bwd_colsum(const float* dy, const float* x, float* dx, long long rows, int C, int round_tf32, unsigned long long drop_seed,
+                         float drop_p, float* colsum, vptr_stream_t stream);
+int vptr_norm_act_bwd_colsum(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                             float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode, float* ws, int round_tf32,
+                             const float* rowscale, int rows_per_group, unsigned long long drop_seed, float drop_p, float* colsum,
+                             vptr_stream_t stream);
 /* gradient clipping pieces (train_NAR.py:85): sqnorm += sum x^2 ; x *= min(1, max_norm/(sqrt(sqnorm)+1e-6)) */
 int vptr_sqnorm_accumulate(const float* x, long long n, double* sqnorm_out, vptr_stream_t stream);
 int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm, vptr_stream_t stream);
@@ -178,6 +195,13 @@ int vptr_mse_gdl_fwd(const float* pred, const float* target, long long planes, i
 /* dpred = dloss * d(mse + gdl)/d(pred); dloss: device scalar or NULL (= 1) */
 int vptr_mse_gdl_bwd(const float* pred, const float* target, const float* dloss, float* dpred, long long planes, int H, int W,
                      vptr_stream_t stream);
+/* BiPatchNCE of cal_lossT (model/criterion.py:206-259 applied to F.normalize'd features, train_NAR.py:36), fused: one CTA per
+ * frame; gt / pred are [F][L][C] channel-last rows, L = h*w <= 64.  S_save (F*64*64 floats) and stats_save (F*256 floats) carry the
+ * cosine matrix and the row / column statistics to the backward; loss_sum: device double zeroed by the caller. */
+int vptr_bipatch_nce_fwd(const float* gt, const float* pred, int F, int L, int C, float temperature, float* S_save, float* stats_save,
+                         double* loss_sum, float* loss_out, vptr_stream_t stream);
+int vptr_bipatch_nce_bwd(const float* gt, const float* pred, const float* S_save, const float* stats_save, const float* dloss, int F,
+                         int L, int C, float temperature, float* dgt, float* dpred, vptr_stream_t stream);
 /* sum of squares over n tensors with one launch (torch.nn.utils.clip_grad_norm_, train_NAR.py:85).  table: device int64
  * [n pointers][n cumulative unit ends]; vec != 0: units are float4 (16-byte aligned tensors, numel % 4 == 0), else floats */
 int vptr_sqnorm_multi(const long long* table, int n, long long total_units, int vec, double* out, vptr_stream_t stream);

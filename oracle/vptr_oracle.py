@@ -329,8 +329,38 @@ def enc_block(sd, x, temporal_pos, ws, nhead, far, rpe=True, lw_pos=None, traini
     return x + y
 
 
-def dec_block(sd, tgt, query_pos, memory, pos_future, pos_past, ws, nhead, rpe=True, lw_pos=None):
-    """VidHRFormerBlockDecNAR.forward (VidHRFormer_modules.py:164-211), TSLMA_flag=False.
+def tslma_attention(sd, memory, query, Tlw_pos, ws, nhead):
+    """TemporalSpatialLocalMultiheadAttention.forward (VidHRFormer_modules.py:246-284) with TemporalLocalPermuteModule (:444-484):
+    per spatial window, the T2*ws^2 query tokens attend the T1*ws^2 memory tokens; Tlw_pos (T1+T2, ws, ws, C) is added to the
+    key (first T1 entries) and query (next T2) after the window permutation.  memory (N,T1,H,W,C), query (N,T2,H,W,C);
+    grids that are not multiples of the window are centre zero-padded first (PadBlock, :527-561)."""
+    N, T1, H, W, C = memory.shape
+    T2 = query.shape[1]
+    (t0, t1), (l0, l1) = pad_offsets(H, ws), pad_offsets(W, ws)
+    mp = F.pad(memory, (0, 0, l0, l1, t0, t1))
+    qp = F.pad(query, (0, 0, l0, l1, t0, t1))
+    Hp, Wp = mp.shape[2], mp.shape[3]
+
+    def perm(x):      # "n t (qh ph) (qw pw) c -> (n qh qw) (t ph pw) c"  (batch-first form of the reference's seq-first permute)
+        n, t = x.shape[:2]
+        x = x.reshape(n, t, Hp // ws, ws, Wp // ws, ws, C).permute(0, 2, 4, 1, 3, 5, 6)
+        return x.reshape(n * (Hp // ws) * (Wp // ws), t * ws * ws, C)
+    km, qm = perm(mp), perm(qp)
+    q_in = qm + Tlw_pos[T1:T1 + T2].reshape(1, T2 * ws * ws, C)
+    k_in = km + Tlw_pos[:T1].reshape(1, T1 * ws * ws, C)
+    Wi, bi = sd["attn.in_proj_weight"], sd["attn.in_proj_bias"]
+    d = C // nhead
+    q = (q_in @ Wi[:C].t() + bi[:C]) * (d ** -0.5)
+    k = k_in @ Wi[C:2 * C].t() + bi[C:2 * C]
+    v = km @ Wi[2 * C:].t() + bi[2 * C:]
+    o = _mha_core(q, k, v, nhead) @ sd["attn.out_proj.weight"].t() + sd["attn.out_proj.bias"]
+    o = o.reshape(N, Hp // ws, Wp // ws, T2, ws, ws, C).permute(0, 3, 1, 4, 2, 5, 6).reshape(N, T2, Hp, Wp, C)
+    return o[:, :, t0:t0 + H, l0:l0 + W]
+
+
+def dec_block(sd, tgt, query_pos, memory, pos_future, pos_past, ws, nhead, rpe=True, lw_pos=None, Tlw_pos=None):
+    """VidHRFormerBlockDecNAR.forward (VidHRFormer_modules.py:164-211); the encoder-decoder attention is the per-pixel temporal
+    cross-attention (:200-206) or, when the block carries TSLMA.* parameters (TSLMA_flag=True, :194-198), tslma_attention.
     tgt, query_pos (N,T2,H,W,C); memory (N,T1,H,W,C).  MlpDWBN here is the LayerNorm flavour (:136,159,390)."""
     N, T2, H, W, C = tgt.shape
     a = _ln(tgt, sd, "norm1")
@@ -343,9 +373,12 @@ def dec_block(sd, tgt, query_pos, memory, pos_future, pos_past, ws, nhead, rpe=T
     y = _gelu(y @ sd["linear1.weight"].t() + sd["linear1.bias"]) @ sd["linear2.weight"].t() + sd["linear2.bias"]
     x = x + y
     z = _ln(x, sd, "norm5")
-    q = z + query_pos + pos_future[None, :, None, None, :]
-    k = memory + pos_past[None, :, None, None, :]
-    x = x + temporal_attention(_sub(sd, "EncDecAttn."), q, k, memory, nhead)
+    if any(k.startswith("TSLMA.") for k in sd):
+        x = x + tslma_attention(_sub(sd, "TSLMA."), memory, z + query_pos, Tlw_pos, ws, nhead)
+    else:
+        q = z + query_pos + pos_future[None, :, None, None, :]
+        k = memory + pos_past[None, :, None, None, :]
+        x = x + temporal_attention(_sub(sd, "EncDecAttn."), q, k, memory, nhead)
     x = x + mlp_dwbn(_sub(sd, "SpatialFFN1."), _ln(x, sd, "norm6").flatten(0, 1), True).reshape(N, T2, H, W, C)
     return x
 
@@ -389,7 +422,8 @@ def vptr_former_nar(sd, past_feats, nhead=8, ws=4, rpe=True, training=False, bn_
     tgt = torch.zeros_like(qp)
     p = "transformer.decoder.layers."
     for i in range(_num_layers(sd, p)):
-        tgt = dec_block(_sub(sd, "%s%d." % (p, i)), tgt, qp, memory, tpos[Tp:], tpos[:Tp], ws, nhead, rpe=rpe, lw_pos=sd["lw_pos"])
+        tgt = dec_block(_sub(sd, "%s%d." % (p, i)), tgt, qp, memory, tpos[Tp:], tpos[:Tp], ws, nhead, rpe=rpe, lw_pos=sd["lw_pos"],
+                        Tlw_pos=sd.get("Tlw_pos"))
     out = _ln(tgt, sd, "transformer.decoder.norm")
     return F.relu(out.permute(0, 1, 4, 2, 3))
 

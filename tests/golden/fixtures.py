@@ -59,4 +59,6 @@ CASES = {
     "nar_rpe": dict(kind="nar", Tp=2, Tf=3, encH=8, encW=8, d_model=48, nhead=4, enc_layers=2, dec_layers=2, ws=4, rpe=True, N=2),
     "far_rpe": dict(kind="far", Tp=2, Tf=3, encH=8, encW=8, d_model=48, nhead=4, enc_layers=2, ws=4, rpe=True, N=2, T_in=4),
     "far_norpe_pad": dict(kind="far", Tp=2, Tf=2, encH=6, encW=6, d_model=48, nhead=4, enc_layers=1, ws=4, rpe=False, N=1, T_in=3),
+    # TSLMA_flag=True: the decoder's encoder-decoder attention is TemporalSpatialLocalMultiheadAttention (off in every reference script)
+    "nar_tslma": dict(kind="nar", Tp=2, Tf=3, encH=8, encW=8, d_model=48, nhead=4, enc_layers=1, dec_layers=2, ws=4, rpe=True, N=2, tslma=True),
 }

@@ -44,7 +44,7 @@ def former_case(model, name, c):
     if c["kind"] == "nar":
         net = model.VPTRFormerNAR(c["Tp"], c["Tf"], encH=c["encH"], encW=c["encW"], d_model=c["d_model"], nhead=c["nhead"],
                                   num_encoder_layers=c["enc_layers"], num_decoder_layers=c["dec_layers"], dropout=0.0,
-                                  window_size=c["ws"], rpe=c["rpe"])
+                                  window_size=c["ws"], TSLMA_flag=c.get("tslma", False), rpe=c["rpe"])
         T_in = c["Tp"]
     else:
         net = model.VPTRFormerFAR(c["Tp"], c["Tf"], encH=c["encH"], encW=c["encW"], d_model=c["d_model"], nhead=c["nhead"],
@@ -118,10 +118,14 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(8)
     model = load_reference("cpu")
+    only = sys.argv[1:]                 # optional: regenerate just the named fixtures
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         if name.startswith("ae_"):
             ae_case(model, name, c)
         else:
             former_case(model, name, c)
-    integer_artefacts(model)
-    pos_528(model)
+    if not only:
+        integer_artefacts(model)
+        pos_528(model)

@@ -37,7 +37,7 @@ def build_former(name, device="cpu"):
     if c["kind"] == "nar":
         net = VPTRFormerNAR(c["Tp"], c["Tf"], encH=c["encH"], encW=c["encW"], d_model=c["d_model"], nhead=c["nhead"],
                             num_encoder_layers=c["enc_layers"], num_decoder_layers=c["dec_layers"], dropout=0.0, window_size=c["ws"],
-                            rpe=c["rpe"])
+                            TSLMA_flag=c.get("tslma", False), rpe=c["rpe"])
         T_in = c["Tp"]
     else:
         net = VPTRFormerFAR(c["Tp"], c["Tf"], encH=c["encH"], encW=c["encW"], d_model=c["d_model"], nhead=c["nhead"],

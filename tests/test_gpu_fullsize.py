@@ -55,6 +55,21 @@ def test_nar_cfg4_geometry_one_clip():
     assert rel_l2(y, yo) < 1e-3
 
 
+def test_nar_tslma_real_width_one_clip():
+    """TSLMA_flag=True (temporal-spatial window cross-attention, reference VidHRFormer_modules.py:219-284) at d_model 528, 10 -> 10
+    frames: 16 queries x 160 keys per (window, future frame) through attention mode 2"""
+    from vptr_b200.model import VPTRFormerNAR
+    torch.manual_seed(2021)
+    net = VPTRFormerNAR(10, 10, encH=8, encW=8, d_model=528, nhead=8, num_encoder_layers=1, num_decoder_layers=2, dropout=0.1,
+                        window_size=4, TSLMA_flag=True, rpe=True).eval()
+    assert any("TSLMA.attn.in_proj_weight" in k for k in net.state_dict()) and not any("EncDecAttn" in k for k in net.state_dict())
+    x = torch.rand(1, 10, 528, 8, 8, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        yo = O.vptr_former_nar({k: v for k, v in net.state_dict().items()}, x, nhead=8, ws=4, rpe=True, training=False)
+        y = net.cuda()(x.cuda())
+    assert rel_l2(y, yo) < 1e-3
+
+
 def test_far_cfg2_shape_one_clip():
     from vptr_b200.model import VPTRFormerFAR
     torch.manual_seed(2021)

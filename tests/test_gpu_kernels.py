@@ -373,3 +373,62 @@ def test_stem_and_head(Ci, H, W):
         (outr * dout).sum().backward()
         dx = ops.head_conv7x7_bwd(dout, out, wh, Fr, 64, Ci, H, W, act)
         assert rel_l2(dx, hr.grad) < 5 * TOL
+
+
+def test_producers_emit_bias_gradient_column_sums():
+    """the kernels that produce a dY also add its column sums to a bias-gradient accumulator (no separate colsum pass)"""
+    from vptr_b200 import ops
+    rows, C = 640, 528
+    x = rnd(rows, C, seed=1)
+    rs = ops.droppath_scales(10, 5, 0.3, "cuda")
+    acc = torch.full((C,), 2.0, device="cuda")
+    y = ops.round_copy(x, True, rs, 64 * C, 77, 0.2, colsum=acc)
+    assert torch.equal(y, ops.round_copy(x, True, rs, 64 * C, 77, 0.2))
+    assert rel_l2(acc - 2.0, y.double().sum(0)) < 1e-5
+    h, du = rnd(rows, 2112, seed=2), rnd(rows, 2112, seed=3)
+    acc = torch.zeros(2112, device="cuda")
+    dh = ops.gelu_bwd(du, h, round_tf32=True, drop_seed=9, drop_p=0.1, colsum=acc)
+    assert torch.equal(dh, ops.gelu_bwd(du, h, round_tf32=True, drop_seed=9, drop_p=0.1))
+    assert rel_l2(acc, dh.double().sum(0)) < 1e-5
+    for mode, ch, hw in ((1, 2112, 64), (0, 528, 64), (2, 2112, 64), (1, 48, 16)):
+        Fr = 5
+        r = Fr * hw
+        xx, dy = rnd(r, ch, seed=4), rnd(r, ch, seed=5)
+        if mode == 1:
+            mean, rstd = ops.group_stats(xx, Fr)
+            gm, bt = rnd(hw, ch, seed=6) * 0.2 + 1, rnd(hw, ch, seed=7) * 0.1
+        else:
+            mean, rstd = xx.mean(0).contiguous(), (xx.var(0, unbiased=False) + 1e-5).rsqrt().contiguous()
+            gm, bt = rnd(ch, seed=6) * 0.2 + 1, rnd(ch, seed=7) * 0.1
+        z = lambda: (torch.zeros_like(gm), torch.zeros_like(bt))
+        dg0, db0 = z()
+        ref = ops.norm_act_bwd(dy, xx, mean, rstd, gm, bt, dg0, db0, hw, mode, round_tf32=True, drop_seed=3, drop_p=0.1)
+        dg1, db1 = z()
+        acc = torch.zeros(ch, device="cuda")
+        out = ops.norm_act_bwd(dy, xx, mean, rstd, gm, bt, dg1, db1, hw, mode, round_tf32=True, drop_seed=3, drop_p=0.1, colsum=acc)
+        assert rel_l2(out, ref) < 1e-6 and rel_l2(dg1, dg0) < 1e-5 and rel_l2(db1, db0) < 1e-5, mode
+        # (train-mode BatchNorm: the column sums of dx vanish mathematically, so the gate is relative to the sum of magnitudes)
+        assert float((acc - out.double().sum(0)).abs().max()) < 1e-5 * float(out.abs().sum(0).max()), mode
+
+
+@pytest.mark.parametrize("mode,ws,H,W,Tq,Tk,nhead,d", [(0, 4, 8, 8, 0, 0, 8, 66), (0, 8, 16, 16, 0, 0, 8, 66), (1, 0, 4, 4, 10, 10, 8, 66),
+                                                      (1, 0, 4, 4, 28, 2, 8, 66), (0, 2, 4, 6, 0, 0, 4, 12)])
+def test_attention_backward_emits_projection_bias_gradients(mode, ws, H, W, Tq, Tk, nhead, d):
+    from vptr_b200 import ops
+    C = nhead * d
+    N = 2
+    rq = N * H * W * (Tq if mode else 1)
+    rk = N * H * W * (Tk if mode else 1)
+    q, k, v, do = rnd(rq, C, seed=1), rnd(rk, C, seed=2), rnd(rk, C, seed=3), rnd(rq, C, seed=4)
+    table = rnd((2 * ws - 1) ** 2, nhead, seed=5) * 0.5 if mode == 0 else None
+    args = (mode, N, H, W, ws, Tq, Tk, nhead, d, False, d ** -0.5)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    dtab = torch.zeros_like(table) if table is not None else None
+    ops.attn_bwd(q, k, v, do, dq, dk, dv, table, dtab, *args)
+    dq2, dk2, dv2 = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    bq, bk, bv = (torch.full((C,), 1.0, device="cuda") for _ in range(3))
+    dtab2 = torch.zeros_like(table) if table is not None else None
+    ops.attn_bwd(q, k, v, do, dq2, dk2, dv2, table, dtab2, *args, dbq=bq, dbk=bk, dbv=bv)
+    assert rel_l2(dq2, dq) < 1e-5 and rel_l2(dk2, dk) < 1e-5 and rel_l2(dv2, dv) < 1e-5
+    for b, t in ((bq, dq), (bk, dk), (bv, dv)):
+        assert float((b - 1.0 - t.double().sum(0)).abs().max()) < 1e-4 * float(t.abs().sum(0).max())

@@ -40,7 +40,7 @@ def _check_grads_vs_golden(net, xin, z, tol):
     assert not bad, bad[:5]
 
 
-@pytest.mark.parametrize("name", ["far_rpe", "far_norpe_pad", "nar_rpe"])
+@pytest.mark.parametrize("name", ["far_rpe", "far_norpe_pad", "nar_rpe", "nar_tslma"])
 def test_former_forward_matches_reference_golden(name):
     z = load_golden(name)
     net, x, c = build_former(name, "cuda")
@@ -64,7 +64,7 @@ def test_former_forward_matches_reference_golden(name):
             assert not torch.equal(sd1[k], sd0[k])
 
 
-@pytest.mark.parametrize("name", ["far_rpe", "far_norpe_pad", "nar_rpe"])
+@pytest.mark.parametrize("name", ["far_rpe", "far_norpe_pad", "nar_rpe", "nar_tslma"])
 def test_former_backward_schedule_exact_fp32(name):
     from vptr_b200 import engine
     z = load_golden(name)
@@ -78,7 +78,7 @@ def test_former_backward_schedule_exact_fp32(name):
     _check_grads_vs_golden(net, xin, z, 2e-4)
 
 
-@pytest.mark.parametrize("name", ["far_rpe", "nar_rpe"])
+@pytest.mark.parametrize("name", ["far_rpe", "nar_rpe", "nar_tslma"])
 def test_former_backward_tf32(name):
     z = load_golden(name)
     net, x, c = build_former(name, "cuda")

@@ -28,6 +28,24 @@ def test_mse_gdl_matches_reference_losses(shape):
     assert rel_l2(pred.grad, gref) < 1e-6
 
 
+@pytest.mark.parametrize("N,T,C,h,w,tau", [(2, 3, 528, 8, 8, 1.0), (1, 2, 40, 4, 6, 0.07), (3, 1, 132, 8, 8, 0.5)])
+def test_fused_bipatch_nce_matches_reference_composition(N, T, C, h, w, tau):
+    import torch.nn.functional as F
+    from vptr_b200.model import BiPatchNCE
+    from vptr_b200.tail import bipatch_nce_normalized
+    g = torch.Generator().manual_seed(8)
+    gf = torch.randn(N, T, h, w, C, generator=g).cuda().permute(0, 1, 4, 2, 3).requires_grad_(True)     # channel-last views, as in the step
+    pf = (torch.randn(N, T, h, w, C, generator=g) + 0.5 * gf.detach().permute(0, 1, 3, 4, 2).cpu()).cuda().permute(0, 1, 4, 2, 3).requires_grad_(True)
+    ref = BiPatchNCE(N, T, h, w, tau).cuda()(F.normalize(gf, p=2.0, dim=2), F.normalize(pf, p=2.0, dim=2))
+    (ref * 0.3).backward()
+    g_ref, p_ref = gf.grad.clone(), pf.grad.clone()
+    gf.grad = pf.grad = None
+    out = bipatch_nce_normalized(gf, pf, tau)
+    (out * 0.3).backward()
+    assert abs(float(out) - float(ref)) <= 5e-6 * abs(float(ref))
+    assert rel_l2(gf.grad, g_ref) < 2e-5 and rel_l2(pf.grad, p_ref) < 2e-5
+
+
 def test_fused_adamw_and_clip_match_torch():
     from vptr_b200.tail import FusedAdamW, grad_sqnorm
     torch.manual_seed(0)

@@ -29,6 +29,7 @@ _SIGS = {
     "vptr_attn_fwd": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
     "vptr_attn_fwd_tcgen05": ([P, L, P, L, P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
     "vptr_attn_bwd": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P], I),
+    "vptr_attn_bwd_bias": ([P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, P, I, I, I, I, I, I, I, I, I, I, F, I, U, F, P, P, P, P], I),
     "vptr_window_index_maps": ([I, I, I, I, P, P, P], I),
     "vptr_causal_mask": ([I, P, P], I),
     "vptr_dwconv3x3": ([P, P, P, P, I, I, I, I, I, P], I),
@@ -49,6 +50,9 @@ _SIGS = {
     "vptr_transpose": ([P, P, I, I, I, I, P], I),
     "vptr_pad_crop": ([P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_sqnorm_accumulate": ([P, L, P, P], I),
+    "vptr_round_copy_colsum": ([P, P, L, I, I, P, I, U, F, P, P], I),
+    "vptr_gelu_bwd_colsum": ([P, P, P, L, I, I, U, F, P, P], I),
+    "vptr_norm_act_bwd_colsum": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P, I, U, F, P, P], I),
     "vptr_clip_scale": ([P, L, P, F, P], I),
     "vptr_conv3x3_tf32": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
     "vptr_split_tf32": ([P, P, L, L, P], I),
@@ -63,6 +67,8 @@ _SIGS = {
     "vptr_mse_gdl_fwd": ([P, P, L, I, I, P, P, P], I),
     "vptr_mse_gdl_bwd": ([P, P, P, P, L, I, I, P], I),
     "vptr_sqnorm_multi": ([P, I, L, I, P, P], I),
+    "vptr_bipatch_nce_fwd": ([P, P, I, I, I, F, P, P, P, P, P], I),
+    "vptr_bipatch_nce_bwd": ([P, P, P, P, P, I, I, I, F, P, P, P], I),
     "vptr_adamw_multi": ([P, I, L, I, F, F, F, F, F, L, P, F, P], I),
     "vptr_nccl_unique_id": ([P], I),
     "vptr_nccl_comm_init": ([P, I, I, P], I),

@@ -24,6 +24,7 @@ struct AttnGeom {
     int round_tf32;  // round stored outputs (they only feed tf32 contractions)
     unsigned long long drop_seed;  // attention-probability dropout (MultiHeadAttentionRPE.py:678 / nn.MultiheadAttention)
     float drop_p;
+    float *dbq, *dbk, *dbv;  // backward, tensor-core paths: column sums of dQ / dK / dV are added here ([nhead*d] each; NULL = off)
 };
 
 // dropout keep-scale of probability (b, h, i, j)
@@ -38,13 +39,24 @@ __device__ __forceinline__ long long window_row(const AttnGeom& g, int b, int l)
     const int ph = l / g.ws, pw = l - ph * g.ws;
     return ((long long)f * g.H + qh * g.ws + ph) * g.W + qw * g.ws + pw;
 }
+// mode 2 (TemporalSpatialLocalMultiheadAttention, model/VidHRFormer_modules.py:219-284,444-484): batch entry b = (clip n, future
+// frame t2, window): its ws^2 queries are that window of frame n*Tq + t2 (exactly mode 0's rows over N*Tq frames) and its Tk*ws^2
+// keys are the same window of ALL Tk memory frames of clip n, key j = (t1, in-window position l) = (j / ws^2, j % ws^2).  The
+// reference attends all Tq*ws^2 queries of a window in one sequence; softmax is per query, so splitting them by frame is exact.
 __device__ __forceinline__ long long q_row(const AttnGeom& g, int b, int i) {
-    if (g.mode == 0) return window_row(g, b, i);
+    if (g.mode != 1) return window_row(g, b, i);
     const int n = b / g.HW, p = b - n * g.HW;
     return ((long long)n * g.Tq + i) * g.HW + p;
 }
 __device__ __forceinline__ long long k_row(const AttnGeom& g, int b, int j) {
     if (g.mode == 0) return window_row(g, b, j);
+    if (g.mode == 2) {
+        const int per = g.nwh * g.nww, L = g.ws * g.ws;
+        const int fq = b / per, r = b - fq * per, n = fq / g.Tq;
+        const int t1 = j / L, l = j - t1 * L;
+        const int qh = r / g.nww, qw = r - qh * g.nww, ph = l / g.ws, pw = l - ph * g.ws;
+        return (((long long)n * g.Tk + t1) * g.H + qh * g.ws + ph) * g.W + qw * g.ws + pw;
+    }
     const int n = b / g.HW, p = b - n * g.HW;
     return ((long long)n * g.Tk + j) * g.HW + p;
 }
@@ -80,6 +92,11 @@ __device__ __forceinline__ void store_rows(const float* tile, float* __restrict_
         for (int c2 = lane; 2 * c2 < g.d; c2 += 32) {
             float2 v = *reinterpret_cast<const float2*>(tile + l * dp + 2 * c2);
             v.x *= mul; v.y *= mul;
+            if (g.mode == 2 && !is_q) {   // a memory token is a key of every future frame's batch entry: accumulate (caller zeroes dK / dV)
+                atomicAdd(r + 2 * c2, v.x);
+                atomicAdd(r + 2 * c2 + 1, v.y);
+                continue;
+            }
             if (g.round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); }
             *reinterpret_cast<float2*>(r + 2 * c2) = v;
         }
@@ -696,14 +713,17 @@ __device__ __forceinline__ void mma_load_wait() {
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+// scol != NULL: the column sums of what is stored accumulate in shared memory (the bias gradient of the projection whose output
+// gradient this is -- in_proj_bias / q,k,v_proj.bias -- so no separate pass re-reads dq / dk / dv; flushed once per CTA)
 template <int W4>
 __device__ __forceinline__ void mma_store_tile(const float* tile, int Cp, float* __restrict__ dst, long long ld, const long long* rows, int L,
-                                               int col0, int round_tf32) {
+                                               int col0, int round_tf32, float* scol = nullptr) {
     for (int e = threadIdx.x; e < L * W4; e += blockDim.x) {
         const int l = e / W4, c = e - l * W4;
         float4 v = *reinterpret_cast<const float4*>(tile + l * Cp + 4 * c);
         if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
         *reinterpret_cast<float4*>(dst + rows[l] * ld + col0 + 4 * c) = v;
+        if (scol) { atomicAdd(scol + 4 * c, v.x); atomicAdd(scol + 4 * c + 1, v.y); atomicAdd(scol + 4 * c + 2, v.z); atomicAdd(scol + 4 * c + 3, v.w); }
     }
 }
 // dropout keep-scales of probabilities (b, h, i, j) and (b, h, i, j + 1), j even: one hash when both fall into one group of four
@@ -726,6 +746,8 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
     using Cfg = MmaCfg<MT, NT, HPC>;
     constexpr int LQP = Cfg::LQP, LKP = Cfg::LKP, LP = Cfg::LP;
     extern __shared__ __align__(16) float sm[];
+    __shared__ float scol[3][HPC * MMA_D];            // column sums of dQ / dK / dV (bias gradients), backward only
+    if (BWD) for (int e = threadIdx.x; e < 3 * HPC * MMA_D; e += blockDim.x) (&scol[0][0])[e] = 0.f;
     constexpr int Cp = mma_pitch(HPC, MMA_D);
     constexpr int W4 = HPC * MMA_D / 4;
     constexpr int D = MMA_D;
@@ -892,11 +914,19 @@ __global__ void __launch_bounds__(HPC * 32) attn_mma_kernel(const float* __restr
         if (!BWD) {
             mma_store_tile<W4>(sq, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
         } else {
-            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32);
-            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
-            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32, g.dbv ? scol[2] : nullptr);
+            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32, g.dbq ? scol[0] : nullptr);
+            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32, g.dbk ? scol[1] : nullptr);
         }
         __syncthreads();
+    }
+    if (BWD && (g.dbq || g.dbk || g.dbv)) {     // all items of this CTA share one head group: flush its bias-gradient columns once
+        const int hc = (blockIdx.x % hgroups) * HPC * D;
+        for (int e = threadIdx.x; e < HPC * D; e += blockDim.x) {
+            if (g.dbq) atomicAdd(g.dbq + hc + e, scol[0][e]);
+            if (g.dbk) atomicAdd(g.dbk + hc + e, scol[1][e]);
+            if (g.dbv) atomicAdd(g.dbv + hc + e, scol[2][e]);
+        }
     }
     if (BWD && d_rpe_table) {
         // the launch makes gridDim.x a multiple of hgroups, so all items of a CTA share one head group
@@ -981,6 +1011,8 @@ __global__ void __launch_bounds__(W64_THREADS, 1) attn_mma64_kernel(const float*
     constexpr int Cp = mma_pitch(HPC, MMA_D);
     constexpr int W4 = HPC * MMA_D / 4;
     extern __shared__ __align__(16) float sm[];
+    __shared__ float scol[3][HPC * MMA_D];            // column sums of dQ / dK / dV (bias gradients), backward only
+    if (BWD) for (int e = threadIdx.x; e < 3 * HPC * MMA_D; e += blockDim.x) (&scol[0][0])[e] = 0.f;
     float* sq = sm;                                   // [64][Cp]   (forward: O staged over it)
     float* sk = sq + L * Cp;                          // [64][Cp]   (backward: dK over it)
     float* sv = sk + L * Cp;                          // [64][Cp]   (backward: dV over it)
@@ -1135,11 +1167,19 @@ __global__ void __launch_bounds__(W64_THREADS, 1) attn_mma64_kernel(const float*
         if (!BWD) {
             mma_store_tile<W4>(sq, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
         } else {
-            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32);
-            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32);
-            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32);
+            mma_store_tile<W4>(sv, Cp, dV, lddv, rk, g.Lk, h0 * D, g.round_tf32, g.dbv ? scol[2] : nullptr);
+            mma_store_tile<W4>(sgo, Cp, O_or_dQ, ldo, rq, g.Lq, h0 * D, g.round_tf32, g.dbq ? scol[0] : nullptr);
+            mma_store_tile<W4>(sk, Cp, dK, lddk, rk, g.Lk, h0 * D, g.round_tf32, g.dbk ? scol[1] : nullptr);
         }
         __syncthreads();
+    }
+    if (BWD && (g.dbq || g.dbk || g.dbv)) {     // all items of this CTA share one head group: flush its bias-gradient columns once
+        const int hc = (blockIdx.x % hgroups) * HPC * D;
+        for (int e = threadIdx.x; e < HPC * D; e += blockDim.x) {
+            if (g.dbq) atomicAdd(g.dbq + hc + e, scol[0][e]);
+            if (g.dbk) atomicAdd(g.dbk + hc + e, scol[1][e]);
+            if (g.dbv) atomicAdd(g.dbv + hc + e, scol[2][e]);
+        }
     }
     if (BWD && d_rpe_table) {
         for (int e = threadIdx.x; e < HPC * bins; e += blockDim.x) sbin[e] = 0.f;
@@ -1167,7 +1207,7 @@ int launch_attn_mma64(const float* Q, long long ldq, const float* K, long long l
     if (rpe_table) floats += (size_t)W64_HPC * bins;
     if (BWD && d_rpe_table) floats += (size_t)W64_HPC * bins;
     const size_t smem = (floats + 16) * sizeof(float) + sizeof(long long) * 2 * W64_L + (size_t)W64_L * W64_L;
-    VPTR_REQUIRE(smem <= 227 * 1024, VPTR_ERR_UNSUPPORTED, "attn_mma64: %zu bytes of shared memory", smem);
+    VPTR_REQUIRE(smem + 2048 <= 227 * 1024, VPTR_ERR_UNSUPPORTED, "attn_mma64: %zu bytes of shared memory", smem);
     auto kern = attn_mma64_kernel<BWD>;
     static size_t attr = 0;
     if (smem > attr) {
@@ -1189,7 +1229,7 @@ int launch_attn_mma64(const float* Q, long long ldq, const float* K, long long l
 // shapes of the wide path: some side in 33..64, head_dim 66, an even number of heads, (2 ws - 1)^2 <= 255 relative positions
 bool attn_mma64_ok(const AttnGeom& g, int nhead, int d, bool rpe) {
     static const bool off = [] { const char* e = getenv("VPTR_ATTN_NO_MMA64"); return e && e[0] == '1'; }();
-    return !off && g.Lq <= 64 && g.Lk <= 64 && (g.Lq > 32 || g.Lk > 32) && d == MMA_D && nhead % 2 == 0 &&
+    return !off && g.mode != 2 && g.Lq <= 64 && g.Lk <= 64 && (g.Lq > 32 || g.Lk > 32) && d == MMA_D && nhead % 2 == 0 &&
            (!rpe || (g.mode == 0 && (2 * g.ws - 1) * (2 * g.ws - 1) <= 255));
 }
 
@@ -1199,7 +1239,7 @@ bool attn_mma_disabled() {
 }
 // shapes the tensor-core path covers: Lq, Lk <= 32, head_dim 66, an even number of heads, 16-byte aligned rows
 bool attn_mma_ok(const AttnGeom& g, int nhead, int d) {
-    return !attn_mma_disabled() && g.Lq <= 32 && g.Lk <= 32 && d == MMA_D && nhead % 2 == 0;
+    return !attn_mma_disabled() && g.mode != 2 && g.Lq <= 32 && g.Lk <= 32 && d == MMA_D && nhead % 2 == 0;
 }
 template <bool BWD>
 int dispatch_attn_mma(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, const float* dO, float* O_or_dQ,
@@ -1226,6 +1266,12 @@ int fill_geom(AttnGeom& g, int mode, int F_or_N, int H, int W, int ws, int Tq, i
         VPTR_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, VPTR_ERR_SHAPE, "window attention: H=%d W=%d not multiples of ws=%d (pad first)", H, W, ws);
         g.H = H; g.W = W; g.ws = ws; g.nwh = H / ws; g.nww = W / ws; g.Lq = g.Lk = ws * ws;
         *batches = F_or_N * g.nwh * g.nww;
+    } else if (mode == 2) {
+        VPTR_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0 && Tq > 0 && Tk > 0 && !causal, VPTR_ERR_SHAPE,
+                     "temporal-spatial window attention: H=%d W=%d ws=%d Tq=%d Tk=%d (grid must be a multiple of the window)", H, W, ws, Tq, Tk);
+        g.H = H; g.W = W; g.ws = ws; g.nwh = H / ws; g.nww = W / ws; g.Tq = Tq; g.Tk = Tk; g.HW = H * W;
+        g.Lq = ws * ws; g.Lk = Tk * ws * ws;
+        *batches = F_or_N * Tq * g.nwh * g.nww;
     } else {
         VPTR_REQUIRE(Tq > 0 && Tk > 0, VPTR_ERR_SHAPE, "temporal attention: Tq=%d Tk=%d", Tq, Tk);
         VPTR_REQUIRE(!causal || Tq == Tk, VPTR_ERR_SHAPE, "causal temporal attention needs Tq == Tk");
@@ -1274,7 +1320,7 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(g.Lq + 2 * g.Lk) * (C + 2) + (((size_t)nhead * g.Lq * (g.Lk + 1) + 1) & ~(size_t)1)) +
                           sizeof(long long) * (size_t)(g.Lq + g.Lk);
-        if (!attn_no_allheads() && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ah <= 220 * 1024 &&
+        if (!attn_no_allheads() && g.mode != 2 && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && ah <= 220 * 1024 &&
             ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)O % 16 == 0)) {
             if (ah > 48 * 1024) cudaFuncSetAttribute(attn_fwd_allheads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ah);
             const int gx = batches < 148 * 8 ? batches : 148 * 8;
@@ -1294,11 +1340,28 @@ extern "C" int vptr_attn_fwd(const float* Q, long long ldq, const float* K, long
     return vptr_check_launch("attn_fwd_kernel");
 }
 
+extern "C" int vptr_attn_bwd_bias(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                                  const float* dO, long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV,
+                                  long long lddv, const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws,
+                                  int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed,
+                                  float drop_p, float* dbq, float* dbk, float* dbv, cudaStream_t stream);
 extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
                              const float* dO, long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV,
                              long long lddv, const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws,
                              int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed,
                              float drop_p, cudaStream_t stream) {
+    return vptr_attn_bwd_bias(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk,
+                              nhead, d, causal, scale, round_tf32, drop_seed, drop_p, nullptr, nullptr, nullptr, stream);
+}
+extern "C" int vptr_colsum(const float* x, float* out, long long rows, int C, long long ld, cudaStream_t stream);
+// Same, and dbq / dbk / dbv ([nhead*d] each, any may be NULL) += the column sums of dQ / dK / dV -- the bias gradients of the q / k / v
+// projections (in_proj_bias of nn.MultiheadAttention, q/k/v_proj.bias of MultiheadAttentionRPE).  The tensor-core kernels produce them
+// while storing the tiles; the scalar fallbacks run the stand-alone column-sum kernel afterwards.
+extern "C" int vptr_attn_bwd_bias(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv,
+                                  const float* dO, long long ldo, float* dQ, long long lddq, float* dK, long long lddk, float* dV,
+                                  long long lddv, const float* rpe_table, float* d_rpe_table, int mode, int F_or_N, int H, int W, int ws,
+                                  int Tq, int Tk, int nhead, int d, int causal, float scale, int round_tf32, unsigned long long drop_seed,
+                                  float drop_p, float* dbq, float* dbk, float* dbv, cudaStream_t stream) {
     AttnGeom g;
     int batches = 0;
     int rc = fill_geom(g, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, &batches);
@@ -1306,6 +1369,17 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
     g.round_tf32 = round_tf32;
     g.drop_seed = drop_seed;
     g.drop_p = drop_p;
+    g.dbq = dbq; g.dbk = dbk; g.dbv = dbv;
+    struct AfterSums {   // scalar fallbacks: bias gradients by the separate column-sum pass
+        float *dbq, *dbk, *dbv; const float *dQ, *dK, *dV; long long lq, lk, lv, rq, rk; int C; cudaStream_t st;
+        int run() const {
+            int r = 0;
+            if (dbq && !r) r = vptr_colsum(dQ, dbq, rq, C, lq, st);
+            if (dbk && !r) r = vptr_colsum(dK, dbk, rk, C, lk, st);
+            if (dbv && !r) r = vptr_colsum(dV, dbv, rk, C, lv, st);
+            return r;
+        }
+    } after{dbq, dbk, dbv, dQ, dK, dV, lddq, lddk, lddv, (long long)batches * g.Lq, (long long)batches * g.Lk, nhead * d, stream};
     VPTR_REQUIRE(batches > 0 && nhead > 0 && d > 0, VPTR_ERR_SHAPE, "vptr_attn_bwd: empty problem");
     if (attn_mma_ok(g, nhead, d) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 &&
         lddv % 4 == 0 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)dO % 16 == 0) &&
@@ -1319,7 +1393,7 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
         const int C = nhead * d;
         const size_t ah = sizeof(float) * ((size_t)(2 * g.Lq + 2 * g.Lk) * (C + 2) + (size_t)2 * nhead * g.Lq * (g.Lk + 1) +
                                            (((size_t)nhead * g.Lq * g.Lk + 1) & ~(size_t)1)) + sizeof(long long) * (size_t)(g.Lq + g.Lk);
-        if (!attn_no_allheads() && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 &&
+        if (!attn_no_allheads() && g.mode != 2 && d % 2 == 0 && C % 4 == 0 && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 &&
             lddk % 4 == 0 && lddv % 4 == 0 && ah <= 220 * 1024 && ((uintptr_t)Q % 16 == 0) && ((uintptr_t)K % 16 == 0) &&
             ((uintptr_t)V % 16 == 0) && ((uintptr_t)dO % 16 == 0) && ((uintptr_t)dQ % 16 == 0) && ((uintptr_t)dK % 16 == 0) &&
             ((uintptr_t)dV % 16 == 0)) {
@@ -1327,7 +1401,8 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
             int gx = batches < 148 * 4 ? batches : 148 * 4;
             attn_bwd_allheads_kernel<<<gx, 256, ah, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, rpe_table,
                                                               d_rpe_table, g, batches);
-            return vptr_check_launch("attn_bwd_allheads_kernel");
+            rc = vptr_check_launch("attn_bwd_allheads_kernel");
+            return rc ? rc : after.run();
         }
     }
     VPTR_REQUIRE(d % 2 == 0 && ldq % 2 == 0 && ldk % 2 == 0 && ldv % 2 == 0 && ldo % 2 == 0 && lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 &&
@@ -1344,7 +1419,8 @@ extern "C" int vptr_attn_bwd(const float* Q, long long ldq, const float* K, long
     dim3 grid(gx, nhead);
     attn_bwd_kernel<<<grid, 128, smem, stream>>>(Q, ldq, K, ldk, V, ldv, dO, ldo, dQ, lddq, dK, lddk, dV, lddv, rpe_table,
                                                  d_rpe_table, g, batches);
-    return vptr_check_launch("attn_bwd_kernel");
+    rc = vptr_check_launch("attn_bwd_kernel");
+    return rc ? rc : after.run();
 }
 
 // Integer artefacts produced by the very index functions the kernels use (bit-exact contract):

@@ -609,7 +609,7 @@ extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float*
                           const float* rpe_table, int mode, int F_or_N, int H, int W, int ws, int Tq, int Tk, int nhead, int d, int causal,
                           float scale, int round_tf32, unsigned long long drop_seed, float drop_p, cudaStream_t stream) {
     vptr_set_error("vptr_attn_fwd_tcgen05: shape outside the kernel's domain (head_dim 66, <= 8 heads, groups of <= 32 tokens, windows of <= 16)");
-    if (d != TC_D || nhead > TC_MAXHEADS || nhead < 1) return VPTR_ERR_UNSUPPORTED;
+    if (d != TC_D || nhead > TC_MAXHEADS || nhead < 1 || mode < 0 || mode > 1) return VPTR_ERR_UNSUPPORTED;
     if ((ldq | ldk | ldv | ldo) % 4 != 0 || ((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) % 16 != 0) return VPTR_ERR_UNSUPPORTED;
     TcGeom g{};
     g.mode = mode; g.nhead = nhead; g.causal = causal; g.scale = scale; g.round_tf32 = round_tf32; g.drop_seed = drop_seed; g.drop_p = drop_p;

@@ -146,6 +146,59 @@ __global__ void __launch_bounds__(256) relu_fwd_kernel(const float* __restrict__
 }
 
 // out[c] += sum_r x[r][c]
+// ---- column-slab variants: a thread owns ONE float4 column and walks a block of rows, so the column sums of what it writes (the
+// bias gradient of the Linear / 1x1 conv that consumes the tensor: db = sum over tokens of dY) accumulate in registers and cost four
+// atomics per thread instead of a separate pass over dY (the stand-alone colsum kernel re-read every dY of the backward: 164
+// launches, 6 ms per cfg1 step).  A block reads whole rows (blockDim.x * 16 B contiguous per row), rows_per_block consecutive rows.
+__global__ void __launch_bounds__(1024) round_copy_colsum_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int C4,
+                                                                 int do_round, const float* __restrict__ rowscale, int group_rows,
+                                                                 unsigned long long seed, float p, float* __restrict__ colsum, int rows_per_block) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= C4) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        const long long i = r * C4 + c4;
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        if (p > 0.f) {
+            const float4 k = vptr_drop_scale4(seed, (unsigned long long)i, p);
+            v.x *= k.x; v.y *= k.y; v.z *= k.z; v.w *= k.w;
+        }
+        if (rowscale) {
+            const float rs = __ldg(rowscale + r / group_rows);
+            v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+        }
+        if (do_round) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+        reinterpret_cast<float4*>(y)[i] = v;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    atomicAdd(colsum + 4 * c4, acc.x); atomicAdd(colsum + 4 * c4 + 1, acc.y); atomicAdd(colsum + 4 * c4 + 2, acc.z); atomicAdd(colsum + 4 * c4 + 3, acc.w);
+}
+__global__ void __launch_bounds__(1024) gelu_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
+                                                               long long rows, int C4, int round_tf32, unsigned long long seed, float p,
+                                                               float* __restrict__ colsum, int rows_per_block) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= C4) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        const long long i = r * C4 + c4;
+        const float4 g = reinterpret_cast<const float4*>(dy)[i];
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        float4 o = make_float4(g.x * vptr_gelu_grad(v.x), g.y * vptr_gelu_grad(v.y), g.z * vptr_gelu_grad(v.z), g.w * vptr_gelu_grad(v.w));
+        if (p > 0.f) {
+            const float4 k = vptr_drop_scale4(seed, (unsigned long long)i, p);
+            o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+        }
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        reinterpret_cast<float4*>(dx)[i] = o;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    atomicAdd(colsum + 4 * c4, acc.x); atomicAdd(colsum + 4 * c4 + 1, acc.y); atomicAdd(colsum + 4 * c4 + 2, acc.z); atomicAdd(colsum + 4 * c4 + 3, acc.w);
+}
+
 __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int C,
                                                      long long ld, int rows_per_block) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,4 +366,34 @@ extern "C" int vptr_clip_scale(float* x, long long n, const double* sqnorm, floa
     if (n <= 0) return VPTR_OK;
     clip_scale_kernel<<<ew_grid(n, 256), 256, 0, stream>>>(x, n, sqnorm, max_norm);
     return vptr_check_launch("clip_scale_kernel");
+}
+
+// launch geometry of the column-slab kernels: blockDim.x = float4 columns (<= 1024, 32-aligned), gridDim.y row blocks sized so that
+// ~4 blocks per SM exist and a thread keeps >= 16 rows (its four atomics amortised)
+static void slab_geometry(long long rows, int C4, int& tx, dim3& grid, int& rpb) {
+    tx = C4 < 1024 ? ((C4 + 31) & ~31) : 1024;
+    const int xb = vptr_cdiv(C4, tx);
+    long long want = (148LL * 4 + xb - 1) / xb;
+    rpb = (int)((rows + want - 1) / want);
+    if (rpb < 16) rpb = 16;
+    grid = dim3(xb, vptr_cdiv(rows, rpb));
+}
+// y = [round](x * dropmask * rowscale[row / group_rows]) over a [rows][C] matrix, and colsum[c] += sum_r y[r][c]
+extern "C" int vptr_round_copy_colsum(const float* x, float* y, long long rows, int C, int do_round, const float* rowscale, int group_rows,
+                                      unsigned long long drop_seed, float drop_p, float* colsum, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && colsum != nullptr, VPTR_ERR_SHAPE, "vptr_round_copy_colsum: rows=%lld C=%d", rows, C);
+    VPTR_REQUIRE(rowscale == nullptr || group_rows > 0, VPTR_ERR_SHAPE, "vptr_round_copy_colsum: group_rows=%d", group_rows);
+    int tx, rpb; dim3 grid;
+    slab_geometry(rows, C / 4, tx, grid, rpb);
+    round_copy_colsum_kernel<<<grid, tx, 0, stream>>>(x, y, rows, C / 4, do_round, rowscale, group_rows > 0 ? group_rows : 1, drop_seed, drop_p, colsum, rpb);
+    return vptr_check_launch("round_copy_colsum_kernel");
+}
+// dx = [round](dy * GELU'(x) * dropmask) over a [rows][C] matrix (dx may alias dy), and colsum[c] += sum_r dx[r][c]
+extern "C" int vptr_gelu_bwd_colsum(const float* dy, const float* x, float* dx, long long rows, int C, int round_tf32, unsigned long long drop_seed,
+                                    float drop_p, float* colsum, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && colsum != nullptr, VPTR_ERR_SHAPE, "vptr_gelu_bwd_colsum: rows=%lld C=%d", rows, C);
+    int tx, rpb; dim3 grid;
+    slab_geometry(rows, C / 4, tx, grid, rpb);
+    gelu_bwd_colsum_kernel<<<grid, tx, 0, stream>>>(dy, x, dx, rows, C / 4, round_tf32, drop_seed, drop_p, colsum, rpb);
+    return vptr_check_launch("gelu_bwd_colsum_kernel");
 }

@@ -516,6 +516,52 @@ __global__ void __launch_bounds__(256) norm_act_bwd_dx_kernel(float* __restrict_
     }
 }
 
+// Column-slab form of the final pass (see elementwise.cu): a thread owns one float4 column and walks rows_per_block rows, so the
+// column sums of dx -- the bias gradient of the 1x1 conv in front of the norm (fc1 / fc2 of MlpDWBN) -- come out of this pass.
+template <int MODE>
+__global__ void __launch_bounds__(1024) norm_act_bwd_dx_colsum_kernel(float* __restrict__ g0dx, const float* __restrict__ x,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ s1,
+                                                                      const float* __restrict__ s2, long long rows, int C4, int hw, float inv_n,
+                                                                      int round_tf32, float* __restrict__ colsum, int rows_per_block) {
+    const int c4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c4 >= C4) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), r = m, g = m, u1 = m, u2 = m;
+    if (MODE != 1) {
+        m = __ldg(reinterpret_cast<const float4*>(mean) + c4); r = __ldg(reinterpret_cast<const float4*>(rstd) + c4);
+        g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        if (MODE == 0) { u1 = __ldg(reinterpret_cast<const float4*>(s1) + c4); u2 = __ldg(reinterpret_cast<const float4*>(s2) + c4); }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int f = (int)(r0 / hw), p = (int)(r0 - (long long)f * hw);      // frame and in-frame position of the current row
+#pragma unroll 4
+    for (long long row = r0; row < r1; ++row) {
+        const long long i = row * C4 + c4;
+        const float4 d = reinterpret_cast<const float4*>(g0dx)[i];
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        float4 o;
+        if (MODE == 1) {
+            const float mm = __ldg(mean + f), rr = __ldg(rstd + f), t1 = __ldg(s1 + f) * inv_n, t2 = __ldg(s2 + f) * inv_n;
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + (long long)p * C4 + c4);
+            o.x = rr * (d.x * gg.x - t1 - (xv.x - mm) * rr * t2); o.y = rr * (d.y * gg.y - t1 - (xv.y - mm) * rr * t2);
+            o.z = rr * (d.z * gg.z - t1 - (xv.z - mm) * rr * t2); o.w = rr * (d.w * gg.w - t1 - (xv.w - mm) * rr * t2);
+            if (++p == hw) { p = 0; ++f; }
+        } else if (MODE == 0) {
+            o.x = g.x * r.x * (d.x - u1.x * inv_n - (xv.x - m.x) * r.x * u2.x * inv_n);
+            o.y = g.y * r.y * (d.y - u1.y * inv_n - (xv.y - m.y) * r.y * u2.y * inv_n);
+            o.z = g.z * r.z * (d.z - u1.z * inv_n - (xv.z - m.z) * r.z * u2.z * inv_n);
+            o.w = g.w * r.w * (d.w - u1.w * inv_n - (xv.w - m.w) * r.w * u2.w * inv_n);
+        } else {
+            o.x = g.x * r.x * d.x; o.y = g.y * r.y * d.y; o.z = g.z * r.z * d.z; o.w = g.w * r.w * d.w;
+        }
+        if (round_tf32) { o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w); }
+        reinterpret_cast<float4*>(g0dx)[i] = o;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    atomicAdd(colsum + 4 * c4, acc.x); atomicAdd(colsum + 4 * c4 + 1, acc.y); atomicAdd(colsum + 4 * c4 + 2, acc.z); atomicAdd(colsum + 4 * c4 + 3, acc.w);
+}
+
 // blocks per frame for the (chunk, frame) grids: enough CTAs to fill the GPU a few times over, >= 2 float4 per thread
 int norm_chunks(int frame4, int frames) {
     int chunks = (frame4 + 2 * 256 - 1) / (2 * 256);
@@ -622,10 +668,22 @@ extern "C" int vptr_norm_act_fwd(const float* x, float* y, const float* res, con
 
 // Backward of y = rowscale*dropout(GELU(norm(x))).  mode 0: train BatchNorm, 1: frame LayerNorm, 2: eval BatchNorm.
 // ws: mode 0/2 -> 2*ch floats; mode 1 -> 2*frames floats.  dgamma/dbeta are accumulated (+=).  dx may alias dy (in place).
+extern "C" int vptr_norm_act_bwd_colsum(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                        const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
+                                        float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed,
+                                        float drop_p, float* colsum, cudaStream_t stream);
 extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                                  const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
                                  float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed,
                                  float drop_p, cudaStream_t stream) {
+    return vptr_norm_act_bwd_colsum(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, rows, ch, hw, mode, ws, round_tf32, rowscale, rows_per_group,
+                                    drop_seed, drop_p, nullptr, stream);
+}
+// colsum != NULL: colsum[c] += sum over rows of dx[.][c] (the bias gradient of the 1x1 conv that produced x), out of the final pass
+extern "C" int vptr_norm_act_bwd_colsum(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                        const float* beta, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int hw, int mode,
+                                        float* ws, int round_tf32, const float* rowscale, int rows_per_group, unsigned long long drop_seed,
+                                        float drop_p, float* colsum, cudaStream_t stream) {
     VPTR_REQUIRE(rows > 0 && ch > 0 && ch % 4 == 0, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld ch=%d (ch %% 4 == 0 required)", rows, ch);
     const DropArgs da{rowscale, rows_per_group > 0 ? rows_per_group : 1, drop_seed, drop_p};
     VPTR_REQUIRE(hw > 0 && rows % hw == 0 && rows / hw < 65536, VPTR_ERR_SHAPE, "vptr_norm_act_bwd: rows=%lld not whole frames of hw=%d", rows, hw);
@@ -636,7 +694,16 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
         int rpb = 128;
         dim3 g2(vptr_cdiv(ch / 4, 128), vptr_cdiv(rows, rpb));
         bn_act_bwd_pass_a_kernel<<<g2, 128, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, dgamma, dbeta, ws, ws + ch, rows, ch, rpb, da);
-        if (mode == 0)
+        if (colsum) {
+            const int C4 = ch / 4, tx = C4 < 1024 ? ((C4 + 31) & ~31) : 1024, xb = vptr_cdiv(C4, tx);
+            int rpbc = (int)((rows + (148 * 4 + xb - 1) / xb - 1) / ((148 * 4 + xb - 1) / xb));
+            if (rpbc < 16) rpbc = 16;
+            const dim3 gc(xb, vptr_cdiv(rows, rpbc));
+            if (mode == 0)
+                norm_act_bwd_dx_colsum_kernel<0><<<gc, tx, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, rows, C4, hw, 1.0f / (float)rows, round_tf32, colsum, rpbc);
+            else
+                norm_act_bwd_dx_colsum_kernel<2><<<gc, tx, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, rows, C4, hw, 0.f, round_tf32, colsum, rpbc);
+        } else if (mode == 0)
             norm_act_bwd_dx_kernel<0><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, frame4, ch / 4, 1.0f / (float)rows, round_tf32);
         else
             norm_act_bwd_dx_kernel<2><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + ch, frame4, ch / 4, 0.f, round_tf32);
@@ -646,7 +713,14 @@ extern "C" int vptr_norm_act_bwd(const float* dy, const float* x, const float* m
         cudaMemsetAsync(ws, 0, sizeof(float) * 2 * frames, stream);
         dim3 g2(vptr_cdiv(gsize / 4, 256), vptr_cdiv(frames, LN3_FPB));
         ln3_act_bwd_pass_ab_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, rstd, gamma, beta, dx, ws, ws + frames, dgamma, dbeta, gsize, ch, frames, da);
-        norm_act_bwd_dx_kernel<1><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, frame4, ch / 4, 1.0f / (float)gsize, round_tf32);
+        if (colsum) {
+            const int C4 = ch / 4, tx = C4 < 1024 ? ((C4 + 31) & ~31) : 1024, xb = vptr_cdiv(C4, tx);
+            int rpbc = (int)((rows + (148 * 4 + xb - 1) / xb - 1) / ((148 * 4 + xb - 1) / xb));
+            if (rpbc < 16) rpbc = 16;
+            const dim3 gc(xb, vptr_cdiv(rows, rpbc));
+            norm_act_bwd_dx_colsum_kernel<1><<<gc, tx, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, rows, C4, hw, 1.0f / (float)gsize, round_tf32, colsum, rpbc);
+        } else
+            norm_act_bwd_dx_kernel<1><<<gdx, 256, 0, stream>>>(dx, x, mean, rstd, gamma, ws, ws + frames, frame4, ch / 4, 1.0f / (float)gsize, round_tf32);
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }

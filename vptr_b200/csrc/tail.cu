@@ -161,6 +161,148 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------- BiPatchNCE (fused)
+// Bidirectional patch-wise contrastive loss of cal_lossT (model/criterion.py:206-259, train_NAR.py:36 with F.normalize over the
+// channel dim of both operands) for one frame per CTA: A = gt features [L][C], B = predicted features [L][C], L = h*w <= 64.
+//   a^ = a / max(|a|, 1e-12), b^ likewise;  S^_ij = a^_i . b^_j;  score1 = S^ / tau (rows: gt -> pred), score2 = score1^T;
+//   loss = 0.5 * (mean_i CE(score1_i, i) + mean_j CE(score2_j, j)) over all F*L rows.
+// Stop-gradients of the reference (negatives detached on the "other" side): with G1 = softmax_row(score1) - I and
+// H_ij = softmax_col(score1)_ij - I (both scaled by 0.5 / (F L tau)),
+//   d a^_i = sum_j G1_ij b^_j + H_ii b^_i ,   d b^_j = sum_i H_ij a^_i + G1_jj a^_j .
+// Forward keeps S^ (16 KB per frame) and the row / column statistics; the backward rebuilds the coefficient matrices from them, so
+// the only big tensors it touches are A, B (read) and dA, dB (written): 4 passes over the features instead of the reference's
+// normalize / rearrange / 4 bmm / mask / cross-entropy chain and its autograd mirror (~60 launches).
+constexpr int NCE_L = 64, NCE_CK = 32, NCE_CKB = 24, NCE_SP = 65;   // (backward: 24-column chunks keep static smem < 48 KB)
+
+__global__ void __launch_bounds__(256) bipatch_nce_fwd_kernel(const float* __restrict__ A, const float* __restrict__ B, int L, int C, float inv_tau,
+                                                              float* __restrict__ S_out, float* __restrict__ stats, double* __restrict__ loss_sum) {
+    __shared__ float sA[NCE_L][NCE_CK + 1], sB[NCE_L][NCE_CK + 1], sS[NCE_L][NCE_SP];
+    __shared__ float sn[2][NCE_L], red[8];
+    const int f = blockIdx.x, tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const float* Af = A + (long long)f * L * C;
+    const float* Bf = B + (long long)f * L * C;
+    float acc[4][4] = {};
+    float nrm = 0.f;                                   // threads 0..63: |a_tid|^2 ; 64..127: |b_(tid-64)|^2
+    for (int c0 = 0; c0 < C; c0 += NCE_CK) {
+        const int ck = min(NCE_CK, C - c0);
+        for (int e = tid; e < NCE_L * NCE_CK; e += 256) {
+            const int r = e / NCE_CK, c = e - r * NCE_CK;
+            const bool ok = r < L && c < ck;
+            sA[r][c] = ok ? Af[(long long)r * C + c0 + c] : 0.f;
+            sB[r][c] = ok ? Bf[(long long)r * C + c0 + c] : 0.f;
+        }
+        __syncthreads();
+        if (tid < 64) { for (int c = 0; c < NCE_CK; ++c) nrm = fmaf(sA[tid][c], sA[tid][c], nrm); }
+        else if (tid < 128) { for (int c = 0; c < NCE_CK; ++c) nrm = fmaf(sB[tid - 64][c], sB[tid - 64][c], nrm); }
+#pragma unroll 4
+        for (int c = 0; c < NCE_CK; ++c) {
+            float a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a[k] = sA[ty * 4 + k][c]; b[k] = sB[tx * 4 + k][c]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    if (tid < 128) sn[tid >> 6][tid & 63] = fmaxf(sqrtf(nrm), 1e-12f);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sS[ty * 4 + i][tx * 4 + j] = acc[i][j] / (sn[0][ty * 4 + i] * sn[1][tx * 4 + j]);
+    __syncthreads();
+    float part = 0.f, lse = 0.f;
+    if (tid < 128) {
+        const int r = tid & 63;
+        const bool col = tid >= 64;
+        if (r < L) {
+            float mx = -INFINITY;
+            for (int k = 0; k < L; ++k) mx = fmaxf(mx, (col ? sS[k][r] : sS[r][k]) * inv_tau);
+            float se = 0.f;
+            for (int k = 0; k < L; ++k) se += __expf((col ? sS[k][r] : sS[r][k]) * inv_tau - mx);
+            lse = mx + __logf(se);
+            part = lse - sS[r][r] * inv_tau;
+        }
+    }
+    float* st = stats + (long long)f * 4 * NCE_L;      // na | nb | lse1 | lse2
+    if (tid < 128) { st[tid] = sn[tid >> 6][tid & 63]; st[128 + tid] = lse; }
+    for (int e = tid; e < NCE_L * NCE_L; e += 256) S_out[(long long)f * NCE_L * NCE_L + e] = sS[e >> 6][e & 63];
+    part = block_sum(part, red);
+    if (tid == 0) atomicAdd(loss_sum, (double)part);
+}
+__global__ void bipatch_nce_loss_kernel(const double* __restrict__ loss_sum, double rows, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) loss[0] = (float)(0.5 * loss_sum[0] / rows);
+}
+__global__ void __launch_bounds__(256) bipatch_nce_bwd_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ S_in,
+                                                              const float* __restrict__ stats, const float* __restrict__ dloss, int L, int C,
+                                                              float inv_tau, float coef, float* __restrict__ dA, float* __restrict__ dB) {
+    __shared__ float sM[NCE_L][NCE_SP], sMt[NCE_L][NCE_SP];   // M_ij (for dA), M'_ij (for dB)
+    __shared__ float sA[NCE_L][NCE_CKB + 1], sB[NCE_L][NCE_CKB + 1];
+    __shared__ float sna[NCE_L], snb[NCE_L], sr[2][NCE_L];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const float* st = stats + (long long)f * 4 * NCE_L;
+    const float up = (dloss ? dloss[0] : 1.f) * coef * inv_tau;        // coef = 0.5 / (F L)
+    if (tid < 64) { sna[tid] = st[tid]; snb[tid] = st[64 + tid]; }
+    for (int e = tid; e < NCE_L * NCE_L; e += 256) {
+        const int i = e >> 6, j = e & 63;
+        float m = 0.f, mt = 0.f;
+        if (i < L && j < L) {
+            const float sc = S_in[(long long)f * NCE_L * NCE_L + e] * inv_tau;
+            const float g1 = __expf(sc - st[128 + i]) - (i == j ? 1.f : 0.f);        // softmax over the row i
+            const float h = __expf(sc - st[192 + j]) - (i == j ? 1.f : 0.f);         // softmax over the column j
+            m = g1 + (i == j ? h : 0.f);
+            mt = h + (i == j ? g1 : 0.f);
+        }
+        sM[i][j] = m * up;
+        sMt[i][j] = mt * up;
+    }
+    __syncthreads();
+    if (tid < 128) {       // r_i = sum_j M_ij S^_ij ; r'_j = sum_i M'_ij S^_ij   (= x^ . dx^ of the normalisation's backward)
+        const int r = tid & 63;
+        const bool col = tid >= 64;
+        float acc = 0.f;
+        const float* Sf = S_in + (long long)f * NCE_L * NCE_L;
+        if (r < L)
+            for (int k = 0; k < L; ++k) acc = fmaf(col ? sMt[k][r] : sM[r][k], col ? Sf[k * NCE_L + r] : Sf[r * NCE_L + k], acc);
+        sr[col ? 1 : 0][r] = acc;
+    }
+    __syncthreads();
+    const float* Af = A + (long long)f * L * C;
+    const float* Bf = B + (long long)f * L * C;
+    float* dAf = dA + (long long)f * L * C;
+    float* dBf = dB + (long long)f * L * C;
+    constexpr int CPT = NCE_CKB / 4;
+    const int r = tid >> 2, cg = (tid & 3) * CPT;
+    for (int c0 = 0; c0 < C; c0 += NCE_CKB) {
+        const int ck = min(NCE_CKB, C - c0);
+        for (int e = tid; e < NCE_L * NCE_CKB; e += 256) {
+            const int rr = e / NCE_CKB, c = e - rr * NCE_CKB;
+            const bool ok = rr < L && c < ck;
+            sA[rr][c] = ok ? Af[(long long)rr * C + c0 + c] / sna[rr] : 0.f;           // normalised rows
+            sB[rr][c] = ok ? Bf[(long long)rr * C + c0 + c] / snb[rr] : 0.f;
+        }
+        __syncthreads();
+        float oa[CPT] = {}, ob[CPT] = {};
+        for (int k = 0; k < L; ++k) {
+            const float m = sM[r][k], mt = sMt[k][r];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) { oa[c] = fmaf(m, sB[k][cg + c], oa[c]); ob[c] = fmaf(mt, sA[k][cg + c], ob[c]); }
+        }
+        if (r < L) {
+            const float ra = sr[0][r], rb = sr[1][r], ia = 1.f / sna[r], ib = 1.f / snb[r];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+                if (cg + c < ck) {
+                    dAf[(long long)r * C + c0 + cg + c] = (oa[c] - sA[r][cg + c] * ra) * ia;
+                    dBf[(long long)r * C + c0 + cg + c] = (ob[c] - sB[r][cg + c] * rb) * ib;
+                }
+        }
+        __syncthreads();
+    }
+}
+
 inline int grid_for(long long units) {
     long long b = (units + 255) / 256;
     const long long cap = 148LL * 16;
@@ -207,4 +349,26 @@ extern "C" int vptr_adamw_multi(const long long* table, int n, long long total_u
     if (vec) adamw_multi_kernel<true><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm);
     else adamw_multi_kernel<false><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm);
     return vptr_check_launch("adamw_multi_kernel");
+}
+
+// gt / pred: [F][L][C] channel-last feature rows of F = N*T frames (L = h*w <= 64).  S_save: F*64*64 floats, stats_save: F*256 floats
+// (kept for the backward); loss_sum: device double zeroed by the caller; loss_out: device float = the BiPatchNCE value.
+extern "C" int vptr_bipatch_nce_fwd(const float* gt, const float* pred, int F, int L, int C, float temperature, float* S_save, float* stats_save,
+                                    double* loss_sum, float* loss_out, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && L > 0 && L <= NCE_L && C > 0 && temperature > 0.f, VPTR_ERR_UNSUPPORTED,
+                 "vptr_bipatch_nce_fwd: F=%d L=%d (<= 64 supported) C=%d temperature=%g", F, L, C, (double)temperature);
+    bipatch_nce_fwd_kernel<<<F, 256, 0, stream>>>(gt, pred, L, C, 1.f / temperature, S_save, stats_save, loss_sum);
+    int rc = vptr_check_launch("bipatch_nce_fwd_kernel");
+    if (rc) return rc;
+    bipatch_nce_loss_kernel<<<1, 32, 0, stream>>>(loss_sum, (double)F * L, loss_out);
+    return vptr_check_launch("bipatch_nce_loss_kernel");
+}
+// d(gt), d(pred) = dloss * d(BiPatchNCE)/d(.) through the reference's stop-gradients and the channel normalisation
+extern "C" int vptr_bipatch_nce_bwd(const float* gt, const float* pred, const float* S_save, const float* stats_save, const float* dloss, int F,
+                                    int L, int C, float temperature, float* dgt, float* dpred, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && L > 0 && L <= NCE_L && C > 0 && temperature > 0.f, VPTR_ERR_UNSUPPORTED,
+                 "vptr_bipatch_nce_bwd: F=%d L=%d (<= 64 supported) C=%d", F, L, C);
+    bipatch_nce_bwd_kernel<<<F, 256, 0, stream>>>(gt, pred, S_save, stats_save, dloss, L, C, 1.f / temperature, (float)(0.5 / ((double)F * L)),
+                                                  dgt, dpred);
+    return vptr_check_launch("bipatch_nce_bwd_kernel");
 }

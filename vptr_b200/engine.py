@@ -143,11 +143,25 @@ def _stacked(*ws):
     return torch.as_strided(w0, (sum(w.shape[0] for w in ws), w0.shape[1]), (w0.shape[1], 1), w0.storage_offset())
 
 
-def _rc(x, rowscale=None, group_elems=0, seed=0, p=0.0):
-    """GEMM-operand copy of x: tf32-rounded and, for the backward of a regularised branch, masked / DropPath-scaled"""
+# Bias gradients (column sums of a dY) are produced by the kernel that writes dY when dY is wide (the 2112-channel tensors of the two
+# FFNs: gelu_bwd, norm+GELU backward) -- measured 34-66 us cheaper per site than a separate pass.  For the 528-wide tensors and inside
+# the attention backward the fused forms LOSE (a 132-float4 row leaves the column-slab kernels with 160-thread blocks; shared-memory
+# atomics in the attention tile store cost +40 %): profiles/r02_op_table_cfg1_colsum_fusion.txt.  Those sites keep vptr_colsum.
+FUSE_COLSUM_MIN_WIDTH = 1024
+
+
+def _rc(x, rowscale=None, group_elems=0, seed=0, p=0.0, colsum=None):
+    """GEMM-operand copy of x: tf32-rounded and, for the backward of a regularised branch, masked / DropPath-scaled.
+    colsum: bias-gradient accumulator that receives the column sums of the copy"""
     if not ROUND_TF32 and rowscale is None and p <= 0.0:
+        if colsum is not None:
+            ops.colsum(x, colsum)
         return x
-    return ops.round_copy(x, ROUND_TF32, rowscale, group_elems, seed, p)
+    if colsum is not None and x.shape[-1] < FUSE_COLSUM_MIN_WIDTH:
+        y = ops.round_copy(x, ROUND_TF32, rowscale, group_elems, seed, p)
+        ops.colsum(y, colsum)
+        return y
+    return ops.round_copy(x, ROUND_TF32, rowscale, group_elems, seed, p, colsum=colsum)
 
 
 class Drop:
@@ -333,10 +347,10 @@ def window_attn_bwd(P, s, dout, dqpos):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     at = pre + ".attn."
     Fr = g.F
-    dy = _rc(ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout, s["dp"], s["rpg"] * C)
+    dy = _rc(ops.pad_hw(dout, Fr, g.H, g.W, g.Hp, g.Wp, g.ph0, g.pw0) if g.padded else dout, s["dp"], s["rpg"] * C,
+             colsum=P.g(at + "out_proj.bias"))
     qkv, o = s["qkv"], s["o"]
     _wgrad(P, at + "out_proj.weight", dy, o)
-    _bgrad(P, at + "out_proj.bias", dy)
     do = ops.gemm(dy, P.wr(at + "out_proj.weight"), b_mn=True)
     dqkv = torch.empty_like(qkv)
     if s["rpe"]:
@@ -435,10 +449,15 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     return out
 
 
-def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None, inplace=False):
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None, inplace=False, colsum=None):
+    """colsum: bias-gradient accumulator of the 1x1 conv in front of this norm (its output gradient is the dx computed here)"""
     gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
     ch = h.shape[1]
-    drop = drop or {}
+    if colsum is not None and ch < FUSE_COLSUM_MIN_WIDTH:      # narrow tensor: separate column-sum pass (see FUSE_COLSUM_MIN_WIDTH)
+        dx = _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd, drop, inplace, None)
+        ops.colsum(dx, colsum)
+        return dx
+    drop = dict(drop or {}, colsum=colsum)
     if layer_norm:
         dg = ops.zeros(g.HW * ch, like=h)
         db = ops.zeros(g.HW * ch, like=h)
@@ -456,14 +475,13 @@ def conv_ffn_bwd(P, s, dout):
     g, pre, ln, lnm, mode = s["g"], s["pre"], s["ln"], s["layer_norm"], s["mode"]
     Ch = s["h1"].shape[1]
     dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT,
-                        drop=dict(rowscale=s["dp"], rows_per_group=s["rpg"], drop_seed=s["s3"], drop_p=s["p"]))
+                        drop=dict(rowscale=s["dp"], rows_per_group=s["rpg"], drop_seed=s["s3"], drop_p=s["p"]), colsum=P.g(pre + ".fc2.bias"))
     u2 = s["u2"]
     if u2 is None:        # lean mode: u2 = drop(GELU(norm2(h2))) again, same dropout seed
         u2 = ops.norm_act_fwd(s["h2"], s["st2"][0], s["st2"][1], s["aff"][1][0], s["aff"][1][1], g.HW, 1 if lnm else 0,
                               round_tf32=ROUND_TF32, drop_seed=s["s2"], drop_p=s["p"])
     _wgrad(P, pre + ".fc2.weight", dh3, u2)
     del u2
-    _bgrad(P, pre + ".fc2.bias", dh3)
     du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
     dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]),
                         inplace=True)
@@ -477,13 +495,12 @@ def conv_ffn_bwd(P, s, dout):
         del u1
         ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
     du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
-    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT, inplace=True)
+    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT, inplace=True, colsum=P.g(pre + ".fc1.bias"))
     b_ = s["b"]
     if b_ is None:        # lean mode
         b_ = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT, save_stats=False)[0]
     _wgrad(P, pre + ".fc1.weight", dh1, b_)
     del b_
-    _bgrad(P, pre + ".fc1.bias", dh1)
     db = ops.gemm(dh1, P.wr(pre + ".fc1.weight").view(Ch, g.C), b_mn=True)
     return ops.layernorm_bwd(db, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dout,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
@@ -515,15 +532,14 @@ def temporal_attn_fwd(P, pre, ln, x, g, pos, causal, save, D=NO_DROP):
 def temporal_attn_bwd(P, s, dout):
     g, C, pre, ln = s["g"], s["g"].C, s["pre"], s["ln"]
     qkv, o = s["qkv"], s["o"]
-    dres, dout = dout, _rc(dout, seed=s["s1"], p=s["p"])
+    dres, dout = dout, _rc(dout, seed=s["s1"], p=s["p"], colsum=P.g(pre + ".out_proj.bias"))
     _wgrad(P, pre + ".out_proj.weight", dout, o)
-    _bgrad(P, pre + ".out_proj.bias", dout)
     do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dqkv = torch.empty_like(qkv)
+    gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     ops.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], do, dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], None, None, 1, g.N,
                  g.H, g.W, 0, g.T, g.T, g.nhead, g.d, s["causal"], g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
     Wi = P.wr(pre + ".in_proj_weight")
-    gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
     if gW is not None:
         z, zp = s["z"], s["zp"]
         if z is None:     # lean mode
@@ -556,65 +572,73 @@ def mlp_fwd(P, pre, ln, x, g, save, D=NO_DROP):
 
 def mlp_bwd(P, s, dout):
     pre, ln = s["pre"], s["ln"]
-    dres, dout = dout, _rc(dout, seed=s["s3"], p=s["p"])
+    dres, dout = dout, _rc(dout, seed=s["s3"], p=s["p"], colsum=P.g(pre + ".linear2.bias"))
     u = s["u"]
     if u is None:         # lean mode
         u = ops.gelu_fwd(s["h"], round_tf32=ROUND_TF32, drop_seed=s["s2"], drop_p=s["p"])
     _wgrad(P, pre + ".linear2.weight", dout, u)
     del u
-    _bgrad(P, pre + ".linear2.bias", dout)
     du = ops.gemm(dout, P.wr(pre + ".linear2.weight"), b_mn=True)
-    dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT, drop_seed=s["s2"], drop_p=s["p"])
+    dh = ops.gelu_bwd(du, s["h"], out=du, round_tf32=RT, drop_seed=s["s2"], drop_p=s["p"], colsum=P.g(pre + ".linear1.bias"))
     y = s["y"]
     if y is None:         # lean mode
         y = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT, save_stats=False)[0]
     _wgrad(P, pre + ".linear1.weight", dh, y)
     del y
-    _bgrad(P, pre + ".linear1.bias", dh)
     dy = ops.gemm(dh, P.wr(pre + ".linear1.weight"), b_mn=True)
     return ops.layernorm_bwd(dy, None, s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), s["mean"], s["rstd"], dres,
                              P.g(ln + ".weight"), P.g(ln + ".bias"))
 
 
 # =================================================================================================== encoder-decoder attention
-def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save, D=NO_DROP):
+def cross_attn_fwd(P, pre, ln, x, g, gm, qadd, mem, mem_k, save, D=NO_DROP, tslma=False):
     """x + MHA(q = LN(x)+query_pos+pos_future, k = memory+pos_past, v = memory) per pixel (VidHRFormer_modules.py:200-206).
-    g: geometry of the target stream, gm: of the memory stream; qadd (T2*H*W, C) = query_pos + pos_future."""
+    g: geometry of the target stream, gm: of the memory stream; qadd (T2*H*W, C) = query_pos + pos_future.
+    tslma: the same projections around the temporal-spatial window attention instead (TemporalSpatialLocalMultiheadAttention,
+    :194-198,219-284): per window, the queries of each future frame attend that window of every memory frame (attention mode 2);
+    qadd = query_pos + Tlw_pos[future], mem_k = memory + Tlw_pos[past]; DropPath per clip (the tensor is (N,T2,H,W,C) there)."""
     C = g.C
     _, zq, mean, rstd = ops.layernorm_fwd(x, P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=qadd, add_div=1, add_mod=qadd.shape[0], round_tf32=RT)
     Wi, bi = P.wr(pre + ".in_proj_weight"), P.w(pre + ".in_proj_bias")
     kv = ops.empty(gm.R, 2 * C, like=x)
     o = ops.empty(g.R, C, like=x)
-    use_tc = RT and ops.attn_tc_temporal_ok(o, kv[:, :C], kv[:, C:], o, g.T, gm.T, g.nhead, g.d)   # tcgen05 forward (q has o's layout)
+    use_tc = RT and not tslma and ops.attn_tc_temporal_ok(o, kv[:, :C], kv[:, C:], o, g.T, gm.T, g.nhead, g.d)   # tcgen05 forward (q has o's layout)
     q = ops.gemm(zq, Wi[:C], bias=bi[:C], round_tf32=use_tc)
     ops.gemm(mem_k, Wi[C:2 * C], out=kv[:, :C], bias=bi[C:2 * C], round_tf32=use_tc)
     ops.gemm(mem, Wi[2 * C:], out=kv[:, C:], bias=bi[2 * C:], round_tf32=use_tc)
-    s_attn, dp = D.seed(), D.path_per_t(g.T)
-    rpg = g.HW                                   # DropPath per future-frame index here (see Drop.path_per_t)
-    (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(q, kv[:, :C], kv[:, C:], o, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d, False,
+    amode, aws = (2, g.ws) if tslma else (1, 0)
+    if tslma:
+        s_attn, dp = D.seed(), D.path()
+        rpg = g.T * g.HW
+    else:
+        s_attn, dp = D.seed(), D.path_per_t(g.T)
+        rpg = g.HW                               # DropPath per future-frame index here (see Drop.path_per_t)
+    (ops.attn_fwd_tcgen05 if use_tc else ops.attn_fwd)(q, kv[:, :C], kv[:, C:], o, None, amode, g.N, g.H, g.W, aws, g.T, gm.T, g.nhead, g.d, False,
                                                        g.scale, round_tf32=RT, drop_seed=s_attn, drop_p=D.p)
     out = ops.gemm(o, P.wr(pre + ".out_proj.weight"), bias=P.w(pre + ".out_proj.bias"), residual=x, rowscale=dp, rows_per_group=rpg)
     if save is not None:
         if g.lean:
             zq = None
         save.append(("xattn", dict(pre=pre, ln=ln, x=x, mean=mean, rstd=rstd, zq=zq, qadd=qadd, q=q, kv=kv, o=o, g=g, gm=gm, mem=mem,
-                                   mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p)))
+                                   mem_k=mem_k, s_attn=s_attn, dp=dp, rpg=rpg, p=D.p, amode=amode, aws=aws)))
     return out
 
 
 def cross_attn_bwd(P, s, dout, dqpos, dmem):
     g, gm, C, pre, ln = s["g"], s["gm"], s["g"].C, s["pre"], s["ln"]
     q, kv, o = s["q"], s["kv"], s["o"]
-    dres, dout = dout, _rc(dout, s["dp"], s["rpg"] * C)
+    dres, dout = dout, _rc(dout, s["dp"], s["rpg"] * C, colsum=P.g(pre + ".out_proj.bias"))
     _wgrad(P, pre + ".out_proj.weight", dout, o)
-    _bgrad(P, pre + ".out_proj.bias", dout)
     do = ops.gemm(dout, P.wr(pre + ".out_proj.weight"), b_mn=True)
     dq = torch.empty_like(q)
-    dkv = torch.empty_like(kv)
-    ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, 1, g.N, g.H, g.W, 0, g.T, gm.T, g.nhead, g.d,
-                 False, g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
-    Wi = P.wr(pre + ".in_proj_weight")
+    # mode 2: a memory token is a key of every future frame's windows -> dK / dV are accumulated (atomics) and rounded afterwards
+    dkv = torch.zeros_like(kv) if s["amode"] == 2 else torch.empty_like(kv)
     gW, gb = P.g(pre + ".in_proj_weight"), P.g(pre + ".in_proj_bias")
+    ops.attn_bwd(q, kv[:, :C], kv[:, C:], do, dq, dkv[:, :C], dkv[:, C:], None, None, s["amode"], g.N, g.H, g.W, s["aws"], g.T, gm.T,
+                 g.nhead, g.d, False, g.scale, round_tf32=RT, drop_seed=s["s_attn"], drop_p=s["p"])
+    if s["amode"] == 2 and RT:
+        dkv = ops.round_copy(dkv)
+    Wi = P.wr(pre + ".in_proj_weight")
     if gW is not None:
         zq = s["zq"]
         if zq is None:    # lean mode
@@ -622,10 +646,11 @@ def cross_attn_bwd(P, s, dout, dqpos, dmem):
                                    add_mod=s["qadd"].shape[0], round_tf32=RT, save_stats=False)[1]
         ops.gemm(dq, zq, out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
         del zq
-        ops.gemm(dkv[:, :C], s["mem_k"], out=gW[C:2 * C], a_mn=True, b_mn=True, accumulate=True)
-        ops.gemm(dkv[:, C:], s["mem"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
         ops.colsum(dq, gb[:C])
         ops.colsum(dkv, gb[C:])
+        ops.gemm(dkv[:, :C], s["mem_k"], out=gW[C:2 * C], a_mn=True, b_mn=True, accumulate=True)
+        ops.gemm(dkv[:, C:], s["mem"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+
     dzq = ops.gemm(dq, Wi[:C], b_mn=True)
     ops.gemm(dkv, Wi[C:], b_mn=True, out=dmem, residual=dmem)     # d(mem) += [dk | dv] [Wk ; Wv]  (memory + pos_past and memory share it)
     if dqpos is not None:
@@ -667,14 +692,19 @@ def encoder_fwd(P, bufs, x, g, n_layers, far, rpe, tpos, lw_tab, training, save,
     return x
 
 
-def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D=NO_DROP):
+def decoder_fwd(P, bufs, tgt, g, gm, n_layers, rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D=NO_DROP, tslma=None):
+    """tslma: None, or dict(q_tab (T2*H*W, C) = query_pos + Tlw_pos[future] over the grid, mem_k = memory + Tlw_pos[past]) when the
+    blocks carry TemporalSpatialLocalMultiheadAttention instead of the per-pixel encoder-decoder attention (TSLMA_flag)"""
     for i in range(n_layers):
         pre = "transformer.decoder.layers.%d" % i
         tgt = window_attn_fwd(P, pre + ".SLMHSA", pre + ".norm1", tgt, g, rpe, qpos, lw_tab, save, D)
         tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN", pre + ".norm2", tgt, g, True, False, save, D)
         tgt = temporal_attn_fwd(P, pre + ".temporal_MHSA", pre + ".norm3", tgt, g, tpos_f, False, save, D)
         tgt = mlp_fwd(P, pre, pre + ".norm4", tgt, g, save, D)
-        tgt = cross_attn_fwd(P, pre + ".EncDecAttn", pre + ".norm5", tgt, g, gm, qadd, mem, mem_k, save, D)
+        if tslma is not None:
+            tgt = cross_attn_fwd(P, pre + ".TSLMA.attn", pre + ".norm5", tgt, g, gm, tslma["q_tab"], mem, tslma["mem_k"], save, D, tslma=True)
+        else:
+            tgt = cross_attn_fwd(P, pre + ".EncDecAttn", pre + ".norm5", tgt, g, gm, qadd, mem, mem_k, save, D)
         tgt = conv_ffn_fwd(P, bufs, pre + ".SpatialFFN1", pre + ".norm6", tgt, g, True, False, save, D)
     return tgt
 

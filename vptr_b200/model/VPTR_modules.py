@@ -160,8 +160,16 @@ class _EncBlockHolder(nn.Module):
         self.norm4 = nn.LayerNorm(d_model)
 
 
+class _TSLMAHolder(nn.Module):
+    """Parameters of TemporalSpatialLocalMultiheadAttention (reference model/VidHRFormer_modules.py:219-246)."""
+
+    def __init__(self, embed_dim, num_heads, dropout):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout)
+
+
 class _DecBlockHolder(nn.Module):
-    def __init__(self, encH, encW, d_model, nhead, dim_feedforward, dropout, window_size, ffn_ratio, rpe):
+    def __init__(self, encH, encW, d_model, nhead, dim_feedforward, dropout, window_size, ffn_ratio, rpe, tslma=False):
         super().__init__()
         self.SLMHSA = _SLMHSAHolder(d_model, nhead, window_size, dropout, rpe)
         self.SpatialFFN = _MlpDWBNHolder(encH, encW, d_model, d_model * ffn_ratio, layer_norm=True)
@@ -172,7 +180,10 @@ class _DecBlockHolder(nn.Module):
         self.linear1 = nn.Linear(d_model, dim_feedforward)
         self.linear2 = nn.Linear(dim_feedforward, d_model)
         self.norm4 = nn.LayerNorm(d_model)
-        self.EncDecAttn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
+        if tslma:        # reference :154-158: TSLMA replaces EncDecAttn (and its state_dict keys)
+            self.TSLMA = _TSLMAHolder(d_model, nhead, dropout)
+        else:
+            self.EncDecAttn = nn.MultiheadAttention(d_model, nhead, dropout=dropout)
         self.SpatialFFN1 = _MlpDWBNHolder(encH, encW, d_model, d_model * ffn_ratio, layer_norm=True)
         self.norm5 = nn.LayerNorm(d_model)
         self.norm6 = nn.LayerNorm(d_model)
@@ -321,7 +332,15 @@ class _NARFunction(torch.autograd.Function):
         qadd = ops.add_rows(qpos, tpos_f, H * W, Tf)                             # query_pos + pos_future (VidHRFormer_modules.py:200)
         mem_k = ops.add_rows(mem, tpos_p, H * W, Tp, round_tf32=E.ROUND_TF32)                             # memory + pos_past
         tgt = ops.zeros(gd.R, C, like=x)                                         # init_tgt = zeros (VidHRFormer.py:48)
-        tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D)
+        tslma = None
+        if mod.TSLMA_flag:   # Tlw_pos (T, ws, ws, C) laid over the grid: row (t, h, w) -> Tlw_pos[t, h % ws, w % ws]
+            ws = mod.window_size
+            hh, ww = torch.arange(H, device=x.device) % ws, torch.arange(W, device=x.device) % ws
+            grid = mod.Tlw_pos[:, hh][:, :, ww]                                  # (Tp+Tf, H, W, C)
+            k_tab = grid[:Tp].reshape(Tp * H * W, C).contiguous()
+            q_tab = (grid[Tp:Tp + Tf].reshape(Tf * H * W, C) + qpos).contiguous() # query = LN5(tgt) + query_pos (+ Tlw_pos after the permute)
+            tslma = dict(q_tab=q_tab, mem_k=ops.add_rows(mem, k_tab, 1, k_tab.shape[0], round_tf32=E.ROUND_TF32))
+        tgt = E.decoder_fwd(P, bufs, tgt, gd, ge, mod.num_decoder_layers, mod.rpe, qpos, qadd, tpos_f, mem, mem_k, lw_tab, save, D, tslma=tslma)
         y = E.final_norm_fwd(P, "transformer.decoder.norm", tgt, True, save)
         ctx.save, ctx.names, ctx.params, ctx.n_enc, ctx.mod = save, names, params, n_enc, mod
         ctx.rounded = P.rounded if (want and E.ROUND_TF32) else None
@@ -358,9 +377,10 @@ class VPTRFormerNAR(nn.Module):
     def __init__(self, num_past_frames, num_future_frames, encH=8, encW=8, d_model=528, nhead=8, num_encoder_layers=6,
                  num_decoder_layers=6, dropout=0.1, window_size=4, Spatial_FFN_hidden_ratio=4, TSLMA_flag=False, rpe=True):
         super().__init__()
-        if TSLMA_flag:
-            raise NotImplementedError("vptr_b200: TSLMA_flag=True (TemporalSpatialLocalMultiheadAttention, off in every reference "
-                                      "script) is not implemented")
+        if TSLMA_flag and (encH % window_size or encW % window_size):
+            raise NotImplementedError("vptr_b200: TSLMA_flag=True needs a feature grid that is a multiple of the window "
+                                      "(%dx%d grid, window %d)" % (encH, encW, window_size))
+        self.TSLMA_flag = TSLMA_flag
         self.num_past_frames, self.num_future_frames = num_past_frames, num_future_frames
         self.nhead, self.d_model = nhead, d_model
         self.num_encoder_layers, self.num_decoder_layers = num_encoder_layers, num_decoder_layers
@@ -369,7 +389,7 @@ class VPTRFormerNAR(nn.Module):
         ff = d_model * Spatial_FFN_hidden_ratio
         enc = _Stack([_EncBlockHolder(encH, encW, d_model, nhead, ff, dropout, window_size, Spatial_FFN_hidden_ratio, False, rpe)
                       for _ in range(num_encoder_layers)], d_model)
-        dec = _Stack([_DecBlockHolder(encH, encW, d_model, nhead, ff, dropout, window_size, Spatial_FFN_hidden_ratio, rpe)
+        dec = _Stack([_DecBlockHolder(encH, encW, d_model, nhead, ff, dropout, window_size, Spatial_FFN_hidden_ratio, rpe, TSLMA_flag)
                       for _ in range(num_decoder_layers)], d_model)
         self.transformer = _TransformerHolder(enc, dec)
         T = num_past_frames + num_future_frames

@@ -161,14 +161,15 @@ def norm_act_fwd(x, mean, rstd, gamma, beta, hw, mode, res=None, out=None, round
 
 
 def norm_act_bwd(dy, x, mean, rstd, gamma, beta, dgamma, dbeta, hw, mode, round_tf32=False, rowscale=None, rows_per_group=0,
-                 drop_seed=0, drop_p=0.0, inplace=False):
-    """inplace: dx overwrites dy (for temporaries); otherwise a fresh buffer (which also holds the intermediate g0)"""
+                 drop_seed=0, drop_p=0.0, inplace=False, colsum=None):
+    """inplace: dx overwrites dy (for temporaries); otherwise a fresh buffer (which also holds the intermediate g0).
+    colsum (ch,): += column sums of dx (the bias gradient of the 1x1 conv in front of the norm), out of the final pass"""
     rows, ch = x.shape
     dx = dy if inplace else torch.empty_like(x)
     n_ws = 2 * ch if mode != 1 else 2 * (rows // hw)
     ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
-    _call("vptr_norm_act_bwd", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
-          _p(ws), int(round_tf32), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _s())
+    _call("vptr_norm_act_bwd_colsum", _p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(dx), _p(dgamma), _p(dbeta), rows, ch, hw, mode,
+          _p(ws), int(round_tf32), _p(rowscale), int(rows_per_group), int(drop_seed), float(drop_p), _p(colsum), _s())
     return dx
 
 
@@ -207,10 +208,11 @@ def attn_fwd_tcgen05(q, k, v, out, rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nh
 
 
 def attn_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, F_or_N, H, W, ws, Tq, Tk, nhead, d, causal, scale, round_tf32=False,
-             drop_seed=0, drop_p=0.0):
-    _call("vptr_attn_bwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
+             drop_seed=0, drop_p=0.0, dbq=None, dbk=None, dbv=None):
+    """dbq / dbk / dbv (nhead*d,): += column sums of dq / dk / dv (bias gradients of the q / k / v projections)"""
+    _call("vptr_attn_bwd_bias", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(do), do.stride(0), _p(dq), dq.stride(0),
           _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(rpe_table), _p(d_rpe_table), mode, F_or_N, H, W, ws, Tq, Tk, nhead, d,
-          int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _s())
+          int(causal), float(scale), int(round_tf32), int(drop_seed), float(drop_p), _p(dbq), _p(dbk), _p(dbv), _s())
 
 
 def window_index_maps(F, H, W, ws, device):
@@ -281,17 +283,30 @@ def gelu_fwd(x, round_tf32=False, drop_seed=0, drop_p=0.0):
     return y
 
 
-def gelu_bwd(dy, x, out=None, round_tf32=False, drop_seed=0, drop_p=0.0):
+def gelu_bwd(dy, x, out=None, round_tf32=False, drop_seed=0, drop_p=0.0, colsum=None):
+    """colsum (C,): += column sums of dx (x is [rows][C]): the bias gradient of the Linear in front of the GELU"""
     dx = torch.empty_like(x) if out is None else out
+    if colsum is not None and x.dim() == 2 and x.shape[1] % 4 == 0:
+        _call("vptr_gelu_bwd_colsum", _p(dy), _p(x), _p(dx), x.shape[0], x.shape[1], int(round_tf32), int(drop_seed), float(drop_p), _p(colsum), _s())
+        return dx
     _call("vptr_gelu_bwd", _p(dy), _p(x), _p(dx), x.numel(), int(round_tf32), int(drop_seed), float(drop_p), _s())
+    if colsum is not None:
+        globals()["colsum"](dx, colsum)
     return dx
 
 
-def round_copy(x, do_round=True, rowscale=None, group_elems=0, drop_seed=0, drop_p=0.0):
+def round_copy(x, do_round=True, rowscale=None, group_elems=0, drop_seed=0, drop_p=0.0, colsum=None):
     """y = [round-to-nearest tf32](x * rowscale[i / group_elems] * dropmask): operands of the tensor-core GEMM are pre-rounded
-    so its truncation is exact; the backward of a dropped / DropPath-scaled branch applies the same mask here."""
+    so its truncation is exact; the backward of a dropped / DropPath-scaled branch applies the same mask here.
+    colsum (C,): += column sums of y ([rows][C]) -- the bias gradient of the Linear whose output gradient y is"""
     y = torch.empty_like(x)
+    if colsum is not None and x.dim() == 2 and x.is_contiguous() and x.shape[1] % 4 == 0 and (rowscale is None or group_elems % x.shape[1] == 0):
+        _call("vptr_round_copy_colsum", _p(x), _p(y), x.shape[0], x.shape[1], int(do_round), _p(rowscale), int(group_elems) // x.shape[1],
+              int(drop_seed), float(drop_p), _p(colsum), _s())
+        return y
     _call("vptr_round_copy", _p(x), _p(y), x.numel(), int(do_round), _p(rowscale), int(group_elems), int(drop_seed), float(drop_p), _s())
+    if colsum is not None:
+        globals()["colsum"](y, colsum)
     return y
 
 

@@ -2,6 +2,8 @@
 
   * `mse_gdl_loss(pred, target)`  = MSELoss()(pred, target) + GDL(alpha=1)(target, pred)   (reference model/criterion.py:105-204,
     cal_lossT train_NAR.py:33-36 / train_FAR.py:32-34): one pass for the value, one pass for d/d(pred);
+  * `bipatch_nce_normalized(gt_f, pred_f)` = BiPatchNCE(...)(F.normalize(gt_f), F.normalize(pred_f)) (criterion.py:206-259,
+    train_NAR.py:36): one forward and one backward kernel, one CTA per frame;
   * `FusedAdamW` -- a torch.optim.AdamW (same constructor, param_groups, state / state_dict layout, so the reference's checkpoint
     code `optimizer_T.state_dict()` / `load_state_dict`, utils/train_summary.py:22-31,139, keeps working) whose `step()` is ONE
     multi-tensor launch, optionally with the `clip_grad_norm_` coefficient (train_NAR.py:85) folded in so clipping costs no pass;
@@ -47,6 +49,43 @@ def mse_gdl_loss(pred, target, parts=False):
     """MSE + GDL(alpha=1), both un-weighted means as cal_lossT uses them.  parts=True also returns the (3,) tensor {total, mse, gdl}."""
     loss, loss3 = _MseGdl.apply(pred, target)
     return (loss, loss3) if parts else loss
+
+
+# ----------------------------------------------------------------------------------------------------- BiPatchNCE
+class _BiPatchNCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gt_rows, pred_rows, temperature):
+        F_, L, C = gt_rows.shape
+        ops._chk(gt_rows, "gt features"); ops._chk(pred_rows, "predicted features")
+        g, p = gt_rows.contiguous(), pred_rows.contiguous()
+        S = torch.empty(F_ * 64 * 64, dtype=torch.float32, device=g.device)
+        stats = torch.empty(F_ * 256, dtype=torch.float32, device=g.device)
+        acc = torch.zeros(1, dtype=torch.float64, device=g.device)
+        loss = torch.empty(1, dtype=torch.float32, device=g.device)
+        _call("vptr_bipatch_nce_fwd", g.data_ptr(), p.data_ptr(), F_, L, C, float(temperature), S.data_ptr(), stats.data_ptr(), acc.data_ptr(),
+              loss.data_ptr(), ops._s())
+        ctx.save_for_backward(g, p, S, stats)
+        ctx.temperature = float(temperature)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        g, p, S, stats = ctx.saved_tensors
+        F_, L, C = g.shape
+        dl = dloss.contiguous().to(torch.float32)
+        dg, dp = torch.empty_like(g), torch.empty_like(p)
+        _call("vptr_bipatch_nce_bwd", g.data_ptr(), p.data_ptr(), S.data_ptr(), stats.data_ptr(), dl.data_ptr(), F_, L, C, ctx.temperature,
+              dg.data_ptr(), dp.data_ptr(), ops._s())
+        return dg, dp, None
+
+
+def bipatch_nce_normalized(gt_f, pred_f, temperature=1.0):
+    """BiPatchNCE(N, T, h, w, temperature)(F.normalize(gt_f, p=2, dim=2), F.normalize(pred_f, p=2, dim=2)) -- the contrastive term of
+    cal_lossT exactly as train_NAR.py:36 composes it -- with the channel normalisation, both score matrices, both cross-entropies
+    and the reference's stop-gradients in ONE forward and ONE backward kernel.  gt_f / pred_f: (N, T, C, h, w), h*w <= 64."""
+    N, T, C, h, w = gt_f.shape
+    rows = lambda t: t.permute(0, 1, 3, 4, 2).reshape(N * T, h * w, C)     # free when t is a channel-last view (as the projector emits)
+    return _BiPatchNCE.apply(rows(gt_f), rows(pred_f), temperature)
 
 
 # ----------------------------------------------------------------------------------------------------- multi-tensor tables

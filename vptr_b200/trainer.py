@@ -79,7 +79,11 @@ class Stage2Trainer:
             loss = self._pixel_loss(pred, future)
             if self.use_bpnce:
                 n, t, _, h, w = pf.shape
-                loss = loss + self.lam_pc * self._bpnce(n, t, h, w, pf.device)(F.normalize(gf, p=2.0, dim=2), F.normalize(pf, p=2.0, dim=2))
+                if self.fused_tail and h * w <= 64:
+                    from . import tail
+                    loss = loss + self.lam_pc * tail.bipatch_nce_normalized(gf, pf, 1.0)
+                else:
+                    loss = loss + self.lam_pc * self._bpnce(n, t, h, w, pf.device)(F.normalize(gf, p=2.0, dim=2), F.normalize(pf, p=2.0, dim=2))
         loss.backward()
         if self.reducer is not None:   # data-parallel gradient mean over NVLink: replaces DistributedDataParallel
             self.reducer.finish()
