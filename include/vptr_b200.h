@@ -225,6 +225,20 @@ int vptr_allreduce_grads(void* comm, float* flat, long long n, double* sqnorm_ou
  * 2 vptr_head_conv7x7_bwd (rows = F, ch = Ci, hw = H = W, mode = Co) */
 long long vptr_workspace_bytes(int op, long long rows, int ch, int hw, int mode);
 
+/* ---- stage-1 autoencoder training (train_AutoEncoder.py:44-86; model/ResNetAutoEncoder.py): train-mode BatchNorm2d and the
+ * gradients stage 2 never needs.  Convolutions run as vptr_im2col + vptr_gemm_tf32 (forward, weight gradient) and
+ * vptr_gemm_tf32 + vptr_col2im (input gradient). ------------------------------------------------------------------------- */
+int vptr_stem_conv7x7_raw(const float* x, const float* wpk, float* out, int F, int Ci, int H, int W, int Co, vptr_stream_t stream);
+/* z = act(BN(x; batch mean / rstd from vptr_bn_stats)) [+ res]; act 0 none, 1 ReLU, 2 ReLU after the residual add */
+int vptr_bn_act_fwd(const float* x, float* z, const float* res, const float* mean, const float* rstd, const float* gamma,
+                    const float* beta, long long rows, int ch, int act, int round_tf32, vptr_stream_t stream);
+int vptr_bn_act_bwd(const float* dz, const float* x, const float* z, const float* mean, const float* rstd, const float* gamma,
+                    float* g0, float* dx, float* dgamma, float* dbeta, long long rows, int ch, int act, float* ws, int round_tf32,
+                    vptr_stream_t stream);
+int vptr_col2im(const float* dcol, float* dx, int F, int H, int W, int C, int k, int stride, int pad, int pad_mode, vptr_stream_t stream);
+int vptr_stem_wgrad(const float* x, const float* dy, float* dw, int F, int Ci, int H, int W, vptr_stream_t stream);
+int vptr_act_bwd(const float* dout, const float* out, float* dpre, long long n, int act, vptr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

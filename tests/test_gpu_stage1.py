@@ -1,0 +1,135 @@
+"""GPU: stage-1 autoencoder training (reference train_AutoEncoder.py:44-86): VPTREnc / VPTRDec in TRAIN mode --
+BatchNorm2d with batch statistics and running-stat updates, every weight gradient -- against the very same nn.Sequential stacks run
+by PyTorch (the holder modules ARE the reference's layer stack, model/ResNetAutoEncoder.py:26-48,70-98, so `.model(x)` is the
+reference computation), and the reference's unmodified train_AutoEncoder.single_iter driving the drop-in modules."""
+import copy
+import math
+import os
+
+import pytest
+import torch
+
+from helpers import probe, rel_l2
+
+import ref_loader as RL
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_stack(seq, x):
+    """the reference computation of a ResnetEncoder / ResnetDecoder layer stack by PyTorch: our ResnetBlock holders carry the
+    reference's conv_block but no forward of their own (reference :153-158: out = x + conv_block(x))"""
+    for m in seq:
+        x = x + m.conv_block(x) if hasattr(m, "conv_block") else m(x)
+    return x
+
+
+def _pair(img_channels, feat_dim, padding_type, out_layer):
+    from vptr_b200.model import VPTRDec, VPTREnc, init_weights
+    import contextlib, io
+    torch.manual_seed(4)
+    enc = VPTREnc(img_channels, feat_dim=feat_dim, n_downsampling=3, padding_type=padding_type).cuda()
+    dec = VPTRDec(img_channels, feat_dim=feat_dim, n_downsampling=3, out_layer=out_layer, padding_type=padding_type).cuda()
+    with contextlib.redirect_stdout(io.StringIO()):
+        init_weights(enc)
+        init_weights(dec)
+    with torch.no_grad():                      # BatchNorm affine away from (1, 0) so their gradients matter
+        for m in list(enc.modules()) + list(dec.modules()):
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    return enc, dec
+
+
+@pytest.mark.parametrize("img_channels,feat_dim,padding_type,out_layer", [(1, 64, "reflect", "Sigmoid"), (3, 48, "zero", "Tanh")])
+def test_train_mode_autoencoder_matches_pytorch_stack(img_channels, feat_dim, padding_type, out_layer):
+    from vptr_b200 import engine
+    enc, dec = _pair(img_channels, feat_dim, padding_type, out_layer)
+    enc_t, dec_t = copy.deepcopy(enc), copy.deepcopy(dec)
+    x = torch.rand(2, 3, img_channels, 64, 64, generator=torch.Generator().manual_seed(1)).cuda()
+    pr = probe((2, 3, img_channels, 64, 64), 3).cuda()
+    # --- PyTorch on the same layer stacks (fp32 cuDNN: allow_tf32 is off in conftest)
+    enc_t.train(); dec_t.train()
+    rec_t = _torch_stack(dec_t.decoder.model, _torch_stack(enc_t.encoder.model, x.flatten(0, 1))).view(2, 3, img_channels, 64, 64)
+    ((rec_t * pr).sum() + rec_t.square().sum()).backward()
+
+    def run(mode_ctx, tol_out, tol_grad):
+        e, d = copy.deepcopy(enc), copy.deepcopy(dec)
+        e.train(); d.train()
+        with mode_ctx:
+            feat = e(x)
+            rec = d(feat)
+            ((rec * pr).sum() + rec.square().sum()).backward()
+        assert tuple(rec.shape) == tuple(rec_t.shape)
+        assert rel_l2(rec, rec_t) < tol_out
+        gmax = max(float(p.grad.norm()) for p in list(enc_t.parameters()) + list(dec_t.parameters()))
+        worst, errs = ("", 0.0), []
+        for (k, p), (_, pt) in zip(list(e.named_parameters()) + list(d.named_parameters()),
+                                   list(enc_t.named_parameters()) + list(dec_t.named_parameters())):
+            assert p.grad is not None, k
+            err = float((p.grad - pt.grad).norm()) / max(float(pt.grad.norm()), 1e-3 * gmax)
+            errs.append(err)
+            if err > worst[1]:
+                worst = (k, err)
+        errs.sort()
+        # the chain has 20 ReLUs behind batch-statistics BatchNorms: a few mask flips and the 1/sigma amplification put single
+        # deep-encoder tensors well above the median, so the gate is on the median and (loosely) on the worst tensor
+        assert errs[len(errs) // 2] < tol_grad and worst[1] < 12 * tol_grad, (errs[len(errs) // 2], worst)
+        for (k, b), (_, bt) in zip(list(e.named_buffers()) + list(d.named_buffers()), list(enc_t.named_buffers()) + list(dec_t.named_buffers())):
+            if k.endswith("num_batches_tracked"):
+                assert int(b) == int(bt) == 1, k
+            else:
+                assert rel_l2(b, bt) < 10 * tol_out, k           # running_mean / running_var updated like nn.BatchNorm2d
+        return worst
+
+    import contextlib
+    w_exact = run(engine.exact_fp32(), 2e-5, 3e-3)                # schedule at fp32 accuracy (FFMA GEMM); ReLU-mask flips set the floor
+    w_tf32 = run(contextlib.nullcontext(), 2e-3, 2e-2)            # product path: tf32 operands through 21 convs with batch-stat BatchNorm
+    print("worst gradient: fp32 schedule %s %.2e, tf32 %s %.2e" % (w_exact + w_tf32))
+
+
+def test_eval_mode_still_uses_running_statistics_after_training_steps():
+    enc, dec = _pair(1, 64, "reflect", "Sigmoid")
+    x = torch.rand(1, 2, 1, 32, 32).cuda()
+    enc.train(); dec.train()
+    with torch.no_grad():
+        dec(enc(x))                                               # updates running stats, no tape
+    enc.eval(); dec.eval()
+    with torch.no_grad():
+        a = dec(enc(x))
+        b = _torch_stack(dec.decoder.model, _torch_stack(enc.encoder.model, x.flatten(0, 1))).view_as(a)
+    assert rel_l2(a, b) < 2e-3
+
+
+@pytest.mark.skipif(RL.ref_root() is None, reason="reference tree not staged (oracle/make_ref.sh)")
+def test_reference_train_autoencoder_single_iter_runs_on_dropin_modules():
+    dev = torch.device("cuda:0")
+    try:
+        ta, model = RL.load_train_script("train_AutoEncoder", dropin=True)
+        assert ta.VPTREnc is model.VPTREnc and os.path.abspath(ta.__file__).startswith(os.path.abspath(RL.ref_root()))
+        torch.manual_seed(2021)
+        enc = model.VPTREnc(1, feat_dim=528, n_downsampling=3).to(dev)
+        dec = model.VPTRDec(1, feat_dim=528, n_downsampling=3, out_layer="Tanh").to(dev)
+        disc = model.VPTRDisc(1, ndf=64, n_layers=3, norm_layer=torch.nn.BatchNorm2d).to(dev)
+        for m in (disc, enc, dec):
+            model.init_weights(m)
+        opt_G = torch.optim.Adam(params=list(enc.parameters()) + list(dec.parameters()), lr=2e-4, betas=(0.5, 0.999))   # train_AutoEncoder.py:138
+        opt_D = torch.optim.Adam(params=disc.parameters(), lr=2e-4, betas=(0.5, 0.999))
+        for k, v in dict(gan_loss=model.GANLoss("vanilla", target_real_label=1.0, target_fake_label=0.0).to(dev), mse_loss=model.MSELoss(),
+                         gdl_loss=model.GDL(alpha=1), lam_gan=0.01).items():
+            setattr(ta, k, v)
+        before = {k: v.detach().clone() for k, v in list(enc.named_parameters()) + list(dec.named_parameters())}
+        g = torch.Generator().manual_seed(3)
+        sample = (torch.rand(2, 2, 1, 64, 64, generator=g) * 2 - 1, torch.rand(2, 2, 1, 64, 64, generator=g) * 2 - 1)
+        losses = []
+        for _ in range(2):
+            d = ta.single_iter(enc, dec, disc, opt_G, opt_D, sample, dev, train_flag=True)
+            assert all(math.isfinite(v) for v in d.values()), d
+            losses.append(d["AE_total"])
+        after = dict(list(enc.named_parameters()) + list(dec.named_parameters()))
+        moved = sum(int(not torch.equal(before[k], after[k].detach())) for k in before)
+        assert moved == len(before), (moved, len(before))
+        d = ta.single_iter(enc, dec, disc, opt_G, opt_D, sample, dev, train_flag=False)
+        assert math.isfinite(d["AE_total"])
+    finally:
+        RL.unload()

@@ -70,6 +70,12 @@ _SIGS = {
     "vptr_bipatch_nce_fwd": ([P, P, I, I, I, F, P, P, P, P, P], I),
     "vptr_bipatch_nce_bwd": ([P, P, P, P, P, I, I, I, F, P, P, P], I),
     "vptr_adamw_multi": ([P, I, L, I, F, F, F, F, F, L, P, F, P], I),
+    "vptr_stem_conv7x7_raw": ([P, P, P, I, I, I, I, I, P], I),
+    "vptr_bn_act_fwd": ([P, P, P, P, P, P, P, L, I, I, I, P], I),
+    "vptr_bn_act_bwd": ([P, P, P, P, P, P, P, P, P, P, L, I, I, P, I, P], I),
+    "vptr_col2im": ([P, P, I, I, I, I, I, I, I, I, P], I),
+    "vptr_stem_wgrad": ([P, P, P, I, I, I, I, P], I),
+    "vptr_act_bwd": ([P, P, P, L, I, P], I),
     "vptr_nccl_unique_id": ([P], I),
     "vptr_nccl_comm_init": ([P, I, I, P], I),
     "vptr_nccl_comm_destroy": ([P], I),

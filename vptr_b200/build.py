@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvptr_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "norm.cu", "attn.cu", "attn_tcgen05.cu", "dwconv.cu", "elementwise.cu", "conv.cu", "tail.cu", "collective.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "gemm_simt.cu", "norm.cu", "attn.cu", "attn_tcgen05.cu", "dwconv.cu", "elementwise.cu", "conv.cu", "tail.cu", "collective.cu", "bn_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

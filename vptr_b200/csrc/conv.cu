@@ -145,7 +145,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
 // 7x7 stem: x NCHW [F][Ci][H][W] (reflect pad 3) -> out NHWC [F][H][W][64] = relu(conv + shift); wpk [(kh,kw,ci)][64] (scale folded)
 constexpr int STEM_CO = 64;
 __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
-                                                           const float* __restrict__ shift, float* __restrict__ out, int Ci, int H, int W) {
+                                                           const float* __restrict__ shift, float* __restrict__ out, int Ci, int H, int W,
+                                                           int relu) {
     extern __shared__ float sm[];
     float* sw = sm;                          // [49*Ci][64]
     float* sp = sm + 49 * Ci * STEM_CO;      // [Ci][22][22]
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restri
     const int oh = oh0 + ty, ow = ow0 + tx;
     float acc[STEM_CO];
 #pragma unroll
-    for (int c = 0; c < STEM_CO; ++c) acc[c] = shift[c];
+    for (int c = 0; c < STEM_CO; ++c) acc[c] = shift ? shift[c] : 0.f;
     for (int kh = 0; kh < 7; ++kh)
         for (int kw = 0; kw < 7; ++kw)
             for (int ci = 0; ci < Ci; ++ci) {
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(256) stem_conv7x7_kernel(const float* __restri
         float4* o = reinterpret_cast<float4*>(out + (((long long)f * H + oh) * W + ow) * STEM_CO);
 #pragma unroll
         for (int c4 = 0; c4 < STEM_CO / 4; ++c4)
-            o[c4] = make_float4(fmaxf(acc[c4 * 4], 0.f), fmaxf(acc[c4 * 4 + 1], 0.f), fmaxf(acc[c4 * 4 + 2], 0.f), fmaxf(acc[c4 * 4 + 3], 0.f));
+            o[c4] = relu ? make_float4(fmaxf(acc[c4 * 4], 0.f), fmaxf(acc[c4 * 4 + 1], 0.f), fmaxf(acc[c4 * 4 + 2], 0.f), fmaxf(acc[c4 * 4 + 3], 0.f))
+                         : make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
     }
 }
 
@@ -457,7 +459,17 @@ extern "C" int vptr_stem_conv7x7(const float* x, const float* wpk, const float* 
     size_t smem = sizeof(float) * ((size_t)49 * Ci * STEM_CO + (size_t)Ci * 484);
     if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(vptr_cdiv(W, 16), vptr_cdiv(H, 16), F);
-    stem_conv7x7_kernel<<<grid, 256, smem, stream>>>(x, wpk, shift, out, Ci, H, W);
+    stem_conv7x7_kernel<<<grid, 256, smem, stream>>>(x, wpk, shift, out, Ci, H, W, 1);
+    return vptr_check_launch("stem_conv7x7_kernel");
+}
+// the same convolution without the folded BatchNorm shift and ReLU (train-mode BatchNorm follows as its own kernels)
+extern "C" int vptr_stem_conv7x7_raw(const float* x, const float* wpk, float* out, int F, int Ci, int H, int W, int Co, cudaStream_t stream) {
+    VPTR_REQUIRE(Co == STEM_CO, VPTR_ERR_UNSUPPORTED, "vptr_stem_conv7x7_raw: Co=%d (only %d, the reference's fixed ngf)", Co, STEM_CO);
+    VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci <= 4 && H > 3 && W > 3, VPTR_ERR_SHAPE, "vptr_stem_conv7x7_raw: F=%d Ci=%d H=%d W=%d", F, Ci, H, W);
+    size_t smem = sizeof(float) * ((size_t)49 * Ci * STEM_CO + (size_t)Ci * 484);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid(vptr_cdiv(W, 16), vptr_cdiv(H, 16), F);
+    stem_conv7x7_kernel<<<grid, 256, smem, stream>>>(x, wpk, nullptr, out, Ci, H, W, 0);
     return vptr_check_launch("stem_conv7x7_kernel");
 }
 

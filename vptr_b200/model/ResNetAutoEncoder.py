@@ -251,3 +251,167 @@ def decoder_backward(dec, saved_all, dout):
         col, _, _ = ops.im2col(d, F_, 2 * h_in, 2 * w_in, Cout, 3, 2, 1, 0, mask=y, round_tf32=E.ROUND_TF32)
         d = ops.gemm(col, wpk, b_mn=True)                                             # (F*h*w, Cin)
     return d
+
+
+# =============================================================================================== stage-1 training (train-mode BatchNorm)
+# train_AutoEncoder.py:44-86 trains VPTREnc / VPTRDec with BatchNorm2d in TRAIN mode (batch statistics, running-stat updates) and needs
+# every weight gradient.  Same kernels as above for the contractions -- im2col + tcgen05 GEMM (forward and weight
+# gradient), GEMM + col2im scatter (input gradient), ConvTranspose2d as GEMM + gather -- with vptr_bn_stats / vptr_bn_act_{fwd,bwd}
+# between them instead of the folded eval-mode scale / shift.  Nothing is cached: the weights change every step.
+def _bn_train_fwd(y, bn, act, res=None):
+    mean, rstd = ops.bn_stats(y, bn.running_mean, bn.running_var, momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps)
+    bn.num_batches_tracked.add_(1)
+    z = ops.bn_act_fwd(y, mean, rstd, bn.weight.data, bn.bias.data, act, res)
+    return z, mean, rstd
+
+
+def _acc(grads, p, g):
+    grads[p] = g if p not in grads else grads[p] + g
+
+
+def _conv_train_fwd(x, F_, H, W, conv, bn, stride, pad_mode, act, res, tape):
+    Cout, Cin = conv.weight.shape[:2]
+    col, Ho, Wo = ops.im2col(x, F_, H, W, Cin, 3, stride, 1, pad_mode, round_tf32=E.ROUND_TF32)
+    wpk = E._rc(ops.pack_conv_weight(conv.weight.data, None, 0).view(Cout, 9 * Cin))
+    y = ops.gemm(col, wpk)
+    del col
+    z, mean, rstd = _bn_train_fwd(y, bn, act, res)
+    if tape is not None:
+        tape.append(dict(kind="conv", x=x, y=y, z=z, mean=mean, rstd=rstd, wpk=wpk, conv=conv, bn=bn, act=act, has_res=res is not None,
+                         geom=(F_, H, W, Cin, Cout, stride, pad_mode)))
+    return z, Ho, Wo
+
+
+def _conv_train_bwd(s, dz, grads):
+    """-> (dx, gradient of the residual operand or None)"""
+    F_, H, W, Cin, Cout, stride, pad_mode = s["geom"]
+    conv, bn = s["conv"], s["bn"]
+    dg, db = torch.zeros_like(bn.weight.data), torch.zeros_like(bn.bias.data)
+    g0, dy = ops.bn_act_bwd(dz, s["y"], s["z"], s["mean"], s["rstd"], bn.weight.data, dg, db, s["act"], round_tf32=E.ROUND_TF32)
+    _acc(grads, bn.weight, dg)
+    _acc(grads, bn.bias, db)
+    col, _, _ = ops.im2col(s["x"], F_, H, W, Cin, 3, stride, 1, pad_mode, round_tf32=E.ROUND_TF32)     # recomputed: 9x the activation is not kept
+    dW = torch.zeros(Cout, 9 * Cin, dtype=torch.float32, device=dy.device)
+    ops.gemm(dy, col, out=dW, a_mn=True, b_mn=True, accumulate=True)
+    del col
+    _acc(grads, conv.weight, dW.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).contiguous())
+    dcol = ops.gemm(dy, s["wpk"], b_mn=True)
+    dx = ops.col2im(dcol, F_, H, W, Cin, 3, stride, 1, pad_mode)
+    dres = None
+    if s["has_res"]:
+        dres = g0 if s["act"] == 2 else dz
+    return dx, dres
+
+
+def encoder_forward_train(enc, x, tape):
+    """train-mode forward of ResnetEncoder (reference :26-51); tape: list that receives what the backward needs, or None"""
+    x = x.contiguous()
+    F_, Ci, H, W = x.shape
+    m = enc.model
+    conv, bn = m[1], m[2]
+    wpk = ops.pack_conv_weight(conv.weight.data, None, 2)                       # [(kh,kw,ci)][64]
+    y = ops.stem_conv7x7_raw(x, wpk, F_, Ci, H, W, conv.weight.shape[0])
+    h, mean, rstd = _bn_train_fwd(y, bn, 1)
+    if tape is not None:
+        tape.append(dict(kind="stem", x=x, y=y, z=h, mean=mean, rstd=rstd, conv=conv, bn=bn, geom=(F_, Ci, H, W)))
+    idx = 4
+    for _ in range(enc.n_downsampling):
+        h, H, W = _conv_train_fwd(h, F_, H, W, m[idx], m[idx + 1], 2, 0, 1, None, tape)
+        idx += 3
+    pad_mode = ops.PAD_MODES[enc.padding_type]
+    for b in range(9):
+        c1, n1, c2, n2 = m[idx + b].convs()
+        if tape is not None:
+            tape.append(dict(kind="block_in"))
+        r, _, _ = _conv_train_fwd(h, F_, H, W, c1, n1, 1, pad_mode, 1, None, tape)
+        h, _, _ = _conv_train_fwd(r, F_, H, W, c2, n2, 1, pad_mode, 2 if b == 8 else 0, h, tape)
+    return h, H, W
+
+
+def encoder_backward_train(tape, dfeat):
+    """-> {parameter: gradient}"""
+    grads = {}
+    d = dfeat
+    pending = None                                        # gradient of the current block's residual operand
+    while tape:
+        s = tape.pop()
+        if s["kind"] == "conv":
+            d, dres = _conv_train_bwd(s, d, grads)
+            if dres is not None:
+                pending = dres
+        elif s["kind"] == "block_in":
+            d = ops.axpby(d, pending)                     # block input feeds conv1 and the residual add
+            pending = None
+        else:                                             # stem: BatchNorm backward + weight gradient (no input gradient: x is the image)
+            F_, Ci, H, W = s["geom"]
+            bn, conv = s["bn"], s["conv"]
+            dg, db = torch.zeros_like(bn.weight.data), torch.zeros_like(bn.bias.data)
+            _, dy = ops.bn_act_bwd(d, s["y"], s["z"], s["mean"], s["rstd"], bn.weight.data, dg, db, 1)
+            _acc(grads, bn.weight, dg)
+            _acc(grads, bn.bias, db)
+            dw = ops.stem_wgrad(s["x"], dy, F_, Ci, H, W)                        # [(kh,kw,ci)][co]
+            _acc(grads, conv.weight, dw.view(7, 7, Ci, -1).permute(3, 2, 0, 1).contiguous())
+    return grads
+
+
+def decoder_forward_train(dec, feat, F_, H, W, tape):
+    m = dec.model
+    h = feat
+    idx = 0
+    for _ in range(dec.n_downsampling):
+        convT, bn = m[idx], m[idx + 1]
+        Cin, Cout = convT.weight.shape[:2]
+        wpk = E._rc(ops.pack_conv_weight(convT.weight.data, None, 1)).view(9 * Cout, Cin)
+        xr = E._rc(h)
+        col = ops.gemm(xr, wpk)
+        y = ops.convT_gather(col, torch.zeros(Cout, dtype=torch.float32, device=h.device), F_, H, W, Cout, relu=False)
+        del col
+        z, mean, rstd = _bn_train_fwd(y, bn, 1)
+        if tape is not None:
+            tape.append(dict(kind="up", x=xr, y=y, z=z, mean=mean, rstd=rstd, wpk=wpk, convT=convT, bn=bn, geom=(F_, H, W, Cin, Cout)))
+        h, H, W = z, 2 * H, 2 * W
+        idx += 3
+    head = m[idx + 1]
+    Co, Ci = head.weight.shape[:2]
+    act = _ACT[dec.out_layer]
+    out = ops.head_conv7x7_fwd(h, ops.pack_conv_weight(head.weight.data, None, 3), head.bias.data, F_, Ci, Co, H, W, act)
+    if tape is not None:
+        tape.append(dict(kind="head", x=h, out=out, head=head, act=act, geom=(F_, H, W, Ci, Co)))
+    return out
+
+
+def decoder_backward_train(tape, dout):
+    """-> (gradient of the input features (F*h*w, C), {parameter: gradient})"""
+    grads = {}
+    s = tape.pop()
+    F_, H, W, Ci, Co = s["geom"]
+    head, out, act, x = s["head"], s["out"], s["act"], s["x"]
+    dout = dout.contiguous()
+    d = ops.head_conv7x7_bwd(dout, out, head.weight.data, F_, Ci, Co, H, W, act)
+    dpre = ops.act_bwd(dout, out, act)                                            # (F, Co, H, W)
+    dpre_cl = dpre.view(F_ * H * W, 1) if Co == 1 else ops.transpose(dpre, F_, Co, H * W).view(F_ * H * W, Co)
+    gb = torch.zeros(Co, dtype=torch.float32, device=d.device)
+    ops.colsum(dpre_cl, gb)
+    _acc(grads, head.bias, gb)
+    dW = torch.zeros(Co, 49 * Ci, dtype=torch.float32, device=d.device)
+    fpc = max(1, (64 << 20) // (H * W * 49 * Ci))                                 # frames per chunk: the 49x im2col stays <= 256 MB
+    for f0 in range(0, F_, fpc):
+        f1 = min(F_, f0 + fpc)
+        col, _, _ = ops.im2col(x[f0 * H * W:f1 * H * W], f1 - f0, H, W, Ci, 7, 1, 3, 1, round_tf32=False)
+        ops.gemm(dpre_cl[f0 * H * W:f1 * H * W], col, out=dW, a_mn=True, b_mn=True, accumulate=True)
+        del col
+    _acc(grads, head.weight, dW.view(Co, 7, 7, Ci).permute(0, 3, 1, 2).contiguous())
+    while tape:
+        s = tape.pop()
+        F_, H, W, Cin, Cout = s["geom"]
+        bn, convT = s["bn"], s["convT"]
+        dg, db = torch.zeros_like(bn.weight.data), torch.zeros_like(bn.bias.data)
+        _, dy = ops.bn_act_bwd(d, s["y"], s["z"], s["mean"], s["rstd"], bn.weight.data, dg, db, 1, round_tf32=E.ROUND_TF32)
+        _acc(grads, bn.weight, dg)
+        _acc(grads, bn.bias, db)
+        dcol, _, _ = ops.im2col(dy, F_, 2 * H, 2 * W, Cout, 3, 2, 1, 0, round_tf32=E.ROUND_TF32)       # adjoint of the output gather
+        dW = torch.zeros(9 * Cout, Cin, dtype=torch.float32, device=d.device)
+        ops.gemm(dcol, s["x"], out=dW, a_mn=True, b_mn=True, accumulate=True)
+        _acc(grads, convT.weight, dW.view(3, 3, Cout, Cin).permute(3, 2, 0, 1).contiguous())
+        d = ops.gemm(dcol, s["wpk"], b_mn=True)
+    return d, grads

@@ -12,7 +12,8 @@ import torch.nn as nn
 from .. import engine as E
 from .. import ops
 from ..position_encoding import pos_1d, pos_2d, pos_3d
-from .ResNetAutoEncoder import ResnetDecoder, ResnetEncoder, decoder_backward, decoder_forward, encoder_forward
+from .ResNetAutoEncoder import (ResnetDecoder, ResnetEncoder, decoder_backward, decoder_backward_train, decoder_forward,
+                                decoder_forward_train, encoder_backward_train, encoder_forward, encoder_forward_train)
 
 
 # ===================================================================================================== ResNet wrappers
@@ -25,12 +26,16 @@ class VPTREnc(nn.Module):
     def forward(self, x):
         """x (N, T, img_channels, H, W) -> (N, T, feat_dim, H/2^n, W/2^n).  Forward only (stage 2 calls it under
         no_grad with BatchNorm in eval mode, train_NAR.py:54-56,190)."""
-        if self.training:
-            raise NotImplementedError("vptr_b200.VPTREnc: train-mode BatchNorm (stage-1 autoencoder training) is not on the "
-                                      "stage-2 hot path; call .eval() as train_NAR.py:190 does")
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise NotImplementedError("vptr_b200.VPTREnc is forward-only (the reference runs it under torch.no_grad())")
         N, T = x.shape[:2]
+        if self.training:       # stage-1 autoencoder training (train_AutoEncoder.py:53-57): batch statistics + every weight gradient
+            _check_input(x, "VPTREnc")
+            params = list(self.encoder.parameters())
+            record = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+            feat = _EncTrainFunction.apply(self.encoder, x.flatten(0, 1), record, *params)
+            H, W = x.shape[-2] >> self.encoder.n_downsampling, x.shape[-1] >> self.encoder.n_downsampling
+            return feat.view(N, T, H, W, self.feat_dim).permute(0, 1, 4, 2, 3)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("vptr_b200.VPTREnc in eval mode is forward-only (the reference runs it under torch.no_grad())")
         feat, H, W = encoder_forward(self.encoder, x.flatten(0, 1))          # (F*H*W, C) channel-last
         return feat.view(N, T, H, W, self.feat_dim).permute(0, 1, 4, 2, 3)   # same values/shape as the reference's NCHW tensor
 
@@ -52,6 +57,39 @@ class _DecFunction(torch.autograd.Function):
         return None, dfeat.view(N, T, H, W, C).permute(0, 1, 4, 2, 3)
 
 
+class _EncTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, frames, record, *params):
+        tape = [] if record else None
+        feat, _, _ = encoder_forward_train(enc, frames, tape)
+        ctx.tape, ctx.params = tape, params
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        grads = encoder_backward_train(ctx.tape, dfeat.contiguous())
+        ctx.tape = None
+        return (None, None, None) + tuple(grads.get(p) for p in ctx.params)
+
+
+class _DecTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, feat, record, *params):
+        N, T, C, H, W = feat.shape
+        feat_cl = _channel_last(feat.flatten(0, 1)).view(N * T * H * W, C)
+        tape = [] if record else None
+        out = decoder_forward_train(dec, feat_cl, N * T, H, W, tape)
+        ctx.tape, ctx.params, ctx.shape = tape, params, (N, T, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, T, C, H, W = ctx.shape
+        dfeat, grads = decoder_backward_train(ctx.tape, dout)
+        ctx.tape = None
+        return (None, dfeat.view(N, T, H, W, C).permute(0, 1, 4, 2, 3), None) + tuple(grads.get(p) for p in ctx.params)
+
+
 class VPTRDec(nn.Module):
     def __init__(self, img_channels, feat_dim=528, n_downsampling=3, out_layer='Tanh', padding_type='reflect'):
         super().__init__()
@@ -61,12 +99,14 @@ class VPTRDec(nn.Module):
     def forward(self, feat):
         """feat (N, T, feat_dim, h, w) -> (N, T, img_channels, H, W).  Differentiable w.r.t. feat; the decoder's own
         weight gradients (computed but never consumed by the reference) are not produced."""
-        if self.training:
-            raise NotImplementedError("vptr_b200.VPTRDec: train-mode BatchNorm (stage-1 autoencoder training) is not on the "
-                                      "stage-2 hot path; call .eval() as train_NAR.py:191 does")
         N, T, C, H, W = feat.shape
         if not feat.is_cuda or feat.dtype != torch.float32:
             raise RuntimeError("vptr_b200.VPTRDec: input must be a CUDA float32 tensor (got %s, %s); there is no CPU fallback" % (feat.device, feat.dtype))
+        if self.training:       # stage-1 autoencoder training: batch statistics, input AND weight gradients
+            params = list(self.decoder.parameters())
+            record = torch.is_grad_enabled() and (feat.requires_grad or any(p.requires_grad for p in params))
+            out = _DecTrainFunction.apply(self.decoder, feat, record, *params)
+            return out.view(N, T, *out.shape[1:])
         if torch.is_grad_enabled() and feat.requires_grad:
             out = _DecFunction.apply(self.decoder, feat)
         else:

@@ -479,3 +479,47 @@ def head_conv7x7_bwd(dout, out, w, F, Ci, Co, H, W, act):
     ws = torch.empty(F * (H + 6) * (W + 6) * Ci + 49 * Co * Ci, dtype=torch.float32, device=dout.device)
     _call("vptr_head_conv7x7_bwd", _p(dout), _p(out), _p(w), _p(dx), F, Ci, Co, H, W, act, _p(ws), _s())
     return dx
+
+
+# --------------------------------------------------------------------------------------------------- stage-1 (train-mode) ResNet pieces
+def stem_conv7x7_raw(x, wpk, F, Ci, H, W, Co):
+    out = torch.empty(F * H * W, Co, dtype=torch.float32, device=x.device)
+    _call("vptr_stem_conv7x7_raw", _p(x), _p(wpk), _p(out), F, Ci, H, W, Co, _s())
+    return out
+
+
+def bn_act_fwd(x, mean, rstd, gamma, beta, act, res=None, round_tf32=False):
+    """act 0: none, 1: ReLU, 2: ReLU after the residual add"""
+    rows, ch = x.shape
+    z = torch.empty_like(x)
+    _call("vptr_bn_act_fwd", _p(x), _p(z), _p(res), _p(mean), _p(rstd), _p(gamma), _p(beta), rows, ch, int(act), int(round_tf32), _s())
+    return z
+
+
+def bn_act_bwd(dz, x, z, mean, rstd, gamma, dgamma, dbeta, act, round_tf32=False):
+    """-> (g0 = activation-masked dz, dx); dgamma / dbeta are accumulated"""
+    rows, ch = x.shape
+    g0 = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    ws = torch.empty(2 * ch, dtype=torch.float32, device=x.device)
+    _call("vptr_bn_act_bwd", _p(_chk(dz)), _p(x), _p(z), _p(mean), _p(rstd), _p(gamma), _p(g0), _p(dx), _p(dgamma), _p(dbeta), rows, ch, int(act),
+          _p(ws), int(round_tf32), _s())
+    return g0, dx
+
+
+def col2im(dcol, F, H, W, C, k, stride, pad, pad_mode):
+    dx = torch.zeros(F * H * W, C, dtype=torch.float32, device=dcol.device)
+    _call("vptr_col2im", _p(dcol), _p(dx), F, H, W, C, k, stride, pad, pad_mode, _s())
+    return dx
+
+
+def stem_wgrad(x, dy, F, Ci, H, W):
+    dw = torch.zeros(49 * Ci, 64, dtype=torch.float32, device=x.device)
+    _call("vptr_stem_wgrad", _p(x), _p(dy), _p(dw), F, Ci, H, W, _s())
+    return dw
+
+
+def act_bwd(dout, out, act):
+    dpre = torch.empty_like(out)
+    _call("vptr_act_bwd", _p(dout), _p(out), _p(dpre), out.numel(), int(act), _s())
+    return dpre
