@@ -287,6 +287,18 @@ def run_cuda(args):
     n = args.batch or c["clips_per_gpu"]
     host_p, host_f = (t.pin_memory() for t in clip_tensors(torch, c, n, rank))
     dev_p, dev_f = host_p.to(device), host_f.to(device)
+    graphed, graph_note = None, "off (--no-graph)"
+    if not args.no_graph and not args.torch_tail and not args.ncu_step:
+        from vptr_b200.trainer import GraphedStep
+        try:     # the whole iteration as ONE CUDA graph launch (same kernels, same math; eager is the same code path un-captured)
+            graphed = GraphedStep(trainer, dev_p, dev_f, warmup=max(args.warmup, 3))
+            graph_note = "whole step captured once, replayed (vptr_b200.trainer.GraphedStep)"
+        except Exception as e:      # capture refused (driver / NCCL combination): run the identical step eagerly and say so
+            graphed, graph_note = None, "capture failed, eager launches: %s" % (str(e).splitlines()[0][:160])
+            trainer.graph_mode = False
+            trainer.tail.opt.device_step(False)
+            torch.cuda.synchronize()
+    run_step = (lambda p, f: graphed.step(p, f)) if graphed is not None else (lambda p, f: trainer.step(p, f))
     l2_flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
 
     def barrier():
@@ -300,11 +312,13 @@ def run_cuda(args):
         ev0.record()
         last = None
         for _ in range(k):
-            if from_host:
+            if from_host and graphed is None:
                 p, f = host_p.to(device, non_blocking=True), host_f.to(device, non_blocking=True)
+            elif from_host:
+                p, f = host_p, host_f       # the graphed step copies pinned host clips straight into its static device buffers
             else:
                 p, f = dev_p, dev_f
-            loss = trainer.step(p, f)
+            loss = run_step(p, f)
             if from_host:
                 last = loss.item()      # device -> host read of the step's result
         ev1.record()
@@ -317,7 +331,7 @@ def run_cuda(args):
         return ms / k, last
 
     for _ in range(args.warmup):
-        trainer.step(dev_p, dev_f)
+        run_step(dev_p, dev_f)
     l2_flush.zero_()
     if args.ncu_step:   # one step between cudaProfilerStart/Stop for `ncu --profile-from-start off`; prints nothing
         torch.cuda.synchronize()
@@ -332,18 +346,29 @@ def run_cuda(args):
     c0 = _lib.launch_count
     ms_dev, _ = timed(args.steps, from_host=False)
     launches = (_lib.launch_count - c0) // max(args.steps, 1)
+    if graphed is not None:      # replays launch no kernel from the host: count the C-ABI launches of one eager step of the same trainer
+        trainer.graph_mode = False
+        trainer.tail.opt.device_step(False)
+        c0 = _lib.launch_count
+        trainer.step(dev_p, dev_f)
+        launches = _lib.launch_count - c0
+        trainer.graph_mode = True
+        trainer.tail.opt.device_step(True)
     ms_e2e, loss_val = timed(args.steps, from_host=True)
     clocks = sampler.stop() if rank == 0 else None
     peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
 
     # --- dominant kernel (tcgen05 TF32 GEMM): CUDA-event time of every launch of one more step -> achieved TFLOP/s
+    if graphed is not None:
+        trainer.graph_mode = False
+        trainer.tail.opt.device_step(False)
     gemm_stats = profile_gemms(torch, ops, lambda: trainer.step(dev_p, dev_f))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    del trainer
+    del trainer, graphed, run_step
     torch.cuda.empty_cache()
     pk = peaks()
     tf32 = measure_tf32_peak(torch, ops)
@@ -361,7 +386,7 @@ def run_cuda(args):
                    "clips_per_gpu": n, "global_clips": n * world, "dropout": args.dropout, "parallelism": "dp%d" % world,
                    "l2": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2; L2 flushed once before timing",
                    "loss": "MSE + GDL" + (" + 0.1*BiPatchNCE" if c["bpnce"] else ""), "optimizer": "AdamW lr 1e-4, clip_grad_norm 1.0",
-                   "tail": "torch" if args.torch_tail else "fused (vptr_b200.tail)",
+                   "tail": "torch" if args.torch_tail else "fused (vptr_b200.tail)", "cuda_graph": graph_note,
                    "step_tflop_algorithmic": round(step_flop / 1e12, 2), "peak_mem_gib": round(peak_mem, 1),
                    "frames_per_clip": fpc},
         "e2e": {"value": round(e2e, 2), "unit": "frames/s", "ms_per_step": round(ms_e2e, 3),
@@ -446,6 +471,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's own)")
     ap.add_argument("--dropout", type=float, default=0.1, help="Transformer dropout / DropPath rate (reference default 0.1, train_NAR.py:199)")
     ap.add_argument("--torch-tail", action="store_true", help="losses / clip / AdamW as the reference's literal PyTorch sequence instead of the fused kernels")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels eagerly instead of replaying one captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (use under ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -239,6 +239,17 @@ int vptr_col2im(const float* dcol, float* dx, int F, int H, int W, int C, int k,
 int vptr_stem_wgrad(const float* x, const float* dy, float* dw, int F, int Ci, int H, int W, vptr_stream_t stream);
 int vptr_act_bwd(const float* dout, const float* out, float* dpre, long long n, int act, vptr_stream_t stream);
 
+/* ---- CUDA-graph support: a whole training step (every entry point above takes borrowed pointers and an explicit stream, allocates
+ * nothing and never synchronises) can be captured once and replayed.  Two pieces of state must change between replays: ---------- */
+/* the dropout / DropPath epoch mixed into every seed: reset >= 0 sets it (0 = eager default), reset < 0 increments it on the device */
+int vptr_rng_advance(long long reset, vptr_stream_t stream);
+/* a device-resident counter (the optimizer's step count): *ctr += inc */
+int vptr_counter_add(long long* ctr, long long inc, vptr_stream_t stream);
+/* vptr_adamw_multi with the update count read from device memory (step_dev) instead of the launch argument */
+int vptr_adamw_multi_dev(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, long long step, const long long* step_dev, const double* sqnorm, float max_norm,
+                         vptr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,9 @@ _SIGS = {
     "vptr_col2im": ([P, P, I, I, I, I, I, I, I, I, P], I),
     "vptr_stem_wgrad": ([P, P, P, I, I, I, I, P], I),
     "vptr_act_bwd": ([P, P, P, L, I, P], I),
+    "vptr_rng_advance": ([L, P], I),
+    "vptr_counter_add": ([P, L, P], I),
+    "vptr_adamw_multi_dev": ([P, I, L, I, F, F, F, F, F, L, P, P, F, P], I),
     "vptr_nccl_unique_id": ([P], I),
     "vptr_nccl_comm_init": ([P, I, I, P], I),
     "vptr_nccl_comm_destroy": ([P], I),

@@ -1435,3 +1435,5 @@ extern "C" int vptr_causal_mask(int T, unsigned char* mask, cudaStream_t stream)
     causal_mask_kernel<<<8, 256, 0, stream>>>(T, mask);
     return vptr_check_launch("causal_mask_kernel");
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(attn)

@@ -679,3 +679,5 @@ extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float*
     }
     return vptr_check_launch("attn_tc_fwd_kernel");
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(attn_tcgen05)

@@ -58,8 +58,19 @@ __device__ __forceinline__ float vptr_round_tf32(float x) {
 // Counter-based RNG for dropout / DropPath: ONE splitmix64 hash per group of four consecutive elements, 16 random bits per
 // element (the fused sites are float4-vectorised, and a hash per element made the 4-warp GEMM epilogue compute-bound).
 // Stateless, so the backward pass regenerates the very mask the forward used instead of storing it.
+// g_vptr_rng_epoch: a per-translation-unit device counter mixed into every seed.  It stays 0 in eager use (the host draws fresh seeds
+// per step); when a whole training step is replayed as a CUDA graph the kernel arguments -- seeds included -- are frozen, so the
+// graph starts with vptr_rng_advance(), which bumps the epoch of every translation unit on the device: each replay draws new masks,
+// and the forward and backward of one replay still agree because the epoch only changes between steps.
+static __device__ unsigned long long g_vptr_rng_epoch = 0;
+#define VPTR_RNG_EPOCH_ACCESSOR(tu)                                                   \
+    extern "C" unsigned long long* vptr_rng_epoch_addr_##tu(void) {                   \
+        unsigned long long* p = nullptr;                                              \
+        cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_vptr_rng_epoch);         \
+        return p;                                                                     \
+    }
 __device__ __forceinline__ unsigned long long vptr_hash4(unsigned long long seed, unsigned long long idx4) {
-    unsigned long long z = idx4 * 0x9E3779B97F4A7C15ULL + seed;
+    unsigned long long z = idx4 * 0x9E3779B97F4A7C15ULL + seed + g_vptr_rng_epoch * 0xD1B54A32D192ED03ULL;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);

@@ -397,3 +397,5 @@ extern "C" int vptr_gelu_bwd_colsum(const float* dy, const float* x, float* dx, 
     gelu_bwd_colsum_kernel<<<grid, tx, 0, stream>>>(dy, x, dx, rows, C / 4, round_tf32, drop_seed, drop_p, colsum, rpb);
     return vptr_check_launch("gelu_bwd_colsum_kernel");
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(elementwise)

@@ -91,3 +91,5 @@ extern "C" int vptr_gemm_simt(const float* A, long long lda, int a_mn, const flo
     gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
     return vptr_check_launch("gemm_simt_kernel");
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(gemm_simt)

@@ -1163,3 +1163,5 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     if (rc) return rc;
     return launch_gemm_2cta<176, 0, 0, 7>(ma, mb, p, stream);
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(gemm_tcgen05)

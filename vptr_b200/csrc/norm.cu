@@ -724,3 +724,5 @@ extern "C" int vptr_norm_act_bwd_colsum(const float* dy, const float* x, const f
     }
     return vptr_check_launch("vptr_norm_act_bwd");
 }
+
+VPTR_RNG_EPOCH_ACCESSOR(norm)

@@ -131,8 +131,13 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 // clip_grad_norm_ coefficient min(1, max_norm / (norm + 1e-6)) is applied to the gradient on the fly (one pass less).
 template <bool VEC>
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const long long* __restrict__ table, int n, long long total, AdamWArgs a,
-                                                          const double* __restrict__ sqnorm) {
+                                                          const double* __restrict__ sqnorm, const long long* __restrict__ step_dev) {
     const long long* ends = table + 4 * n;
+    if (step_dev) {      // step count lives on the device (captured graphs: the host-side value would be frozen into the launch)
+        const double st = (double)*step_dev;
+        a.bias_corr1 = (float)(1.0 - pow((double)a.beta1, st));
+        a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, st));
+    }
     float clip = 1.f;
     if (sqnorm) clip = fminf(1.f, a.max_norm / ((float)sqrt(*sqnorm) + 1e-6f));
     for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
@@ -338,16 +343,26 @@ extern "C" int vptr_sqnorm_multi(const long long* table, int n, long long total_
 }
 // One AdamW step over n tensors (table: device int64 [param][grad][exp_avg][exp_avg_sq][ends], n entries each).
 // step >= 1 is the update count AFTER this step (bias corrections 1 - beta^step).  sqnorm != NULL: fused clip_grad_norm_(max_norm).
+extern "C" int vptr_adamw_multi_dev(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
+                                    float weight_decay, long long step, const long long* step_dev, const double* sqnorm, float max_norm,
+                                    cudaStream_t stream);
 extern "C" int vptr_adamw_multi(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
                                 float weight_decay, long long step, const double* sqnorm, float max_norm, cudaStream_t stream) {
+    return vptr_adamw_multi_dev(table, n, total_units, vec, lr, beta1, beta2, eps, weight_decay, step, nullptr, sqnorm, max_norm, stream);
+}
+// step_dev != NULL: the update count (AFTER this step) is read from device memory instead of `step`
+extern "C" int vptr_adamw_multi_dev(const long long* table, int n, long long total_units, int vec, float lr, float beta1, float beta2, float eps,
+                                    float weight_decay, long long step, const long long* step_dev, const double* sqnorm, float max_norm,
+                                    cudaStream_t stream) {
     if (n <= 0 || total_units <= 0) return VPTR_OK;
-    VPTR_REQUIRE(step >= 1, VPTR_ERR_SHAPE, "vptr_adamw_multi: step=%lld must be >= 1", step);
+    VPTR_REQUIRE(step >= 1 || step_dev != nullptr, VPTR_ERR_SHAPE, "vptr_adamw_multi: step=%lld must be >= 1", step);
+    if (step < 1) step = 1;
     AdamWArgs a;
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
     a.bias_corr1 = (float)(1.0 - pow((double)beta1, (double)step));
     a.bias_corr2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-    if (vec) adamw_multi_kernel<true><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm);
-    else adamw_multi_kernel<false><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm);
+    if (vec) adamw_multi_kernel<true><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm, step_dev);
+    else adamw_multi_kernel<false><<<grid_for(total_units), 256, 0, stream>>>(table, n, total_units, a, sqnorm, step_dev);
     return vptr_check_launch("adamw_multi_kernel");
 }
 

@@ -193,10 +193,21 @@ class GradReducer:
                     rest.append(p)
         else:
             rest = self.params
-        allreduce_mean_grads(rest, self.world)
-        self.rest = rest
         if self.native is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
-            if self.done:
-                self.sqnorm = self.sq
+            # the remainder (frame queries, final norms, gradients outside the flat buffer: a few MB) goes through the library's
+            # communicator too, packed into one temporary -- no torch collective inside the step, so the step stays graph-capturable
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.side)
+            gs = [p.grad for p in rest if p.grad is not None]
+            if gs:
+                flat = torch.cat([g.reshape(-1) for g in gs])
+                self.native.allreduce_mean_(flat, self.sq, cur)
+                off = 0
+                for g in gs:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+            self.sqnorm, self.rest = self.sq, []
+        else:
+            allreduce_mean_grads(rest, self.world)
+            self.rest = rest
         self.works, self.done = [], []

@@ -147,6 +147,19 @@ class FusedAdamW(torch.optim.AdamW):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, foreach=False, fused=False)
         self._tables = {}
+        self._dev_step = False      # True: the update count lives in device memory (CUDA-graph replay; see device_step())
+        self._ctrs = {}
+
+    def device_step(self, on=True):
+        """keep the step count on the device (vptr_counter_add + vptr_adamw_multi_dev) so that a captured graph of step() stays correct
+        when replayed; call note_replayed() after each replay to keep the host-side state['step'] (checkpoints) in sync"""
+        self._dev_step = on
+        self._ctrs = {}
+
+    def note_replayed(self, n=1):
+        for st in self.state.values():
+            if "step" in st:
+                st["step"] += n
 
     @torch.no_grad()
     def step(self, closure=None, grad_sqnorm=None, max_norm=0.0):
@@ -186,8 +199,15 @@ class FusedAdamW(torch.optim.AdamW):
                 _check(sub, "parameters"); _check(grads, "gradients"); _check(ms, "exp_avg"); _check(vs, "exp_avg_sq")
                 tab = self._tables.setdefault((gi, k, len(sub)), _Table())
                 t, n, total, vec = tab.get([[p.data for p in sub], grads, ms, vs])
-                _call("vptr_adamw_multi", t.data_ptr(), n, total, vec, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                      float(group["weight_decay"]), step, 0 if grad_sqnorm is None else grad_sqnorm.data_ptr(), float(max_norm), ops._s())
+                ctr = 0
+                if self._dev_step:
+                    c = self._ctrs.get((gi, k))
+                    if c is None:
+                        c = self._ctrs[(gi, k)] = torch.tensor([step - 1], dtype=torch.int64, device=sub[0].device)
+                    _call("vptr_counter_add", c.data_ptr(), 1, ops._s())
+                    ctr = c.data_ptr()
+                _call("vptr_adamw_multi_dev", t.data_ptr(), n, total, vec, float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                      float(group["weight_decay"]), step, ctr, 0 if grad_sqnorm is None else grad_sqnorm.data_ptr(), float(max_norm), ops._s())
         return loss
 
 

@@ -32,6 +32,7 @@ class Stage2Trainer:
         else:
             self.opt = optimizer if optimizer is not None else torch.optim.AdamW(params=self.params, lr=lr)
         self.reducer = parallel.GradReducer(self.params, world) if world > 1 else None
+        self.graph_mode = False
 
     # ------------------------------------------------------------------------------------------------ losses
     def _bpnce(self, n, t, h, w, device):
@@ -51,6 +52,9 @@ class Stage2Trainer:
     # ------------------------------------------------------------------------------------------------ one iteration
     def step(self, past, future):
         T, enc, dec = self.T, self.enc, self.dec
+        if self.graph_mode:      # first node of a captured step: new dropout / DropPath epoch for this replay (common.cuh)
+            from . import _lib, ops
+            _lib.call("vptr_rng_advance", -1, ops._s())
         if self.kind == "far":
             with torch.no_grad():
                 feats = enc(torch.cat([past, future[:, :-1]], dim=1))          # train_FAR.py:53-55
@@ -96,3 +100,47 @@ class Stage2Trainer:
             torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_grad_norm, norm_type=2)   # :85
             self.opt.step()                                                                          # :86
         return loss
+
+
+class GraphedStep:
+    """One training iteration captured as a CUDA graph and replayed (stage-2 shapes are static: same clip shape every step).
+
+    Every kernel of the step is a C-ABI call on borrowed pointers with an explicit stream, the optimizer's step count and the dropout
+    epoch live on the device (vptr_counter_add / vptr_rng_advance), and -- with more than one rank -- the gradient reduction is the
+    library's own NCCL communicator on a forked side stream, so the whole of `Stage2Trainer.step` (ResNet encoder, Transformer forward
+    and backward, decoder, losses, all-reduce, clip, AdamW) becomes ONE graph launch: ~1 500 kernel launches and their host-side
+    Python disappear from the critical path.  Requires the fused tail.  The replayed step reads its clips from static device buffers
+    (`step(past, future)` copies into them) and returns the static loss tensor."""
+
+    def __init__(self, trainer, past, future, warmup=3):
+        if not trainer.fused_tail:
+            raise RuntimeError("vptr_b200.trainer.GraphedStep needs fused_tail=True (torch.optim.AdamW keeps its step count on the host)")
+        self.trainer = trainer
+        self.past, self.future = past.clone(), future.clone()
+        trainer.graph_mode = True
+        trainer.tail.opt.device_step(True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):               # eager warm-up on a side stream (allocator, lazy tables, optimizer state)
+            for _ in range(warmup):
+                trainer.step(self.past, self.future)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()                    # the warm-up's cached blocks would otherwise double the footprint next to the graph's pool
+        self.graph = torch.cuda.CUDAGraph()
+        try:     # (the warm-up ran on another stream than the capture; the mismatch warning is about exactly that and harmless here)
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except Exception:
+            pass
+        with torch.cuda.graph(self.graph, capture_error_mode="relaxed"):
+            self.loss = trainer.step(self.past, self.future)
+        trainer.tail.opt.note_replayed(-1)          # capturing ran the host code of one step but executed nothing on the device
+        self.replays = 0
+
+    def step(self, past, future):
+        self.past.copy_(past, non_blocking=True)
+        self.future.copy_(future, non_blocking=True)
+        self.graph.replay()
+        self.trainer.tail.opt.note_replayed()
+        self.replays += 1
+        return self.loss
