@@ -84,7 +84,7 @@ def test_train_mode_autoencoder_matches_pytorch_stack(img_channels, feat_dim, pa
 
     import contextlib
     w_exact = run(engine.exact_fp32(), 2e-5, 3e-3)                # schedule at fp32 accuracy (FFMA GEMM); ReLU-mask flips set the floor
-    w_tf32 = run(contextlib.nullcontext(), 2e-3, 2e-2)            # product path: tf32 operands through 21 convs with batch-stat BatchNorm
+    w_tf32 = run(contextlib.nullcontext(), 4e-3, 2e-2)            # product path: tf32 operands through 21 convs with batch-stat BatchNorm
     print("worst gradient: fp32 schedule %s %.2e, tf32 %s %.2e" % (w_exact + w_tf32))
 
 

@@ -268,11 +268,72 @@ class Geom:
         self.padded = pad_h + pad_w > 0
 
 
+# Weight-gradient GEMMs are off the backward's critical path (nothing downstream reads dW before the optimizer), so they are issued on
+# a SIDE stream: while the tensor cores work through dY^T X, the main stream's HBM-bound kernels (norm + GELU backward, LayerNorm
+# backward, attention backward, depthwise conv) run on the same SMs next to the GEMM's one CTA per SM.  Two tcgen05 GEMMs cannot
+# share an SM (shared memory / TMEM), so a side GEMM simply alternates with the main stream's input-gradient GEMMs.  The main stream
+# joins the side work of sub-block i at the end of sub-block i+1 (lagged: the trailing weight gradients of a sub-block overlap with
+# the head of the next one); operands stay referenced until then so the caching allocator cannot hand their memory out early.
+# Inside a captured CUDA graph this is an ordinary fork / join of the capture.
+# MEASURED (profiles/r02_bench_cfg1_wgrad_overlap.json.log): no gain -- cfg1 166.5 ms with the fork vs 164.8 ms without, cfg2 85.2 vs
+# 85.3 ms.  A side GEMM holds one CTA (210 KB of shared memory) on every SM, so the main stream's next input-gradient GEMM queues
+# behind it and the critical path stretches by what the overlap saved; the HBM-bound kernels next to it slow down by their share of
+# the bandwidth.  Kept as an opt-in switch, OFF by default.
+OVERLAP_WGRAD = False
+
+
+_SIDE_STREAMS = {}      # one side stream per device, created once (never inside a graph capture: the warm-up steps come first)
+
+
+def _side_stream(P):
+    st = getattr(P, "side", None)
+    if st is None:
+        dev = torch.cuda.current_device()
+        st = _SIDE_STREAMS.get(dev)
+        if st is None:
+            st = _SIDE_STREAMS[dev] = torch.cuda.Stream()
+        P.side = st
+        P.side_refs, P.side_prev = [], None
+    return st
+
+
+def _wgrad_raw(P, dY, X, out):
+    """out += dY^T X on the side stream (see OVERLAP_WGRAD)"""
+    if not (OVERLAP_WGRAD and dY.is_cuda):
+        ops.gemm(dY, X, out=out, a_mn=True, b_mn=True, accumulate=True)
+        return
+    st = _side_stream(P)
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        ops.gemm(dY, X, out=out, a_mn=True, b_mn=True, accumulate=True)
+    P.side_refs.append((dY, X))
+
+
+def _entry_done(P):
+    """end of one sub-block's backward: lagged join of the side stream (waits for the PREVIOUS sub-block's weight gradients)"""
+    if getattr(P, "side", None) is None:
+        return
+    ev = torch.cuda.Event()
+    ev.record(P.side)
+    if P.side_prev is not None:
+        torch.cuda.current_stream().wait_event(P.side_prev[0])
+        P.side_prev[1].clear()
+    P.side_prev, P.side_refs = (ev, P.side_refs), []
+
+
+def join_side(P):
+    """full join: every weight gradient issued so far is ordered before whatever the main stream does next"""
+    if getattr(P, "side", None) is None:
+        return
+    torch.cuda.current_stream().wait_stream(P.side)
+    P.side_refs, P.side_prev = [], None
+
+
 def _wgrad(P, name, dY, X):
     """dW[name] += dY^T X (contraction over tokens; both operands read as stored)."""
     g = P.g(name)
     if g is not None:
-        ops.gemm(dY, X, out=g.view(g.shape[0], -1), a_mn=True, b_mn=True, accumulate=True)
+        _wgrad_raw(P, dY, X, g.view(g.shape[0], -1))
 
 
 def _bgrad(P, name, dY):
@@ -380,8 +441,8 @@ def window_attn_bwd(P, s, dout, dqpos):
         Wi = P.wr(at + "in_proj_weight")
         gW, gb = P.g(at + "in_proj_weight"), P.g(at + "in_proj_bias")
         if gW is not None:
-            ops.gemm(dqkv[:, :2 * C], aq_in, out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
-            ops.gemm(dqkv[:, 2 * C:], a_in, out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+            _wgrad_raw(P, dqkv[:, :2 * C], aq_in, gW[:2 * C])
+            _wgrad_raw(P, dqkv[:, 2 * C:], a_in, gW[2 * C:])
             ops.colsum(dqkv, gb)
         d_aq = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
         d_a = ops.gemm(dqkv[:, 2 * C:], Wi[2 * C:], b_mn=True)
@@ -545,8 +606,8 @@ def temporal_attn_bwd(P, s, dout):
         if z is None:     # lean mode
             z, zp, _, _ = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), add=s["pos"], add_div=g.HW, add_mod=g.T,
                                             round_tf32=RT, save_stats=False)
-        ops.gemm(dqkv[:, :2 * C], zp, out=gW[:2 * C], a_mn=True, b_mn=True, accumulate=True)
-        ops.gemm(dqkv[:, 2 * C:], z, out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        _wgrad_raw(P, dqkv[:, :2 * C], zp, gW[:2 * C])
+        _wgrad_raw(P, dqkv[:, 2 * C:], z, gW[2 * C:])
         del z, zp
         ops.colsum(dqkv, gb)
     dzp = ops.gemm(dqkv[:, :2 * C], Wi[:2 * C], b_mn=True)
@@ -644,12 +705,12 @@ def cross_attn_bwd(P, s, dout, dqpos, dmem):
         if zq is None:    # lean mode
             zq = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), want_y=False, add=s["qadd"], add_div=1,
                                    add_mod=s["qadd"].shape[0], round_tf32=RT, save_stats=False)[1]
-        ops.gemm(dq, zq, out=gW[:C], a_mn=True, b_mn=True, accumulate=True)
+        _wgrad_raw(P, dq, zq, gW[:C])
         del zq
         ops.colsum(dq, gb[:C])
         ops.colsum(dkv, gb[C:])
-        ops.gemm(dkv[:, :C], s["mem_k"], out=gW[C:2 * C], a_mn=True, b_mn=True, accumulate=True)
-        ops.gemm(dkv[:, C:], s["mem"], out=gW[2 * C:], a_mn=True, b_mn=True, accumulate=True)
+        _wgrad_raw(P, dkv[:, :C], s["mem_k"], gW[C:2 * C])
+        _wgrad_raw(P, dkv[:, C:], s["mem"], gW[2 * C:])
 
     dzq = ops.gemm(dq, Wi[:C], b_mn=True)
     ops.gemm(dkv, Wi[C:], b_mn=True, out=dmem, residual=dmem)     # d(mem) += [dk | dv] [Wk ; Wv]  (memory + pos_past and memory share it)
@@ -720,6 +781,7 @@ def _layer_done(P, pre):
     a layer, so the last one of its backward)"""
     if GRAD_READY is None or P.gflat is None:
         return
+    join_side(P)                 # the layer's weight gradients (side stream) must be final before its slice is reduced
     layer = pre.rsplit(".", 1)[0] + "."
     span = [P.goff[k] for k in P.goff if k.startswith(layer)]
     if span:
@@ -746,4 +808,5 @@ def backward_tape(P, save, dout, dqpos=None, dmem=None, stop=0):
             d = final_norm_bwd(P, s, d)
         else:
             raise RuntimeError("unknown tape entry " + kind)
+        _entry_done(P)
     return d

@@ -344,6 +344,7 @@ class _FARFunction(torch.autograd.Function):
         ctx.rounded = None
         d = _tokens(dout)
         dx = E.backward_tape(P, ctx.save, d)
+        E.join_side(P)
         ctx.save = None
         grads = tuple(P.g(n) for n in ctx.names)
         return (None, dx.view(N, T, H, W, C).permute(0, 1, 4, 2, 3), None, None) + grads
@@ -397,6 +398,7 @@ class _NARFunction(torch.autograd.Function):
         dmem = ops.zeros(N * Tp * H * W, C, like=dout)
         E.backward_tape(P, ctx.save, _tokens(dout), dqpos=dqpos, dmem=dmem, stop=ctx.n_enc)   # decoder (+ its final norm)
         dx = E.backward_tape(P, ctx.save, dmem)                                                # encoder norm + encoder
+        E.join_side(P)
         ctx.save = None
         grads = tuple(P.g(n) for n in ctx.names)
         return (None, dx.view(N, Tp, H, W, C).permute(0, 1, 4, 2, 3), None, None) + grads
