@@ -41,8 +41,8 @@ def test_nar_cfg3_shape_one_clip():
 
 def test_nar_cfg4_geometry_one_clip():
     """the stress geometry of cfg4 (16x16 feature grid, 8x8 windows = 64-token groups, 10 -> 30 frames, LayerNorm((2112,16,16))) at
-    d_model 528 with one encoder and one decoder layer: exercises the fallback kernels (scalar window attention, generic
-    temporal shapes, register-window depthwise conv) at the real dimensions"""
+    d_model 528 with one encoder and one decoder layer: the wide tensor-core window attention (attn_mma64_kernel), the 30 x 30 / 30 x 10
+    temporal shapes and the register-window depthwise conv at the real dimensions"""
     from vptr_b200.model import VPTRFormerNAR
     torch.manual_seed(2021)
     net = VPTRFormerNAR(10, 30, encH=16, encW=16, d_model=528, nhead=8, num_encoder_layers=1, num_decoder_layers=1, dropout=0.1,
