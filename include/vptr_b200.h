@@ -167,6 +167,11 @@ int vptr_clip_scale(float* x, long long n, const double* sqnorm, float max_norm,
 int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
                       const float* residual, int act, int flags, int w_planes /* 1, or 2 = [hi|lo] tf32 weight split */,
                       vptr_stream_t stream);
+/* the same convolution for H, W multiples of 8 beyond 8x8 (16x16 grid of 128x128 frames) on the raw-tile kernel: xq from
+ * vptr_pad_nhwc_quad = every 8x8 quadrant with its own halo, [F*(H/8)*(W/8)][10][10][C] */
+int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                           const float* residual, int act, int flags, int w_planes, vptr_stream_t stream);
+int vptr_pad_nhwc_quad(const float* x, float* out, int F, int H, int W, int C, int pad_mode, int round_tf32, vptr_stream_t stream);
 /* out[r] = [ rna_tf32(w[r]) | rna_tf32(w[r] - hi) ]: the two tf32 planes of a weight matrix (rows of K -> rows of 2K) */
 int vptr_split_tf32(const float* w, float* out, long long rows, long long K, vptr_stream_t stream);
 int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, int C, int pad, int pad_mode, int round_tf32, vptr_stream_t stream);

@@ -108,3 +108,37 @@ def test_implicit_gemm_conv3x3(Fr, H, W, Ci, Co, mode):
     xp = F.pad(xn, (1,) * 4, mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
     ref = torch.relu(F.conv2d(xp, w.double(), bias.double())).permute(0, 2, 3, 1).reshape(-1, Co) + res.double()
     assert rel_l2(y, ref) < 3e-5     # fp32 accumulation over K = 9*Ci
+
+
+@pytest.mark.parametrize("Fr,H,W,Ci,Co,mode", [(3, 16, 16, 48, 64, "reflect"), (1, 16, 24, 32, 180, "zero"), (5, 24, 8, 16, 24, "replicate"),
+                                                (2, 16, 16, 528, 528, "reflect")])
+def test_quadrant_conv3x3(Fr, H, W, Ci, Co, mode):
+    """grids beyond 8x8 on the raw-tile kernel: every 8x8 quadrant with its own halo (vptr_pad_nhwc_quad) is one "frame" of
+    conv3x3_w8_kernel, the epilogue maps rows back into the full frame -- vs F.conv2d (+ bias, ReLU, residual, [hi|lo] weights),
+    odd quadrant counts exercising the masked last pair tile"""
+    import torch.nn.functional as F
+    from vptr_b200 import ops
+    assert ops.conv3x3_quad_ok(H, W)
+    x = tf32_exact((Fr * H * W, Ci), 21)
+    w = tf32_exact((Co, Ci, 3, 3), 22) * 0.25
+    bias, res = torch.randn(Co, device="cuda"), torch.randn(Fr * H * W, Co, device="cuda")
+    xq = ops.pad_nhwc_quad(x, Fr, H, W, Ci, ops.PAD_MODES[mode], round_tf32=False)
+    xp = F.pad(x.view(Fr, H, W, Ci).permute(0, 3, 1, 2).double(), (1,) * 4,
+               mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
+    # the tiled copy itself, bit for bit: quadrant (qy, qx) = the 10x10 patch of the padded frame at (8 qy, 8 qx)
+    patches = xp.float().unfold(2, 10, 8).unfold(3, 10, 8).permute(0, 2, 3, 4, 5, 1).reshape(-1, Ci)
+    assert torch.equal(xq, patches)
+    wpk = ops.pack_conv_weight(w, None, 0).view(Co, 9 * Ci)
+    y = ops.conv3x3_tf32_quad(xq, wpk, Fr, H, W, Ci, Co, bias=bias, residual=res, act=ops.ACT_RELU)
+    ref = torch.relu(F.conv2d(xp, w.double(), bias.double())).permute(0, 2, 3, 1).reshape(-1, Co) + res.double()
+    assert rel_l2(y, ref) < 3e-5
+    w2 = torch.randn(Co, Ci, 3, 3, device="cuda") * 0.25
+    y2 = ops.conv3x3_tf32_quad(xq, ops.split_tf32(ops.pack_conv_weight(w2, None, 0).view(Co, 9 * Ci)), Fr, H, W, Ci, Co, w_planes=2)
+    assert rel_l2(y2, F.conv2d(xp, w2.double()).permute(0, 2, 3, 1).reshape(-1, Co)) < 3e-5
+    # and agrees with the generic per-tap implicit GEMM where that one applies
+    if ops.conv3x3_implicit_ok(H, W):
+        xpad = ops.pad_nhwc(x, Fr, H, W, Ci, 1, ops.PAD_MODES[mode], round_tf32=False)
+        yg = ops.conv3x3_tf32(xpad, wpk, Fr, H, W, Ci, Co, bias=bias, residual=res, act=ops.ACT_RELU)
+        assert rel_l2(y, yg) < 2e-5     # two fp32 summation orders over K = 9*Ci
+    with pytest.raises(RuntimeError):      # the raw-tile epilogue has no GELU: refused, not silently skipped
+        ops.conv3x3_tf32_quad(xq, wpk, Fr, H, W, Ci, Co, act=ops.ACT_GELU)

@@ -30,8 +30,10 @@ def test_public_api_surface_matches_reference_names():
         m.VPTRDec(1, out_layer="Softmax")
     with pytest.raises(NotImplementedError):
         m.VPTREnc(1, padding_type="circular")
-    with pytest.raises(NotImplementedError):
-        m.VPTRFormerNAR(2, 2, d_model=48, nhead=4, TSLMA_flag=True)
+    net = m.VPTRFormerNAR(2, 2, d_model=48, nhead=4, TSLMA_flag=True)      # TSLMA decoder (reference VidHRFormer_modules.py:219-284)
+    assert any("TSLMA.attn.in_proj_weight" in k for k in net.state_dict())
+    with pytest.raises(NotImplementedError):        # its window partition needs the grid to be a multiple of the window
+        m.VPTRFormerNAR(2, 2, encH=6, encW=6, d_model=48, nhead=4, window_size=4, TSLMA_flag=True)
 
 
 def test_no_cpu_fallback():
@@ -42,7 +44,7 @@ def test_no_cpu_fallback():
     enc = VPTREnc(1, feat_dim=16).eval()
     with pytest.raises(RuntimeError):
         enc(torch.zeros(1, 1, 1, 32, 32))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):       # stage-1 (train-mode BatchNorm) path: CUDA only as well
         enc.train()(torch.zeros(1, 1, 1, 32, 32))
 
 

@@ -55,6 +55,8 @@ _SIGS = {
     "vptr_norm_act_bwd_colsum": ([P, P, P, P, P, P, P, P, P, L, I, I, I, P, I, P, I, U, F, P, P], I),
     "vptr_clip_scale": ([P, L, P, F, P], I),
     "vptr_conv3x3_tf32": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
+    "vptr_conv3x3_tf32_quad": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
+    "vptr_pad_nhwc_quad": ([P, P, I, I, I, I, I, I, P], I),
     "vptr_split_tf32": ([P, P, L, L, P], I),
     "vptr_pad_nhwc": ([P, P, I, I, I, I, I, I, I, P], I),
     "vptr_im2col": ([P, P, P, I, I, I, I, I, I, I, I, I, P], I),

@@ -76,6 +76,27 @@ __global__ void __launch_bounds__(256) pad_nhwc_kernel(const float* __restrict__
     }
 }
 
+// Quadrant-tiled padded copy for vptr_conv3x3_tf32_quad: out[(f, qy, qx)][ph][pw][c] = x[f][pad_index(qy*8 + ph - 1)][pad_index(qx*8 + pw - 1)][c],
+// ph, pw in 0..9 -- every 8x8 quadrant with its own 1-pixel halo (neighbouring quadrant, or the frame border's padding rule)
+__global__ void __launch_bounds__(256) pad_nhwc_quad_kernel(const float* __restrict__ x, float* __restrict__ out, unsigned total4, int H, int W,
+                                                            int C4, int pad_mode, int round_tf32) {
+    const int qw = W / 8, qh = H / 8;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int c = (int)(i % (unsigned)C4);
+        unsigned t = i / (unsigned)C4;
+        const int pw = (int)(t % 10u); t /= 10u;
+        const int ph = (int)(t % 10u); t /= 10u;
+        const int qx = (int)(t % (unsigned)qw); t /= (unsigned)qw;
+        const int qy = (int)(t % (unsigned)qh);
+        const long long f = (long long)(t / (unsigned)qh);
+        const int ih = pad_index(qy * 8 + ph - 1, H, pad_mode), iw = pad_index(qx * 8 + pw - 1, W, pad_mode);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && iw >= 0) v = reinterpret_cast<const float4*>(x)[((f * H + ih) * W + iw) * C4 + c];
+        if (round_tf32) { v.x = vptr_round_tf32(v.x); v.y = vptr_round_tf32(v.y); v.z = vptr_round_tf32(v.z); v.w = vptr_round_tf32(v.w); }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
 // ConvTranspose2d(k3,s2,p1,op1) output gather: out[f][oh][ow][co] = relu( sum_{kh,kw} col[(f,ih,iw)][(kh,kw,co)] + shift[co] )
 // with oh = 2*ih - 1 + kh.
 template <typename IDX>
@@ -429,6 +450,15 @@ extern "C" int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, in
     if (total4 < 0x7fffffffLL) pad_nhwc_kernel<unsigned><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
     else pad_nhwc_kernel<long long><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
     return vptr_check_launch("pad_nhwc_kernel");
+}
+
+extern "C" int vptr_pad_nhwc_quad(const float* x, float* out, int F, int H, int W, int C, int pad_mode, int round_tf32, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0 && C > 0 && C % 4 == 0, VPTR_ERR_SHAPE,
+                 "vptr_pad_nhwc_quad: F=%d H=%d W=%d C=%d (H, W multiples of 8)", F, H, W, C);
+    const long long total4 = (long long)F * (H / 8) * (W / 8) * 100 * (C / 4);
+    VPTR_REQUIRE(total4 < 0xffffffffLL, VPTR_ERR_SHAPE, "vptr_pad_nhwc_quad: tensor too large for 32-bit indexing");
+    pad_nhwc_quad_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, (unsigned)total4, H, W, C / 4, pad_mode, round_tf32);
+    return vptr_check_launch("pad_nhwc_quad_kernel");
 }
 
 extern "C" int vptr_convT_gather(const float* col, const float* shift, float* out, int F, int H, int W, int Cout, int relu,

@@ -47,6 +47,7 @@ struct GemmParams {
     // implicit-GEMM 3x3 convolution (A = 4-D TMA view of the padded NHWC activation): 0 = plain GEMM
     int conv_taps, conv_cpt, conv_kw, conv_bh, conv_tiles_per_frame, conv_bf, conv_C;
     int conv_w8;       // W == 8 implicit conv (conv3x3_w8_kernel): tile rows are ordered (oh, frame, ow) -- see epi_row()
+    int conv_qw, conv_qh;   // > 0: the "frames" of the W == 8 kernel are 8x8 quadrants of larger frames (conv_qw x conv_qh per frame)
     int conv_planes;
     long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
 };
@@ -189,7 +190,11 @@ __device__ __noinline__ float4 epilogue_options(const GemmParams& p, float4 o, i
 __device__ __forceinline__ int epi_row(const GemmParams& p, int m_base, int rr) {
     if (!p.conv_w8) return m_base + rr;
     const int L = (m_base & 127) + rr, g = L >> 3;
-    return (m_base & ~127) + (g & 1) * 64 + (g >> 1) * 8 + (L & 7);
+    if (!p.conv_qw) return (m_base & ~127) + (g & 1) * 64 + (g >> 1) * 8 + (L & 7);
+    // quadrant mode: quadrant fq = (frame f, quadrant row qy, quadrant column qx) -> row of the full (conv_qh*8) x (conv_qw*8) frame
+    const int fq = ((m_base >> 7) << 1) + (g & 1), nq = p.conv_qw * p.conv_qh;
+    const int f = fq / nq, q = fq - f * nq, qy = q / p.conv_qw, qx = q - qy * p.conv_qw;
+    return ((f * p.conv_qh + qy) * 8 + (g >> 1)) * (p.conv_qw * 8) + qx * 8 + (L & 7);
 }
 template <int NCOLS>
 __device__ __forceinline__ float4 load_bias(const GemmParams& p, int lane, int n_base) {
@@ -1065,7 +1070,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 0; p.conv_cpt = 1; p.conv_kw = 1; p.conv_bh = 1; p.conv_tiles_per_frame = 1; p.conv_bf = 1; p.conv_C = 0;
-    p.conv_w8 = 0; p.conv_planes = 1;
+    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = 1;
 
     CUtensorMap ma, mb;
     int rc;
@@ -1102,6 +1107,54 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
 // w_planes = 2: w is [Cout][2][9*C] = tf32 hi part followed by the tf32 lo part of each weight (vptr_split_tf32): the contraction
 // runs over both planes (2x the MMA work), which removes the weight-rounding half of the tf32 error (used by the frozen encoder,
 // whose 21 chained convolutions otherwise land at 1.16e-3 relative, just outside the 1e-3 gate).
+// Same convolution for H, W multiples of 8 larger than 8 (the 16x16 grid of 128x128 frames), on the raw-tile kernel: xq is the
+// QUADRANT-tiled padded activation from vptr_pad_nhwc_quad -- every 8x8 quadrant of a frame with its own 1-pixel halo,
+// [F * (H/8) * (W/8)][10][10][C] -- so each quadrant is an 8x8 "frame" of conv3x3_w8_kernel and only the epilogue's row mapping
+// (epi_row) knows about the larger frame.  23 % more padded bytes than one (H+2)x(W+2) copy, but one TMA box per channel slice
+// serves all 9 taps: the generic per-(tap, slice) path ran cfg4's encoder convs at 329 TFLOP/s executed against 848 on the 8x8 grid.
+extern "C" int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                                      const float* residual, int act, int flags, int w_planes, cudaStream_t stream) {
+    VPTR_REQUIRE(w_planes == 1 || w_planes == 2, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32_quad: w_planes must be 1 or 2");
+    VPTR_REQUIRE(F > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0 && C > 0 && Cout > 0, VPTR_ERR_SHAPE,
+                 "vptr_conv3x3_tf32_quad: F=%d H=%d W=%d (H, W multiples of 8)", F, H, W);
+    VPTR_REQUIRE(C % 4 == 0 && Cout % 4 == 0 && ((uintptr_t)xq % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
+                 VPTR_ERR_ALIGN, "vptr_conv3x3_tf32_quad: channels must be multiples of 4 and pointers 16-byte aligned");
+    VPTR_REQUIRE(!(flags & 1), VPTR_ERR_UNSUPPORTED, "vptr_conv3x3_tf32_quad: accumulate mode not supported");
+    VPTR_REQUIRE(act == 0 || act == 2, VPTR_ERR_UNSUPPORTED, "vptr_conv3x3_tf32_quad: act %d (the raw-tile epilogue has none / ReLU only)", act);
+    const long long FQ = (long long)F * (H / 8) * (W / 8);
+    VPTR_REQUIRE(FQ * 64 < 0x7fffffffLL, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32_quad: too many rows");
+    GemmParams p;
+    p.M = (int)((long long)F * H * W); p.N = Cout; p.K = 9 * C;
+    p.m_tiles = (int)((FQ + 3) / 4);              // pair tile = 4 quadrants = 256 output pixels
+    p.n_tiles = vptr_cdiv(Cout, 176);
+    p.conv_cpt = vptr_cdiv(C, BLOCK_K);
+    p.total_chunks = w_planes * 9 * p.conv_cpt;
+    p.k_splits = 1; p.chunks_per_split = p.total_chunks;
+    p.D = out; p.ldd = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout;
+    p.alpha = 1.f; p.act = act; p.flags = flags;
+    p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
+    p.dbg = g_gemm_dbg;
+    p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = 8; p.conv_tiles_per_frame = 1; p.conv_bf = 2; p.conv_C = C;
+    p.conv_w8 = 1; p.conv_qw = W / 8; p.conv_qh = H / 8; p.conv_planes = w_planes;
+    CUtensorMap ma, mb;
+    int rc = make_map_nhwc_w8(&ma, xq, FQ, C);
+    if (rc) return rc;
+    rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_w8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM_BYTES);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(conv3x3_w8, smem=%d): %s", CW_SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    int clusters = num_sms() / 2;
+    if (total < clusters) clusters = total;
+    conv3x3_w8_kernel<<<2 * clusters, NUM_THREADS, CW_SMEM_BYTES, stream>>>(ma, mb, p);
+    return vptr_check_launch("conv3x3_w8_kernel(quad)");
+}
+
 extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
                                  const float* residual, int act, int flags, int w_planes, cudaStream_t stream) {
     VPTR_REQUIRE(w_planes == 1 || w_planes == 2, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32: w_planes must be 1 or 2");
@@ -1133,12 +1186,12 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = bh; p.conv_tiles_per_frame = tiles_per_frame; p.conv_bf = bf; p.conv_C = C;
-    p.conv_w8 = 0; p.conv_planes = w_planes;
+    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = w_planes;
     // rows of a tile beyond F*H*W (frames past the end) are zero-filled by TMA and masked by the epilogue (m < M) only when tiles
     // map to whole frames in order, which holds for both tilings above.
     CUtensorMap ma, mb;
     static const bool generic_only = [] { const char* e = getenv("VPTR_CONV_GENERIC"); return e && e[0] == '1'; }();
-    if (H == 8 && W == 8 && !generic_only) {   // raw-tile kernel: one TMA box per channel slice serves all 9 taps (and both planes)
+    if (H == 8 && W == 8 && !generic_only && (act == 0 || act == 2)) {   // raw-tile kernel (its epilogue has no GELU): one TMA box per channel slice serves all 9 taps (and both planes)
         p.conv_w8 = 1; p.conv_planes = w_planes;
         p.m_tiles = vptr_cdiv(F, 4);           // pair tile = 4 frames = 256 output pixels
         int rc = make_map_nhwc_w8(&ma, xpad, F, C);

@@ -169,10 +169,15 @@ def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_a
         # implicit GEMM: 4-D TMA boxes of the padded activation feed the tcgen05 kernel directly (no im2col matrix)
         # The frozen encoder chains 21 convolutions; with plain tf32 weights its features land at 1.16e-3 relative (just outside
         # the 1e-3 gate), so the weights enter as two tf32 planes [hi|lo] (2x MMA work, weight rounding error removed).
-        xpad = ops.pad_nhwc(x, F_, H, W, Cin, 1, pad_mode, round_tf32=E.ROUND_TF32)
         w2 = wk
-        y = ops.conv3x3_tf32(xpad, w2, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE,
-                             w_planes=2 if E.ROUND_TF32 else 1)
+        if ops.conv3x3_quad_ok(H, W):      # 16x16 (and larger) grids: quadrant-tiled padded copy -> the 8x8 raw-tile kernel
+            xq = ops.pad_nhwc_quad(x, F_, H, W, Cin, pad_mode, round_tf32=E.ROUND_TF32)
+            y = ops.conv3x3_tf32_quad(xq, w2, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE,
+                                      w_planes=2 if E.ROUND_TF32 else 1)
+        else:
+            xpad = ops.pad_nhwc(x, F_, H, W, Cin, 1, pad_mode, round_tf32=E.ROUND_TF32)
+            y = ops.conv3x3_tf32(xpad, w2, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE,
+                                 w_planes=2 if E.ROUND_TF32 else 1)
         if residual is not None and act_after_residual:
             y = ops.relu_fwd(y, out=y)
         return y, H, W

@@ -428,6 +428,24 @@ def conv3x3_tf32(xpad, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NO
     return out
 
 
+def conv3x3_quad_ok(H, W):
+    """grids the quadrant-tiled raw-tile convolution covers (beyond the native 8x8 one)"""
+    return H % 8 == 0 and W % 8 == 0 and (H > 8 or W > 8) and os.environ.get("VPTR_CONV_GENERIC", "") != "1"
+
+
+def pad_nhwc_quad(x, F, H, W, C, pad_mode, round_tf32=True):
+    out = torch.empty(F * (H // 8) * (W // 8) * 100, C, dtype=torch.float32, device=x.device)
+    _call("vptr_pad_nhwc_quad", _p(x), _p(out), F, H, W, C, pad_mode, int(round_tf32), _s())
+    return out
+
+
+def conv3x3_tf32_quad(xq, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NONE, round_tf32=False, w_planes=1):
+    out = torch.empty(F * H * W, Cout, dtype=torch.float32, device=xq.device)
+    _call("vptr_conv3x3_tf32_quad", _p(xq), _p(w), _p(out), F, H, W, C, Cout, _p(bias), _p(residual), int(act), 2 if round_tf32 else 0,
+          int(w_planes), _s())
+    return out
+
+
 def split_tf32(w):
     """[rows][K] -> [rows][2K]: tf32 hi plane followed by the tf32 lo plane"""
     rows, K = w.shape
