@@ -12,6 +12,7 @@ cases = [
     ("fwd 2112->528 +res", dict(M=R, N=528, K=2112, res=True)),
     ("conv3x3 K=4752", dict(M=R, N=528, K=4752)),
     ("dgrad 528<-528", dict(M=R, N=528, K=528, b_mn=True)),
+    ("dgrad 528<-1056 +res", dict(M=R, N=528, K=1056, b_mn=True, res=True)),
     ("dgrad 528<-2112", dict(M=R, N=528, K=2112, b_mn=True)),
     ("dgrad 2112<-528", dict(M=R, N=2112, K=528, b_mn=True)),
     ("wgrad 528x528", dict(M=528, N=528, K=R, a_mn=True, b_mn=True, acc=True)),

@@ -49,6 +49,7 @@ struct GemmParams {
     int conv_w8;       // W == 8 implicit conv (conv3x3_w8_kernel): tile rows are ordered (oh, frame, ow) -- see epi_row()
     int conv_qw, conv_qh;   // > 0: the "frames" of the W == 8 kernel are 8x8 quadrants of larger frames (conv_qw x conv_qh per frame)
     int conv_planes;
+    int epi_tma;     // 2-CTA kernel: the output tile leaves through TMA bulk stores (epilogue_tile_tma) instead of per-lane stores
     long long* dbg;  // optional timeline buffer (tools/bench_gemm.py): block 0 records clock64() per tile
 };
 
@@ -333,6 +334,187 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
     else epilogue_tile_mode<BLOCK_N, 0, false>(p, taddr, sT, lane, m_base, n0, wait_full);
 }
 
+// ---- TMA-store epilogue (2-CTA kernel, outputs without a residual operand or split-K reduction) --------------------------------
+// The K = 528 GEMMs of the path are epilogue-bound: with per-lane stores a 128 x 176 tile costs ~14 k cycles (tcgen05.ld -> smem
+// transpose -> ld.shared -> 128-byte row-segment STGs, each warp instruction touching 4-8 different lines) against ~9.7 k cycles
+// of main loop at the sustained TF32 rate.  Here every lane keeps its accumulator ROW (what tcgen05.ld delivers), applies the
+// epilogue math in registers, writes the 32-column chunk into a warp-private staging tile in the SWIZZLE_128B pattern (16-byte
+// chunk j of row r at r*128 + ((j ^ (r & 7)) << 4): conflict-free) and ONE lane hands the 32 x 32 tile to the TMA engine
+// (cp.async.bulk.tensor store; out-of-range rows / columns are clipped by the tensor map).  Two staging tiles per warp: the store
+// of chunk c drains while chunk c+1 is computed; the tcgen05.ld of chunk c+1 is in flight during the math of chunk c.
+constexpr int EPI_TMA_TILE = 4096;      // 32 rows x 128 B
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+template <int NCOLS, int MODE, bool RES>
+__device__ __forceinline__ void epilogue_chunk_tma(const GemmParams& p, const CUtensorMap* map, const float* v, uint8_t* buf, int lane,
+                                                   int m_base, int n_base, float rs) {
+    const int m = min(m_base + lane, p.M - 1);      // rows past M are clipped by the store; keep their side look-ups in range
+#pragma unroll
+    for (int j = 0; j < NCOLS / 4; ++j) {
+        const int n = n_base + 4 * j;
+        float4 o = make_float4(v[4 * j] * p.alpha, v[4 * j + 1] * p.alpha, v[4 * j + 2] * p.alpha, v[4 * j + 3] * p.alpha);
+        if (p.bias && n < p.N) {      // warp-uniform address: one broadcast transaction, L1-resident after the first tile
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        }
+        if (MODE == 3) o = epilogue_options(p, o, m, n);
+        if (MODE == 5) {
+            const float4 k = vptr_drop_scale4(p.drop_seed, ((unsigned long long)m * p.N + n) >> 2, p.drop_p);
+            o.x *= k.x; o.y *= k.y; o.z *= k.z; o.w *= k.w;
+        }
+        if (MODE == 4 || MODE == 5) {
+            if (p.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            o.x *= rs; o.y *= rs; o.z *= rs; o.w *= rs;
+        }
+        const uint32_t off = NCOLS == 32 ? lane * 128 + ((j ^ (lane & 7)) << 4) : lane * (NCOLS * 4) + (j << 4);
+        if (RES) {      // the residual chunk was bulk-loaded into this very tile: add in place
+            const float4 r = *reinterpret_cast<const float4*>(buf + off);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (MODE == 1 || (MODE >= 3 && (p.flags & 2))) {
+            o.x = vptr_round_tf32(o.x); o.y = vptr_round_tf32(o.y); o.z = vptr_round_tf32(o.z); o.w = vptr_round_tf32(o.w);
+        }
+        *reinterpret_cast<float4*>(buf + off) = o;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map, buf, n_base, m_base);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+template <int BLOCK_N, int MODE, class WaitFn>
+__device__ __forceinline__ void epilogue_tile_tma_mode(const GemmParams& p, const CUtensorMap* map32, const CUtensorMap* map16, uint32_t taddr,
+                                                       uint8_t* sbuf, uint32_t& nstore, int lane, int m_base, int n0, WaitFn wait_full) {
+    constexpr int NFULL = BLOCK_N / 32;
+    constexpr bool TAIL = (BLOCK_N % 32) != 0;
+    const RowScale rsc = (MODE == 4 || MODE == 5) ? load_rowscale(p, m_base) : RowScale{1.f, 1.f, 0x7fffffff};
+    const float rs = (m_base + lane) < rsc.boundary ? rsc.s0 : rsc.s1;
+    const bool rows_live = m_base < p.M;            // warp-uniform
+    wait_full();
+    float v[32];
+    tmem_ld32(taddr, v);
+#pragma unroll 1
+    for (int c = 0; c < NFULL; ++c) {
+        float cur[32];
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = v[i];
+        if (c + 1 < NFULL) tmem_ld32(taddr + (c + 1) * 32, v);
+        else if (TAIL) tmem_ld16(taddr + NFULL * 32, v);
+        const int n_base = n0 + c * 32;
+        if (rows_live && n_base < p.N) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store issued two chunks ago has left its tile
+            __syncwarp();
+            epilogue_chunk_tma<32, MODE, false>(p, map32, cur, sbuf + (nstore & 1) * EPI_TMA_TILE, lane, m_base, n_base, rs);
+            ++nstore;
+        }
+    }
+    if (TAIL) {
+        tmem_ld_wait();
+        const int n_base = n0 + NFULL * 32;
+        if (rows_live && n_base < p.N) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            epilogue_chunk_tma<16, MODE, false>(p, map16, v, sbuf + (nstore & 1) * EPI_TMA_TILE, lane, m_base, n_base, rs);
+            ++nstore;
+        }
+    }
+}
+// Residual variant: the residual chunk is bulk-LOADED into the staging tile T-2 chunks ahead (T tiles per warp rotate: being
+// loaded / being combined / being stored), the lane adds its accumulator row in place and the same tile is bulk-stored.  With
+// per-lane residual loads the 528 -> 528 out-projections sat at 15-23 k cycles per tile (1-3 k cycles of load latency per chunk
+// that nothing overlapped) against 9.4 k of main loop; the bulk loads queue behind the operand stages in the SM's TMA pipe, so
+// one chunk of lookahead (T = 3) still left 11 k cycles per tile, two chunks (T = 4) 8.5 k (tools/gemm_timeline.py, RES=1).
+struct ResPipe {
+    uint8_t* buf;        // T staging tiles of this warp
+    uint64_t* bar;       // T mbarriers (one per tile)
+    uint32_t k;          // running chunk counter (selects the tile)
+    uint32_t phases;     // bit b: parity the next wait on bar[b] expects
+};
+template <int BLOCK_N>
+struct ResChunks {
+    static constexpr int NFULL = BLOCK_N / 32;
+    static constexpr bool TAIL = (BLOCK_N % 32) != 0;
+    static constexpr int NCH = NFULL + (TAIL ? 1 : 0);
+};
+// residual chunk `ci` of the tile at (m_base, n0) -> staging tile (rp.k + ahead) % T; nothing is issued for chunks outside the matrix
+template <int BLOCK_N, int T>
+__device__ __forceinline__ void res_issue(const GemmParams& p, const CUtensorMap* r32, const CUtensorMap* r16, ResPipe& rp, uint32_t ahead,
+                                          int m_base, int n0, int ci) {
+    const int n_base = n0 + ci * 32;
+    if (m_base >= p.M || n_base >= p.N) return;
+    const uint32_t b = (rp.k + ahead) % (uint32_t)T;
+    const bool tail = ResChunks<BLOCK_N>::TAIL && ci == ResChunks<BLOCK_N>::NFULL;
+    mbar_expect_tx(&rp.bar[b], tail ? 32 * 64 : 32 * 128);
+    tma_load_2d(tail ? r16 : r32, &rp.bar[b], rp.buf + b * EPI_TMA_TILE, n_base, m_base);
+}
+template <int BLOCK_N, int T, int MODE, class WaitFn>
+__device__ __forceinline__ void epilogue_tile_tma_res_mode(const GemmParams& p, const CUtensorMap* d32, const CUtensorMap* d16,
+                                                           const CUtensorMap* r32, const CUtensorMap* r16, uint32_t taddr, ResPipe& rp, int lane,
+                                                           int m_base, int n0, bool has_next, int next_m_base, int next_n0, WaitFn wait_full) {
+    using RC = ResChunks<BLOCK_N>;
+    const RowScale rsc = (MODE == 4 || MODE == 5) ? load_rowscale(p, m_base) : RowScale{1.f, 1.f, 0x7fffffff};
+    const float rs = (m_base + lane) < rsc.boundary ? rsc.s0 : rsc.s1;
+    wait_full();
+    float v[32];
+    tmem_ld32(taddr, v);
+#pragma unroll 1
+    for (int c = 0; c < RC::NCH; ++c) {
+        if (lane == 0) {   // staging tile (k + T-2) % T was last read by the store issued two chunks ago
+            constexpr int AHEAD = T - 2;
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (c + AHEAD < RC::NCH) res_issue<BLOCK_N, T>(p, r32, r16, rp, AHEAD, m_base, n0, c + AHEAD);
+            else if (has_next) res_issue<BLOCK_N, T>(p, r32, r16, rp, AHEAD, next_m_base, next_n0, c + AHEAD - RC::NCH);
+        }
+        float cur[32];
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cur[i] = v[i];
+        if (c + 1 < RC::NFULL) tmem_ld32(taddr + (c + 1) * 32, v);
+        else if (RC::TAIL && c + 1 == RC::NFULL) tmem_ld16(taddr + RC::NFULL * 32, v);
+        const int n_base = n0 + c * 32;
+        if (m_base < p.M && n_base < p.N) {
+            const uint32_t b = rp.k % (uint32_t)T;
+            mbar_wait(&rp.bar[b], (rp.phases >> b) & 1u);
+            rp.phases ^= 1u << b;
+            if (RC::TAIL && c == RC::NFULL) epilogue_chunk_tma<16, MODE, true>(p, d16, cur, rp.buf + b * EPI_TMA_TILE, lane, m_base, n_base, rs);
+            else epilogue_chunk_tma<32, MODE, true>(p, d32, cur, rp.buf + b * EPI_TMA_TILE, lane, m_base, n_base, rs);
+        } else if (lane == 0) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");     // empty group: keeps "two chunks ago" == "two groups ago"
+        }
+        ++rp.k;
+    }
+}
+template <int BLOCK_N, int T, class WaitFn>
+__device__ __forceinline__ void epilogue_tile_tma_res(const GemmParams& p, const CUtensorMap* d32, const CUtensorMap* d16, const CUtensorMap* r32,
+                                                      const CUtensorMap* r16, uint32_t taddr, ResPipe& rp, int lane, int m_base, int n0,
+                                                      bool has_next, int next_m_base, int next_n0, WaitFn wait_full) {
+    const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+    const bool inline_ok = (p.act == 0 || p.act == 2) && (p.rowscale == nullptr || p.rows_per_group >= 32);
+#define VPTR_EPI_RES(MODE) epilogue_tile_tma_res_mode<BLOCK_N, T, MODE>(p, d32, d16, r32, r16, taddr, rp, lane, m_base, n0, has_next, next_m_base, next_n0, wait_full)
+    if (fancy && inline_ok && p.drop_p > 0.f && p.act == 0) VPTR_EPI_RES(5);
+    else if (fancy && inline_ok && p.drop_p <= 0.f) VPTR_EPI_RES(4);
+    else if (fancy) VPTR_EPI_RES(3);
+    else if (p.flags & 2) VPTR_EPI_RES(1);
+    else VPTR_EPI_RES(0);
+#undef VPTR_EPI_RES
+}
+
+template <int BLOCK_N, class WaitFn>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* map32, const CUtensorMap* map16, uint32_t taddr,
+                                                  uint8_t* sbuf, uint32_t& nstore, int lane, int m_base, int n0, WaitFn wait_full) {
+    const bool fancy = p.act != 0 || p.drop_p > 0.f || p.rowscale != nullptr;
+    const bool inline_ok = (p.act == 0 || p.act == 2) && (p.rowscale == nullptr || p.rows_per_group >= 32);
+    if (fancy && inline_ok && p.drop_p > 0.f && p.act == 0) epilogue_tile_tma_mode<BLOCK_N, 5>(p, map32, map16, taddr, sbuf, nstore, lane, m_base, n0, wait_full);
+    else if (fancy && inline_ok && p.drop_p <= 0.f) epilogue_tile_tma_mode<BLOCK_N, 4>(p, map32, map16, taddr, sbuf, nstore, lane, m_base, n0, wait_full);
+    else if (fancy) epilogue_tile_tma_mode<BLOCK_N, 3>(p, map32, map16, taddr, sbuf, nstore, lane, m_base, n0, wait_full);
+    else if (p.flags & 2) epilogue_tile_tma_mode<BLOCK_N, 1>(p, map32, map16, taddr, sbuf, nstore, lane, m_base, n0, wait_full);
+    else epilogue_tile_tma_mode<BLOCK_N, 0>(p, map32, map16, taddr, sbuf, nstore, lane, m_base, n0, wait_full);
+}
+
 template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
 struct GemmCfg {
     static constexpr int A_BYTES = BLOCK_M * 128;
@@ -554,33 +736,40 @@ __device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t desc_a,
         : "memory");
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES, int EPI_TILES = 2>
 struct Gemm2Cfg {
     static constexpr int HALF_N = BLOCK_N / 2;
     static constexpr int A_BYTES = BLOCK_M * 128;
     static constexpr int B_GROUPS = HALF_N / 32;                       // MN-major only
     static constexpr int B_BYTES = B_MN ? B_GROUPS * 4096 : HALF_N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_BYTES + 1024;
+    static constexpr int EPI_BYTES = 4 * EPI_TILES * EPI_TMA_TILE;   // TMA staging tiles per epilogue warp: 2, or 3 with a bulk-loaded
+                                                                      // residual (the transpose tiles of the per-lane path alias them)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
+    static_assert(EPI_BYTES >= 4 * 32 * EPI_PITCH * 4, "transpose tiles must fit");
     static_assert(BLOCK_N % 16 == 0 && BLOCK_N <= 256, "UMMA N constraint for M=256");
     static_assert(!B_MN || HALF_N % 32 == 0, "MN-major B halves must be whole 32-float groups");
     static_assert(B_MN || HALF_N % 8 == 0, "K-major B halves must be whole 8-row swizzle groups");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES, int EPI_TILES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES>;
+gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                      const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_d16,
+                      const __grid_constant__ CUtensorMap tma_r, const __grid_constant__ CUtensorMap tma_r16, const GemmParams p) {
+    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES, EPI_TILES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* epi_base = smem + STAGES * Cfg::STAGE_BYTES;          // 1024-byte aligned (swizzled TMA staging tiles)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_base + Cfg::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* epi_tiles = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);
+    uint64_t* res_bar = tmem_empty + 3;                            // 4 warps x EPI_TILES residual-tile barriers (EPI_TILES > 2)
+    static_assert((2 * STAGES + 4 + 1 + (EPI_TILES > 2 ? 4 * EPI_TILES : 0)) * 8 <= 256, "barrier block");
+    float* epi_tiles = reinterpret_cast<float*>(epi_base);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -593,6 +782,7 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        if (p.epi_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_d) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);    // the leader's expect_tx arrive (used in the leader only; the peer's TMA bytes
                                            // can only land in the same phase because it waits on the multicast empty barrier)
@@ -601,6 +791,10 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);   // multicast tcgen05.commit
             mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs (used in the leader only)
+        }
+        if (EPI_TILES > 2) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_r) : "memory");
+            for (int i = 0; i < 4 * EPI_TILES; ++i) mbar_init(&res_bar[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -714,6 +908,19 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         const int q = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t nstore = 0;
+        uint8_t* sbuf = epi_base + (warp - 2) * EPI_TILES * EPI_TMA_TILE;
+        ResPipe rp{sbuf, res_bar + (warp - 2) * EPI_TILES, 0u, 0u};
+        auto tile_origin = [&](int tile, int& mb, int& nb) {
+            const int mn = tile % (p.m_tiles * p.n_tiles);
+            mb = ((mn / p.n_tiles) * 2 + (int)rank) * BLOCK_M + q * 32;
+            nb = (mn % p.n_tiles) * BLOCK_N;
+        };
+        if (EPI_TILES > 2 && p.epi_tma == 2 && cluster_id < total_tiles && lane == 0) {   // residual of the very first chunk(s)
+            int mb, nb;
+            tile_origin(cluster_id, mb, nb);
+            for (int a = 0; a < EPI_TILES - 2; ++a) res_issue<BLOCK_N, EPI_TILES>(p, &tma_r, &tma_r16, rp, a, mb, nb, a);
+        }
         for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
             const int mn = tile % (p.m_tiles * p.n_tiles);
             const int n_tile = mn % p.n_tiles;
@@ -723,17 +930,29 @@ gemm_tf32_2cta_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
             const bool stamp = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
             if (stamp) p.dbg[(tile / n_clusters) * 8 + 3] = clock64();
-            epilogue_tile<BLOCK_N, false>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+            auto wait_full = [&] {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 if (stamp) p.dbg[(tile / n_clusters) * 8 + 4] = clock64();
                 tcgen05_fence_after();
-            });
+            };
+            if (EPI_TILES > 2 && p.epi_tma == 2) {
+                const bool has_next = tile + n_clusters < total_tiles;
+                int nmb = 0, nnb = 0;
+                if (has_next) tile_origin(tile + n_clusters, nmb, nnb);
+                epilogue_tile_tma_res<BLOCK_N, (EPI_TILES > 2 ? EPI_TILES : 3)>(p, &tma_d, &tma_d16, &tma_r, &tma_r16, taddr, rp, lane, m_base, n_tile * BLOCK_N, has_next, nmb, nnb,
+                                               wait_full);
+            } else if (p.epi_tma == 1) {
+                epilogue_tile_tma<BLOCK_N>(p, &tma_d, &tma_d16, taddr, sbuf, nstore, lane, m_base, n_tile * BLOCK_N, wait_full);
+            } else {
+                epilogue_tile<BLOCK_N, false>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, wait_full);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
             if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0) p.dbg[(tile / n_clusters) * 8 + 5] = clock64();
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores of this warp complete
     }
 
     tcgen05_fence_before();
@@ -1000,10 +1219,11 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
 }
 
 
-template <int BLOCK_N, int A_MN, int B_MN, int STAGES>
-int launch_gemm_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t stream) {
-    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES>;
-    auto kern = gemm_tf32_2cta_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+struct EpiMaps { CUtensorMap d, d16, r, r16; };
+template <int BLOCK_N, int A_MN, int B_MN, int STAGES, int EPI_TILES = 2>
+int launch_gemm_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const EpiMaps& em, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BLOCK_N, A_MN, B_MN, STAGES, EPI_TILES>;
+    auto kern = gemm_tf32_2cta_kernel<BLOCK_N, A_MN, B_MN, STAGES, EPI_TILES>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -1013,7 +1233,7 @@ int launch_gemm_2cta(const CUtensorMap& ma, const CUtensorMap& mb, const GemmPar
     int total = p.m_tiles * p.n_tiles * p.k_splits;
     int clusters = num_sms() / 2;
     if (total < clusters) clusters = total;
-    kern<<<2 * clusters, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, p);
+    kern<<<2 * clusters, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ma, mb, em.d, em.d16, em.r, em.r16, p);
     return vptr_check_launch("gemm_tf32_2cta_kernel");
 }
 
@@ -1070,7 +1290,7 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     p.rowscale = rowscale; p.rows_per_group = rows_per_group; p.drop_seed = drop_seed; p.drop_p = drop_p;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 0; p.conv_cpt = 1; p.conv_kw = 1; p.conv_bh = 1; p.conv_tiles_per_frame = 1; p.conv_bf = 1; p.conv_C = 0;
-    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = 1;
+    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = 1; p.epi_tma = 0;
 
     CUtensorMap ma, mb;
     int rc;
@@ -1083,14 +1303,44 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
 
     if (two_cta) {
         constexpr int ST2 = 7;
-        if (wide) {
-            if (!a_mn) return launch_gemm_2cta<256, 0, 0, 6>(ma, mb, p, stream);
-            return launch_gemm_2cta<256, 1, 0, 6>(ma, mb, p, stream);
+        constexpr int ST2_MN = 6;       // 192-column MN-major B stages are 28 KB: six of them beside the 32 KB of epilogue staging tiles
+        // Outputs that are not split-K reductions leave through TMA bulk stores (epilogue_tile_tma).  With a residual operand and
+        // K <= 1280 the residual is bulk-loaded as well: K <= 640 with four staging tiles per warp (loads two chunks ahead) and five
+        // operand stages, longer K with three tiles and six stages; beyond that the main loop hides the per-lane epilogue and its
+        // seventh operand stage is worth more (measured at M = 40960, N = 528: K = 528 91 -> 71 us, K = 1056 99 -> 91 us,
+        // K = 2112 145 us per-lane against 150-160 us).
+        static const bool no_tma_epi = [] { const char* e = getenv("VPTR_GEMM_EPI_STG"); return e && e[0] == '1'; }();
+        const bool res_cfg = residual != nullptr && !wide && !a_mn && p.total_chunks <= 40;
+        p.epi_tma = (no_tma_epi || (flags & 1)) ? 0 : (residual == nullptr ? 1 : (res_cfg ? 2 : 0));
+        EpiMaps em{ma, ma, ma, ma};
+        if (p.epi_tma) {
+            rc = make_map_2d(&em.d, D, N, M, ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+            rc = make_map_2d(&em.d16, D, N, M, ldd, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
         }
-        if (!a_mn && !b_mn) return launch_gemm_2cta<176, 0, 0, ST2>(ma, mb, p, stream);
-        if (!a_mn && b_mn) return launch_gemm_2cta<192, 0, 1, ST2>(ma, mb, p, stream);
-        if (a_mn && b_mn) return launch_gemm_2cta<192, 1, 1, ST2>(ma, mb, p, stream);
-        return launch_gemm_2cta<176, 1, 0, ST2>(ma, mb, p, stream);
+        if (p.epi_tma == 2) {
+            rc = make_map_2d(&em.r, residual, N, M, ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+            if (rc) return rc;
+            rc = make_map_2d(&em.r16, residual, N, M, ldr, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+            if (rc) return rc;
+        }
+        if (wide) {
+            if (!a_mn) return launch_gemm_2cta<256, 0, 0, 6>(ma, mb, em, p, stream);
+            return launch_gemm_2cta<256, 1, 0, 6>(ma, mb, em, p, stream);
+        }
+        if (p.epi_tma == 2 && p.total_chunks <= 20) {      // short K: epilogue-bound, residual loads two chunks ahead
+            if (!b_mn) return launch_gemm_2cta<176, 0, 0, 5, 4>(ma, mb, em, p, stream);
+            return launch_gemm_2cta<192, 0, 1, 5, 4>(ma, mb, em, p, stream);
+        }
+        if (p.epi_tma == 2) {
+            if (!b_mn) return launch_gemm_2cta<176, 0, 0, 6, 3>(ma, mb, em, p, stream);
+            return launch_gemm_2cta<192, 0, 1, 6, 3>(ma, mb, em, p, stream);
+        }
+        if (!a_mn && !b_mn) return launch_gemm_2cta<176, 0, 0, ST2>(ma, mb, em, p, stream);
+        if (!a_mn && b_mn) return launch_gemm_2cta<192, 0, 1, ST2_MN>(ma, mb, em, p, stream);
+        if (a_mn && b_mn) return launch_gemm_2cta<192, 1, 1, ST2_MN>(ma, mb, em, p, stream);
+        return launch_gemm_2cta<176, 1, 0, ST2>(ma, mb, em, p, stream);
     }
     constexpr int ST = 5;
     if (!a_mn && !b_mn) return launch_gemm<BN1, 0, 0, ST>(ma, mb, p, stream);
@@ -1136,7 +1386,7 @@ extern "C" int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* ou
     p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = 8; p.conv_tiles_per_frame = 1; p.conv_bf = 2; p.conv_C = C;
-    p.conv_w8 = 1; p.conv_qw = W / 8; p.conv_qh = H / 8; p.conv_planes = w_planes;
+    p.conv_w8 = 1; p.conv_qw = W / 8; p.conv_qh = H / 8; p.conv_planes = w_planes; p.epi_tma = 0;
     CUtensorMap ma, mb;
     int rc = make_map_nhwc_w8(&ma, xq, FQ, C);
     if (rc) return rc;
@@ -1186,7 +1436,7 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
     p.dbg = g_gemm_dbg;
     p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = bh; p.conv_tiles_per_frame = tiles_per_frame; p.conv_bf = bf; p.conv_C = C;
-    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = w_planes;
+    p.conv_w8 = 0; p.conv_qw = 0; p.conv_qh = 0; p.conv_planes = w_planes; p.epi_tma = 0;
     // rows of a tile beyond F*H*W (frames past the end) are zero-filled by TMA and masked by the epilogue (m < M) only when tiles
     // map to whole frames in order, which holds for both tilings above.
     CUtensorMap ma, mb;
@@ -1214,7 +1464,7 @@ extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, 
     if (rc) return rc;
     rc = make_map_2d(&mb, w, (long long)w_planes * 9 * C, Cout, (long long)w_planes * 9 * C, BLOCK_K, 176 / 2, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    return launch_gemm_2cta<176, 0, 0, 7>(ma, mb, p, stream);
+    return launch_gemm_2cta<176, 0, 0, 7>(ma, mb, EpiMaps{ma, ma, ma, ma}, p, stream);
 }
 
 VPTR_RNG_EPOCH_ACCESSOR(gemm_tcgen05)
