@@ -280,6 +280,10 @@ def test_elementwise_helpers():
     out = torch.ones(48, device="cuda")
     ops.colsum(x, out)
     assert rel_l2(out, x.sum(0) + 1) < 1e-5
+    x50 = rnd(301, 50, seed=4)              # a width that is not a multiple of 4 takes the scalar kernel
+    out50 = torch.ones(50, device="cuda")
+    ops.colsum(x50, out50)
+    assert rel_l2(out50, x50.sum(0) + 1) < 1e-5
     # widths that are multiples of 528 take the tiled kernel, also on a column slice of a wider buffer and a ragged row count
     big = rnd(4099, 1584, seed=9)
     for sl in (slice(0, 528), slice(528, 1584), slice(0, 1584)):
