@@ -1349,15 +1349,8 @@ extern "C" int vptr_gemm_tf32(const float* A, long long lda, int a_mn, const flo
     return launch_gemm<BN1, 1, 0, ST>(ma, mb, p, stream);
 }
 
-// Implicit-GEMM 3x3 stride-1 convolution on the tcgen05 kernel (ResnetBlock convs, reference model/ResNetAutoEncoder.py:138,151):
-//   out[(f,oh,ow)][co] = act( sum_{kh,kw,ci} xpad[f][oh+kh][ow+kw][ci] * w[co][(kh,kw,ci)] + bias[co] ) (+ residual)
-// xpad: NHWC activation already padded by 1 (zero / reflect / replicate: vptr_pad_nhwc) [F][H+2][W+2][C]; w: [Cout][9*C]
-// (vptr_pack_conv_weight mode 0).  No im2col matrix is materialised: each k-chunk's A tile is a 4-D TMA box of xpad.
-// Returns VPTR_ERR_UNSUPPORTED when the grid does not tile into 128-pixel boxes (caller falls back to im2col + vptr_gemm_tf32).
-// w_planes = 2: w is [Cout][2][9*C] = tf32 hi part followed by the tf32 lo part of each weight (vptr_split_tf32): the contraction
-// runs over both planes (2x the MMA work), which removes the weight-rounding half of the tf32 error (used by the frozen encoder,
-// whose 21 chained convolutions otherwise land at 1.16e-3 relative, just outside the 1e-3 gate).
-// Same convolution for H, W multiples of 8 larger than 8 (the 16x16 grid of 128x128 frames), on the raw-tile kernel: xq is the
+// The 3x3 stride-1 convolution of vptr_conv3x3_tf32 (below) for H, W multiples of 8 larger than 8 (the 16x16 grid of 128x128
+// frames; reference model/ResNetAutoEncoder.py:138,151 at n_downsampling 3), on the raw-tile kernel: xq is the
 // QUADRANT-tiled padded activation from vptr_pad_nhwc_quad -- every 8x8 quadrant of a frame with its own 1-pixel halo,
 // [F * (H/8) * (W/8)][10][10][C] -- so each quadrant is an 8x8 "frame" of conv3x3_w8_kernel and only the epilogue's row mapping
 // (epi_row) knows about the larger frame.  23 % more padded bytes than one (H+2)x(W+2) copy, but one TMA box per channel slice
@@ -1405,6 +1398,14 @@ extern "C" int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* ou
     return vptr_check_launch("conv3x3_w8_kernel(quad)");
 }
 
+// Implicit-GEMM 3x3 stride-1 convolution on the tcgen05 kernel (ResnetBlock convs, reference model/ResNetAutoEncoder.py:138,151):
+//   out[(f,oh,ow)][co] = act( sum_{kh,kw,ci} xpad[f][oh+kh][ow+kw][ci] * w[co][(kh,kw,ci)] + bias[co] ) (+ residual)
+// xpad: NHWC activation already padded by 1 (zero / reflect / replicate: vptr_pad_nhwc) [F][H+2][W+2][C]; w: [Cout][9*C]
+// (vptr_pack_conv_weight mode 0).  No im2col matrix is materialised: each k-chunk's A tile is a 4-D TMA box of xpad.
+// Returns VPTR_ERR_UNSUPPORTED when the grid does not tile into 128-pixel boxes (caller falls back to im2col + vptr_gemm_tf32).
+// w_planes = 2: w is [Cout][2][9*C] = tf32 hi part followed by the tf32 lo part of each weight (vptr_split_tf32): the contraction
+// runs over both planes (2x the MMA work), which removes the weight-rounding half of the tf32 error (used by the frozen encoder,
+// whose 21 chained convolutions otherwise land at 1.16e-3 relative, just outside the 1e-3 gate).
 extern "C" int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
                                  const float* residual, int act, int flags, int w_planes, cudaStream_t stream) {
     VPTR_REQUIRE(w_planes == 1 || w_planes == 2, VPTR_ERR_SHAPE, "vptr_conv3x3_tf32: w_planes must be 1 or 2");
