@@ -100,15 +100,19 @@ def test_trainer_fused_tail_matches_torch_tail(kind):
         past, fut = torch.rand(2, 3, 1, 64, 64, generator=g).to(dev), torch.rand(2, 3, 1, 64, 64, generator=g).to(dev)
         losses = [float(tr.step(past, fut)) for _ in range(2)]
         res.append((losses, {k: v.detach().clone() for k, v in T.named_parameters()}))
+    print("losses torch tail %s fused tail %s" % (res[0][0], res[1][0]))
     for a, b in zip(res[0][0], res[1][0]):
         assert abs(a - b) <= 1e-4 * abs(a), (res[0][0], res[1][0])
     # AdamW's first steps move every weight by ~lr * g/|g|: elements whose gradient is cancellation noise (k_proj.bias: softmax is
     # shift invariant; fc1.bias in front of a norm) may step either way, so the gate is absolute, in units of the learning rate
-    # (two steps of 1e-4 each), and statistical over all parameters
+    # and statistical over all parameters.  Hard bound: |m_hat| / sqrt(v_hat) <= 1.0013 in AdamW's first two steps, so one trainer moves
+    # a weight by at most 2.003 lr and two trainers whose noise gradients have opposite signs end up to 4.006 lr apart (2.4 lr
+    # observed in 2 of 8 runs: the split-K reductions sum in a different order from run to run)
     big = tot = 0
     for k in res[0][1]:
         d = (res[1][1][k] - res[0][1][k]).abs()
-        assert float(d.max()) <= 2.05e-4, k
+        assert float(d.max()) <= 4.05e-4, k
         big += int((d > 2e-5).sum())
         tot += d.numel()
-    assert big < 0.002 * tot, (big, tot)
+    print("weights that moved apart by more than 0.1 lr-steps: %d of %d" % (big, tot))
+    assert big < 0.003 * tot, (big, tot)       # measured 4e-4 ... 6.5e-4 of the NAR weights, 5e-6 of the FAR ones
