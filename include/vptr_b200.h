@@ -144,6 +144,10 @@ int vptr_relu_fwd(const float* x, float* y, long long n, vptr_stream_t stream);
 int vptr_relu_bwd(const float* dy, const float* y, float* dx, long long n, vptr_stream_t stream);
 int vptr_colsum(const float* x, float* out, long long rows, int C, long long ld, vptr_stream_t stream);
 int vptr_transpose(const float* in, float* out, int batch, int R, int C, int accumulate, vptr_stream_t stream);
+/* n transposes in one launch: device table of n x 5 int64 {src, dst, R, C, cumulative 32x32-tile count}; dst[c][r] (+)= src[r][c]
+ * (LayerNorm((ch,H,W)) affine weights and depthwise 3x3 weights into the engine's channel-last layout and their gradients back:
+ * reference model/VidHRFormer_modules.py:386-442) */
+int vptr_transpose_multi(const long long* table, int n, int total_tiles, int accumulate, vptr_stream_t stream);
 /* PadBlock (model/VidHRFormer_modules.py:527-561): dir 0 centre zero-pad, dir 1 crop */
 int vptr_pad_crop(const float* in, float* out, int F, int H, int W, int Hp, int Wp, int ph0, int pw0, int C, int dir,
                   vptr_stream_t stream);

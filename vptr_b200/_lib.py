@@ -48,6 +48,7 @@ _SIGS = {
     "vptr_relu_bwd": ([P, P, P, L, P], I),
     "vptr_colsum": ([P, P, L, I, L, P], I),
     "vptr_transpose": ([P, P, I, I, I, I, P], I),
+    "vptr_transpose_multi": ([P, I, I, I, P], I),
     "vptr_pad_crop": ([P, P, I, I, I, I, I, I, I, I, I, P], I),
     "vptr_sqnorm_accumulate": ([P, L, P, P], I),
     "vptr_round_copy_colsum": ([P, P, L, I, I, P, I, U, F, P, P], I),

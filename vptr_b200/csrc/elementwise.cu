@@ -251,6 +251,34 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     }
 }
 
+// Several 2-D transposes in ONE launch (the frame-LayerNorm affine weights (ch,H,W) <-> the engine's [hw][ch] layout and the
+// depthwise 3x3 weights, forward; their gradients back, accumulate mode): 232 separate 8-10 us launches per cfg1 step were
+// 2.2 ms of launch-latency-sized kernels.  table: n entries of 5 int64 {src, dst, R, C, cumulative 32x32-tile count}.
+__global__ void __launch_bounds__(256) transpose_multi_kernel(const long long* __restrict__ table, int n, int accumulate) {
+    __shared__ float tile[32][33];
+    int e = 0;
+    while (e + 1 < n && (long long)blockIdx.x >= table[e * 5 + 4]) ++e;
+    const float* in = reinterpret_cast<const float*>(table[e * 5]);
+    float* out = reinterpret_cast<float*>(table[e * 5 + 1]);
+    const int R = (int)table[e * 5 + 2], C = (int)table[e * 5 + 3];
+    const int local = (int)(blockIdx.x - (e ? table[(e - 1) * 5 + 4] : 0));
+    const int ctiles = (C + 31) / 32;
+    const int c0 = (local % ctiles) * 32, r0 = (local / ctiles) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        tile[j][tx] = (r < R && c < C) ? in[(long long)r * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, r = r0 + tx;
+        if (r < R && c < C) {
+            float* o = out + (long long)c * R + r;
+            if (accumulate) *o += tile[tx][j]; else *o = tile[tx][j];
+        }
+    }
+}
+
 // centre zero-pad [F][H][W][C] -> [F][Hp][Wp][C] (dir 0) or crop back (dir 1). They are each other's adjoint.
 __global__ void __launch_bounds__(256) pad_crop_kernel(const float* __restrict__ in, float* __restrict__ out, int F, int H, int W, int Hp,
                                                        int Wp, int ph0, int pw0, int C4, int dir) {
@@ -374,6 +402,11 @@ extern "C" int vptr_transpose(const float* in, float* out, int batch, int R, int
     dim3 grid(vptr_cdiv(C, 32), vptr_cdiv(R, 32), batch);
     transpose_kernel<<<grid, 256, 0, stream>>>(in, out, R, C, accumulate);
     return vptr_check_launch("transpose_kernel");
+}
+extern "C" int vptr_transpose_multi(const long long* table, int n, int total_tiles, int accumulate, cudaStream_t stream) {
+    VPTR_REQUIRE(table != nullptr && n > 0 && total_tiles > 0, VPTR_ERR_SHAPE, "vptr_transpose_multi: n=%d tiles=%d", n, total_tiles);
+    transpose_multi_kernel<<<total_tiles, 256, 0, stream>>>(table, n, accumulate);
+    return vptr_check_launch("transpose_multi_kernel");
 }
 extern "C" int vptr_pad_crop(const float* in, float* out, int F, int H, int W, int Hp, int Wp, int ph0, int pw0, int C, int dir,
                              cudaStream_t stream) {

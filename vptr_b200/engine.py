@@ -456,13 +456,34 @@ def window_attn_bwd(P, s, dout, dqpos):
 
 
 # =================================================================================================== conv FFN (MlpDWBN)
-def _ffn_norm_params(P, pre, name, hw, layer_norm):
-    """(gamma, beta) in engine layout: BatchNorm (ch,) as is; LayerNorm((ch,H,W)) re-laid [hw][ch]."""
-    w, b = P.w(pre + "." + name + ".weight"), P.w(pre + "." + name + ".bias")
-    if not layer_norm:
-        return w, b
-    ch = w.shape[0]
-    return ops.transpose(w, 1, ch, hw), ops.transpose(b, 1, ch, hw)
+_FFN_NORMS = ("norm1", "norm2", "norm3")
+
+
+def _ffn_layout(P, pre, hw, layer_norm):
+    """[(parameter name, rows, cols)] of the MlpDWBN parameters the kernels read in another layout than nn.Module stores them:
+    the depthwise 3x3 weights (Ch,1,3,3) -> [9][Ch], and -- LayerNorm((ch,H,W)) flavour -- the three norms' affine (ch,H,W) -> [hw][ch]"""
+    items = []
+    if layer_norm:
+        for n in _FFN_NORMS:
+            ch = P.w(pre + "." + n + ".weight").shape[0]
+            items += [(pre + "." + n + ".weight", ch, hw), (pre + "." + n + ".bias", ch, hw)]
+    items.append((pre + ".dw3x3.weight", P.w(pre + ".dw3x3.weight").shape[0], 9))
+    return items
+
+
+def _ffn_params_cl(P, pre, hw, layer_norm):
+    """engine-layout copies of those parameters: ONE batched transpose launch per block (was seven)"""
+    items = _ffn_layout(P, pre, hw, layer_norm)
+    flat = ops.empty(sum(r * c for _, r, c in items), like=P.w(items[0][0]))
+    out, off, entries = {}, 0, []
+    for name, r, c in items:
+        out[name] = flat[off:off + r * c]
+        entries.append((P.w(name), out[name], r, c))
+        off += r * c
+    ops.transpose_multi((pre, "fwd", flat.device.index), entries)
+    aff = tuple((out[pre + "." + n + ".weight"], out[pre + "." + n + ".bias"]) if layer_norm
+                else (P.w(pre + "." + n + ".weight"), P.w(pre + "." + n + ".bias")) for n in _FFN_NORMS)
+    return aff, out[pre + ".dw3x3.weight"]
 
 
 def _ffn_norm_stats(P, pre, name, h, g, layer_norm, training, bufs):
@@ -483,22 +504,19 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     Ch = w1.shape[0]
     h1 = ops.gemm(b_, w1.view(Ch, g.C), bias=P.w(pre + ".fc1.bias"))
     st1 = _ffn_norm_stats(P, pre, "norm1", h1, g, layer_norm, training, bufs)
-    g1, b1 = _ffn_norm_params(P, pre, "norm1", g.HW, layer_norm)
+    ((g1, b1), (g2, b2), (g3, b3)), w9 = _ffn_params_cl(P, pre, g.HW, layer_norm)
     u1 = ops.norm_act_fwd(h1, st1[0], st1[1], g1, b1, g.HW, mode)
-    w9 = ops.transpose(P.w(pre + ".dw3x3.weight"), 1, Ch, 9)
     if layer_norm:   # frame-LayerNorm statistics of the conv output come out of the conv kernel itself
         h2, st2 = ops.dwconv3x3_stats(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
     else:
         h2 = ops.dwconv3x3(u1, w9, P.w(pre + ".dw3x3.bias"), g.F, g.H, g.W)
         st2 = _ffn_norm_stats(P, pre, "norm2", h2, g, layer_norm, training, bufs)
-    g2, b2 = _ffn_norm_params(P, pre, "norm2", g.HW, layer_norm)
     s2, s3, dp = D.seed(), D.seed(), D.path()
     rpg = g.T * g.HW
     u2 = ops.norm_act_fwd(h2, st2[0], st2[1], g2, b2, g.HW, mode, round_tf32=ROUND_TF32, drop_seed=s2, drop_p=D.p)
     w2 = P.wr(pre + ".fc2.weight")
     h3 = ops.gemm(u2, w2.view(g.C, Ch), bias=P.w(pre + ".fc2.bias"))
     st3 = _ffn_norm_stats(P, pre, "norm3", h3, g, layer_norm, training, bufs)
-    g3, b3 = _ffn_norm_params(P, pre, "norm3", g.HW, layer_norm)
     out = ops.norm_act_fwd(h3, st3[0], st3[1], g3, b3, g.HW, mode, res=x, rowscale=dp, rows_per_group=rpg, drop_seed=s3, drop_p=D.p)
     if save is not None:
         bwd_mode = mode if (layer_norm or training) else 2
@@ -510,23 +528,33 @@ def conv_ffn_fwd(P, bufs, pre, ln, x, g, layer_norm, training, save, D=NO_DROP):
     return out
 
 
-def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, drop=None, inplace=False, colsum=None):
-    """colsum: bias-gradient accumulator of the 1x1 conv in front of this norm (its output gradient is the dx computed here)"""
-    gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
+def _ffn_grads_cl(P, pre, hw, layer_norm, like):
+    """zeroed engine-layout accumulators for the gradients of _ffn_layout's parameters (one buffer, one fill) and the entries
+    that fold them back into the flat gradient buffer (one batched transpose-accumulate at the end of the block's backward)"""
+    items = _ffn_layout(P, pre, hw, layer_norm)
+    flat = ops.zeros(sum(r * c for _, r, c in items), like=like)
+    acc, off, entries = {}, 0, []
+    for name, r, c in items:
+        acc[name] = flat[off:off + r * c]
+        if P.g(name) is not None:
+            entries.append((acc[name], P.g(name), c, r))
+        off += r * c
+    return acc, entries
+
+
+def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, acc, rnd=False, drop=None, inplace=False, colsum=None):
+    """colsum: bias-gradient accumulator of the 1x1 conv in front of this norm (its output gradient is the dx computed here);
+    acc: the block's engine-layout gradient accumulators (_ffn_grads_cl)"""
     ch = h.shape[1]
     if colsum is not None and ch < FUSE_COLSUM_MIN_WIDTH:      # narrow tensor: separate column-sum pass (see FUSE_COLSUM_MIN_WIDTH)
-        dx = _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd, drop, inplace, None)
+        dx = _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, acc, rnd, drop, inplace, None)
         ops.colsum(dx, colsum)
         return dx
     drop = dict(drop or {}, colsum=colsum)
-    if layer_norm:
-        dg = ops.zeros(g.HW * ch, like=h)
-        db = ops.zeros(g.HW * ch, like=h)
-        dx = ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], dg, db, g.HW, mode, round_tf32=rnd, inplace=inplace, **drop)
-        if gw is not None:
-            ops.transpose(dg, 1, g.HW, ch, out=gw, accumulate=True)
-            ops.transpose(db, 1, g.HW, ch, out=gb, accumulate=True)
-        return dx
+    if layer_norm:      # frame-LayerNorm affine gradients accumulate [hw][ch]; conv_ffn_bwd folds them back in one launch
+        return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], acc[pre + "." + name + ".weight"], acc[pre + "." + name + ".bias"],
+                                g.HW, mode, round_tf32=rnd, inplace=inplace, **drop)
+    gw, gb = P.g(pre + "." + name + ".weight"), P.g(pre + "." + name + ".bias")
     if gw is None:
         gw, gb = ops.zeros(ch, like=h), ops.zeros(ch, like=h)
     return ops.norm_act_bwd(dy, h, st[0], st[1], aff[0], aff[1], gw, gb, g.HW, mode, round_tf32=rnd, inplace=inplace, **drop)
@@ -535,7 +563,8 @@ def _ffn_norm_bwd(P, pre, name, dy, h, st, aff, g, layer_norm, mode, rnd=False, 
 def conv_ffn_bwd(P, s, dout):
     g, pre, ln, lnm, mode = s["g"], s["pre"], s["ln"], s["layer_norm"], s["mode"]
     Ch = s["h1"].shape[1]
-    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, rnd=RT,
+    acc, fold = _ffn_grads_cl(P, pre, g.HW, lnm, dout)
+    dh3 = _ffn_norm_bwd(P, pre, "norm3", dout, s["h3"], s["st3"], s["aff"][2], g, lnm, mode, acc, rnd=RT,
                         drop=dict(rowscale=s["dp"], rows_per_group=s["rpg"], drop_seed=s["s3"], drop_p=s["p"]), colsum=P.g(pre + ".fc2.bias"))
     u2 = s["u2"]
     if u2 is None:        # lean mode: u2 = drop(GELU(norm2(h2))) again, same dropout seed
@@ -544,19 +573,20 @@ def conv_ffn_bwd(P, s, dout):
     _wgrad(P, pre + ".fc2.weight", dh3, u2)
     del u2
     du2 = ops.gemm(dh3, P.wr(pre + ".fc2.weight").view(g.C, Ch), b_mn=True)
-    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, drop=dict(drop_seed=s["s2"], drop_p=s["p"]),
+    dh2 = _ffn_norm_bwd(P, pre, "norm2", du2, s["h2"], s["st2"], s["aff"][1], g, lnm, mode, acc, drop=dict(drop_seed=s["s2"], drop_p=s["p"]),
                         inplace=True)
     gdw, gdb = P.g(pre + ".dw3x3.weight"), P.g(pre + ".dw3x3.bias")
     if gdw is not None:
-        dw9 = ops.zeros(9 * Ch, like=dh2)
+        dw9 = acc[pre + ".dw3x3.weight"]
         u1 = s["u1"]
         if u1 is None:    # lean mode
             u1 = ops.norm_act_fwd(s["h1"], s["st1"][0], s["st1"][1], s["aff"][0][0], s["aff"][0][1], g.HW, 1 if lnm else 0)
         ops.dwconv3x3_wgrad(u1, dh2, dw9, gdb, g.F, g.H, g.W)
         del u1
-        ops.transpose(dw9, 1, 9, Ch, out=gdw, accumulate=True)
     du1 = ops.dwconv3x3(dh2, s["w9"], None, g.F, g.H, g.W, flip=True)
-    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, rnd=RT, inplace=True, colsum=P.g(pre + ".fc1.bias"))
+    dh1 = _ffn_norm_bwd(P, pre, "norm1", du1, s["h1"], s["st1"], s["aff"][0], g, lnm, mode, acc, rnd=RT, inplace=True, colsum=P.g(pre + ".fc1.bias"))
+    if fold:            # engine-layout gradients -> (ch,H,W) / (Ch,1,3,3) slices of the flat gradient buffer, one launch
+        ops.transpose_multi((pre, "bwd", dout.device.index), fold, accumulate=True)
     b_ = s["b"]
     if b_ is None:        # lean mode
         b_ = ops.layernorm_fwd(s["x"], P.w(ln + ".weight"), P.w(ln + ".bias"), round_tf32=RT, save_stats=False)[0]

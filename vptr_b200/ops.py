@@ -364,6 +364,36 @@ def colsum(x, out):
     _call("vptr_colsum", _p(x), _p(out), rows, C, x.stride(0), _s())
 
 
+_TR_TABLES = {}
+_PINNED_KEEPALIVE = []      # host tables whose H2D copy was captured into a CUDA graph: replays read them again, never free them
+
+
+def pinned_table(values, device):
+    """int64 device table from a Python list through a pinned host buffer (async copy).  Returns (device tensor, host tensor): the
+    caller keeps the host tensor alive at least until the copy ran; if the copy is being captured into a CUDA graph the host
+    buffer is kept for the life of the process (a replay re-reads it)."""
+    host = torch.tensor(values, dtype=torch.int64).pin_memory()
+    dev = host.to(device, non_blocking=True)
+    if torch.cuda.is_current_stream_capturing():
+        _PINNED_KEEPALIVE.append(host)
+    return dev, host
+
+
+def transpose_multi(site, entries, accumulate=False):
+    """entries [(src, dst, R, C)]: dst[c][r] (+)= src[r][c] for every entry in ONE launch.  `site` names the call site: its pointer
+    table is rebuilt only when a pointer or shape changes."""
+    key = tuple(v for s_, d_, R, C in entries for v in (s_.data_ptr(), d_.data_ptr(), R, C))
+    ent = _TR_TABLES.get(site)
+    if ent is None or ent[0] != key:
+        rows, acc = [], 0
+        for s_, d_, R, C in entries:
+            acc += ((R + 31) // 32) * ((C + 31) // 32)
+            rows += [s_.data_ptr(), d_.data_ptr(), R, C, acc]
+        dev, host = pinned_table(rows, entries[0][0].device)
+        ent = _TR_TABLES[site] = (key, dev, host, acc)
+    _call("vptr_transpose_multi", _p(ent[1]), len(entries), ent[3], int(accumulate), _s())
+
+
 def transpose(x, batch, R, C, out=None, accumulate=False):
     """[batch][R][C] -> [batch][C][R] (out += when accumulate)."""
     if out is None:

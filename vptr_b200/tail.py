@@ -106,9 +106,8 @@ class _Table:
             for t in first:
                 acc += t.numel() // unit
                 ends.append(acc)
-            host = torch.tensor(list(key) + ends, dtype=torch.int64).pin_memory()
-            self.dev = host.to(first[0].device, non_blocking=True)
-            self._host = host            # keep the pinned source alive until the copy has run
+            # (pinned source kept alive until the copy has run -- for good when the copy is captured into a CUDA graph)
+            self.dev, self._host = ops.pinned_table(list(key) + ends, first[0].device)
             self.key, self.n, self.total, self.vec = key, len(first), acc, int(vec)
         return self.dev, self.n, self.total, self.vec
 
