@@ -8,6 +8,6 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${1:-700}
 timeout $T compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_kernels.py tests/test_gpu_tail.py \
-    tests/test_gpu_models.py tests/test_gpu_stage1.py tests/test_gpu_rollout.py -x -q -m gpu 2>&1 | grep -v "Host Frame\|Device Frame" | tail -8 | tee gpurun_out/sanitizer.log
+    tests/test_gpu_models.py tests/test_gpu_stage1.py tests/test_gpu_rollout.py -q -m gpu 2>&1 | grep -v "Host Frame\|Device Frame" | tail -8 | tee gpurun_out/sanitizer.log
 timeout 400 compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu \
     -k "attention_core or dwconv or layernorm or norm_act or head or elementwise" 2>&1 | grep -v "Host Frame\|Device Frame" | tail -8 | tee -a gpurun_out/sanitizer.log
