@@ -268,35 +268,41 @@ __global__ void __launch_bounds__(256) head_conv7x7_kernel(const float* __restri
             out[(((long long)f * Co + co) * H + oh) * W + ow] = head_act(acc[co] + bias[co], act);
 }
 
-// 7x7 head, fast path for Ci == 64 and W in {16, 32, 64}: the channel contraction is separated from the spatial gather.
+// 7x7 head, fast path for Ci == 64 and W in {16, 32, 64} or a multiple of 64: the channel contraction is separated from the
+// spatial gather.
 //   phase 1 (per input pixel, one thread): P[pixel][tap] = sum_c x[pixel][c] * w[tap][c] for all 49 taps -- the pixel's 64
 //           channels sit in registers, the weights are warp-broadcast float4 shared loads (4 FMAs per load);
 //   phase 2 (per output pixel): out = act(bias + sum_tap P[reflect(y+ky-3)][reflect(x+kx-3)][tap]) -- 49 conflict-free loads.
-// A block walks one frame top to bottom, HEAD_ROWS image rows per step, keeping P of the last HEAD_ROWS + 6 rows in a shared
-// ring [row][tap][x]; reflect padding is index arithmetic, so no halo is recomputed and x is read exactly once.
+// A block walks one frame (W <= 64) or one 64-column band of it (wider frames: cfg4's 128 x 128) top to bottom, ROWS image rows
+// per step, keeping P of the last ROWS + 6 rows in a shared ring [row][tap][column]; reflect padding is index arithmetic.  A
+// band needs the 3 columns on either side of it that exist in the image (the reflected ones map back into the band), so a wide
+// frame recomputes 3-6 of 64 columns of P; x is otherwise read exactly once.
 // (The direct kernel above spends 4.2 ms on the cfg1 decoder output, 40x its HBM floor: 16-way bank conflicts on the patch
-// loads and two shared loads per FMA pair.)
+// loads and two shared loads per FMA pair -- and 16.8 ms on cfg4's, which it served until the banded form existed.)
 __global__ void __launch_bounds__(512) head_conv7x7_p_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
                                                              const float* __restrict__ bias, float* __restrict__ out, int Co, int H, int W,
-                                                             int act) {
+                                                             int act, int TW, int ROWS, int NCP) {
     extern __shared__ __align__(16) float sm[];
-    const int ROWS = 512 / W, RING = ROWS + 6;
+    const int RING = ROWS + 6;
     float* sw = sm;                   // [49][64]
-    float* ring = sm + 49 * 64;       // [RING][49][W]
+    float* ring = sm + 49 * 64;       // [RING][49][NCP]
     const int f = blockIdx.x, co = blockIdx.y;
+    const int x0 = blockIdx.z * TW;                                   // first output column of this band
+    const int c_lo = max(x0 - 3, 0), ncol = min(x0 + TW + 3, W) - c_lo;   // input columns whose P this band needs
     for (int e = threadIdx.x; e < 49 * 64; e += 512) sw[e] = wpk[((long long)(e >> 6) * Co + co) * 64 + (e & 63)];
     __syncthreads();
-    const int lr = threadIdx.x / W, xx = threadIdx.x - lr * W;
+    const int lr = threadIdx.x / ncol, xx = threadIdx.x - lr * ncol;      // phase 1: (row in step, input column)
+    const int orows = 512 / TW, lr2 = threadIdx.x / TW, ox = threadIdx.x - lr2 * TW;   // phase 2: (row, output column)
     const float b = bias[co];
     int emitted = 0;
     for (int r0 = 0; r0 < H; r0 += ROWS) {
         const int row = r0 + lr;
-        if (row < H) {
+        if (lr < ROWS && row < H) {
             float4 v[16];
-            const float4* px = reinterpret_cast<const float4*>(x + (((long long)f * H + row) * W + xx) * 64);
+            const float4* px = reinterpret_cast<const float4*>(x + (((long long)f * H + row) * W + c_lo + xx) * 64);
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = __ldg(px + q);
-            float* dst = ring + (size_t)(row % RING) * 49 * W + xx;
+            float* dst = ring + (size_t)(row % RING) * 49 * NCP + xx;
 #pragma unroll 7
             for (int tap = 0; tap < 49; ++tap) {
                 const float4* wv = reinterpret_cast<const float4*>(sw + tap * 64);
@@ -306,27 +312,27 @@ __global__ void __launch_bounds__(512) head_conv7x7_p_kernel(const float* __rest
                     const float4 k = wv[q];
                     s0 = fmaf(v[q].x, k.x, s0); s1 = fmaf(v[q].y, k.y, s1); s2 = fmaf(v[q].z, k.z, s2); s3 = fmaf(v[q].w, k.w, s3);
                 }
-                dst[tap * W] = (s0 + s1) + (s2 + s3);
+                dst[tap * NCP] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncthreads();
         const int r_hi = min(r0 + ROWS, H) - 1;
         const int ready_to = (r_hi == H - 1) ? H - 1 : r_hi - 3;
-        for (int orow = emitted + lr; orow <= ready_to; orow += ROWS) {
+        for (int orow = emitted + lr2; orow <= ready_to; orow += orows) {
             float acc = b;
 #pragma unroll
             for (int ky = 0; ky < 7; ++ky) {
                 int ir = orow + ky - 3;
                 ir = ir < 0 ? -ir : (ir >= H ? 2 * (H - 1) - ir : ir);
-                const float* rp = ring + (size_t)(ir % RING) * 49 * W + ky * 7 * W;
+                const float* rp = ring + (size_t)(ir % RING) * 49 * NCP + ky * 7 * NCP - c_lo;
 #pragma unroll
                 for (int kx = 0; kx < 7; ++kx) {
-                    int ic = xx + kx - 3;
+                    int ic = x0 + ox + kx - 3;
                     ic = ic < 0 ? -ic : (ic >= W ? 2 * (W - 1) - ic : ic);
-                    acc += rp[kx * W + ic];
+                    acc += rp[kx * NCP + ic];
                 }
             }
-            out[(((long long)f * Co + co) * H + orow) * W + xx] = head_act(acc, act);
+            out[(((long long)f * Co + co) * H + orow) * W + x0 + ox] = head_act(acc, act);
         }
         emitted = ready_to + 1;
         __syncthreads();
@@ -507,17 +513,23 @@ extern "C" int vptr_head_conv7x7_fwd(const float* x, const float* wpk, const flo
                                      int act, cudaStream_t stream) {
     VPTR_REQUIRE(F > 0 && F < 65536 && Ci > 0 && Ci % 4 == 0 && Co > 0 && Co <= HEAD_MAXCO && H > 3 && W > 3, VPTR_ERR_SHAPE,
                  "vptr_head_conv7x7_fwd: F=%d Ci=%d Co=%d H=%d W=%d", F, Ci, Co, H, W);
-    if (Ci == 64 && (W == 16 || W == 32 || W == 64) && H >= 512 / W && H > 6) {
-        const int ring = 512 / W + 6;
-        const size_t psm = sizeof(float) * ((size_t)49 * 64 + (size_t)ring * 49 * W);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(head_conv7x7_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(head_conv7x7_p): %s", cudaGetErrorString(e));
-            attr_set = true;
+    const bool one_band = W == 16 || W == 32 || W == 64;
+    if (Ci == 64 && (one_band || (W > 64 && W % 64 == 0)) && H > 6) {
+        const int TW = one_band ? W : 64;                       // output columns per block
+        const int ncol_max = one_band ? W : (W > 128 ? 70 : 67);    // band + the in-image halo columns
+        const int ROWS = 512 / ncol_max, NCP = (ncol_max + 3) & ~3;
+        if (H >= ROWS) {
+            const size_t psm = sizeof(float) * ((size_t)49 * 64 + (size_t)(ROWS + 6) * 49 * NCP);
+            VPTR_REQUIRE(psm <= 200 * 1024, VPTR_ERR_SHAPE, "vptr_head_conv7x7_fwd: ring of %zu bytes", psm);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(head_conv7x7_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(head_conv7x7_p): %s", cudaGetErrorString(e));
+                attr_set = true;
+            }
+            head_conv7x7_p_kernel<<<dim3(F, Co, W / TW), 512, psm, stream>>>(x, wpk, bias, out, Co, H, W, act, TW, ROWS, NCP);
+            return vptr_check_launch("head_conv7x7_p_kernel");
         }
-        head_conv7x7_p_kernel<<<dim3(F, Co), 512, psm, stream>>>(x, wpk, bias, out, Co, H, W, act);
-        return vptr_check_launch("head_conv7x7_p_kernel");
     }
     size_t smem = sizeof(float) * ((size_t)484 * 16 + (size_t)49 * Co * 16);
     dim3 grid(vptr_cdiv(W, 16), vptr_cdiv(H, 16), F);
