@@ -354,7 +354,8 @@ def test_convT_gather_and_backward():
     assert rel_l2(dx, xr.grad) < TOL
 
 
-@pytest.mark.parametrize("Ci,H,W", [(1, 32, 24), (3, 32, 24), (1, 64, 64), (3, 16, 32), (1, 40, 16), (1, 128, 128), (3, 24, 192)])
+@pytest.mark.parametrize("Ci,H,W", [(1, 32, 24), (3, 32, 24), (1, 64, 64), (3, 16, 32), (1, 40, 16), (1, 128, 128), (3, 24, 192),
+                                    (3, 64, 64), (4, 32, 64), (3, 128, 128), (2, 40, 16)])
 def test_stem_and_head(Ci, H, W):
     """W in {16, 32, 64} takes the ring-buffered head kernel (head_conv7x7_p_kernel) one frame per block, multiples of 64 beyond
     that (128: cfg4; 192: an interior band with halo columns on both sides) in 64-column bands, other widths the direct kernel"""
