@@ -183,7 +183,7 @@ def test_temporal_attention_core(Tq, Tk, causal):
     assert rel_l2(dq, qr.grad) < 1e-4 and rel_l2(dkv, kvr.grad) < 1e-4
 
 
-@pytest.mark.parametrize("case", ["window", "window_tail", "temporal", "causal29", "cross"])
+@pytest.mark.parametrize("case", ["window", "window_tail", "temporal", "causal29", "cross", "temporal30", "cross30x10"])
 def test_attention_tcgen05_forward(case):
     """The tcgen05 / TMA / TMEM forward (vptr_attn_fwd_tcgen05, opt-in VPTR_ATTN_TC=1) against the fp32 oracle core.  Operands enter
     the tensor core as TF32, so q/k/v are pre-rounded (as their producing GEMMs do) and the gate is 1e-3 instead of 2e-5."""
@@ -204,7 +204,8 @@ def test_attention_tcgen05_forward(case):
         oref = torch.zeros(rows, C, device="cuda").index_put((tmap.t().reshape(-1),), ob.reshape(-1, C))
     else:
         N, H, W = 2, 8, 8
-        Tq, Tk, causal = {"temporal": (10, 10, False), "causal29": (29, 29, True), "cross": (28, 2, False)}[case]
+        Tq, Tk, causal = {"temporal": (10, 10, False), "causal29": (29, 29, True), "cross": (28, 2, False), "temporal30": (30, 30, False),
+                          "cross30x10": (30, 10, False)}[case]
         HW = H * W
         q, kv = ops.round_copy(rnd(N * Tq * HW, C, seed=1)), ops.round_copy(rnd(N * Tk * HW, 2 * C, seed=2))
         o = torch.full_like(q, float("nan"))

@@ -176,7 +176,7 @@ __host__ __device__ constexpr int seq_span(int TQ) {
 }
 // FQ = FK = 0: window fast path (8x8 grid, 4x4 windows) or the generic mask path, chosen at run time.
 // FQ, FK > 0 : temporal / enc-dec attention with compile-time query / key counts (T = 10 of cfg1, 29 of cfg2, 28 and 28 x 2 of
-//              cfg3): a row's keys are the FK contiguous columns of its own pixel sequence, picked out of a window of
+//              cfg3, 30 and 30 x 10 of cfg4): a row's keys are the FK contiguous columns of its own pixel sequence, picked out of a window of
 //              seq_span(FQ) * FK columns the warp loads once from TMEM.
 template <int FQ, int FK>
 __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_fwd_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ rpe_table,
@@ -665,6 +665,8 @@ extern "C" int vptr_attn_fwd_tcgen05(const float* Q, long long ldq, const float*
         else if (Tq == 29 && Tk == 29) kern = attn_tc_fwd_kernel<29, 29>;
         else if (Tq == 28 && Tk == 28) kern = attn_tc_fwd_kernel<28, 28>;
         else if (Tq == 28 && Tk == 2) kern = attn_tc_fwd_kernel<28, 2>;
+        else if (Tq == 30 && Tk == 30) kern = attn_tc_fwd_kernel<30, 30>;     // cfg4 (10 -> 30 frames): decoder temporal self-attention
+        else if (Tq == 30 && Tk == 10) kern = attn_tc_fwd_kernel<30, 10>;     // cfg4: encoder-decoder attention
     }
     cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     VPTR_REQUIRE(ea == cudaSuccess, (int)ea, "cudaFuncSetAttribute(attn_tc_fwd): %s", cudaGetErrorString(ea));

@@ -191,7 +191,7 @@ def attn_tc_window_ok(q, k, v, out, H, W, ws, nhead, d):
             and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
 
 
-ATTN_TC_SEQ_SHAPES = ((10, 10), (29, 29), (28, 28), (28, 2))   # (Tq, Tk) with compile-time fast paths: cfg1, cfg2 (FAR), cfg3
+ATTN_TC_SEQ_SHAPES = ((10, 10), (29, 29), (28, 28), (28, 2), (30, 30), (30, 10))   # (Tq, Tk) with compile-time fast paths: cfg1, cfg2 (FAR), cfg3, cfg4
 
 
 def attn_tc_temporal_ok(q, k, v, out, Tq, Tk, nhead, d):
