@@ -26,3 +26,18 @@ for ch in (2112, 528):
             ts.append(e0.elapsed_time(e1))
         t = sorted(ts[2:])[len(ts[2:]) // 2] * 1e-3
         print("norm_act_bwd ln3 ch=%4d %-17s %7.1f us   %.2f TB/s of the 3-pass minimum" % (ch, name, t * 1e6, 3 * rows * ch * 4 / t / 1e12))
+
+    # forward (read x, write y = 2 passes)
+    y = torch.empty_like(x)
+    for name, kw in (("plain", {}), ("dropout+droppath+res", dict(rowscale=rs, rows_per_group=10 * hw, drop_seed=5, drop_p=0.1, res=dy))):
+        ts = []
+        for it in range(7):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.norm_act_fwd(x, mean, rstd, gm, bt, hw, 1, out=y, round_tf32=True, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts[2:])[len(ts[2:]) // 2] * 1e-3
+        print("norm_act_fwd ln3 ch=%4d %-22s %7.1f us   %.2f TB/s of the 2-pass minimum" % (ch, name, t * 1e6, 2 * rows * ch * 4 / t / 1e12))
