@@ -11,6 +11,11 @@ from helpers import ROOT, build_former
 
 def test_library_loads_and_exports_every_declared_symbol():
     from vptr_b200 import _lib
+    import shutil
+    so = os.path.join(ROOT, "vptr_b200", "libvptr_b200.so")
+    if not os.path.exists(so) and shutil.which("nvcc"):      # fresh checkout: the library is a build artefact (__graft_entry__.build)
+        from vptr_b200 import build as B
+        B.build()
     l = _lib.lib()
     hdr = open(os.path.join(ROOT, "include", "vptr_b200.h")).read()
     declared = set(re.findall(r"\b(vptr_[A-Za-z0-9_]+)\s*\(", hdr))
