@@ -252,6 +252,36 @@ def measure_tf32_peak(torch, ops):
             "peak": max(cublas, own, conv)}
 
 
+def kernel_rooflines(gemm_stats, hbm_gbs, tf32_peak):
+    """north_star: "achieved fraction of the attention-GEMM and conv rooflines" -- from the CUDA-event pairs profile_gemms() puts
+    around every attention-core and 3x3-convolution launch of one real training step (in-step clocks and cache state, not a
+    kernel looped alone): the attention cores against the HBM rate (algorithmic bytes: q, k, v read + o written forward;
+    q, k, v, do read + dq, dk, dv written backward), the encoder's raw-tile convolution against the dense TF32 rate of this run."""
+    out = {}
+    names = {"attn_fwd_window": "window attention forward (attn_tc_fwd_kernel: tcgen05/TMEM/TMA where the shape has a fast path, else mma.sync 3xTF32)",
+             "attn_bwd_window": "window attention backward (attn_mma_kernel / attn_mma64_kernel: mma.sync 3xTF32; no tcgen05 backward yet)",
+             "attn_fwd_temporal": "temporal / enc-dec attention forward (attn_tc_fwd_kernel for the compile-time (Tq,Tk) shapes)",
+             "attn_bwd_temporal": "temporal / enc-dec attention backward (attn_mma_kernel)"}
+    for kind, label in names.items():
+        k = gemm_stats["kinds"].get(kind)
+        if k and k["ms"] > 0:
+            gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+            out[kind] = {"kernel": label, "launches_per_step": k["n"], "avg_launch_us": round(1e3 * k["ms"] / k["n"], 1), "bound": "hbm",
+                         "achieved": round(gbs, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(gbs / hbm_gbs, 4)}
+    k = gemm_stats["kinds"].get("conv3x3")
+    if k and k["ms"] > 0:
+        alg = k["flop"] / (k["ms"] * 1e-3) / 1e12
+        ex = k["flop_executed"] / (k["ms"] * 1e-3) / 1e12
+        out["encoder_conv3x3"] = {"kernel": "conv3x3_w8_kernel (tcgen05 implicit GEMM on the raw padded tile; 8x8 grid or 8x8 quadrants)",
+                                  "launches_per_step": k["n"], "avg_launch_us": round(1e3 * k["ms"] / k["n"], 1), "bound": "tensor",
+                                  "achieved": round(alg, 1), "executed": round(ex, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                                  "frac": round(alg / tf32_peak, 4), "frac_executed": round(ex / tf32_peak, 4),
+                                  "note": "two tf32 weight planes (hi/lo): executed MMA work is twice the algorithmic FLOPs"}
+    out["ncu"] = ("tensor-pipe / DRAM figures of the same kernels under ncu --set full: profiles/r01_ncu_attn_tcgen05.txt, r02_ncu_attn_cfg1.txt, "
+                  "r02_ncu_attn_mma64.txt, r01_ncu_conv3x3_w8.txt, r02_ncu_conv_quad.txt")
+    return out
+
+
 def gemm_traffic():
     """per-launch DRAM bytes of the dominant kernel from the committed ncu capture of one step (profiles/r02_gemm_traffic.json)"""
     try:
@@ -369,6 +399,12 @@ def run_cuda(args):
     torch.cuda.empty_cache()
     pk = peaks()
     tf32 = measure_tf32_peak(torch, ops)
+    # The sustained figures above are taken with the tensor pipe saturated for ~0.5 s, i.e. at the power-capped clock; inside the
+    # step the raw-tile convolution runs between memory-bound kernels at a higher clock and EXECUTES more than that.  A denominator
+    # this library's own kernel beats in the same run would be no roofline, so the highest demonstrated rate wins.
+    kconv = gemm_stats["kinds"].get("conv3x3")
+    tf32["own_conv3x3_in_step_tflops_executed"] = round(kconv["flop_executed"] / (kconv["ms"] * 1e-3) / 1e12, 1) if kconv and kconv["ms"] > 0 else 0.0
+    tf32["peak"] = max(tf32["peak"], tf32["own_conv3x3_in_step_tflops_executed"])
     fpc = frames_per_clip(c)
     frames = n * fpc * world
     value = frames / (ms_dev * 1e-3)
@@ -398,14 +434,17 @@ def run_cuda(args):
                      "algorithmic_bytes_per_launch": round(gemm_stats["bytes"] / max(gemm_stats["launches"], 1)),
                      "algorithmic_flop_per_launch": round(gemm_stats["flop"] / max(gemm_stats["launches"], 1)),
                      "avg_launch_us": round(1e3 * gemm_stats["ms"] / max(gemm_stats["launches"], 1), 2),
-                     "peak_note": "dense TF32 measured on this box in this run, sustained: max(cuBLAS torch.matmul allow_tf32 %.1f at 8192^3, own tcgen05 GEMM %.1f at 8192^3, "
-                                  "own raw-tile 3x3 conv kernel %.1f executed) TFLOP/s; MEASURED_PEAKS.json (%s) bf16 sustained %.1f"
-                                  % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], tf32["own_conv3x3_tf32_tflops_executed"], pk["src"], pk["bf16"]),
+                     "peak_note": "dense TF32 measured on this box in this run: max(cuBLAS torch.matmul allow_tf32 %.1f at 8192^3 sustained, own tcgen05 GEMM %.1f "
+                                  "at 8192^3 sustained, own raw-tile 3x3 conv kernel %.1f executed looped alone, %.1f executed inside the step) TFLOP/s; "
+                                  "MEASURED_PEAKS.json (%s) bf16 sustained %.1f"
+                                  % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], tf32["own_conv3x3_tf32_tflops_executed"],
+                                     tf32["own_conv3x3_in_step_tflops_executed"], pk["src"], pk["bf16"]),
                      "launches_per_step": gemm_stats["launches"], "gemm_ms_per_step": round(gemm_stats["ms"], 3),
                      "gemm_share_of_step": round(gemm_stats["ms"] / ms_dev, 3), "gemm_tflop_per_step": round(gemm_stats["flop"] / 1e12, 3)},
         "model_flops_utilisation": {"achieved_tflops": round(step_flop / (ms_dev * 1e-3) / 1e12, 1),
                                     "of_tf32_peak": round(step_flop / (ms_dev * 1e-3) / 1e12 / tf32["peak"], 4)},
     }
+    line["kernel_rooflines"] = kernel_rooflines(gemm_stats, pk["hbm"], tf32["peak"])
     if c["kind"] == "far":
         line["config"]["future_frames_only_per_s"] = round(n * c["Tf"] * world / (ms_dev * 1e-3), 2)
     if not args.no_cpu_baseline and world == 1:
@@ -418,44 +457,65 @@ def run_cuda(args):
 
 
 def profile_gemms(torch, ops, step_fn):
-    """re-runs one step with a CUDA-event pair around every vptr_gemm_tf32 / implicit-conv launch (same stream)"""
-    records = []
+    """re-runs one step with a CUDA-event pair around every vptr_gemm_tf32 / implicit-conv launch (same stream) -- the roofline
+    kernel family -- and around every attention-core launch (kernel_rooflines)"""
+    records = []      # (e0, e1, flop, bytes, kind, executed flop)
+
+    def timed(kind, fn, flop, nbytes, executed=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        records.append((e0, e1, flop, nbytes, kind, flop if executed is None else executed))
+        return r
+
     orig = ops.gemm
 
     def wrapped(A, B, out=None, a_mn=False, b_mn=False, **kw):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig(A, B, out=out, a_mn=a_mn, b_mn=b_mn, **kw)
-        e1.record()
         K, M = (A.shape if a_mn else A.shape[::-1])
         N = B.shape[1] if b_mn else B.shape[0]
         nbytes = 4.0 * (M * K + N * K + M * N * (2 if kw.get("residual") is not None or kw.get("accumulate") else 1))
-        records.append((e0, e1, 2.0 * M * N * K, nbytes))
-        return r
+        return timed("gemm", lambda: orig(A, B, out=out, a_mn=a_mn, b_mn=b_mn, **kw), 2.0 * M * N * K, nbytes)
 
-    orig_conv = ops.conv3x3_tf32
+    orig_conv, orig_quad = ops.conv3x3_tf32, ops.conv3x3_tf32_quad
 
-    def wrapped_conv(xpad, w, F_, H, W, C, Cout, **kw):      # implicit-GEMM convolution: same kernel family, A via 4-D TMA
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig_conv(xpad, w, F_, H, W, C, Cout, **kw)
-        e1.record()
-        nbytes = 4.0 * (xpad.numel() + w.numel() + F_ * H * W * Cout * (2 if kw.get("residual") is not None else 1))
-        records.append((e0, e1, 2.0 * F_ * H * W * Cout * 9 * C, nbytes))
-        return r
+    def conv_wrapper(fn):       # implicit-GEMM convolution: same kernel family, A via 4-D TMA boxes of the padded activation
+        def w_(xpad, w, F_, H, W, C, Cout, **kw):
+            nbytes = 4.0 * (xpad.numel() + w.numel() + F_ * H * W * Cout * (2 if kw.get("residual") is not None else 1))
+            flop = 2.0 * F_ * H * W * Cout * 9 * C
+            return timed("conv3x3", lambda: fn(xpad, w, F_, H, W, C, Cout, **kw), flop, nbytes, flop * kw.get("w_planes", 1))
+        return w_
+
+    o_fwd, o_tc, o_bwd = ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd
+
+    def fwd_wrapper(fn):
+        def w_(q, k, v, out, rpe_table, mode, *a, **kw):
+            nbytes = 4.0 * q.shape[1] * (2 * q.shape[0] + 2 * k.shape[0])
+            return timed("attn_fwd_window" if mode == 0 else "attn_fwd_temporal", lambda: fn(q, k, v, out, rpe_table, mode, *a, **kw), 0.0, nbytes)
+        return w_
+
+    def bwd_wrapper(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, *a, **kw):
+        nbytes = 4.0 * q.shape[1] * (3 * q.shape[0] + 4 * k.shape[0])
+        return timed("attn_bwd_window" if mode == 0 else "attn_bwd_temporal",
+                     lambda: o_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, *a, **kw), 0.0, nbytes)
 
     ops.gemm = wrapped
-    ops.conv3x3_tf32 = wrapped_conv
+    ops.conv3x3_tf32, ops.conv3x3_tf32_quad = conv_wrapper(orig_conv), conv_wrapper(orig_quad)
+    ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd = fwd_wrapper(o_fwd), fwd_wrapper(o_tc), bwd_wrapper
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
-        ops.conv3x3_tf32 = orig_conv
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in records)
-    flop = sum(f for _, _, f, _ in records)
-    nbytes = sum(b for _, _, _, b in records)
-    return {"ms": ms, "flop": flop, "bytes": nbytes, "launches": len(records), "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+        ops.conv3x3_tf32, ops.conv3x3_tf32_quad = orig_conv, orig_quad
+        ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd = o_fwd, o_tc, o_bwd
+    kinds = {}
+    for e0, e1, f, b_, kind, fx in records:
+        k = kinds.setdefault(kind, {"ms": 0.0, "flop": 0.0, "flop_executed": 0.0, "bytes": 0.0, "n": 0})
+        k["ms"] += e0.elapsed_time(e1); k["flop"] += f; k["flop_executed"] += fx; k["bytes"] += b_; k["n"] += 1
+    fam = [kinds[k] for k in ("gemm", "conv3x3") if k in kinds]       # the tcgen05 GEMM family: the roofline kernel
+    ms, flop, nbytes, n = (sum(k[x] for k in fam) for x in ("ms", "flop", "bytes", "n"))
+    return {"ms": ms, "flop": flop, "bytes": nbytes, "launches": n, "tflops": flop / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "kinds": kinds}
 
 
 def main():
