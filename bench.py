@@ -272,11 +272,11 @@ def kernel_rooflines(gemm_stats, hbm_gbs, tf32_peak):
     if k and k["ms"] > 0:
         alg = k["flop"] / (k["ms"] * 1e-3) / 1e12
         ex = k["flop_executed"] / (k["ms"] * 1e-3) / 1e12
-        out["encoder_conv3x3"] = {"kernel": "conv3x3_w8_kernel (tcgen05 implicit GEMM on the raw padded tile; 8x8 grid or 8x8 quadrants)",
+        out["encoder_conv3x3"] = {"kernel": "conv3x3_w8_bf16x3_kernel (tcgen05 implicit GEMM on the raw padded tile; 8x8 grid or 8x8 quadrants; operands as two bf16 planes, three kind::f16 passes)",
                                   "launches_per_step": k["n"], "avg_launch_us": round(1e3 * k["ms"] / k["n"], 1), "bound": "tensor",
                                   "achieved": round(alg, 1), "executed": round(ex, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                                   "frac": round(alg / tf32_peak, 4), "frac_executed": round(ex / tf32_peak, 4),
-                                  "note": "two tf32 weight planes (hi/lo): executed MMA work is twice the algorithmic FLOPs"}
+                                  "note": "executed = TF32-pass equivalents: hi*hi + lo*hi + hi*lo bf16 passes cost 1.5 tf32 passes (the two-plane TF32 form cost 2)"}
     out["ncu"] = ("tensor-pipe / DRAM figures of the same kernels under ncu --set full: profiles/r01_ncu_attn_tcgen05.txt, r02_ncu_attn_cfg1.txt, "
                   "r02_ncu_attn_mma64.txt, r01_ncu_conv3x3_w8.txt, r02_ncu_conv_quad.txt")
     return out
@@ -400,8 +400,9 @@ def run_cuda(args):
     pk = peaks()
     tf32 = measure_tf32_peak(torch, ops)
     # The sustained figures above are taken with the tensor pipe saturated for ~0.5 s, i.e. at the power-capped clock; inside the
-    # step the raw-tile convolution runs between memory-bound kernels at a higher clock and EXECUTES more than that.  A denominator
-    # this library's own kernel beats in the same run would be no roofline, so the highest demonstrated rate wins.
+    # step the raw-tile convolution runs between memory-bound kernels at a higher clock and EXECUTES more than that (in TF32-pass
+    # equivalents).  A denominator this library's own kernel beats in the same run would be no roofline, so the highest
+    # demonstrated rate wins.
     kconv = gemm_stats["kinds"].get("conv3x3")
     tf32["own_conv3x3_in_step_tflops_executed"] = round(kconv["flop_executed"] / (kconv["ms"] * 1e-3) / 1e12, 1) if kconv and kconv["ms"] > 0 else 0.0
     tf32["peak"] = max(tf32["peak"], tf32["own_conv3x3_in_step_tflops_executed"])
@@ -435,7 +436,7 @@ def run_cuda(args):
                      "algorithmic_flop_per_launch": round(gemm_stats["flop"] / max(gemm_stats["launches"], 1)),
                      "avg_launch_us": round(1e3 * gemm_stats["ms"] / max(gemm_stats["launches"], 1), 2),
                      "peak_note": "dense TF32 measured on this box in this run: max(cuBLAS torch.matmul allow_tf32 %.1f at 8192^3 sustained, own tcgen05 GEMM %.1f "
-                                  "at 8192^3 sustained, own raw-tile 3x3 conv kernel %.1f executed looped alone, %.1f executed inside the step) TFLOP/s; "
+                                  "at 8192^3 sustained, own two-plane TF32 raw-tile 3x3 conv kernel %.1f executed looped alone, the step's raw-tile conv %.1f TF32-pass equivalents executed inside the step) TFLOP/s; "
                                   "MEASURED_PEAKS.json (%s) bf16 sustained %.1f"
                                   % (tf32["cublas_tf32_tflops"], tf32["own_gemm_tf32_tflops"], tf32["own_conv3x3_tf32_tflops_executed"],
                                      tf32["own_conv3x3_in_step_tflops_executed"], pk["src"], pk["bf16"]),
@@ -477,13 +478,16 @@ def profile_gemms(torch, ops, step_fn):
         nbytes = 4.0 * (M * K + N * K + M * N * (2 if kw.get("residual") is not None or kw.get("accumulate") else 1))
         return timed("gemm", lambda: orig(A, B, out=out, a_mn=a_mn, b_mn=b_mn, **kw), 2.0 * M * N * K, nbytes)
 
-    orig_conv, orig_quad = ops.conv3x3_tf32, ops.conv3x3_tf32_quad
+    orig_conv, orig_quad, orig_bf = ops.conv3x3_tf32, ops.conv3x3_tf32_quad, ops.conv3x3_bf16x3
 
-    def conv_wrapper(fn):       # implicit-GEMM convolution: same kernel family, A via 4-D TMA boxes of the padded activation
+    def conv_wrapper(fn, bf16x3=False):   # implicit-GEMM convolution: same kernel family, A via 4-D TMA boxes of the padded activation
         def w_(xpad, w, F_, H, W, C, Cout, **kw):
-            nbytes = 4.0 * (xpad.numel() + w.numel() + F_ * H * W * Cout * (2 if kw.get("residual") is not None else 1))
+            nbytes = float(xpad.numel() * xpad.element_size() + w.numel() * w.element_size()
+                           + 4 * F_ * H * W * Cout * (2 if kw.get("residual") is not None else 1))
             flop = 2.0 * F_ * H * W * Cout * 9 * C
-            return timed("conv3x3", lambda: fn(xpad, w, F_, H, W, C, Cout, **kw), flop, nbytes, flop * kw.get("w_planes", 1))
+            # executed work in TF32-pass equivalents: two tf32 weight planes = 2 passes; three bf16 passes = 1.5 (a kind::f16
+            # instruction contracts twice the elements of a kind::tf32 one in the same time)
+            return timed("conv3x3", lambda: fn(xpad, w, F_, H, W, C, Cout, **kw), flop, nbytes, flop * (1.5 if bf16x3 else kw.get("w_planes", 1)))
         return w_
 
     o_fwd, o_tc, o_bwd = ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd
@@ -500,14 +504,14 @@ def profile_gemms(torch, ops, step_fn):
                      lambda: o_bwd(q, k, v, do, dq, dk, dv, rpe_table, d_rpe_table, mode, *a, **kw), 0.0, nbytes)
 
     ops.gemm = wrapped
-    ops.conv3x3_tf32, ops.conv3x3_tf32_quad = conv_wrapper(orig_conv), conv_wrapper(orig_quad)
+    ops.conv3x3_tf32, ops.conv3x3_tf32_quad, ops.conv3x3_bf16x3 = conv_wrapper(orig_conv), conv_wrapper(orig_quad), conv_wrapper(orig_bf, True)
     ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd = fwd_wrapper(o_fwd), fwd_wrapper(o_tc), bwd_wrapper
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops.gemm = orig
-        ops.conv3x3_tf32, ops.conv3x3_tf32_quad = orig_conv, orig_quad
+        ops.conv3x3_tf32, ops.conv3x3_tf32_quad, ops.conv3x3_bf16x3 = orig_conv, orig_quad, orig_bf
         ops.attn_fwd, ops.attn_fwd_tcgen05, ops.attn_bwd = o_fwd, o_tc, o_bwd
     kinds = {}
     for e0, e1, f, b_, kind, fx in records:

@@ -176,6 +176,14 @@ int vptr_conv3x3_tf32(const float* xpad, const float* w, float* out, int F, int 
 int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* out, int F, int H, int W, int C, int Cout, const float* bias,
                            const float* residual, int act, int flags, int w_planes, vptr_stream_t stream);
 int vptr_pad_nhwc_quad(const float* x, float* out, int F, int H, int W, int C, int pad_mode, int round_tf32, vptr_stream_t stream);
+/* the ResnetBlock convolution (reference model/ResNetAutoEncoder.py:138,151) with both operands as two bf16 planes (x = hi + lo,
+ * w = hi + lo) and three bf16 tensor-core passes (hi*hi + lo*hi + hi*lo, fp32 accumulate): ~2^-16 per product instead of tf32's
+ * 2^-11, at 1.5 instead of 2 TF32-pass equivalents.  H, W multiples of 8 (8x8 included), C % 8 == 0.
+ *   xq2: vptr_pad_nhwc_quad_bf16x2 -> [2][F*(H/8)*(W/8)][10][10][C] bf16;  w2: vptr_split_bf16x2 -> [Cout][2][9*C] bf16 */
+int vptr_conv3x3_bf16x3(const void* xq2, const void* w2, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                        const float* residual, int act, int flags, vptr_stream_t stream);
+int vptr_pad_nhwc_quad_bf16x2(const float* x, void* out, int F, int H, int W, int C, int pad_mode, vptr_stream_t stream);
+int vptr_split_bf16x2(const float* w, void* out, long long rows, long long K, vptr_stream_t stream);
 /* out[r] = [ rna_tf32(w[r]) | rna_tf32(w[r] - hi) ]: the two tf32 planes of a weight matrix (rows of K -> rows of 2K) */
 int vptr_split_tf32(const float* w, float* out, long long rows, long long K, vptr_stream_t stream);
 int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, int C, int pad, int pad_mode, int round_tf32, vptr_stream_t stream);

@@ -14,6 +14,11 @@ def tf32_exact(shape, seed):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32).cuda()   # low 13 mantissa bits cleared: exact in tf32
 
 
+def rnd(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g).cuda()
+
+
 def ref_gemm(A, B, a_mn, b_mn):
     A64 = A.double().t() if a_mn else A.double()
     B64 = B.double() if b_mn else B.double().t()
@@ -143,3 +148,33 @@ def test_quadrant_conv3x3(Fr, H, W, Ci, Co, mode):
         assert rel_l2(y, yg) < 2e-5     # two fp32 summation orders over K = 9*Ci
     with pytest.raises(RuntimeError):      # the raw-tile epilogue has no GELU: refused, not silently skipped
         ops.conv3x3_tf32_quad(xq, wpk, Fr, H, W, Ci, Co, act=ops.ACT_GELU)
+
+
+@pytest.mark.parametrize("Fr,H,W,Ci,Co,mode", [(5, 8, 8, 48, 64, "reflect"), (3, 16, 16, 64, 180, "zero"), (7, 24, 8, 16, 24, "replicate"),
+                                                (4, 8, 8, 528, 528, "reflect"), (2, 16, 16, 528, 528, "reflect")])
+def test_conv3x3_bf16x3(Fr, H, W, Ci, Co, mode):
+    """the ResnetBlock convolution with both operands as two bf16 planes and three bf16 tensor-core passes (hi*hi + lo*hi + hi*lo)
+    on the raw-tile kernel: arbitrary fp32 inputs (nothing pre-rounded), within ~2^-16 of fp64 -- 8x8 grid and quadrant grids,
+    channel counts that end inside a 64-channel slice, odd quadrant counts (masked last pair tile), bias / ReLU / residual"""
+    import torch.nn.functional as F
+    from vptr_b200 import ops
+    x = rnd(Fr * H * W, Ci, seed=31)
+    w = rnd(Co, Ci, 3, 3, seed=32) * 0.25
+    bias, res = torch.randn(Co, device="cuda"), torch.randn(Fr * H * W, Co, device="cuda")
+    xq2 = ops.pad_nhwc_quad_bf16x2(x, Fr, H, W, Ci, ops.PAD_MODES[mode])
+    xp = F.pad(x.view(Fr, H, W, Ci).permute(0, 3, 1, 2).double(), (1,) * 4,
+               mode={"zero": "constant", "reflect": "reflect", "replicate": "replicate"}[mode])
+    # the two planes: hi = bf16(x), lo = bf16(x - hi), tiled like vptr_pad_nhwc_quad
+    patches = xp.float().unfold(2, 10, 8).unfold(3, 10, 8).permute(0, 2, 3, 4, 5, 1).reshape(-1, Ci)
+    hi = patches.bfloat16()
+    assert torch.equal(xq2[0], hi) and torch.equal(xq2[1], (patches - hi.float()).bfloat16())
+    w2 = ops.split_bf16x2(ops.pack_conv_weight(w, None, 0).view(Co, 9 * Ci))
+    y = ops.conv3x3_bf16x3(xq2, w2, Fr, H, W, Ci, Co, bias=bias, residual=res, act=ops.ACT_RELU)
+    ref = torch.relu(F.conv2d(xp, w.double(), bias.double())).permute(0, 2, 3, 1).reshape(-1, Co) + res.double()
+    err = rel_l2(y, ref)
+    print("bf16x3 conv rel_l2 vs fp64: %.2e" % err)
+    assert err < 3e-5
+    y0 = ops.conv3x3_bf16x3(xq2, w2, Fr, H, W, Ci, Co)
+    assert rel_l2(y0, F.conv2d(xp, w.double()).permute(0, 2, 3, 1).reshape(-1, Co)) < 3e-5
+    with pytest.raises(RuntimeError):
+        ops.conv3x3_bf16x3(xq2, w2, Fr, H, W, Ci, Co, act=ops.ACT_GELU)

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GEMM = ["tests/test_gpu_gemm.py"]
 ATTN = ["tests/test_gpu_kernels.py", "tests/test_gpu_dropout.py", "-k", "attention"]
 MODEL = ["tests/test_gpu_fullsize.py", "-k", "cfg1 or cfg3 or far"]
+ENCODER = ["tests/test_gpu_models.py", "tests/test_gpu_fullsize.py", "-k", "autoencoder or packed"]
 DWCONV = ["tests/test_gpu_kernels.py", "-k", "dwconv"]
 
 SWITCHES = [
@@ -22,6 +23,7 @@ SWITCHES = [
     ("VPTR_GEMM_NARROW", "1", GEMM),          # 256 x 176 pair tiles also for the wide (N >= 1024) outputs
     ("VPTR_GEMM_EPI_STG", "1", GEMM),         # per-lane store epilogue instead of TMA bulk stores / bulk-loaded residual
     ("VPTR_CONV_GENERIC", "1", GEMM),         # per-(tap, slice) 4-D TMA box conv instead of the raw-tile kernel (8x8 and quadrant grids)
+    ("VPTR_CONV_TF32", "1", ENCODER),         # ResnetBlock convs on the two-plane TF32 raw-tile kernel instead of the bf16x3 one
     ("VPTR_ATTN_TC", "0", MODEL),             # engine keeps the attention forward on the mma.sync kernels (no tcgen05 forward)
     # (VPTR_ATTN_TC=1 makes vptr_attn_fwd itself route to the single-pass TF32 tcgen05 kernel, which changes the numerics to the
     #  tcgen05 tolerance by design; that kernel's generic mask path is covered directly by test_attention_tcgen05_forward)

@@ -58,6 +58,9 @@ _SIGS = {
     "vptr_conv3x3_tf32": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
     "vptr_conv3x3_tf32_quad": ([P, P, P, I, I, I, I, I, P, P, I, I, I, P], I),
     "vptr_pad_nhwc_quad": ([P, P, I, I, I, I, I, I, P], I),
+    "vptr_conv3x3_bf16x3": ([P, P, P, I, I, I, I, I, P, P, I, I, P], I),
+    "vptr_pad_nhwc_quad_bf16x2": ([P, P, I, I, I, I, I, P], I),
+    "vptr_split_bf16x2": ([P, P, L, L, P], I),
     "vptr_split_tf32": ([P, P, L, L, P], I),
     "vptr_pad_nhwc": ([P, P, I, I, I, I, I, I, I, P], I),
     "vptr_im2col": ([P, P, P, I, I, I, I, I, I, I, I, I, P], I),

@@ -6,6 +6,7 @@
 //   * the 7x7 stem (Cimg -> 64, reads the NCHW frames directly) and the 7x7 head (64 -> Cimg, + bias, Tanh|Sigmoid,
 //     writes NCHW frames) as direct HBM-bound kernels, and the head's input gradient.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -456,6 +457,58 @@ extern "C" int vptr_pad_nhwc(const float* x, float* out, int F, int H, int W, in
     if (total4 < 0x7fffffffLL) pad_nhwc_kernel<unsigned><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
     else pad_nhwc_kernel<long long><<<ew_grid(total4, 256), 256, 0, stream>>>(x, out, total4, H, W, C / 4, pad, pad_mode, round_tf32);
     return vptr_check_launch("pad_nhwc_kernel");
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): ~16 significant bits in two bf16 planes (operands of the bf16x3 convolution)
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// quadrant-tiled padded copy as TWO bf16 planes: out[plane][(f, qy, qx)][ph][pw][c], plane 0 = hi, 1 = lo (vptr_conv3x3_bf16x3)
+__global__ void __launch_bounds__(256) pad_nhwc_quad_bf16x2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, unsigned total4,
+                                                                   int H, int W, int C4, int pad_mode) {
+    const int qw = W / 8, qh = H / 8;
+    const size_t plane = (size_t)total4 * 4;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+        const int c = (int)(i % (unsigned)C4);
+        unsigned t = i / (unsigned)C4;
+        const int pw = (int)(t % 10u); t /= 10u;
+        const int ph = (int)(t % 10u); t /= 10u;
+        const int qx = (int)(t % (unsigned)qw); t /= (unsigned)qw;
+        const int qy = (int)(t % (unsigned)qh);
+        const long long f = (long long)(t / (unsigned)qh);
+        const int ih = pad_index(qy * 8 + ph - 1, H, pad_mode), iw = pad_index(qx * 8 + pw - 1, W, pad_mode);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ih >= 0 && iw >= 0) v = reinterpret_cast<const float4*>(x)[((f * H + ih) * W + iw) * C4 + c];
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(out + (size_t)i * 4) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(out + plane + (size_t)i * 4) = *reinterpret_cast<const uint2*>(l);
+    }
+}
+// out[r] = [ bf16 hi plane of w[r][0..K) | bf16 lo plane ]  (weights of vptr_conv3x3_bf16x3)
+__global__ void __launch_bounds__(256) split_bf16x2_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long rows, long long K) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * K; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K, k = i - r * K;
+        __nv_bfloat16 h, l;
+        split_bf16(w[i], h, l);
+        out[r * 2 * K + k] = h;
+        out[r * 2 * K + K + k] = l;
+    }
+}
+
+extern "C" int vptr_pad_nhwc_quad_bf16x2(const float* x, void* out, int F, int H, int W, int C, int pad_mode, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0 && C > 0 && C % 8 == 0, VPTR_ERR_SHAPE,
+                 "vptr_pad_nhwc_quad_bf16x2: F=%d H=%d W=%d C=%d (H, W, C multiples of 8)", F, H, W, C);
+    const long long total4 = (long long)F * (H / 8) * (W / 8) * 100 * (C / 4);
+    VPTR_REQUIRE(total4 < 0xffffffffLL, VPTR_ERR_SHAPE, "vptr_pad_nhwc_quad_bf16x2: tensor too large for 32-bit indexing");
+    pad_nhwc_quad_bf16x2_kernel<<<ew_grid(total4, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), (unsigned)total4, H, W, C / 4, pad_mode);
+    return vptr_check_launch("pad_nhwc_quad_bf16x2_kernel");
+}
+extern "C" int vptr_split_bf16x2(const float* w, void* out, long long rows, long long K, cudaStream_t stream) {
+    VPTR_REQUIRE(rows > 0 && K > 0, VPTR_ERR_SHAPE, "vptr_split_bf16x2: rows=%lld K=%lld", rows, K);
+    split_bf16x2_kernel<<<ew_grid(rows * K, 256), 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(out), rows, K);
+    return vptr_check_launch("split_bf16x2_kernel");
 }
 
 extern "C" int vptr_pad_nhwc_quad(const float* x, float* out, int F, int H, int W, int C, int pad_mode, int round_tf32, cudaStream_t stream) {

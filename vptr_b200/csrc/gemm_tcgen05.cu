@@ -1124,6 +1124,172 @@ conv3x3_w8_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
 }
 
+// =============================================================================================
+// The same raw-tile convolution with BOTH operands split into two bf16 planes (x = x_hi + x_lo, w = w_hi + w_lo, each rounded to
+// nearest bf16) and three kind::f16 MMAs per product -- x_hi w_hi + x_lo w_hi + x_hi w_lo, fp32 accumulation; the dropped
+// x_lo w_lo term is ~2^-16 relative.  Against the two-plane TF32 form above (x rounded to tf32, w = hi + lo in tf32) this
+//   * removes the activation rounding (2^-11 -> 2^-16 per product: the frozen encoder's features land ~10x closer to fp32), and
+//   * executes 3 bf16 passes = 1.5 TF32-pass equivalents instead of 2 (a kind::f16 instruction contracts 16 elements in the
+//     time a kind::tf32 one contracts 8): 25 % less tensor-pipe time on a kernel that is 88-89 % tensor-bound.
+// A 128-byte swizzle row holds 64 bf16 channels, so a channel slice is 64 wide and needs two raw tiles (hi, lo planes; the planes are
+// stacked along the frame dimension of the padded buffer, [2][F][10][10][C] bf16).  Weight chunk j = tap * 2 + plane: the hi chunk
+// serves two MMA groups (x_hi, x_lo), the lo chunk one (x_hi).
+constexpr int CB_BSTAGES = 8;
+constexpr int CB_SMEM_BYTES = 4 * CW_A_BYTES + CB_BSTAGES * CW_B_BYTES + 256 + 4 * 32 * EPI_PITCH * 4 + 1024;
+static_assert(CB_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv3x3_w8_bf16x3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p, int frames_total) {
+    constexpr int BLOCK_N = 176;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sAraw = smem;                                  // [2 slots][hi, lo] raw tiles
+    uint8_t* sBring = smem + 4 * CW_A_BYTES;
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(sBring + CB_BSTAGES * CW_B_BYTES);
+    uint64_t* b_empty = b_full + CB_BSTAGES;
+    uint64_t* a_full = b_empty + CB_BSTAGES;
+    uint64_t* a_empty = a_full + 2;
+    uint64_t* tmem_full = a_empty + 2;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* epi_tiles = reinterpret_cast<float*>(sBring + CB_BSTAGES * CW_B_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    constexpr int SLICE = 64;                               // bf16 channels per 128-byte row
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+        for (int s = 0; s < CB_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&a_full[a], 1);
+            mbar_init(&a_empty[a], 1);
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {   // ===== TMA producer (both CTAs) =====
+        int bs = 0, ab = 0;
+        uint32_t bphase = 0, aphase = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+            const int f0 = (m_pair * 2 + (int)rank) * 2;
+            const int n0 = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
+            for (int cs = 0; cs < p.conv_cpt; ++cs) {
+                mbar_wait(&a_empty[ab], aphase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&a_full[ab], 4 * CW_A_BYTES);      // hi + lo tiles of both CTAs
+                    tma_load_4d_2cta(&tma_a, &a_full[ab], sAraw + (2 * ab) * CW_A_BYTES, cs * SLICE, 0, f0, 0);
+                    tma_load_4d_2cta(&tma_a, &a_full[ab], sAraw + (2 * ab + 1) * CW_A_BYTES, cs * SLICE, 0, frames_total + f0, 0);
+                }
+                __syncwarp();
+                if (++ab == 2) { ab = 0; aphase ^= 1; }
+                for (int j = 0; j < 18; ++j) {                                       // j = tap * 2 + weight plane
+                    mbar_wait(&b_empty[bs], bphase ^ 1);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&b_full[bs], 2 * CW_B_BYTES);
+                        tma_load_2d_2cta(&tma_b, &b_full[bs], sBring + bs * CW_B_BYTES, ((j & 1) * 9 + (j >> 1)) * p.conv_C + cs * SLICE, n0);
+                    }
+                    __syncwarp();
+                    if (++bs == CB_BSTAGES) { bs = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {   // ===== MMA issuer (leader CTA) =====
+            // kind::f16 descriptor: fp32 accumulate (bit 4), A and B formats BF16 (1), K-major both, N, M = 256
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((2 * BLOCK_M) >> 4) << 24);
+            int bs = 0, ab = 0, acc = 0;
+            uint32_t bphase = 0, aphase = 0, acc_phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int cs = 0; cs < p.conv_cpt; ++cs) {
+                    mbar_wait(&a_full[ab], aphase);
+                    tcgen05_fence_after();
+                    const uint32_t a_hi = smem_u32(sAraw + (2 * ab) * CW_A_BYTES), a_lo = a_hi + CW_A_BYTES;
+                    for (int j = 0; j < 18; ++j) {
+                        const int tap = j >> 1, kh = tap / 3, kw = tap - kh * 3;
+                        const uint32_t tap_off = uint32_t(kh * 20 + kw) * 128u;                 // [h][frame][w] rows of 128 B
+                        mbar_wait(&b_full[bs], bphase);
+                        tcgen05_fence_after();
+                        const uint32_t b_base = smem_u32(sBring + bs * CW_B_BYTES);
+                        if (elect_one()) {
+                            const int groups = (j & 1) ? 1 : 2;       // w_hi: x_hi and x_lo; w_lo: x_hi only
+                            for (int gq = 0; gq < groups; ++gq) {
+                                const uint32_t a_tap = (gq ? a_lo : a_hi) + tap_off;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {         // 4 x 16 bf16 = one 128-byte row
+                                    const uint64_t da = make_smem_desc(a_tap + k * 32, 16, 1280, 2);
+                                    const uint64_t db = make_smem_desc(b_base + k * 32, 16, 1024, 2);
+                                    umma_bf16_2cta(d_tmem, da, db, idesc, (cs > 0 || j > 0 || gq > 0 || k > 0) ? 1u : 0u);
+                                }
+                            }
+                            umma_commit_2cta(&b_empty[bs]);
+                            if (j == 17) umma_commit_2cta(&a_empty[ab]);
+                        }
+                        __syncwarp();
+                        if (++bs == CB_BSTAGES) { bs = 0; bphase ^= 1; }
+                    }
+                    if (++ab == 2) { ab = 0; aphase ^= 1; }
+                }
+                if (elect_one()) umma_commit_2cta(&tmem_full[acc]);
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {   // ===== epilogue warps 2..5 of both CTAs =====
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+            const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
+            const int m_base = (m_pair * 2 + (int)rank) * BLOCK_M + q * 32;
+            float* sT = epi_tiles + (warp - 2) * 32 * EPI_PITCH;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BLOCK_N);
+            epilogue_tile<BLOCK_N, true>(p, taddr, sT, lane, m_base, n_tile * BLOCK_N, [&] {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+            });
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1188,6 +1354,32 @@ int make_map_nhwc_w8(CUtensorMap* map, const float* ptr, long long F, long long 
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(w8) failed (%d): F=%lld C=%lld", (int)r, F, C);
+    return VPTR_OK;
+}
+
+// bf16 raw-tile map: [2 planes * F][10][10][C] bf16 viewed as (c, w, frame, h); box {64, 10, 2, 10}
+int make_map_nhwc_w8_bf16(CUtensorMap* map, const void* ptr, long long F2, long long C) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, 10, (cuuint64_t)F2, 10};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)100 * C * 2, (cuuint64_t)10 * C * 2};
+    cuuint32_t box[4] = {64, 10, 2, 10};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(w8 bf16) failed (%d): F2=%lld C=%lld", (int)r, F2, C);
+    return VPTR_OK;
+}
+int make_map_2d_bf16(CUtensorMap* map, const void* ptr, long long inner, long long outer, long long pitch, int box_inner, int box_outer) {
+    EncodeTiledFn enc = get_encode_fn();
+    VPTR_REQUIRE(enc != nullptr, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VPTR_REQUIRE(r == CUDA_SUCCESS, VPTR_ERR_DRIVER, "cuTensorMapEncodeTiled(2d bf16) failed (%d): inner=%lld outer=%lld", (int)r, inner, outer);
     return VPTR_OK;
 }
 
@@ -1396,6 +1588,54 @@ extern "C" int vptr_conv3x3_tf32_quad(const float* xq, const float* w, float* ou
     if (total < clusters) clusters = total;
     conv3x3_w8_kernel<<<2 * clusters, NUM_THREADS, CW_SMEM_BYTES, stream>>>(ma, mb, p);
     return vptr_check_launch("conv3x3_w8_kernel(quad)");
+}
+
+// 3x3 stride-1 convolution, H and W multiples of 8, on the bf16x3 raw-tile kernel (conv3x3_w8_bf16x3_kernel): xq2 = the two bf16
+// planes of the quadrant-tiled padded activation from vptr_pad_nhwc_quad_bf16x2, [2][F*(H/8)*(W/8)][10][10][C] bf16; w2 = the two
+// bf16 planes of the packed weights from vptr_split_bf16x2, [Cout][2][9*C] bf16.  fp32 output, same epilogue options as
+// vptr_conv3x3_tf32_quad (bias, ReLU, residual, tf32 rounding of the stored values).  C % 8 == 0 (16-byte TMA rows).
+// Replaces nn.Conv2d(k3,s1) + folded eval BatchNorm of the ResnetBlocks (reference model/ResNetAutoEncoder.py:138,151).
+extern "C" int vptr_conv3x3_bf16x3(const void* xq2, const void* w2, float* out, int F, int H, int W, int C, int Cout, const float* bias,
+                                   const float* residual, int act, int flags, cudaStream_t stream) {
+    VPTR_REQUIRE(F > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0 && C > 0 && Cout > 0, VPTR_ERR_SHAPE,
+                 "vptr_conv3x3_bf16x3: F=%d H=%d W=%d (H, W multiples of 8)", F, H, W);
+    VPTR_REQUIRE(C % 8 == 0 && Cout % 4 == 0 && ((uintptr_t)xq2 % 16 == 0) && ((uintptr_t)w2 % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                     ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
+                 VPTR_ERR_ALIGN, "vptr_conv3x3_bf16x3: C %% 8, Cout %% 4 and 16-byte aligned pointers required");
+    VPTR_REQUIRE(!(flags & 1), VPTR_ERR_UNSUPPORTED, "vptr_conv3x3_bf16x3: accumulate mode not supported");
+    VPTR_REQUIRE(act == 0 || act == 2, VPTR_ERR_UNSUPPORTED, "vptr_conv3x3_bf16x3: act %d (the raw-tile epilogue has none / ReLU only)", act);
+    const long long FQ = (long long)F * (H / 8) * (W / 8);
+    VPTR_REQUIRE(FQ * 64 < 0x3fffffffLL, VPTR_ERR_SHAPE, "vptr_conv3x3_bf16x3: too many rows");
+    GemmParams p;
+    p.M = (int)((long long)F * H * W); p.N = Cout; p.K = 9 * C;
+    p.m_tiles = (int)((FQ + 3) / 4);
+    p.n_tiles = vptr_cdiv(Cout, 176);
+    p.conv_cpt = vptr_cdiv(C, 64);
+    p.total_chunks = 18 * p.conv_cpt;
+    p.k_splits = 1; p.chunks_per_split = p.total_chunks;
+    p.D = out; p.ldd = Cout; p.bias = bias; p.residual = residual; p.ldr = Cout;
+    p.alpha = 1.f; p.act = act; p.flags = flags;
+    p.rowscale = nullptr; p.rows_per_group = 1; p.drop_seed = 0; p.drop_p = 0.f;
+    p.dbg = nullptr;
+    p.conv_taps = 9; p.conv_kw = 3; p.conv_bh = 8; p.conv_tiles_per_frame = 1; p.conv_bf = 2; p.conv_C = C;
+    p.conv_w8 = 1; p.conv_planes = 2; p.epi_tma = 0;
+    p.conv_qw = (H == 8 && W == 8) ? 0 : W / 8; p.conv_qh = (H == 8 && W == 8) ? 0 : H / 8;
+    CUtensorMap ma, mb;
+    int rc = make_map_nhwc_w8_bf16(&ma, xq2, 2 * FQ, C);
+    if (rc) return rc;
+    rc = make_map_2d_bf16(&mb, w2, 2LL * 9 * C, Cout, 2LL * 9 * C, 64, 176 / 2);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_w8_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CB_SMEM_BYTES);
+        VPTR_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(conv3x3_w8_bf16x3, smem=%d): %s", CB_SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int total = p.m_tiles * p.n_tiles;
+    int clusters = num_sms() / 2;
+    if (total < clusters) clusters = total;
+    conv3x3_w8_bf16x3_kernel<<<2 * clusters, NUM_THREADS, CB_SMEM_BYTES, stream>>>(ma, mb, p, (int)FQ);
+    return vptr_check_launch("conv3x3_w8_bf16x3_kernel");
 }
 
 // Implicit-GEMM 3x3 stride-1 convolution on the tcgen05 kernel (ResnetBlock convs, reference model/ResNetAutoEncoder.py:138,151):

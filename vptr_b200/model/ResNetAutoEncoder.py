@@ -157,14 +157,27 @@ def _conv3x3(x, F_, H, W, conv, bn, stride, pad_mode, relu, residual=None, act_a
     Cout, Cin = conv.weight.shape[:2]
     implicit = stride == 1 and not ops.FORCE_SIMT and ops.conv3x3_implicit_ok(H, W) and Cin % 4 == 0 and Cout % 4 == 0
 
+    bf16x3 = implicit and ops.conv3x3_bf16x3_ok(H, W, Cin)
+
     def build():
         scale, shift = ops.bn_fold(bn)
         wraw = ops.pack_conv_weight(conv.weight.data, scale, 0).view(Cout, 9 * Cin)
+        if bf16x3:
+            return ops.split_bf16x2(wraw), shift
         if implicit:
             return (ops.split_tf32(wraw) if E.ROUND_TF32 else wraw), shift
         return E._rc(wraw), shift
 
-    wk, shift = _packed(conv, "conv3x3-implicit" if implicit else "conv3x3-gemm", bn, (conv.weight,) + _bn_tensors(bn), build)
+    wk, shift = _packed(conv, "conv3x3-bf16x3" if bf16x3 else ("conv3x3-implicit" if implicit else "conv3x3-gemm"), bn,
+                        (conv.weight,) + _bn_tensors(bn), build)
+    if bf16x3:
+        # raw-tile implicit GEMM with both operands as two bf16 planes and three bf16 tensor-core passes: ~2^-16 per product (the
+        # two-plane TF32 form below rounds the activations to tf32) at 3/4 of its tensor-pipe time
+        xq2 = ops.pad_nhwc_quad_bf16x2(x, F_, H, W, Cin, pad_mode)
+        y = ops.conv3x3_bf16x3(xq2, wk, F_, H, W, Cin, Cout, bias=shift, residual=residual, act=ops.ACT_RELU if relu else ops.ACT_NONE)
+        if residual is not None and act_after_residual:
+            y = ops.relu_fwd(y, out=y)
+        return y, H, W
     if implicit:
         # implicit GEMM: 4-D TMA boxes of the padded activation feed the tcgen05 kernel directly (no im2col matrix)
         # The frozen encoder chains 21 convolutions; with plain tf32 weights its features land at 1.16e-3 relative (just outside

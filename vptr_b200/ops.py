@@ -476,6 +476,33 @@ def conv3x3_tf32_quad(xq, w, F, H, W, C, Cout, bias=None, residual=None, act=ACT
     return out
 
 
+CONV_BF16X3 = os.environ.get("VPTR_CONV_TF32", "") != "1"     # ResnetBlock convs on the bf16x3 raw-tile kernel (else two-plane TF32)
+
+
+def conv3x3_bf16x3_ok(H, W, C):
+    return CONV_BF16X3 and H % 8 == 0 and W % 8 == 0 and C % 8 == 0 and os.environ.get("VPTR_CONV_GENERIC", "") != "1"
+
+
+def pad_nhwc_quad_bf16x2(x, F, H, W, C, pad_mode):
+    out = torch.empty(2, F * (H // 8) * (W // 8) * 100, C, dtype=torch.bfloat16, device=x.device)
+    _call("vptr_pad_nhwc_quad_bf16x2", _p(x), _p(out), F, H, W, C, pad_mode, _s())
+    return out
+
+
+def split_bf16x2(w):
+    """(rows, K) fp32 -> (rows, 2K) bf16: [hi plane | lo plane] per row"""
+    rows, K = w.shape
+    out = torch.empty(rows, 2 * K, dtype=torch.bfloat16, device=w.device)
+    _call("vptr_split_bf16x2", _p(w), _p(out), rows, K, _s())
+    return out
+
+
+def conv3x3_bf16x3(xq2, w2, F, H, W, C, Cout, bias=None, residual=None, act=ACT_NONE, round_tf32=False):
+    out = torch.empty(F * H * W, Cout, dtype=torch.float32, device=xq2.device)
+    _call("vptr_conv3x3_bf16x3", _p(xq2), _p(w2), _p(out), F, H, W, C, Cout, _p(bias), _p(residual), int(act), 2 if round_tf32 else 0, _s())
+    return out
+
+
 def split_tf32(w):
     """[rows][K] -> [rows][2K]: tf32 hi plane followed by the tf32 lo plane"""
     rows, K = w.shape
