@@ -278,7 +278,7 @@ def kernel_rooflines(gemm_stats, hbm_gbs, tf32_peak):
                                   "frac": round(alg / tf32_peak, 4), "frac_executed": round(ex / tf32_peak, 4),
                                   "note": "executed = TF32-pass equivalents: hi*hi + lo*hi + hi*lo bf16 passes cost 1.5 tf32 passes (the two-plane TF32 form cost 2)"}
     out["ncu"] = ("tensor-pipe / DRAM figures of the same kernels under ncu --set full: profiles/r01_ncu_attn_tcgen05.txt, r02_ncu_attn_cfg1.txt, "
-                  "r02_ncu_attn_mma64.txt, r01_ncu_conv3x3_w8.txt, r02_ncu_conv_quad.txt")
+                  "r02_ncu_attn_mma64.txt, r01_ncu_conv3x3_w8.txt, r02_ncu_conv_quad.txt, r02_ncu_conv_bf16x3.txt (98 % tensor pipe)")
     return out
 
 
